@@ -1,0 +1,114 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference, which does not exist on
+the GPU box):   python oracle/make_golden.py
+The reference is imported from where it lies (never copied).  Fixtures are kept
+small; the weights are re-created deterministically by
+`oracle.cidnet_oracle.make_state_dict(seed)` (numpy PCG64) and a checksum of
+them is stored so drift is detected.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+from oracle import cidnet_oracle as O  # noqa: E402
+from net.CIDNet import CIDNet          # noqa: E402  (the reference)
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+torch.set_grad_enabled(False)
+
+
+def checksum(sd):
+    return float(sum(v.double().abs().sum().item() for v in sd.values()))
+
+
+def hvi_cases():
+    """HVIT / PHVIT vectors, incl. ties, greys, black, white and `gated` flags."""
+    out = {}
+    kinds = ["uniform", "dark", "grid8", "grey8", "onehot", "const:0", "const:0.5", "const:1"]
+    for k_val in (0.2, 0.37):
+        model = CIDNet().eval()
+        model.trans.density_k.data.fill_(k_val)
+        for kind in kinds:
+            x = O.make_input(kind, 1, 24, 40, seed=7)
+            hvi = model.trans.HVIT(x)
+            rgb = model.trans.PHVIT(hvi)
+            tag = f"{kind}|k={k_val}"
+            out[tag + "|x"] = x.numpy()
+            out[tag + "|hvi"] = hvi.numpy()
+            out[tag + "|rgb"] = rgb.numpy()
+    # PHVIT on out-of-range HVI input (what the network actually feeds it) + gates
+    model = CIDNet().eval()
+    model.trans.density_k.data.fill_(0.2)
+    rng = np.random.default_rng(11)
+    hv = torch.from_numpy(rng.uniform(-1.3, 1.3, (1, 3, 24, 40)).astype(np.float32))
+    model.trans.HVIT(torch.rand(1, 3, 8, 8))       # sets this_k
+    out["phvit_wild|in"] = hv.numpy()
+    out["phvit_wild|plain"] = model.trans.PHVIT(hv).numpy()
+    model.trans.gated, model.trans.gated2 = True, True
+    model.trans.alpha_s, model.trans.alpha = 1.3, 0.8
+    out["phvit_wild|gated"] = model.trans.PHVIT(hv).numpy()
+    fresh = CIDNet().eval()                          # this_k == 0 path (:14)
+    out["phvit_wild|k0"] = fresh.trans.PHVIT(hv).numpy()
+    np.savez_compressed(os.path.join(OUT, "hvi_cases.npz"), **out)
+    print("hvi_cases", len(out))
+
+
+def forward_cases():
+    taps_wanted = ["hvi", "i_enc0", "hv_0", "i_enc1", "hv_1", "I_LCA1", "HV_LCA1", "i_enc2", "hv_2",
+                   "I_LCA3", "HV_LCA4", "hvd3", "id3", "HV_LCA5", "id1", "hvd1", "out_hvi"]
+    for seed, perturb, kind, (B, H, W) in [(0, True, "uniform", (2, 32, 48)),
+                                           (1, False, "dark", (1, 40, 24)),
+                                           (2, True, "grid8", (1, 16, 16))]:
+        sd = O.make_state_dict(seed, perturb)
+        model = CIDNet().eval()
+        model.load_state_dict(sd, strict=True)
+        x = O.make_input(kind, B, H, W, seed=100 + seed)
+        y = model(x)
+        # intermediates through forward hooks on the reference's own sub-modules
+        caps = {}
+        hooks = []
+        for name in ["IE_block0", "HVE_block0", "IE_block1", "HVE_block1", "I_LCA1", "HV_LCA1", "IE_block2",
+                     "HVE_block2", "I_LCA3", "HV_LCA4", "HVD_block3", "ID_block3", "HV_LCA5", "ID_block1",
+                     "HVD_block1"]:
+            hooks.append(getattr(model, name).register_forward_hook(
+                lambda m, i, o, name=name: caps.__setitem__(name, o.detach().clone())))
+        y2 = model(x)
+        assert torch.equal(y, y2)
+        for h in hooks:
+            h.remove()
+        model.trans.gated, model.trans.gated2 = True, True
+        model.trans.alpha_s, model.trans.alpha = 1.3, 0.9
+        yg = model(x)
+        out = {"x": x.numpy(), "y": y.numpy(), "y_gated": yg.numpy(),
+               "seed": np.int64(seed), "perturb": np.int64(perturb),
+               "weights_abs_sum": np.float64(checksum(sd))}
+        ren = {"IE_block0": "i_enc0", "HVE_block0": "hv_0", "IE_block1": "i_enc1", "HVE_block1": "hv_1",
+               "IE_block2": "i_enc2", "HVE_block2": "hv_2", "HVD_block3": "hvd3", "ID_block3": "id3",
+               "ID_block1": "id1", "HVD_block1": "hvd1"}
+        for k_, v in caps.items():
+            out["tap|" + ren.get(k_, k_)] = v.numpy().astype(np.float32)
+        np.savez_compressed(os.path.join(OUT, f"forward_s{seed}.npz"), **out)
+        print("forward", seed, y.shape, float(y.mean()))
+    del taps_wanted
+
+
+def state_dict_keys():
+    model = CIDNet()
+    with open(os.path.join(OUT, "state_dict_keys.txt"), "w") as f:
+        for k_, v in model.state_dict().items():
+            f.write(f"{k_} {list(v.shape)}\n")
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    hvi_cases()
+    forward_cases()
+    state_dict_keys()
