@@ -1,0 +1,79 @@
+"""ctypes binding of libcidnet_b200.so (C ABI: include/cidnet_b200.h)."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcidnet_b200.so")
+
+OK, ERR_INVALID, ERR_ARCH, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4
+
+
+class CidnetError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libcidnet_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+# name -> (restype, argtypes); must list every symbol include/cidnet_b200.h declares
+SIGNATURES = {
+    "cidnet_last_error": (C.c_char_p, []),
+    "cidnet_abi_version": (C.c_int, []),
+    "cidnet_act_dtype": (C.c_int, []),
+    "cidnet_hvit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "cidnet_phvit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
+                               C.c_int, C.c_float, C.c_int, C.c_float, C.c_void_p]),
+    "cidnet_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "cidnet_destroy": (C.c_int, [C.c_void_p]),
+    "cidnet_set_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
+    "cidnet_finalize_weights": (C.c_int, [C.c_void_p]),
+    "cidnet_workspace_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    "cidnet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float, C.c_void_p]),
+    "cidnet_forward_launches": (C.c_int, [C.c_void_p]),
+    "cidnet_read_tap": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int), C.c_void_p]),
+    # unit-test hook (csrc/test_hooks.cu): x, w_host, aux, ln_host, out, B, Cin, H, W, Cout, ksize, mode, flat, prelu, stream
+    "cidnet_test_conv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_float, C.c_void_p]),
+}
+
+
+def lib():
+    """Load the shared library; fail loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python hvi-cidnet_b200/build.py` "
+                "(there is no CPU/PyTorch fallback for the CIDNet hot path)")
+        h = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(h, name)          # AttributeError if the .so lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def check(code):
+    if code != OK:
+        raise CidnetError(code, lib().cidnet_last_error().decode("utf-8", "replace"))
+
+
+def require_cuda_f32(t, name):
+    import torch
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{name} is on {t.device}: the B200-native CIDNet path has no CPU fallback; move it to an sm_100 CUDA device")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32 (got {t.dtype})")
+    return t.contiguous()
+
+
+def stream_ptr(device):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

@@ -1,0 +1,626 @@
+// Model context, weight folding/packing and the forward schedule behind the C ABI.
+//
+// Graph = /root/reference/net/CIDNet.py:71-122 with the dead I_LCA5 (:105) skipped.
+// Every activation is NHWC, 16-bit (act_t), channel pitch rounded up to 8; the HVI image
+// is kept as fp32 NCHW for the global residual (:119).
+#include "cab.cuh"
+#include "conv_gemm.cuh"
+#include "iel.cuh"
+#include "stem_head.cuh"
+#include "weights.cuh"
+
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace cidnet;
+
+namespace {
+
+const int kCh[4] = {36, 36, 72, 144};
+const int kHeads[4] = {1, 2, 4, 8};
+
+struct LcaWeights {
+    bool live = true;
+    int C = 0, Cp = 0, heads = 0, h = 0, hp = 0;
+    float *wq = nullptr, *wk = nullptr, *wv = nullptr;   // depthwise [9][Cp]
+    float* temp = nullptr;                               // [heads]
+    float* wo = nullptr;                                 // [C][C]
+    PackedWeights fold_tmpl;                             // geometry of the per-image folded weights
+    PackedWeights w_in;                                  // project_in (LN folded), rows [x1 hp | x2 hp]
+    float *dw0 = nullptr, *dw1 = nullptr, *dw2 = nullptr;
+    PackedWeights w_out;                                 // project_out  h -> C
+};
+
+struct StageWeights {      // the I_/HV_ pair of one of the 6 LCA stages
+    LcaWeights lca[2];     // 0 = I_LCA, 1 = HV_LCA
+    PackedWeights qkv[2];  // GEMM on the I tensor: [q_I | kv_HV];  on the HV tensor: [q_HV | kv_I]
+};
+
+struct DownWeights { PackedWeights w; float prelu = 0.25f; };
+struct UpWeights { PackedWeights w3; PackedWeights w1; float prelu = 0.25f; };
+
+struct Tap { const void* ptr; int C, H, W, pitch; bool f32_nchw; };
+
+}  // namespace
+
+struct cidnet_ctx {
+    int device = 0;
+    bool finalized = false;
+    std::map<std::string, std::vector<float>> raw;
+    float k_host = 0.2f;
+    float* k_dev = nullptr;
+    float *stem_whv = nullptr, *stem_wi = nullptr, *head_wi = nullptr, *head_whv = nullptr;
+    DownWeights down[2][3];    // [branch 0=I,1=HV][block1..3]
+    UpWeights up[2][3];        // [branch][block3, block2, block1]  (index 0 = block3)
+    StageWeights stage[6];
+    std::vector<void*> owned;  // every cudaMalloc'ed pointer (freed in destroy)
+    std::map<std::string, Tap> taps;
+    int last_B = 0;
+    int launches = 0;
+};
+
+namespace {
+
+// ---------------------------------------------------------------- weights ---
+const std::vector<std::string>& all_keys() {
+    static std::vector<std::string> keys;
+    if (!keys.empty()) return keys;
+    auto lca = [&](const std::string& p) {
+        for (const char* s : {".norm.weight", ".norm.bias", ".gdfn.project_in.weight", ".gdfn.dwconv.weight",
+                              ".gdfn.dwconv1.weight", ".gdfn.dwconv2.weight", ".gdfn.project_out.weight",
+                              ".ffn.temperature", ".ffn.q.weight", ".ffn.q_dwconv.weight", ".ffn.kv.weight",
+                              ".ffn.kv_dwconv.weight", ".ffn.project_out.weight"})
+            keys.push_back(p + s);
+    };
+    for (const char* br : {"HVE", "IE"}) {
+        keys.push_back(std::string(br) + "_block0.1.weight");
+        for (int n = 1; n <= 3; ++n) {
+            keys.push_back(std::string(br) + "_block" + std::to_string(n) + ".prelu.weight");
+            keys.push_back(std::string(br) + "_block" + std::to_string(n) + ".down.0.weight");
+        }
+    }
+    for (const char* br : {"HVD", "ID"}) {
+        keys.push_back(std::string(br) + "_block0.1.weight");
+        for (int n = 1; n <= 3; ++n) {
+            const std::string p = std::string(br) + "_block" + std::to_string(n);
+            keys.push_back(p + ".prelu.weight");
+            keys.push_back(p + ".up_scale.0.weight");
+            keys.push_back(p + ".up.weight");
+        }
+    }
+    for (const char* br : {"HV", "I"})
+        for (int n = 1; n <= 6; ++n) lca(std::string(br) + "_LCA" + std::to_string(n));
+    keys.push_back("trans.density_k");
+    return keys;
+}
+
+int64_t expected_numel(const std::string& key) {
+    // shapes of SURVEY App. B, derived from the key
+    auto lvl_of_lca = [](int n) { return n <= 3 ? n : 7 - n; };   // LCA1,6 -> 1; 2,5 -> 2; 3,4 -> 3
+    if (key == "trans.density_k") return 1;
+    if (key.find("prelu.weight") != std::string::npos) return 1;
+    if (key == "HVE_block0.1.weight") return 36 * 3 * 9;
+    if (key == "IE_block0.1.weight") return 36 * 9;
+    if (key == "HVD_block0.1.weight") return 2 * 36 * 9;
+    if (key == "ID_block0.1.weight") return 36 * 9;
+    const size_t bpos = key.find("_block");
+    if (bpos != std::string::npos) {
+        const int n = key[bpos + 6] - '0';
+        if (key.find(".down.0.weight") != std::string::npos) return (int64_t)kCh[n] * kCh[n - 1] * 9;
+        if (key.find(".up_scale.0.weight") != std::string::npos) return (int64_t)kCh[n - 1] * kCh[n] * 9;
+        if (key.find(".up.weight") != std::string::npos) return (int64_t)kCh[n - 1] * 2 * kCh[n - 1];
+    }
+    const size_t lpos = key.find("_LCA");
+    if (lpos != std::string::npos) {
+        const int n = key[lpos + 4] - '0';
+        const int C = kCh[lvl_of_lca(n)], heads = kHeads[lvl_of_lca(n)], h = (int)(C * 2.66);
+        if (key.find(".norm.") != std::string::npos) return C;
+        if (key.find("project_in") != std::string::npos) return (int64_t)2 * h * C;
+        if (key.find(".gdfn.dwconv.weight") != std::string::npos) return (int64_t)2 * h * 9;
+        if (key.find(".gdfn.dwconv1") != std::string::npos || key.find(".gdfn.dwconv2") != std::string::npos) return (int64_t)h * 9;
+        if (key.find(".gdfn.project_out") != std::string::npos) return (int64_t)C * h;
+        if (key.find("temperature") != std::string::npos) return heads;
+        if (key.find(".ffn.q.weight") != std::string::npos) return (int64_t)C * C;
+        if (key.find(".ffn.q_dwconv") != std::string::npos) return (int64_t)C * 9;
+        if (key.find(".ffn.kv.weight") != std::string::npos) return (int64_t)2 * C * C;
+        if (key.find(".ffn.kv_dwconv") != std::string::npos) return (int64_t)2 * C * 9;
+        if (key.find(".ffn.project_out") != std::string::npos) return (int64_t)C * C;
+    }
+    return -1;
+}
+
+int dev_f32(cidnet_ctx* ctx, float** dst, const std::vector<float>& v) {
+    int rc = upload_f32(dst, v);
+    if (!rc && *dst) ctx->owned.push_back(*dst);
+    return rc;
+}
+void own(cidnet_ctx* ctx, PackedWeights& p) {
+    if (p.w) ctx->owned.push_back(p.w);
+    if (p.bias) ctx->owned.push_back(p.bias);
+    if (p.wsum) ctx->owned.push_back(p.wsum);
+}
+
+// depthwise weight [n][1][3][3] rows [r0, r0+n) -> fp32 [9][pitch] tap-major, zero padded
+std::vector<float> dw_tapmajor(const std::vector<float>& w, int r0, int n, int pitch, int dst0 = 0,
+                               std::vector<float>* into = nullptr) {
+    std::vector<float> local;
+    std::vector<float>& out = into ? *into : local;
+    if (!into) out.assign((size_t)9 * pitch, 0.f);
+    for (int c = 0; c < n; ++c)
+        for (int t = 0; t < 9; ++t) out[(size_t)t * pitch + dst0 + c] = w[(size_t)(r0 + c) * 9 + t];
+    return out;
+}
+
+int build_lca(cidnet_ctx* ctx, const std::string& pfx, int level, LcaWeights* L) {
+    auto& R = ctx->raw;
+    const int C = kCh[level], heads = kHeads[level], h = (int)(C * 2.66), hp = round_up(h, 16), Cp = act_pitch(C);
+    L->C = C; L->Cp = Cp; L->heads = heads; L->h = h; L->hp = hp;
+    int rc;
+    if ((rc = dev_f32(ctx, &L->wq, dw_tapmajor(R[pfx + ".ffn.q_dwconv.weight"], 0, C, Cp)))) return rc;
+    if ((rc = dev_f32(ctx, &L->wk, dw_tapmajor(R[pfx + ".ffn.kv_dwconv.weight"], 0, C, Cp)))) return rc;
+    if ((rc = dev_f32(ctx, &L->wv, dw_tapmajor(R[pfx + ".ffn.kv_dwconv.weight"], C, C, Cp)))) return rc;
+    if ((rc = dev_f32(ctx, &L->temp, R[pfx + ".ffn.temperature"]))) return rc;
+    if ((rc = dev_f32(ctx, &L->wo, R[pfx + ".ffn.project_out.weight"]))) return rc;
+    // geometry of the folded per-image weights (C x C, 1x1)
+    PackedWeights& f = L->fold_tmpl;
+    f.cin = C; f.taps = 1; f.kchunks = ceil_div(C, 64); f.n_out = C; f.n_img = 1;
+    choose_blocking(C, &f.block_n, &f.n_blocks);
+    f.n_rows = f.block_n * f.n_blocks;
+    // IEL
+    const float* lnw = R[pfx + ".norm.weight"].data();
+    const float* lnb = R[pfx + ".norm.bias"].data();
+    const std::vector<float>& pin = R[pfx + ".gdfn.project_in.weight"];
+    std::vector<WeightSegment> segs{{pin.data(), h, 0, lnw, lnb}, {pin.data() + (size_t)h * C, h, hp, lnw, lnb}};
+    if ((rc = pack_conv_segments(&L->w_in, segs, C, 1, 2 * hp, true))) return rc;
+    own(ctx, L->w_in);
+    std::vector<float> dw0((size_t)9 * 2 * hp, 0.f);
+    dw_tapmajor(R[pfx + ".gdfn.dwconv.weight"], 0, h, 2 * hp, 0, &dw0);
+    dw_tapmajor(R[pfx + ".gdfn.dwconv.weight"], h, h, 2 * hp, hp, &dw0);
+    if ((rc = dev_f32(ctx, &L->dw0, dw0))) return rc;
+    if ((rc = dev_f32(ctx, &L->dw1, dw_tapmajor(R[pfx + ".gdfn.dwconv1.weight"], 0, h, hp)))) return rc;
+    if ((rc = dev_f32(ctx, &L->dw2, dw_tapmajor(R[pfx + ".gdfn.dwconv2.weight"], 0, h, hp)))) return rc;
+    if ((rc = pack_conv_weights(&L->w_out, R[pfx + ".gdfn.project_out.weight"].data(), C, h, 1, nullptr, C, nullptr, nullptr))) return rc;
+    own(ctx, L->w_out);
+    return CIDNET_OK;
+}
+
+int build_weights(cidnet_ctx* ctx) {
+    auto& R = ctx->raw;
+    for (const std::string& k : all_keys())
+        CIDNET_CHECK(R.count(k) && (int64_t)R[k].size() == expected_numel(k), CIDNET_ERR_STATE,
+                     "finalize_weights: missing or mis-sized state_dict tensor '" + k + "'");
+    int rc;
+    ctx->k_host = R["trans.density_k"][0];
+    if ((rc = dev_f32(ctx, &ctx->k_dev, R["trans.density_k"]))) return rc;
+    {   // stem / head weights, tap-input major fp32
+        const auto& whv = R["HVE_block0.1.weight"];   // [36][3][9]
+        std::vector<float> a(27 * 36), b(9 * 36), c(9 * 36), d(2 * 9 * 36);
+        for (int o = 0; o < 36; ++o)
+            for (int i = 0; i < 27; ++i) a[i * 36 + o] = whv[o * 27 + i];
+        const auto& wi = R["IE_block0.1.weight"];     // [36][1][9]
+        for (int o = 0; o < 36; ++o)
+            for (int t = 0; t < 9; ++t) b[t * 36 + o] = wi[o * 9 + t];
+        const auto& wid = R["ID_block0.1.weight"];    // [1][36][9]
+        for (int ci = 0; ci < 36; ++ci)
+            for (int t = 0; t < 9; ++t) c[t * 36 + ci] = wid[ci * 9 + t];
+        const auto& whd = R["HVD_block0.1.weight"];   // [2][36][9]
+        for (int o = 0; o < 2; ++o)
+            for (int ci = 0; ci < 36; ++ci)
+                for (int t = 0; t < 9; ++t) d[(o * 9 + t) * 36 + ci] = whd[(o * 36 + ci) * 9 + t];
+        if ((rc = dev_f32(ctx, &ctx->stem_whv, a))) return rc;
+        if ((rc = dev_f32(ctx, &ctx->stem_wi, b))) return rc;
+        if ((rc = dev_f32(ctx, &ctx->head_wi, c))) return rc;
+        if ((rc = dev_f32(ctx, &ctx->head_whv, d))) return rc;
+    }
+    const char* enc[2] = {"IE", "HVE"};
+    const char* dec[2] = {"ID", "HVD"};
+    for (int br = 0; br < 2; ++br) {
+        for (int n = 1; n <= 3; ++n) {
+            const std::string p = std::string(enc[br]) + "_block" + std::to_string(n);
+            DownWeights& D = ctx->down[br][n - 1];
+            if ((rc = pack_conv_weights(&D.w, R[p + ".down.0.weight"].data(), kCh[n], kCh[n - 1], 9, nullptr, kCh[n], nullptr, nullptr))) return rc;
+            own(ctx, D.w);
+            D.prelu = R[p + ".prelu.weight"][0];
+        }
+        for (int n = 3; n >= 1; --n) {
+            // NormUpsample(in = kCh[n], out = kCh[n-1]):  1x1(cat[up(conv3(x)), skip]) =
+            //   up((Wa o conv3)(x)) + Wb * skip   -- the 1x1 commutes with the bilinear resampling.
+            const std::string p = std::string(dec[br]) + "_block" + std::to_string(n);
+            UpWeights& U = ctx->up[br][3 - n];
+            const int cin = kCh[n], co = kCh[n - 1];
+            const auto& w3 = R[p + ".up_scale.0.weight"];   // [co][cin][9]
+            const auto& wu = R[p + ".up.weight"];           // [co][2co]
+            std::vector<float> comp((size_t)co * cin * 9), wb((size_t)co * co);
+            for (int o = 0; o < co; ++o) {
+                for (int i = 0; i < cin * 9; ++i) {
+                    double s = 0.0;
+                    for (int m = 0; m < co; ++m) s += (double)wu[(size_t)o * 2 * co + m] * w3[(size_t)m * cin * 9 + i];
+                    comp[(size_t)o * cin * 9 + i] = (float)s;
+                }
+                for (int m = 0; m < co; ++m) wb[(size_t)o * co + m] = wu[(size_t)o * 2 * co + co + m];
+            }
+            if ((rc = pack_conv_weights(&U.w3, comp.data(), co, cin, 9, nullptr, co, nullptr, nullptr))) return rc;
+            own(ctx, U.w3);
+            if ((rc = pack_conv_weights(&U.w1, wb.data(), co, co, 1, nullptr, co, nullptr, nullptr))) return rc;
+            own(ctx, U.w1);
+            U.prelu = R[p + ".prelu.weight"][0];
+        }
+    }
+    for (int n = 1; n <= 6; ++n) {
+        const int level = n <= 3 ? n : 7 - n;
+        StageWeights& S = ctx->stage[n - 1];
+        const std::string pi = "I_LCA" + std::to_string(n), ph = "HV_LCA" + std::to_string(n);
+        S.lca[0].live = (n != 5);       // I_LCA5 is dead in the reference graph (CIDNet.py:105 vs :109)
+        S.lca[1].live = true;
+        if (S.lca[0].live && (rc = build_lca(ctx, pi, level, &S.lca[0]))) return rc;
+        if ((rc = build_lca(ctx, ph, level, &S.lca[1]))) return rc;
+        const int C = kCh[level], Cp = act_pitch(C);
+        const std::string pf[2] = {pi, ph};
+        for (int src = 0; src < 2; ++src) {
+            // GEMM on tensor `src` (0 = I, 1 = HV): q of LCA[src] (x = own tensor), k,v of LCA[1-src] (y = this tensor)
+            const std::string &own_p = pf[src], &oth_p = pf[1 - src];
+            std::vector<WeightSegment> segs;
+            if (S.lca[src].live)
+                segs.push_back({R[own_p + ".ffn.q.weight"].data(), C, 0, R[own_p + ".norm.weight"].data(), R[own_p + ".norm.bias"].data()});
+            if (S.lca[1 - src].live) {
+                const float* kv = R[oth_p + ".ffn.kv.weight"].data();
+                const float* lw = R[oth_p + ".norm.weight"].data();
+                const float* lb = R[oth_p + ".norm.bias"].data();
+                segs.push_back({kv, C, Cp, lw, lb});
+                segs.push_back({kv + (size_t)C * C, C, 2 * Cp, lw, lb});
+            }
+            if ((rc = pack_conv_segments(&S.qkv[src], segs, C, 1, 3 * Cp, true))) return rc;
+            own(ctx, S.qkv[src]);
+        }
+    }
+    return CIDNET_OK;
+}
+
+// -------------------------------------------------------------- workspace ---
+struct Bump {
+    uint8_t* base; int64_t off = 0;
+    explicit Bump(void* b) : base(reinterpret_cast<uint8_t*>(b)) {}
+    template <typename T> T* take(int64_t count) {
+        off = (off + 1023) & ~int64_t(1023);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * (int64_t)sizeof(T);
+        return p;
+    }
+};
+
+struct Plan {
+    int B, H[4], W[4];
+    float* hvi; float* out_hvi;
+    act_t *i_enc0, *hv_0, *id1, *hvd1;                     // L0, pitch 40
+    act_t *enc_i[4], *enc_hv[4];                           // enc_x[l] = output of block l (level l), l = 1..3
+    act_t *lca_i[7], *lca_hv[7];                           // outputs of LCA n = 1..6
+    act_t *dec_i[4], *dec_hv[4];                           // dec_x[l] = output of up block l+1 -> level l (l = 1, 2)
+    act_t *tup_i[4], *tup_hv[4];                           // low-res pre-composed conv outputs at level l (l = 1..3)
+    // per-level scratch for an LCA stage pair
+    act_t *qkv[4][2], *v[4][2], *xp[4][2], *tin[4][2], *g[4][2], *mfold[4][2];
+    float* stats; int64_t stats_bytes;
+    float *gram[6][2], *sq[6][2], *sk[6][2];
+    int64_t bytes;
+};
+
+void make_plan(Plan* P, void* ws, int B, int H, int W) {
+    Bump bp(ws);
+    P->B = B;
+    for (int l = 0; l < 4; ++l) { P->H[l] = H >> l; P->W[l] = W >> l; }
+    auto px = [&](int l) { return (int64_t)B * P->H[l] * P->W[l]; };
+    P->hvi = bp.take<float>(px(0) * 3);
+    P->out_hvi = bp.take<float>(px(0) * 3);
+    P->i_enc0 = bp.take<act_t>(px(0) * 40); P->hv_0 = bp.take<act_t>(px(0) * 40);
+    P->id1 = bp.take<act_t>(px(0) * 40);    P->hvd1 = bp.take<act_t>(px(0) * 40);
+    for (int l = 1; l <= 3; ++l) {
+        const int Cp = act_pitch(kCh[l]);
+        P->enc_i[l] = bp.take<act_t>(px(l) * Cp); P->enc_hv[l] = bp.take<act_t>(px(l) * Cp);
+        const int Cup = act_pitch(kCh[l - 1]);
+        P->tup_i[l] = bp.take<act_t>(px(l) * Cup); P->tup_hv[l] = bp.take<act_t>(px(l) * Cup);
+        if (l <= 2) { P->dec_i[l] = bp.take<act_t>(px(l) * Cp); P->dec_hv[l] = bp.take<act_t>(px(l) * Cp); }
+        const int h = (int)(kCh[l] * 2.66), hp = round_up(h, 16);
+        PackedWeights f; choose_blocking(kCh[l], &f.block_n, &f.n_blocks);
+        const int64_t fold_elems = (int64_t)B * f.block_n * f.n_blocks * ceil_div(kCh[l], 64) * 64;
+        for (int s = 0; s < 2; ++s) {
+            P->qkv[l][s] = bp.take<act_t>(px(l) * 3 * Cp);
+            P->v[l][s] = bp.take<act_t>(px(l) * Cp);
+            P->xp[l][s] = bp.take<act_t>(px(l) * Cp);
+            P->tin[l][s] = bp.take<act_t>(px(l) * 2 * hp);
+            P->g[l][s] = bp.take<act_t>(px(l) * hp);
+            P->mfold[l][s] = bp.take<act_t>(fold_elems);
+        }
+    }
+    for (int n = 1; n <= 6; ++n) {
+        const int l = n <= 3 ? n : 7 - n;
+        P->lca_i[n] = bp.take<act_t>(px(l) * act_pitch(kCh[l]));
+        P->lca_hv[n] = bp.take<act_t>(px(l) * act_pitch(kCh[l]));
+    }
+    // attention statistics: one contiguous region, cleared by a single memset per forward
+    bp.off = (bp.off + 1023) & ~int64_t(1023);
+    const int64_t s0 = bp.off;
+    P->stats = bp.take<float>(0);
+    for (int n = 1; n <= 6; ++n) {
+        const int l = n <= 3 ? n : 7 - n;
+        const int C = kCh[l], Cp = act_pitch(C), heads = kHeads[l];
+        for (int s = 0; s < 2; ++s) {
+            P->gram[n - 1][s] = bp.take<float>((int64_t)B * heads * 324);
+            P->sq[n - 1][s] = bp.take<float>((int64_t)B * Cp);
+            P->sk[n - 1][s] = bp.take<float>((int64_t)B * Cp);
+        }
+    }
+    P->stats_bytes = bp.off - s0;
+    P->bytes = bp.off + 1024;
+}
+
+// ---------------------------------------------------------------- forward ---
+struct Fwd {
+    cidnet_ctx* ctx; Plan P; cudaStream_t st; int launches = 0;
+
+    void tap(const std::string& name, const void* p, int C, int l, int pitch, bool f32 = false) {
+        ctx->taps[name] = Tap{p, C, P.H[l], P.W[l], pitch, f32};
+    }
+    int gemm(ConvGemmLaunch& L) { ++launches; return launch_conv_gemm(L, st); }
+
+    int down(int br, int n, const act_t* in, act_t* out) {   // level n-1 -> n
+        const DownWeights& D = ctx->down[br][n - 1];
+        ConvGemmLaunch L;
+        L.mode = EPI_DOWN; L.in = in; L.B = P.B; L.H = P.H[n - 1]; L.W = P.W[n - 1]; L.in_pitch = act_pitch(kCh[n - 1]);
+        L.wt = &D.w; L.out = out; L.out_pitch = act_pitch(kCh[n]); L.prelu = D.prelu;
+        return gemm(L);
+    }
+    int up(int br, int n, const act_t* x, const act_t* skip, act_t* t, act_t* out) {   // level n -> n-1
+        const UpWeights& U = ctx->up[br][3 - n];
+        ConvGemmLaunch A;
+        A.mode = EPI_STORE; A.in = x; A.B = P.B; A.H = P.H[n]; A.W = P.W[n]; A.in_pitch = act_pitch(kCh[n]);
+        A.wt = &U.w3; A.out = t; A.out_pitch = act_pitch(kCh[n - 1]);
+        int rc = gemm(A);
+        if (rc) return rc;
+        ConvGemmLaunch Bq;
+        Bq.mode = EPI_UP; Bq.in = skip; Bq.B = P.B; Bq.H = P.H[n - 1]; Bq.W = P.W[n - 1]; Bq.in_pitch = act_pitch(kCh[n - 1]);
+        Bq.flat = true; Bq.wt = &U.w1; Bq.out = out; Bq.out_pitch = act_pitch(kCh[n - 1]);
+        Bq.up = t; Bq.up_pitch = act_pitch(kCh[n - 1]); Bq.prelu = U.prelu;
+        return gemm(Bq);
+    }
+
+    // one LCA stage: I_LCA(x_i, x_hv) and HV_LCA(x_hv, x_i)   (net/LCA.py:78-81, 90-93)
+    int lca_stage(int n, const act_t* x_i, const act_t* x_hv, act_t* out_i, act_t* out_hv) {
+        const int l = n <= 3 ? n : 7 - n;
+        StageWeights& S = ctx->stage[n - 1];
+        const int C = kCh[l], Cp = act_pitch(C), heads = kHeads[l];
+        const int H = P.H[l], W = P.W[l];
+        const act_t* x[2] = {x_i, x_hv};
+        act_t* out[2] = {out_i, out_hv};
+        int rc;
+        // 1. LayerNorm + q / kv 1x1 of both branches: one GEMM per input tensor
+        for (int s = 0; s < 2; ++s) {
+            ConvGemmLaunch L;
+            L.mode = EPI_LN; L.in = x[s]; L.B = P.B; L.H = H; L.W = W; L.in_pitch = Cp; L.flat = true;
+            L.wt = &S.qkv[s]; L.out = P.qkv[l][s]; L.out_pitch = 3 * Cp;
+            if ((rc = gemm(L))) return rc;
+        }
+        // 2. depthwise 3x3 + Gram + norms (q, k never leave the SM)
+        int probs[2], np = 0;
+        for (int s = 0; s < 2; ++s) if (S.lca[s].live) probs[np++] = s;
+        {
+            CabDwArgs a; memset(&a, 0, sizeof a);
+            for (int i = 0; i < np; ++i) {
+                const int s = probs[i];
+                a.q[i] = P.qkv[l][s]; a.q_pitch[i] = 3 * Cp;
+                a.k[i] = P.qkv[l][1 - s] + Cp; a.v[i] = P.qkv[l][1 - s] + 2 * Cp; a.kv_pitch[i] = 3 * Cp;
+                a.wq[i] = S.lca[s].wq; a.wk[i] = S.lca[s].wk; a.wv[i] = S.lca[s].wv;
+                a.v_out[i] = P.v[l][s];
+                a.gram[i] = P.gram[n - 1][s]; a.sq[i] = P.sq[n - 1][s]; a.sk[i] = P.sk[n - 1][s];
+            }
+            a.v_pitch = Cp; a.B = P.B; a.H = H; a.W = W; a.C = C; a.heads = heads; a.nprob = np;
+            ++launches;
+            if ((rc = launch_cab_dw_gram(a, st))) return rc;
+        }
+        // 3. normalise + temperature + softmax + fold into project_out
+        {
+            CabFoldArgs f; memset(&f, 0, sizeof f);
+            for (int i = 0; i < np; ++i) {
+                const int s = probs[i];
+                f.gram[i] = P.gram[n - 1][s]; f.sq[i] = P.sq[n - 1][s]; f.sk[i] = P.sk[n - 1][s];
+                f.temp[i] = S.lca[s].temp; f.wo[i] = S.lca[s].wo; f.m_out[i] = P.mfold[l][s];
+            }
+            const PackedWeights& t = S.lca[probs[0]].fold_tmpl;
+            f.B = P.B; f.C = C; f.Cp = Cp; f.heads = heads; f.nprob = np; f.n_rows = t.n_rows; f.kt = t.ktot();
+            ++launches;
+            if ((rc = launch_cab_fold(f, st))) return rc;
+        }
+        for (int i = 0; i < np; ++i) {
+            const int s = probs[i];
+            LcaWeights& Lw = S.lca[s];
+            // 4. x' = x + (W_o * blockdiag(attn_b)) v      (per-image 1x1)
+            PackedWeights fw = Lw.fold_tmpl; fw.w = P.mfold[l][s]; fw.n_img = P.B > 1 ? P.B : 1;
+            ConvGemmLaunch A;
+            A.mode = EPI_STORE; A.in = P.v[l][s]; A.B = P.B; A.H = H; A.W = W; A.in_pitch = Cp; A.flat = true;
+            A.wt = &fw; A.out = P.xp[l][s]; A.out_pitch = Cp; A.res = x[s]; A.res_pitch = Cp;
+            if (P.B == 1) fw.n_img = 1;
+            if ((rc = gemm(A))) return rc;
+            // 5. LayerNorm + project_in
+            ConvGemmLaunch Bq;
+            Bq.mode = EPI_LN; Bq.in = P.xp[l][s]; Bq.B = P.B; Bq.H = H; Bq.W = W; Bq.in_pitch = Cp; Bq.flat = true;
+            Bq.wt = &Lw.w_in; Bq.out = P.tin[l][s]; Bq.out_pitch = 2 * Lw.hp;
+            if ((rc = gemm(Bq))) return rc;
+        }
+        // 6. IEL gate (dw 3x3 -> dw 3x3 + tanh + residual -> product)
+        {
+            IelGateArgs g; memset(&g, 0, sizeof g);
+            for (int i = 0; i < np; ++i) {
+                const int s = probs[i];
+                g.t[i] = P.tin[l][s]; g.g[i] = P.g[l][s];
+                g.w0[i] = S.lca[s].dw0; g.w1[i] = S.lca[s].dw1; g.w2[i] = S.lca[s].dw2;
+            }
+            g.B = P.B; g.H = H; g.W = W; g.hp = S.lca[probs[0]].hp; g.nprob = np;
+            ++launches;
+            if ((rc = launch_iel_gate(g, st))) return rc;
+        }
+        // 7. project_out (+ residual for I_LCA only)
+        for (int i = 0; i < np; ++i) {
+            const int s = probs[i];
+            LcaWeights& Lw = S.lca[s];
+            ConvGemmLaunch Cq;
+            Cq.mode = EPI_STORE; Cq.in = P.g[l][s]; Cq.B = P.B; Cq.H = H; Cq.W = W; Cq.in_pitch = Lw.hp; Cq.flat = true;
+            Cq.wt = &Lw.w_out; Cq.out = out[s]; Cq.out_pitch = Cp;
+            if (s == 0) { Cq.res = P.xp[l][s]; Cq.res_pitch = Cp; }
+            if ((rc = gemm(Cq))) return rc;
+            tap(std::string(s == 0 ? "I_LCA" : "HV_LCA") + std::to_string(n), out[s], C, l, Cp);
+            tap(std::string(s == 0 ? "I_LCA" : "HV_LCA") + std::to_string(n) + ".after_cab", P.xp[l][s], C, l, Cp);
+        }
+        return CIDNET_OK;
+    }
+
+    int run(const float* rgb_in, float* rgb_out, const float* k_dev, int gated, float alpha_s, int gated2, float alpha) {
+        int rc;
+        CIDNET_CUDA_OK(cudaMemsetAsync(P.stats, 0, (size_t)P.stats_bytes, st));
+        StemArgs sa{rgb_in, P.hvi, P.i_enc0, P.hv_0, ctx->stem_whv, ctx->stem_wi, k_dev ? k_dev : ctx->k_dev,
+                    ctx->k_host, P.B, P.H[0], P.W[0], 40};
+        ++launches;
+        if ((rc = launch_stem(sa, st))) return rc;
+        tap("hvi", P.hvi, 3, 0, 0, true); tap("i_enc0", P.i_enc0, 36, 0, 40); tap("hv_0", P.hv_0, 36, 0, 40);
+        if ((rc = down(0, 1, P.i_enc0, P.enc_i[1]))) return rc;
+        if ((rc = down(1, 1, P.hv_0, P.enc_hv[1]))) return rc;
+        tap("i_enc1", P.enc_i[1], 36, 1, 40); tap("hv_1", P.enc_hv[1], 36, 1, 40);
+        if ((rc = lca_stage(1, P.enc_i[1], P.enc_hv[1], P.lca_i[1], P.lca_hv[1]))) return rc;
+        if ((rc = down(0, 2, P.lca_i[1], P.enc_i[2]))) return rc;
+        if ((rc = down(1, 2, P.lca_hv[1], P.enc_hv[2]))) return rc;
+        tap("i_enc2", P.enc_i[2], 72, 2, 72); tap("hv_2", P.enc_hv[2], 72, 2, 72);
+        if ((rc = lca_stage(2, P.enc_i[2], P.enc_hv[2], P.lca_i[2], P.lca_hv[2]))) return rc;
+        // block3 consumes the PRE-LCA2 tensors (CIDNet.py:94-95)
+        if ((rc = down(0, 3, P.enc_i[2], P.enc_i[3]))) return rc;
+        if ((rc = down(1, 3, P.enc_hv[2], P.enc_hv[3]))) return rc;
+        tap("i_enc3", P.enc_i[3], 144, 3, 144); tap("hv_3", P.enc_hv[3], 144, 3, 144);
+        if ((rc = lca_stage(3, P.enc_i[3], P.enc_hv[3], P.lca_i[3], P.lca_hv[3]))) return rc;
+        // LCA4: both consume the LCA3 outputs (HV_LCA4 sees i_enc4, CIDNet.py:101)
+        if ((rc = lca_stage(4, P.lca_i[3], P.lca_hv[3], P.lca_i[4], P.lca_hv[4]))) return rc;
+        if ((rc = up(1, 3, P.lca_hv[4], P.lca_hv[2], P.tup_hv[3], P.dec_hv[2]))) return rc;
+        if ((rc = up(0, 3, P.lca_i[4], P.lca_i[2], P.tup_i[3], P.dec_i[2]))) return rc;
+        tap("hvd3", P.dec_hv[2], 72, 2, 72); tap("id3", P.dec_i[2], 72, 2, 72);
+        // stage 5: I_LCA5 is dead, only HV_LCA5(hv_3, i_dec3)
+        if ((rc = lca_stage(5, P.dec_i[2], P.dec_hv[2], nullptr, P.lca_hv[5]))) return rc;
+        if ((rc = up(1, 2, P.lca_hv[5], P.lca_hv[1], P.tup_hv[2], P.dec_hv[1]))) return rc;
+        if ((rc = up(0, 2, P.dec_i[2], P.lca_i[1], P.tup_i[2], P.dec_i[1]))) return rc;   // takes i_dec3 (:109)
+        tap("hvd2", P.dec_hv[1], 36, 1, 40); tap("id2", P.dec_i[1], 36, 1, 40);
+        if ((rc = lca_stage(6, P.dec_i[1], P.dec_hv[1], P.lca_i[6], P.lca_hv[6]))) return rc;
+        if ((rc = up(0, 1, P.lca_i[6], P.i_enc0, P.tup_i[1], P.id1))) return rc;
+        if ((rc = up(1, 1, P.lca_hv[6], P.hv_0, P.tup_hv[1], P.hvd1))) return rc;
+        tap("id1", P.id1, 36, 0, 40); tap("hvd1", P.hvd1, 36, 0, 40);
+        HeadArgs ha{P.id1, P.hvd1, P.hvi, rgb_out, P.out_hvi, ctx->head_wi, ctx->head_whv,
+                    k_dev ? k_dev : ctx->k_dev, ctx->k_host, alpha_s, alpha, gated, gated2, P.B, P.H[0], P.W[0], 40};
+        ++launches;
+        if ((rc = launch_head(ha, st))) return rc;
+        tap("out_hvi", P.out_hvi, 3, 0, 0, true);
+        return CIDNET_OK;
+    }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------ C ABI ---
+extern "C" int cidnet_create(cidnet_ctx** out, int device) {
+    CIDNET_CHECK(out != nullptr, CIDNET_ERR_INVALID, "create: null out pointer");
+    *out = nullptr;
+    int ndev = 0;
+    CIDNET_CUDA_OK(cudaGetDeviceCount(&ndev));
+    CIDNET_CHECK(device >= 0 && device < ndev, CIDNET_ERR_INVALID, "create: no such CUDA device");
+    cudaDeviceProp prop;
+    CIDNET_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    CIDNET_CHECK(prop.major == 10, CIDNET_ERR_ARCH,
+                 std::string("create: device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                     std::to_string(prop.minor) + "; this library contains sm_100a code only (no fallback)");
+    cidnet_ctx* c = new cidnet_ctx();
+    c->device = device;
+    *out = c;
+    return CIDNET_OK;
+}
+
+static void release_device(cidnet_ctx* ctx) {
+    for (void* p : ctx->owned) cudaFree(p);
+    ctx->owned.clear();
+    ctx->finalized = false;
+}
+
+extern "C" int cidnet_destroy(cidnet_ctx* ctx) {
+    if (!ctx) return CIDNET_OK;
+    cudaSetDevice(ctx->device);
+    release_device(ctx);
+    delete ctx;
+    return CIDNET_OK;
+}
+
+extern "C" int cidnet_set_weight(cidnet_ctx* ctx, const char* key, const float* host, int64_t numel) {
+    CIDNET_CHECK(ctx && key && host, CIDNET_ERR_INVALID, "set_weight: null argument");
+    const int64_t want = expected_numel(key);
+    CIDNET_CHECK(want > 0, CIDNET_ERR_INVALID, std::string("set_weight: unexpected key '") + key + "'");
+    CIDNET_CHECK(want == numel, CIDNET_ERR_INVALID,
+                 std::string("set_weight: size mismatch for '") + key + "': got " + std::to_string(numel) +
+                     ", expected " + std::to_string(want));
+    ctx->raw[key].assign(host, host + numel);
+    ctx->finalized = false;
+    return CIDNET_OK;
+}
+
+extern "C" int cidnet_finalize_weights(cidnet_ctx* ctx) {
+    CIDNET_CHECK(ctx, CIDNET_ERR_INVALID, "finalize_weights: null ctx");
+    CIDNET_CUDA_OK(cudaSetDevice(ctx->device));
+    CIDNET_CUDA_OK(cudaDeviceSynchronize());   // previous packed weights may still be in use
+    release_device(ctx);
+    for (int i = 0; i < 6; ++i) ctx->stage[i] = StageWeights();
+    int rc = build_weights(ctx);
+    if (rc) { release_device(ctx); return rc; }
+    ctx->finalized = true;
+    return CIDNET_OK;
+}
+
+extern "C" int64_t cidnet_workspace_bytes(int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0 || H % 8 || W % 8) return 0;
+    Plan P;
+    make_plan(&P, nullptr, B, H, W);
+    return P.bytes;
+}
+
+extern "C" int cidnet_forward(cidnet_ctx* ctx, const float* rgb_in, float* rgb_out, int B, int H, int W,
+                              void* workspace, int64_t workspace_bytes, const float* k_dev,
+                              int gated, float alpha_s, int gated2, float alpha, void* stream) {
+    CIDNET_CHECK(ctx, CIDNET_ERR_INVALID, "forward: null ctx");
+    CIDNET_CHECK(ctx->finalized, CIDNET_ERR_STATE, "forward: weights not finalized (call cidnet_finalize_weights)");
+    CIDNET_CHECK(B >= 0 && H > 0 && W > 0, CIDNET_ERR_INVALID, "forward: bad shape");
+    CIDNET_CHECK(H % 8 == 0 && W % 8 == 0, CIDNET_ERR_INVALID,
+                 "forward: H and W must be multiples of 8 (got " + std::to_string(H) + "x" + std::to_string(W) +
+                     "); the reference fails in torch.cat for such inputs, callers pad first");
+    if (B == 0) return CIDNET_OK;
+    CIDNET_CHECK(rgb_in && rgb_out && workspace, CIDNET_ERR_INVALID, "forward: null pointer");
+    CIDNET_CHECK((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, CIDNET_ERR_INVALID, "forward: workspace must be 1024-byte aligned");
+    Fwd f;
+    f.ctx = ctx; f.st = (cudaStream_t)stream;
+    make_plan(&f.P, workspace, B, H, W);
+    CIDNET_CHECK(workspace_bytes >= f.P.bytes, CIDNET_ERR_STATE,
+                 "forward: workspace too small: need " + std::to_string(f.P.bytes) + " bytes");
+    ctx->taps.clear();
+    ctx->last_B = B;
+    int rc = f.run(rgb_in, rgb_out, k_dev, gated, alpha_s, gated2, alpha);
+    ctx->launches = f.launches;
+    return rc;
+}
+
+extern "C" int cidnet_forward_launches(cidnet_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int cidnet_read_tap(cidnet_ctx* ctx, const char* name, float* dst, int64_t dst_numel, int* dims,
+                               void* stream) {
+    CIDNET_CHECK(ctx && name && dims, CIDNET_ERR_INVALID, "read_tap: null argument");
+    auto it = ctx->taps.find(name);
+    CIDNET_CHECK(it != ctx->taps.end(), CIDNET_ERR_INVALID, std::string("read_tap: unknown tap '") + name + "'");
+    const Tap& t = it->second;
+    dims[0] = t.C; dims[1] = t.H; dims[2] = t.W;
+    if (dst == nullptr) return CIDNET_OK;      // query only
+    const int64_t n = (int64_t)ctx->last_B * t.C * t.H * t.W;
+    CIDNET_CHECK(dst_numel >= n, CIDNET_ERR_INVALID, "read_tap: destination too small");
+    if (t.f32_nchw) {
+        CIDNET_CUDA_OK(cudaMemcpyAsync(dst, t.ptr, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        return CIDNET_OK;
+    }
+    return launch_nhwc_to_nchw(reinterpret_cast<const act_t*>(t.ptr), dst, ctx->last_B, t.C, t.H, t.W, t.pitch,
+                               (cudaStream_t)stream);
+}

@@ -1,0 +1,70 @@
+// Shared declarations for libcidnet_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/cidnet_b200.h"
+
+namespace cidnet {
+
+// Storage type of the internal NHWC activations and of the tensor-core operands.
+// fp16 (10-bit mantissa) keeps the end-to-end error ~10x below the 2e-3 contract
+// (SURVEY App. E); build with -DCIDNET_ACT_BF16 for bf16 operands instead.
+#ifdef CIDNET_ACT_BF16
+typedef __nv_bfloat16 act_t;
+#define CIDNET_UMMA_FMT 1u
+__host__ __device__ __forceinline__ float act2f(act_t v) { return __bfloat162float(v); }
+__host__ __device__ __forceinline__ act_t f2act(float v) { return __float2bfloat16_rn(v); }
+#else
+typedef __half act_t;
+#define CIDNET_UMMA_FMT 0u
+__host__ __device__ __forceinline__ float act2f(act_t v) { return __half2float(v); }
+__host__ __device__ __forceinline__ act_t f2act(float v) { return __float2half_rn(v); }
+#endif
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define CIDNET_CUDA_OK(expr)                                                              \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            return ::cidnet::fail(CIDNET_ERR_CUDA, std::string(#expr) + ": " +            \
+                                                       cudaGetErrorString(_e));           \
+        }                                                                                 \
+    } while (0)
+
+#define CIDNET_CHECK(cond, code, msg)                                                     \
+    do {                                                                                  \
+        if (!(cond)) return ::cidnet::fail((code), (msg));                                \
+    } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+// pitch (in elements) of an NHWC activation with C channels: multiple of 8 so that
+// every pixel row is 16-byte aligned (TMA global strides must be multiples of 16 B).
+static inline int act_pitch(int C) { return round_up(C, 8); }
+
+// 8 packed activations <-> 8 floats (one 16-byte vector)
+struct alignas(16) act8 { act_t v[8]; };
+
+__device__ __forceinline__ void load8(const act_t* p, float* f) {
+    uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const act_t* a = reinterpret_cast<const act_t*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = act2f(a[i]);
+}
+__device__ __forceinline__ void store8(act_t* p, const float* f) {
+    uint4 raw;
+    act_t* a = reinterpret_cast<act_t*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = f2act(f[i]);
+    *reinterpret_cast<uint4*>(p) = raw;
+}
+
+}  // namespace cidnet

@@ -1,0 +1,66 @@
+// Host-side description of one implicit-GEMM convolution launch (conv_gemm.cu).
+#pragma once
+#include "common.cuh"
+
+namespace cidnet {
+
+enum EpiMode {
+    EPI_STORE = 0,  // out = acc (+ residual) [-> PReLU]
+    EPI_LN    = 1,  // out = rstd[p] * (acc - mean[p] * wsum[n]) + bias[n]   (LayerNorm folded into the 1x1)
+    EPI_DOWN  = 2,  // out = PReLU(bilinear_x0.5(acc))                        (NormDownsample)
+    EPI_UP    = 3,  // out = PReLU(acc + bilinear_x2(t)[p, n])                (NormUpsample tail)
+};
+
+// Weights of one GEMM, packed on the device as act_t [n_img][n_rows][taps*kchunks*64]
+// (K-major, every tap's Cin zero-padded to kchunks*64 so each TMA box is one swizzle atom).
+struct PackedWeights {
+    act_t* w = nullptr;
+    int n_rows = 0;      // rows present in memory (>= n_blocks*block_n, zero padded)
+    int n_out = 0;       // output channels actually stored (row index == output channel)
+    int cin = 0;
+    int taps = 1;
+    int kchunks = 1;
+    int block_n = 16;
+    int n_blocks = 1;
+    int n_img = 1;       // >1: per-image weights (CAB fold), indexed by batch
+    float* bias = nullptr;   // [n_rows]  (EPI_LN)
+    float* wsum = nullptr;   // [n_rows]  (EPI_LN)
+    int ktot() const { return taps * kchunks * 64; }
+};
+
+static inline void choose_blocking(int n_out, int* block_n, int* n_blocks) {
+    int nb = ceil_div(n_out, 256);
+    int bn = round_up(ceil_div(n_out, nb), 16);
+    *block_n = bn;
+    *n_blocks = nb;
+}
+
+struct ConvGemmLaunch {
+    EpiMode mode = EPI_STORE;
+    // input activation, NHWC act_t
+    const act_t* in = nullptr;
+    int B = 0, H = 0, W = 0, in_pitch = 0;
+    bool flat = false;            // 1x1 only: tile over the flattened H*W axis (128 consecutive pixels)
+    const PackedWeights* wt = nullptr;
+    // output
+    act_t* out = nullptr;
+    int out_pitch = 0;
+    // EPI_STORE extras
+    const act_t* res = nullptr;
+    int res_pitch = 0;
+    bool use_prelu = false;
+    float prelu = 0.f;
+    // EPI_LN
+    float ln_eps = 1e-6f;
+    // EPI_UP: low-resolution tensor t [B, H/2, W/2, up_pitch] to be upsampled x2 and added
+    const act_t* up = nullptr;
+    int up_pitch = 0;
+};
+
+int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream);
+
+// layout helpers (tests / taps only)
+int launch_nchw_to_nhwc(const float* src, act_t* dst, int B, int C, int H, int W, int pitch, cudaStream_t s);
+int launch_nhwc_to_nchw(const act_t* src, float* dst, int B, int C, int H, int W, int pitch, cudaStream_t s);
+
+}  // namespace cidnet

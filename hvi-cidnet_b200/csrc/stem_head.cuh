@@ -1,0 +1,26 @@
+#pragma once
+#include "common.cuh"
+
+namespace cidnet {
+
+struct StemArgs {
+    const float* rgb; float* hvi; act_t* i_enc0; act_t* hv_0;
+    const float* w_hv;   // [27][36] fp32 (input-tap major)
+    const float* w_i;    // [9][36]
+    const float* k_dev;  // optional: density_k read on the device (no host sync)
+    float k_host;
+    int B, H, W, pitch;
+};
+int launch_stem(const StemArgs& a, cudaStream_t stream);
+
+struct HeadArgs {
+    const act_t* i_dec1; const act_t* hv_1; const float* hvi; float* rgb;
+    float* out_hvi_dbg;  // optional fp32 NCHW tap of output_hvi
+    const float* w_i;    // [9][36]
+    const float* w_hv;   // [2][9][36]
+    const float* k_dev; float k_host; float alpha_s; float alpha; int gated; int gated2;
+    int B, H, W, pitch;
+};
+int launch_head(const HeadArgs& a, cudaStream_t stream);
+
+}  // namespace cidnet

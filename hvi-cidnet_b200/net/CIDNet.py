@@ -1,0 +1,220 @@
+"""Host-side mirror of the reference's `net.CIDNet.CIDNet` (/root/reference/net/CIDNet.py:8-126).
+
+Drop-in surface kept: constructor `CIDNet(channels=[36,36,72,144], heads=[1,2,4,8], norm=False)`,
+`forward(x)`, `HVIT(x)`, the `trans` sub-module with its mutable knobs, the 191-tensor fp32
+`state_dict` (strict-loadable from the reference's `.pth` files) and the
+`PyTorchModelHubMixin` methods.  The sub-modules below are PARAMETER CONTAINERS only -- they
+give the parameters the reference's names, shapes and default initialisation, and are never
+called.  All arithmetic of `forward` runs in libcidnet_b200.so (sm_100a CUDA, C ABI in
+include/cidnet_b200.h); there is no PyTorch / CPU fallback.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from .HVI_transform import RGB_HVI
+
+try:  # the reference mixes this in (CIDNet.py:6,8); keep from_pretrained/save_pretrained when available
+    from huggingface_hub import PyTorchModelHubMixin
+except Exception:  # pragma: no cover
+    class PyTorchModelHubMixin:  # type: ignore
+        pass
+
+_CHANNELS = [36, 36, 72, 144]
+_HEADS = [1, 2, 4, 8]
+
+
+class _Norm(nn.Module):
+    """parameters of transformer_utils.LayerNorm (:14-15)"""
+    def __init__(self, c):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
+
+
+def _conv(ci, co, k, groups=1):
+    return nn.Conv2d(ci, co, kernel_size=k, stride=1, padding=k // 2, groups=groups, bias=False)
+
+
+class _CAB(nn.Module):
+    """parameters of LCA.CAB (:8-17)"""
+    def __init__(self, dim, heads):
+        super().__init__()
+        self.temperature = nn.Parameter(torch.ones(heads, 1, 1))
+        self.q, self.q_dwconv = _conv(dim, dim, 1), _conv(dim, dim, 3, groups=dim)
+        self.kv, self.kv_dwconv = _conv(dim, dim * 2, 1), _conv(dim * 2, dim * 2, 3, groups=dim * 2)
+        self.project_out = _conv(dim, dim, 1)
+
+
+class _IEL(nn.Module):
+    """parameters of LCA.IEL (:46-57)"""
+    def __init__(self, dim):
+        super().__init__()
+        h = int(dim * 2.66)
+        self.project_in = _conv(dim, h * 2, 1)
+        self.dwconv = _conv(h * 2, h * 2, 3, groups=h * 2)
+        self.dwconv1, self.dwconv2 = _conv(h, h, 3, groups=h), _conv(h, h, 3, groups=h)
+        self.project_out = _conv(h, dim, 1)
+
+
+class _LCA(nn.Module):
+    """HV_LCA / I_LCA (:71-93): `ffn` is the attention, `gdfn` the IEL (reference naming)."""
+    def __init__(self, dim, heads):
+        super().__init__()
+        self.gdfn, self.norm, self.ffn = _IEL(dim), _Norm(dim), _CAB(dim, heads)
+
+
+class _Down(nn.Module):
+    def __init__(self, ci, co):
+        super().__init__()
+        self.prelu = nn.PReLU()
+        self.down = nn.Sequential(_conv(ci, co, 3), nn.Identity())
+
+
+class _Up(nn.Module):
+    def __init__(self, ci, co):
+        super().__init__()
+        self.prelu = nn.PReLU()
+        self.up_scale = nn.Sequential(_conv(ci, co, 3), nn.Identity())
+        self.up = _conv(co * 2, co, 1)
+
+
+def _block0(ci, co):
+    return nn.Sequential(nn.Identity(), nn.Conv2d(ci, co, 3, stride=1, padding=0, bias=False))
+
+
+class CIDNet(nn.Module, PyTorchModelHubMixin):
+    def __init__(self, channels=[36, 36, 72, 144], heads=[1, 2, 4, 8], norm=False):
+        super(CIDNet, self).__init__()
+        if list(channels) != _CHANNELS or list(heads) != _HEADS:
+            raise NotImplementedError("the B200 kernels are specialised for channels=[36,36,72,144], heads=[1,2,4,8] "
+                                      "(the only configuration the reference's call sites and weights use)")
+        if norm:
+            raise NotImplementedError("norm=True (extra LayerNorms, transformer_utils.py:35-36,55) has no shipped weights")
+        c1, c2, c3, c4 = channels
+        for br, cin0, cout0 in (("HV", 3, 2), ("I", 1, 1)):
+            setattr(self, f"{br}E_block0", _block0(cin0, c1))
+            for n, (ci, co) in enumerate(((c1, c2), (c2, c3), (c3, c4)), start=1):
+                setattr(self, f"{br}E_block{n}", _Down(ci, co))
+            for n, (ci, co) in ((3, (c4, c3)), (2, (c3, c2)), (1, (c2, c1))):
+                setattr(self, f"{br}D_block{n}", _Up(ci, co))
+            setattr(self, f"{br}D_block0", _block0(c1, cout0))
+        for br in ("HV", "I"):
+            for n, lvl in ((1, 1), (2, 2), (3, 3), (4, 3), (5, 2), (6, 1)):
+                setattr(self, f"{br}_LCA{n}", _LCA(channels[lvl], heads[lvl]))
+        self.trans = RGB_HVI()
+        # ---- native state (not part of the state_dict) ----
+        self._ctx = None
+        self._ctx_device = None
+        self._synced = None
+        self._workspaces = {}
+
+    # ------------------------------------------------------------------ native context
+    def _weights_signature(self):
+        return tuple((p._version, p.data_ptr()) for n, p in self.named_parameters() if n != "trans.density_k")
+
+    def _ensure_ctx(self, device):
+        lib = _lib.lib()
+        if self._ctx is None or self._ctx_device != device:
+            self._release()
+            ctx = C.c_void_p()
+            _lib.check(lib.cidnet_create(C.byref(ctx), device.index if device.index is not None else torch.cuda.current_device()))
+            self._ctx, self._ctx_device, self._synced = ctx, device, None
+        sig = self._weights_signature()
+        if self._synced != sig:
+            self.sync_weights()
+            self._synced = sig
+        return self._ctx
+
+    def sync_weights(self):
+        """(re)pack the current parameters into the kernels' device layouts.  Called automatically
+        when a parameter's version changes (load_state_dict, optimizer steps); call it by hand after
+        editing a parameter through `.data`."""
+        lib = _lib.lib()
+        if self._ctx is None:
+            return
+        for name, p in self.state_dict().items():
+            t = p.detach().to("cpu", torch.float32).contiguous()
+            _lib.check(lib.cidnet_set_weight(self._ctx, name.encode(), t.data_ptr(), t.numel()))
+        with torch.cuda.device(self._ctx_device):
+            _lib.check(lib.cidnet_finalize_weights(self._ctx))
+
+    def _release(self):
+        ctx = self.__dict__.get("_ctx")
+        if ctx is not None:
+            try:
+                _lib.lib().cidnet_destroy(ctx)
+            except Exception:
+                pass
+        self.__dict__["_ctx"] = None
+        self.__dict__["_workspaces"] = {}
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _workspace(self, B, H, W, device):
+        key = (B, H, W, str(device))
+        ws = self._workspaces.get(key)
+        if ws is None:
+            nbytes = _lib.lib().cidnet_workspace_bytes(B, H, W)
+            ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+            self._workspaces = {key: ws}        # keep only the latest shape
+        off = (-ws.data_ptr()) % 1024
+        return ws, ws.data_ptr() + off, ws.numel() - off
+
+    # ------------------------------------------------------------------ reference surface
+    def forward(self, x):
+        dtypes = x.dtype
+        if not isinstance(x, torch.Tensor) or not x.is_cuda:
+            raise RuntimeError(f"CIDNet.forward: input is on {getattr(x, 'device', None)}; the B200-native path has no "
+                               "CPU fallback -- move the model and the input to an sm_100 CUDA device")
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise RuntimeError(f"CIDNet.forward expects [B,3,H,W], got {tuple(x.shape)}")
+        B, _, H, W = x.shape
+        if H % 8 or W % 8:
+            raise RuntimeError(f"Sizes of tensors must match: H and W must be multiples of 8, got {H}x{W} "
+                               "(the reference fails in torch.cat at transformer_utils.py:64; pad first)")
+        k = self.trans.density_k
+        if k.device != x.device:
+            raise RuntimeError(f"model parameters are on {k.device} but the input is on {x.device}")
+        xin = x.contiguous() if dtypes == torch.float32 else x.float().contiguous()
+        out = torch.empty_like(xin)
+        if B == 0:
+            return out.to(dtypes)
+        with torch.cuda.device(x.device):
+            ctx = self._ensure_ctx(x.device)
+            ws, ws_ptr, ws_bytes = self._workspace(B, H, W, x.device)
+            t = self.trans
+            kd = k.detach()
+            kptr = kd.data_ptr() if kd.dtype == torch.float32 else None
+            t._note_hvit_called()                                   # this_k = k.item(), lazily (HVI_transform.py:38)
+            _lib.check(_lib.lib().cidnet_forward(ctx, xin.data_ptr(), out.data_ptr(), B, H, W, ws_ptr, ws_bytes, kptr,
+                                                 int(bool(t.gated)), float(t.alpha_s), int(bool(t.gated2)),
+                                                 float(t.alpha), _lib.stream_ptr(x.device)))
+        return out if dtypes == torch.float32 else out.to(dtypes)
+
+    def HVIT(self, x):
+        hvi = self.trans.HVIT(x)
+        return hvi
+
+    # ------------------------------------------------------------------ test / profiling helpers
+    def read_tap(self, name):
+        """fp32 NCHW copy of a named internal activation of the LAST forward (parity tests)."""
+        lib = _lib.lib()
+        dims = (C.c_int * 3)()
+        _lib.check(lib.cidnet_read_tap(self._ctx, name.encode(), None, 0, dims, None))
+        Cc, H, W = dims[0], dims[1], dims[2]
+        B = next(iter(self._workspaces))[0]
+        out = torch.empty(B, Cc, H, W, device=self._ctx_device)
+        with torch.cuda.device(self._ctx_device):
+            _lib.check(lib.cidnet_read_tap(self._ctx, name.encode(), out.data_ptr(), out.numel(), dims,
+                                           _lib.stream_ptr(self._ctx_device)))
+        return out
+
+    def num_launches(self):
+        return int(_lib.lib().cidnet_forward_launches(self._ctx)) if self._ctx is not None else 0

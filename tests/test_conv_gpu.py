@@ -1,0 +1,117 @@
+"""GPU parity of the TMA + tcgen05 implicit-GEMM convolution kernel (all four
+epilogues) against torch fp32 references computed on operand values rounded to
+the kernel's 16-bit storage type (fp32 accumulate both sides)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import cidnet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _act_dtype():
+    from hvi_cidnet_b200 import _lib
+    return torch.float16 if _lib.lib().cidnet_act_dtype() == 0 else torch.bfloat16
+
+
+def _r(t):
+    return t.to(_act_dtype()).float()
+
+
+def run_conv(x, w, aux=None, ln=None, mode=0, flat=0, prelu=0.0):
+    from hvi_cidnet_b200 import _lib
+    B, Cin, H, W = x.shape
+    Cout, _, k, _ = w.shape
+    Ho, Wo = (H // 2, W // 2) if mode == 2 else (H, W)
+    out = torch.empty(B, Cout, Ho, Wo, device="cuda")
+    xd = x.cuda().contiguous()
+    wh = w.contiguous()
+    auxd = aux.cuda().contiguous() if aux is not None else None
+    lnh = ln.contiguous() if ln is not None else None
+    rc = _lib.lib().cidnet_test_conv(xd.data_ptr(), wh.data_ptr(), auxd.data_ptr() if auxd is not None else None,
+                                     lnh.data_ptr() if lnh is not None else None, out.data_ptr(),
+                                     B, Cin, H, W, Cout, k, mode, flat, float(prelu),
+                                     C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc)
+    return out.cpu()
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-6))
+
+
+CASES_1x1 = [(36, 36), (72, 72), (144, 144), (36, 120), (72, 216), (144, 432), (36, 190), (72, 382), (144, 766),
+             (95, 36), (191, 72), (383, 144)]
+
+
+@pytest.mark.parametrize("cin,cout", CASES_1x1)
+@pytest.mark.parametrize("flat", [0, 1])
+def test_conv1x1_store(cin, cout, flat):
+    g = torch.Generator().manual_seed(cin * 1000 + cout)
+    x = torch.randn(2, cin, 24, 40, generator=g)
+    w = torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5
+    ref = F.conv2d(_r(x), _r(w))
+    out = run_conv(x, w, flat=flat)
+    assert _rel(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("cin,cout,hw", [(36, 36, (16, 32)), (36, 72, (24, 40)), (72, 144, (10, 22)), (144, 72, (9, 13)),
+                                         (72, 36, (8, 16)), (36, 36, (50, 75))])
+def test_conv3x3_store_zero_pad(cin, cout, hw):
+    g = torch.Generator().manual_seed(cin + cout)
+    x = torch.randn(2, cin, *hw, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5
+    ref = F.conv2d(_r(x), _r(w), padding=1)
+    out = run_conv(x, w)
+    assert _rel(out, ref) < 2e-3
+
+
+def test_store_residual_and_prelu():
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1, 72, 16, 24, generator=g)
+    w = torch.randn(72, 72, 1, 1, generator=g) / 72 ** 0.5
+    res = torch.randn(1, 72, 16, 24, generator=g)
+    ref = F.conv2d(_r(x), _r(w)) + _r(res)
+    ref = torch.where(ref >= 0, ref, 0.2 * ref)
+    out = run_conv(x, w, aux=res, flat=1, prelu=0.2)
+    assert _rel(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("cin,cout", [(36, 120), (72, 216), (144, 432), (36, 190), (144, 766)])
+def test_conv1x1_layernorm_folded(cin, cout):
+    g = torch.Generator().manual_seed(cin)
+    x = torch.randn(2, cin, 16, 24, generator=g) * 2.0 + 0.7     # non-zero mean: exercises the mean correction
+    w = torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5
+    lw = 1.0 + 0.3 * torch.randn(cin, generator=g)
+    lb = 0.2 * torch.randn(cin, generator=g)
+    ref = F.conv2d(O.layer_norm_cf(_r(x), lw, lb), w)
+    out = run_conv(x, w, ln=torch.cat([lw, lb]), mode=1, flat=1)
+    assert _rel(out, ref) < 4e-3
+
+
+@pytest.mark.parametrize("cin,cout,hw", [(36, 36, (32, 48)), (36, 72, (16, 32)), (72, 144, (24, 40)), (36, 36, (400, 600))])
+def test_conv3x3_down(cin, cout, hw):
+    g = torch.Generator().manual_seed(cin + 7)
+    x = torch.randn(1, cin, *hw, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5
+    y = F.conv2d(_r(x), _r(w), padding=1)
+    ref = O.prelu(O.bilinear_ac(y, hw[0] // 2, hw[1] // 2), torch.tensor([0.17]))
+    out = run_conv(x, w, mode=2, prelu=0.17)
+    assert _rel(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("c,hw", [(36, (32, 48)), (72, (16, 24)), (36, (200, 304))])
+def test_conv1x1_up(c, hw):
+    g = torch.Generator().manual_seed(c + 11)
+    skip = torch.randn(2, c, *hw, generator=g)
+    t = torch.randn(2, c, hw[0] // 2, hw[1] // 2, generator=g)
+    w = torch.randn(c, c, 1, 1, generator=g) / c ** 0.5
+    ref = F.conv2d(_r(skip), _r(w)) + O.bilinear_ac(_r(t), hw[0], hw[1])
+    ref = O.prelu(ref, torch.tensor([0.3]))
+    for flat in (0, 1):
+        out = run_conv(skip, w, aux=t, mode=3, flat=flat, prelu=0.3)
+        assert _rel(out, ref) < 2e-3

@@ -1,0 +1,102 @@
+"""End-to-end GPU parity of CIDNet.forward (C ABI -> sm_100a kernels) against the CPU oracle and
+the reference-generated golden outputs.  Contract (BASELINE.json north_star): max-abs <= 2e-3 and
+PSNR >= 50 dB on the clamped RGB output; operands/activations are 16-bit (fp16 by default, fp32
+accumulate), the oracle is strict fp32."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cidnet_oracle as O
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+MAXABS, PSNR = 2e-3, 50.0
+
+
+@pytest.fixture(scope="module")
+def model():
+    from hvi_cidnet_b200.net.CIDNet import CIDNet
+    return CIDNet().cuda().eval()
+
+
+def _check(y, ref):
+    y, ref = y.clamp(0, 1), ref.clamp(0, 1)
+    err = float((y - ref).abs().max())
+    ps = O.psnr(y, ref)
+    assert err <= MAXABS and ps >= PSNR, f"max-abs {err:.3e}, PSNR {ps:.1f} dB"
+    return err, ps
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_golden_reference_outputs(model, seed):
+    g = np.load(os.path.join(GOLDEN, f"forward_s{seed}.npz"))
+    sd = O.make_state_dict(int(g["seed"]), bool(g["perturb"]))
+    model.load_state_dict(sd, strict=True)
+    model.trans.gated = model.trans.gated2 = False
+    x = torch.from_numpy(g["x"]).cuda()
+    with torch.no_grad():
+        y = model(x).cpu()
+    _check(y, torch.from_numpy(g["y"]))
+    # per-stage taps against the reference's own sub-module outputs
+    for key in g.files:
+        if key.startswith("tap|"):
+            ref = torch.from_numpy(g[key])
+            got = model.read_tap(key[4:]).cpu()
+            scale = float(ref.abs().max())
+            assert float((got - ref).abs().max()) <= 1.5e-2 * max(scale, 1.0), key
+    model.trans.gated, model.trans.gated2, model.trans.alpha_s, model.trans.alpha = True, True, 1.3, 0.9
+    with torch.no_grad():
+        yg = model(x).cpu()
+    _check(yg, torch.from_numpy(g["y_gated"]))
+    model.trans.gated = model.trans.gated2 = False
+    model.trans.alpha = 1.0
+
+
+@pytest.mark.parametrize("kind,shape", [("uniform", (1, 400, 600)), ("dark", (1, 400, 600)), ("grid8", (2, 200, 304)),
+                                        ("uniform", (3, 64, 72)), ("const:0.5", (1, 32, 32)), ("const:0", (1, 16, 24))])
+def test_against_oracle(model, kind, shape):
+    sd = O.make_state_dict(5, True)
+    model.load_state_dict(sd, strict=True)
+    x = O.make_input(kind, *shape, seed=21)
+    with torch.no_grad():
+        ref = O.forward(x, sd)
+        y = model(x.cuda()).cpu()
+    _check(y, ref)
+
+
+def test_default_init_state_dict_round_trip(model, tmp_path):
+    """torch.save(state_dict) -> torch.load(map_location=cpu) -> strict load (eval_SID_blur.py:22)."""
+    from hvi_cidnet_b200.net.CIDNet import CIDNet
+    torch.manual_seed(0)
+    fresh = CIDNet()
+    path = os.path.join(tmp_path, "w.pth")
+    torch.save(fresh.state_dict(), path)
+    sd = torch.load(path, map_location=lambda storage, loc: storage)
+    model.load_state_dict(sd, strict=True)
+    x = O.make_input("uniform", 1, 64, 96, seed=2)
+    with torch.no_grad():
+        y = model(x.cuda()).cpu()
+        ref = O.forward(x, {k: v.float() for k, v in sd.items()})
+    _check(y, ref)
+    assert abs(model.trans.this_k - 0.2) < 1e-6        # set by forward's HVIT (HVI_transform.py:38)
+
+
+def test_shape_errors(model):
+    with pytest.raises(RuntimeError):
+        model(torch.rand(1, 3, 20, 24, device="cuda"))      # H % 8 != 0: reference dies in torch.cat
+    with pytest.raises(RuntimeError):
+        model(torch.rand(1, 3, 16, 16))                      # CPU tensor: no fallback
+    assert model(torch.empty(0, 3, 16, 16, device="cuda")).shape == (0, 3, 16, 16)
+
+
+def test_batch_independence(model):
+    """images are independent units (attention is per image): a batch equals its images run alone."""
+    sd = O.make_state_dict(7, True)
+    model.load_state_dict(sd, strict=True)
+    x = O.make_input("uniform", 3, 48, 64, seed=4).cuda()
+    with torch.no_grad():
+        yb = model(x)
+        ys = torch.cat([model(x[i:i + 1]) for i in range(3)])
+    assert float((yb - ys).abs().max()) <= 1e-5

@@ -1,0 +1,91 @@
+"""GPU parity of the fused HVIT / PHVIT kernels (through the C ABI) against the
+CPU oracle and the reference-generated golden vectors.  Contract (BASELINE.json
+north_star): max-abs <= 1e-5 per direction, fp32."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cidnet_oracle as O
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def trans():
+    from hvi_cidnet_b200.net.HVI_transform import RGB_HVI
+    return RGB_HVI().cuda()
+
+
+def _wrap_pixels(ours, ref):
+    """pixels where |diff| is large because h%1 sits on the 0/1 wrap:
+    reported separately instead of loosening the tolerance."""
+    d = (ours - ref).abs().amax(dim=1)
+    return int((d > TOL).sum())
+
+
+def test_golden_vectors(trans):
+    g = np.load(os.path.join(GOLDEN, "hvi_cases.npz"))
+    tags = sorted({k.rsplit("|", 1)[0] for k in g.files if "|k=" in k})
+    for tag in tags:
+        k = float(tag.split("k=")[1])
+        trans.density_k.data.fill_(k)
+        x = torch.from_numpy(g[tag + "|x"]).cuda()
+        hvi = trans.HVIT(x).cpu()
+        assert float((hvi - torch.from_numpy(g[tag + "|hvi"])).abs().max()) <= TOL, tag
+        rgb = trans.PHVIT(torch.from_numpy(g[tag + "|hvi"]).cuda()).cpu()
+        assert _wrap_pixels(rgb, torch.from_numpy(g[tag + "|rgb"])) == 0, tag
+
+
+def test_phvit_wild_and_gates(trans):
+    g = np.load(os.path.join(GOLDEN, "hvi_cases.npz"))
+    hv = torch.from_numpy(g["phvit_wild|in"]).cuda()
+    trans.density_k.data.fill_(0.2)
+    trans.HVIT(torch.rand(1, 3, 8, 8, device="cuda"))
+    assert abs(trans.this_k - 0.2) < 1e-6
+    assert float((trans.PHVIT(hv).cpu() - torch.from_numpy(g["phvit_wild|plain"])).abs().max()) <= TOL
+    trans.gated, trans.gated2, trans.alpha_s, trans.alpha = True, True, 1.3, 0.8
+    assert float((trans.PHVIT(hv).cpu() - torch.from_numpy(g["phvit_wild|gated"])).abs().max()) <= TOL
+    trans.gated, trans.gated2, trans.alpha = False, False, 1.0
+    from hvi_cidnet_b200.net.HVI_transform import RGB_HVI
+    fresh = RGB_HVI().cuda()     # this_k == 0
+    assert float((fresh.PHVIT(hv).cpu() - torch.from_numpy(g["phvit_wild|k0"])).abs().max()) <= TOL
+
+
+@pytest.mark.parametrize("kind", ["uniform", "dark", "grid8", "grey8", "onehot"])
+@pytest.mark.parametrize("shape", [(2, 200, 304), (1, 37, 53), (3, 1, 1)])
+def test_against_oracle(trans, kind, shape):
+    B, H, W = shape
+    trans.density_k.data.fill_(0.2)
+    x = O.make_input(kind, B, H, W, seed=5)
+    ref_hvi = O.hvit(x, np.float32(0.2).item())
+    hvi = trans.HVIT(x.cuda()).cpu()
+    assert float((hvi - ref_hvi).abs().max()) <= TOL
+    ref_rgb = O.phvit(ref_hvi, np.float32(0.2).item())
+    rgb = trans.PHVIT(ref_hvi.cuda()).cpu()
+    bad = _wrap_pixels(rgb, ref_rgb)
+    assert bad == 0, f"{bad} pixels differ by more than {TOL}"
+
+
+def test_empty_and_errors(trans):
+    x = torch.empty(0, 3, 8, 8, device="cuda")
+    assert trans.HVIT(x).shape == (0, 3, 8, 8)
+    with pytest.raises(RuntimeError):
+        trans.HVIT(torch.rand(1, 4, 8, 8, device="cuda"))
+    with pytest.raises(TypeError):
+        trans.HVIT(torch.rand(1, 3, 8, 8, device="cuda").half())
+
+
+def test_full_hd_round_trip_properties(trans):
+    """Size-independent properties at BASELINE cfg-3 frame size: PHVIT(HVIT(x)) ~= x
+    (grey pixels come back within 1e-4 by construction, App. A) and I == max(rgb)."""
+    trans.density_k.data.fill_(0.2)
+    x = torch.rand(4, 3, 1080, 1920, device="cuda")
+    hvi = trans.HVIT(x)
+    assert torch.equal(hvi[:, 2], x.amax(dim=1))
+    assert float(hvi[:, :2].abs().max()) <= 1.0 + 1e-6
+    back = trans.PHVIT(hvi)
+    assert float((back - x).abs().max()) <= 2e-4
