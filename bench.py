@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- CIDNet inference throughput (megapixels/s) on B200, per the driver contract.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg4|cfg3]
+
+A "step" is ONE pass of the hot path (CIDNet.forward through the C ABI / sm_100a kernels)
+over one batch of synthetic input of the named shape.  Default workload = BASELINE.json
+configs[1]: 1x3x640x1120 (LOL-Blur.pth when present, else seeded random-init weights through
+a real .pth round trip).  Multi-GPU: one process per GPU (torchrun), images are independent
+units -> every rank runs its own batch, no data-path collective ("weak" scaling); the timing
+is the max over ranks of the device-timed region.
+
+JSON line keys: see the contract in the task description; extras: roofline (dominant kernel,
+timed live with CUDA events recorded on the launching stream around every kernel launch),
+kernels (per-kernel share), cpu_baseline (oracle port on host cores, bounded sample), e2e
+(pinned host -> H2D -> forward -> D2H every step), clocks, gpu_launches.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (B, H, W, description)
+    "cfg1": (1, 400, 600, "CIDNet 1x3x400x600 (LOLv1 shape)"),
+    "cfg2": (1, 640, 1120, "CIDNet 1x3x640x1120 (BASELINE.json configs[1])"),
+    "cfg4": (64, 400, 600, "CIDNet 64x3x400x600 batch (per rank: 64/N images)"),
+    "cfg5": (1, 2160, 3840, "CIDNet 1x3x2160x3840 single 4K image on one GPU"),
+}
+METRIC = "CIDNet inference megapixels/s"
+UNIT = "MP/s"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def find_weights():
+    for p in (os.environ.get("CIDNET_WEIGHTS"), os.path.join(ROOT, "LOL-Blur.pth"), "/root/reference/LOL-Blur.pth"):
+        if p and os.path.exists(p):
+            return p
+    return None
+
+
+def make_weights(tmpdir="/tmp"):
+    """state_dict for the bench: shipped LOL-Blur.pth if present, else seeded random-init saved and
+    re-loaded through a real .pth file (same path a user takes: eval_SID_blur.py:22)."""
+    import torch
+    w = find_weights()
+    if w:
+        return torch.load(w, map_location="cpu"), "LOL-Blur.pth"
+    from oracle.cidnet_oracle import make_state_dict
+    sd = make_state_dict(0, perturb=False)
+    path = os.path.join(tmpdir, f"cidnet_bench_{os.getpid()}.pth")
+    torch.save(sd, path)
+    sd = torch.load(path, map_location="cpu")
+    os.remove(path)
+    return sd, "seeded random-init (.pth round trip; LOL-Blur.pth absent)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU eval path (demo.py:26-27,55-57) timed on the host cores.
+    /root/reference does not exist on the GPU box, so the arm runs the oracle port of the same
+    algorithm (oracle/cidnet_oracle.py, pinned to the reference by tests/golden) with all host threads,
+    including the dead I_LCA5 the reference executes."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import cidnet_oracle as O
+    O.FAST_BILINEAR = True
+    torch.set_grad_enabled(False)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B, H, W, desc = WORKLOADS[args.workload]
+    sd, wdesc = make_weights()
+    sd = {k: v.float() for k, v in sd.items()}
+    sample_B, sample_H, sample_W = 1, H, W
+    x = O.make_input("uniform", sample_B, sample_H, sample_W, seed=1234)
+    t0 = time.perf_counter(); O.forward(x, sd, run_dead_block=True); t1 = time.perf_counter() - t0
+    budget = 150.0
+    if (args.steps + args.warmup) * t1 > budget:      # bounded sample: a centre crop (multiple of 8)
+        f = max(0.1, (budget / ((args.steps + args.warmup) * t1)) ** 0.5)
+        sample_H, sample_W = max(64, int(H * f) // 8 * 8), max(64, int(W * f) // 8 * 8)
+        x = O.make_input("uniform", 1, sample_H, sample_W, seed=1234)
+    for _ in range(args.warmup):
+        O.forward(x, sd, run_dead_block=True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.forward(x, sd, run_dead_block=True)
+    dt = time.perf_counter() - t0
+    mp = sample_H * sample_W / 1e6
+    val = mp * args.steps / dt
+    sample = f"{args.steps} forwards of 1x3x{sample_H}x{sample_W} (fp32, torch CPU, {torch.get_num_threads()} threads)"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "weights": wdesc},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(sd, H, W, seconds=12.0):
+    import torch
+    from oracle import cidnet_oracle as O
+    O.FAST_BILINEAR = True
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    h, w = min(H, 400), min(W, 600)          # cfg1 frame: the reference's own CPU-runnable case
+    x = O.make_input("uniform", 1, h, w, seed=1234)
+    sdf = {k: v.float() for k, v in sd.items()}
+    with torch.no_grad():
+        O.forward(x, sdf, run_dead_block=True)
+        n, t0 = 0, time.perf_counter()
+        while True:
+            O.forward(x, sdf, run_dead_block=True)
+            n += 1
+            dt = time.perf_counter() - t0
+            if dt > seconds or n >= 20:
+                break
+    return {"value": h * w * n / dt / 1e6, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} forwards of 1x3x{h}x{w}, fp32 torch CPU (oracle port incl. dead I_LCA5), {dt:.1f} s"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from hvi_cidnet_b200.net.CIDNet import CIDNet
+
+    torch.set_grad_enabled(False)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the CIDNet hot path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+
+    B, H, W, desc = WORKLOADS[args.workload]
+    if args.workload == "cfg4":
+        B = max(1, B // world)               # batch-sharded: fixed total, per-rank share
+    sd, wdesc = make_weights()
+    model = CIDNet().to(dev).eval()
+    model.load_state_dict(sd, strict=True)
+
+    # inputs: a ring of distinct images whose total size exceeds L2, so no step finds its input
+    # (or the previous step's intermediates, which are rewritten every step) in cache
+    img_bytes = B * 3 * H * W * 4
+    ring = max(2, min(64, -(-2 * L2_BYTES // img_bytes)))
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    xs = [torch.rand(B, 3, H, W, device=dev, generator=g) for _ in range(ring)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value) ---------------------------------------------------
+    for i in range(max(3, args.warmup)):
+        model(xs[i % ring])
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        y = model(xs[i % ring])
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = model.num_launches() * args.steps
+
+    # ---- per-kernel events, same steps (roofline) -----------------------------------------
+    model.set_profiling(True)
+    agg = {}
+    for i in range(args.steps):
+        model(xs[i % ring])
+        for name, ms, by, fl in model.read_profile():
+            a = agg.setdefault(name, [0.0, 0.0, 0.0, 0])
+            a[0] += ms; a[1] += by; a[2] += fl; a[3] += 1
+    model.set_profiling(False)
+    clocks = sampler.stop()
+
+    # ---- end to end through the public API with HOST buffers --------------------------------
+    hx = [torch.rand(B, 3, H, W).pin_memory() for _ in range(min(ring, 4))]
+    hy = torch.empty(B, 3, H, W).pin_memory()
+    for i in range(3):
+        hy.copy_(model(hx[i % len(hx)].to(dev, non_blocking=True)), non_blocking=True)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        xin = hx[i % len(hx)].to(dev, non_blocking=True)
+        hy.copy_(model(xin), non_blocking=True)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    if world > 1:
+        t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = float(t[0]), float(t[1])
+    mp_step_all = B * H * W * world / 1e6
+    value = mp_step_all * args.steps / (ms_total / 1e3)
+    e2e_value = mp_step_all * args.steps / (ms_e2e / 1e3)
+
+    if rank == 0:
+        kern = []
+        tot = sum(a[0] for a in agg.values())
+        for name, (ms, by, fl, n) in agg.items():
+            kern.append({"name": name, "launches_per_step": n // args.steps, "ms_per_step": ms / args.steps,
+                         "share": ms / tot if tot else 0.0,
+                         "GBps": by / ms / 1e6 if ms else 0.0, "TFLOPs": fl / ms / 1e9 if ms else 0.0})
+        kern.sort(key=lambda k: -k["ms_per_step"])
+        top = kern[0]
+        roof = {"kernel": top["name"], "bound": "hbm", "achieved": top["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": top["GBps"] / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                "share_of_step": top["share"], "tensor_TFLOPs": top["TFLOPs"],
+                "note": "achieved = algorithmic bytes (DESIGN.md) / CUDA-event time of that kernel inside the forward"}
+        cpu = cpu_baseline_sample(sd, H, W)
+        act = "fp16" if __import__("hvi_cidnet_b200._lib", fromlist=["lib"]).lib().cidnet_act_dtype() == 0 else "bf16"
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak" if args.workload != "cfg4" else "strong",
+                "vs_baseline": None, "dtype": act, "data": "synthetic",
+                "config": {"workload": f"{args.workload}: {desc}", "per_rank_batch": B, "H": H, "W": W, "weights": wdesc,
+                           "l2": f"inputs rotate over a ring of {ring} distinct images ({ring * img_bytes >> 20} MiB > L2); "
+                                 "all intermediates are rewritten every step",
+                           "accumulate": "fp32", "parallelism": f"dp{world} (independent images, no collective)"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": img_bytes, "d2h_bytes_per_step": img_bytes,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "roofline": roof, "kernels": kern[:12], "cpu_baseline": cpu, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

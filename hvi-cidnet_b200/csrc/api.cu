@@ -58,6 +58,12 @@ struct cidnet_ctx {
     std::map<std::string, Tap> taps;
     int last_B = 0;
     int launches = 0;
+    // optional per-launch profiling (bench.py roofline): event i is recorded BEFORE launch i,
+    // one more after the last launch
+    bool profiling = false;
+    std::vector<cudaEvent_t> events;
+    struct Rec { std::string name; double bytes; double flops; };
+    std::vector<Rec> recs;
 };
 
 namespace {
@@ -360,27 +366,52 @@ struct Fwd {
     void tap(const std::string& name, const void* p, int C, int l, int pitch, bool f32 = false) {
         ctx->taps[name] = Tap{p, C, P.H[l], P.W[l], pitch, f32};
     }
-    int gemm(ConvGemmLaunch& L) { ++launches; return launch_conv_gemm(L, st); }
+    // profiling mark: called right before every kernel launch
+    void mark(const std::string& name, double bytes, double flops) {
+        ++launches;
+        if (!ctx->profiling) return;
+        const size_t i = ctx->recs.size();
+        if (ctx->events.size() <= i + 1) {
+            ctx->events.resize(i + 2, nullptr);
+        }
+        for (size_t j = i; j <= i + 1; ++j)
+            if (ctx->events[j] == nullptr) cudaEventCreate(&ctx->events[j]);
+        cudaEventRecord(ctx->events[i], st);
+        ctx->recs.push_back({name, bytes, flops});
+    }
+    void finish_marks() {
+        if (ctx->profiling && !ctx->recs.empty()) cudaEventRecord(ctx->events[ctx->recs.size()], st);
+    }
+    int gemm(ConvGemmLaunch& L, const std::string& name) {
+        const PackedWeights& w = *L.wt;
+        const double px_in = (double)L.B * L.H * L.W;
+        const double px_out = L.mode == EPI_DOWN ? px_in / 4 : px_in;
+        double bytes = px_in * w.cin * 2 + px_out * w.n_out * 2 + (double)w.n_out * w.cin * w.taps * 2 * (w.n_img > 1 ? L.B : 1);
+        if (L.res) bytes += px_out * w.n_out * 2;
+        if (L.up) bytes += px_out / 4 * w.n_out * 2;
+        mark(name, bytes, 2.0 * px_in * w.n_out * w.cin * w.taps);
+        return launch_conv_gemm(L, st);
+    }
 
     int down(int br, int n, const act_t* in, act_t* out) {   // level n-1 -> n
         const DownWeights& D = ctx->down[br][n - 1];
         ConvGemmLaunch L;
         L.mode = EPI_DOWN; L.in = in; L.B = P.B; L.H = P.H[n - 1]; L.W = P.W[n - 1]; L.in_pitch = act_pitch(kCh[n - 1]);
         L.wt = &D.w; L.out = out; L.out_pitch = act_pitch(kCh[n]); L.prelu = D.prelu;
-        return gemm(L);
+        return gemm(L, "down" + std::to_string(n) + ".conv3x3_bilinear_prelu");
     }
     int up(int br, int n, const act_t* x, const act_t* skip, act_t* t, act_t* out) {   // level n -> n-1
         const UpWeights& U = ctx->up[br][3 - n];
         ConvGemmLaunch A;
         A.mode = EPI_STORE; A.in = x; A.B = P.B; A.H = P.H[n]; A.W = P.W[n]; A.in_pitch = act_pitch(kCh[n]);
         A.wt = &U.w3; A.out = t; A.out_pitch = act_pitch(kCh[n - 1]);
-        int rc = gemm(A);
+        int rc = gemm(A, "up" + std::to_string(n) + ".conv3x3_composed");
         if (rc) return rc;
         ConvGemmLaunch Bq;
         Bq.mode = EPI_UP; Bq.in = skip; Bq.B = P.B; Bq.H = P.H[n - 1]; Bq.W = P.W[n - 1]; Bq.in_pitch = act_pitch(kCh[n - 1]);
         Bq.flat = true; Bq.wt = &U.w1; Bq.out = out; Bq.out_pitch = act_pitch(kCh[n - 1]);
         Bq.up = t; Bq.up_pitch = act_pitch(kCh[n - 1]); Bq.prelu = U.prelu;
-        return gemm(Bq);
+        return gemm(Bq, "up" + std::to_string(n) + ".skip1x1_bilinear_prelu");
     }
 
     // one LCA stage: I_LCA(x_i, x_hv) and HV_LCA(x_hv, x_i)   (net/LCA.py:78-81, 90-93)
@@ -397,7 +428,7 @@ struct Fwd {
             ConvGemmLaunch L;
             L.mode = EPI_LN; L.in = x[s]; L.B = P.B; L.H = H; L.W = W; L.in_pitch = Cp; L.flat = true;
             L.wt = &S.qkv[s]; L.out = P.qkv[l][s]; L.out_pitch = 3 * Cp;
-            if ((rc = gemm(L))) return rc;
+            if ((rc = gemm(L, "L" + std::to_string(l) + ".ln_qkv_1x1"))) return rc;
         }
         // 2. depthwise 3x3 + Gram + norms (q, k never leave the SM)
         int probs[2], np = 0;
@@ -413,7 +444,7 @@ struct Fwd {
                 a.gram[i] = P.gram[n - 1][s]; a.sq[i] = P.sq[n - 1][s]; a.sk[i] = P.sk[n - 1][s];
             }
             a.v_pitch = Cp; a.B = P.B; a.H = H; a.W = W; a.C = C; a.heads = heads; a.nprob = np;
-            ++launches;
+            mark("L" + std::to_string(l) + ".cab_dw3x3_gram", (double)np * P.B * H * W * 8.0 * C, (double)np * P.B * H * W * (2.0 * 27 * C + 2.0 * 18 * C));
             if ((rc = launch_cab_dw_gram(a, st))) return rc;
         }
         // 3. normalise + temperature + softmax + fold into project_out
@@ -426,7 +457,7 @@ struct Fwd {
             }
             const PackedWeights& t = S.lca[probs[0]].fold_tmpl;
             f.B = P.B; f.C = C; f.Cp = Cp; f.heads = heads; f.nprob = np; f.n_rows = t.n_rows; f.kt = t.ktot();
-            ++launches;
+            mark("L" + std::to_string(l) + ".cab_softmax_fold", (double)np * P.B * (C * C * 6.0), (double)np * P.B * 36.0 * C * C);
             if ((rc = launch_cab_fold(f, st))) return rc;
         }
         for (int i = 0; i < np; ++i) {
@@ -438,12 +469,12 @@ struct Fwd {
             A.mode = EPI_STORE; A.in = P.v[l][s]; A.B = P.B; A.H = H; A.W = W; A.in_pitch = Cp; A.flat = true;
             A.wt = &fw; A.out = P.xp[l][s]; A.out_pitch = Cp; A.res = x[s]; A.res_pitch = Cp;
             if (P.B == 1) fw.n_img = 1;
-            if ((rc = gemm(A))) return rc;
+            if ((rc = gemm(A, "L" + std::to_string(l) + ".cab_attnv_proj_res"))) return rc;
             // 5. LayerNorm + project_in
             ConvGemmLaunch Bq;
             Bq.mode = EPI_LN; Bq.in = P.xp[l][s]; Bq.B = P.B; Bq.H = H; Bq.W = W; Bq.in_pitch = Cp; Bq.flat = true;
             Bq.wt = &Lw.w_in; Bq.out = P.tin[l][s]; Bq.out_pitch = 2 * Lw.hp;
-            if ((rc = gemm(Bq))) return rc;
+            if ((rc = gemm(Bq, "L" + std::to_string(l) + ".ln_iel_project_in"))) return rc;
         }
         // 6. IEL gate (dw 3x3 -> dw 3x3 + tanh + residual -> product)
         {
@@ -454,7 +485,7 @@ struct Fwd {
                 g.w0[i] = S.lca[s].dw0; g.w1[i] = S.lca[s].dw1; g.w2[i] = S.lca[s].dw2;
             }
             g.B = P.B; g.H = H; g.W = W; g.hp = S.lca[probs[0]].hp; g.nprob = np;
-            ++launches;
+            mark("L" + std::to_string(l) + ".iel_gate", (double)np * P.B * H * W * 6.0 * S.lca[probs[0]].h, (double)np * P.B * H * W * 2.0 * 36 * S.lca[probs[0]].h);
             if ((rc = launch_iel_gate(g, st))) return rc;
         }
         // 7. project_out (+ residual for I_LCA only)
@@ -465,9 +496,8 @@ struct Fwd {
             Cq.mode = EPI_STORE; Cq.in = P.g[l][s]; Cq.B = P.B; Cq.H = H; Cq.W = W; Cq.in_pitch = Lw.hp; Cq.flat = true;
             Cq.wt = &Lw.w_out; Cq.out = out[s]; Cq.out_pitch = Cp;
             if (s == 0) { Cq.res = P.xp[l][s]; Cq.res_pitch = Cp; }
-            if ((rc = gemm(Cq))) return rc;
+            if ((rc = gemm(Cq, "L" + std::to_string(l) + ".iel_project_out"))) return rc;
             tap(std::string(s == 0 ? "I_LCA" : "HV_LCA") + std::to_string(n), out[s], C, l, Cp);
-            tap(std::string(s == 0 ? "I_LCA" : "HV_LCA") + std::to_string(n) + ".after_cab", P.xp[l][s], C, l, Cp);
         }
         return CIDNET_OK;
     }
@@ -477,7 +507,7 @@ struct Fwd {
         CIDNET_CUDA_OK(cudaMemsetAsync(P.stats, 0, (size_t)P.stats_bytes, st));
         StemArgs sa{rgb_in, P.hvi, P.i_enc0, P.hv_0, ctx->stem_whv, ctx->stem_wi, k_dev ? k_dev : ctx->k_dev,
                     ctx->k_host, P.B, P.H[0], P.W[0], 40};
-        ++launches;
+        mark("L0.stem_hvit_block0", (double)P.B * P.H[0] * P.W[0] * 168.0, (double)P.B * P.H[0] * P.W[0] * 2.0 * 1296);
         if ((rc = launch_stem(sa, st))) return rc;
         tap("hvi", P.hvi, 3, 0, 0, true); tap("i_enc0", P.i_enc0, 36, 0, 40); tap("hv_0", P.hv_0, 36, 0, 40);
         if ((rc = down(0, 1, P.i_enc0, P.enc_i[1]))) return rc;
@@ -509,8 +539,9 @@ struct Fwd {
         tap("id1", P.id1, 36, 0, 40); tap("hvd1", P.hvd1, 36, 0, 40);
         HeadArgs ha{P.id1, P.hvd1, P.hvi, rgb_out, P.out_hvi, ctx->head_wi, ctx->head_whv,
                     k_dev ? k_dev : ctx->k_dev, ctx->k_host, alpha_s, alpha, gated, gated2, P.B, P.H[0], P.W[0], 40};
-        ++launches;
+        mark("L0.head_block0_phvit", (double)P.B * P.H[0] * P.W[0] * 168.0, (double)P.B * P.H[0] * P.W[0] * 2.0 * 972);
         if ((rc = launch_head(ha, st))) return rc;
+        finish_marks();
         tap("out_hvi", P.out_hvi, 3, 0, 0, true);
         return CIDNET_OK;
     }
@@ -546,6 +577,7 @@ extern "C" int cidnet_destroy(cidnet_ctx* ctx) {
     if (!ctx) return CIDNET_OK;
     cudaSetDevice(ctx->device);
     release_device(ctx);
+    for (cudaEvent_t e : ctx->events) if (e) cudaEventDestroy(e);
     delete ctx;
     return CIDNET_OK;
 }
@@ -599,6 +631,7 @@ extern "C" int cidnet_forward(cidnet_ctx* ctx, const float* rgb_in, float* rgb_o
     CIDNET_CHECK(workspace_bytes >= f.P.bytes, CIDNET_ERR_STATE,
                  "forward: workspace too small: need " + std::to_string(f.P.bytes) + " bytes");
     ctx->taps.clear();
+    ctx->recs.clear();
     ctx->last_B = B;
     int rc = f.run(rgb_in, rgb_out, k_dev, gated, alpha_s, gated2, alpha);
     ctx->launches = f.launches;
@@ -623,4 +656,22 @@ extern "C" int cidnet_read_tap(cidnet_ctx* ctx, const char* name, float* dst, in
     }
     return launch_nhwc_to_nchw(reinterpret_cast<const act_t*>(t.ptr), dst, ctx->last_B, t.C, t.H, t.W, t.pitch,
                                (cudaStream_t)stream);
+}
+
+// ---- per-launch profiling (bench.py's roofline; events on the launching stream) ------------
+extern "C" int cidnet_profile_enable(cidnet_ctx* ctx, int enable) {
+    CIDNET_CHECK(ctx, CIDNET_ERR_INVALID, "profile_enable: null ctx");
+    ctx->profiling = enable != 0;
+    return CIDNET_OK;
+}
+extern "C" int cidnet_profile_count(cidnet_ctx* ctx) { return ctx ? (int)ctx->recs.size() : 0; }
+extern "C" int cidnet_profile_get(cidnet_ctx* ctx, int i, char* name, int name_cap, float* ms, double* alg_bytes,
+                                  double* flops) {
+    CIDNET_CHECK(ctx && i >= 0 && i < (int)ctx->recs.size(), CIDNET_ERR_INVALID, "profile_get: bad index");
+    const auto& r = ctx->recs[i];
+    if (name && name_cap > 0) { snprintf(name, name_cap, "%s", r.name.c_str()); }
+    if (alg_bytes) *alg_bytes = r.bytes;
+    if (flops) *flops = r.flops;
+    if (ms) CIDNET_CUDA_OK(cudaEventElapsedTime(ms, ctx->events[i], ctx->events[i + 1]));
+    return CIDNET_OK;
 }

@@ -216,5 +216,23 @@ class CIDNet(nn.Module, PyTorchModelHubMixin):
                                            _lib.stream_ptr(self._ctx_device)))
         return out
 
+    def set_profiling(self, enable):
+        """record a CUDA event before every kernel launch of forward() (see cidnet_profile_*)."""
+        if self._ctx is None:
+            raise RuntimeError("run one forward first")
+        _lib.check(_lib.lib().cidnet_profile_enable(self._ctx, int(bool(enable))))
+
+    def read_profile(self):
+        """[(name, ms, algorithmic_bytes, flops)] of the last profiled forward (synchronises)."""
+        lib = _lib.lib()
+        torch.cuda.synchronize(self._ctx_device)
+        out = []
+        buf = C.create_string_buffer(96)
+        ms, by, fl = C.c_float(), C.c_double(), C.c_double()
+        for i in range(lib.cidnet_profile_count(self._ctx)):
+            _lib.check(lib.cidnet_profile_get(self._ctx, i, buf, 96, C.byref(ms), C.byref(by), C.byref(fl)))
+            out.append((buf.value.decode(), float(ms.value), float(by.value), float(fl.value)))
+        return out
+
     def num_launches(self):
         return int(_lib.lib().cidnet_forward_launches(self._ctx)) if self._ctx is not None else 0

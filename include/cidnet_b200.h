@@ -86,6 +86,16 @@ CIDNET_API int cidnet_forward_launches(cidnet_ctx* ctx);
 CIDNET_API int cidnet_read_tap(cidnet_ctx* ctx, const char* name, float* dst, int64_t dst_numel,
                     int* dims, void* stream);
 
+/* ---- per-launch profiling ----------------------------------------------------
+ * With profiling enabled, cidnet_forward records a CUDA event on `stream` before
+ * every kernel launch (and one after the last).  After synchronising, record i
+ * gives the kernel's name, its device time, and its ALGORITHMIC bytes / flops
+ * (DESIGN.md "kernels and rooflines") -- what bench.py's `roofline` is built from. */
+CIDNET_API int cidnet_profile_enable(cidnet_ctx* ctx, int enable);
+CIDNET_API int cidnet_profile_count(cidnet_ctx* ctx);
+CIDNET_API int cidnet_profile_get(cidnet_ctx* ctx, int i, char* name, int name_cap, float* ms,
+                                  double* alg_bytes, double* flops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,8 @@ import torch.nn.functional as F
 PI = 3.141592653589793  # net/HVI_transform.py:4
 EPS = 1e-8
 
+FAST_BILINEAR = False   # bench.py's CPU baseline sets this; tests use the explicit restatement
+
 CHANNELS = (36, 36, 72, 144)
 HEADS = (1, 2, 4, 8)
 
@@ -126,6 +128,8 @@ def bilinear_ac(x: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
     """Bilinear resampling with align_corners=True, written out explicitly
     (ratio (in-1)/(out-1) in fp32, i0=(int)src, i1=i0+(i0<in-1), lam=src-i0),
     the semantics of nn.UpsamplingBilinear2d at transformer_utils.py:40,59."""
+    if FAST_BILINEAR:   # timing runs only: the ATen kernel the reference itself calls (equal to 5e-7)
+        return F.interpolate(x, size=(out_h, out_w), mode="bilinear", align_corners=True)
     B, C, H, W = x.shape
 
     def axis(n_in, n_out):
