@@ -23,7 +23,7 @@ const int kHeads[4] = {1, 2, 4, 8};
 struct LcaWeights {
     bool live = true;
     int C = 0, Cp = 0, heads = 0, h = 0, hp = 0;
-    float *wq = nullptr, *wk = nullptr, *wv = nullptr;   // depthwise [9][Cp]
+    float* wqkv = nullptr;                               // depthwise weights [9][3*Cp]: q_dwconv | kv_dwconv (k) | (v)
     float* temp = nullptr;                               // [heads]
     float* wo = nullptr;                                 // [C][C]
     PackedWeights fold_tmpl;                             // geometry of the per-image folded weights
@@ -163,9 +163,13 @@ int build_lca(cidnet_ctx* ctx, const std::string& pfx, int level, LcaWeights* L)
     const int C = kCh[level], heads = kHeads[level], h = (int)(C * 2.66), hp = round_up(h, 16), Cp = act_pitch(C);
     L->C = C; L->Cp = Cp; L->heads = heads; L->h = h; L->hp = hp;
     int rc;
-    if ((rc = dev_f32(ctx, &L->wq, dw_tapmajor(R[pfx + ".ffn.q_dwconv.weight"], 0, C, Cp)))) return rc;
-    if ((rc = dev_f32(ctx, &L->wk, dw_tapmajor(R[pfx + ".ffn.kv_dwconv.weight"], 0, C, Cp)))) return rc;
-    if ((rc = dev_f32(ctx, &L->wv, dw_tapmajor(R[pfx + ".ffn.kv_dwconv.weight"], C, C, Cp)))) return rc;
+    {
+        std::vector<float> wqkv((size_t)9 * 3 * Cp, 0.f);
+        dw_tapmajor(R[pfx + ".ffn.q_dwconv.weight"], 0, C, 3 * Cp, 0, &wqkv);
+        dw_tapmajor(R[pfx + ".ffn.kv_dwconv.weight"], 0, C, 3 * Cp, Cp, &wqkv);
+        dw_tapmajor(R[pfx + ".ffn.kv_dwconv.weight"], C, C, 3 * Cp, 2 * Cp, &wqkv);
+        if ((rc = dev_f32(ctx, &L->wqkv, wqkv))) return rc;
+    }
     if ((rc = dev_f32(ctx, &L->temp, R[pfx + ".ffn.temperature"]))) return rc;
     if ((rc = dev_f32(ctx, &L->wo, R[pfx + ".ffn.project_out.weight"]))) return rc;
     // geometry of the folded per-image weights (C x C, 1x1)
@@ -304,7 +308,7 @@ struct Plan {
     act_t *dec_i[4], *dec_hv[4];                           // dec_x[l] = output of up block l+1 -> level l (l = 1, 2)
     act_t *tup_i[4], *tup_hv[4];                           // low-res pre-composed conv outputs at level l (l = 1..3)
     // per-level scratch for an LCA stage pair
-    act_t *qkv[4][2], *v[4][2], *xp[4][2], *tin[4][2], *g[4][2], *mfold[4][2];
+    act_t *qkv[4][2], *qkvdw[4][2], *xp[4][2], *tin[4][2], *g[4][2], *mfold[4][2];
     float* stats; int64_t stats_bytes;
     float *gram[6][2], *sq[6][2], *sk[6][2];
     int64_t bytes;
@@ -330,7 +334,7 @@ void make_plan(Plan* P, void* ws, int B, int H, int W) {
         const int64_t fold_elems = (int64_t)B * f.block_n * f.n_blocks * ceil_div(kCh[l], 64) * 64;
         for (int s = 0; s < 2; ++s) {
             P->qkv[l][s] = bp.take<act_t>(px(l) * 3 * Cp);
-            P->v[l][s] = bp.take<act_t>(px(l) * Cp);
+            P->qkvdw[l][s] = bp.take<act_t>(px(l) * 3 * Cp);
             P->xp[l][s] = bp.take<act_t>(px(l) * Cp);
             P->tin[l][s] = bp.take<act_t>(px(l) * 2 * hp);
             P->g[l][s] = bp.take<act_t>(px(l) * hp);
@@ -430,22 +434,29 @@ struct Fwd {
             L.wt = &S.qkv[s]; L.out = P.qkv[l][s]; L.out_pitch = 3 * Cp;
             if ((rc = gemm(L, "L" + std::to_string(l) + ".ln_qkv_1x1"))) return rc;
         }
-        // 2. depthwise 3x3 + Gram + norms (q, k never leave the SM)
+        // 2. depthwise 3x3 of [q | k | v] (+ sum q^2, sum k^2), then the Gram on the tensor cores
         int probs[2], np = 0;
         for (int s = 0; s < 2; ++s) if (S.lca[s].live) probs[np++] = s;
         {
-            CabDwArgs a; memset(&a, 0, sizeof a);
+            Dw3Args a; memset(&a, 0, sizeof a);
+            GramLaunch gl; memset(&gl, 0, sizeof gl);
             for (int i = 0; i < np; ++i) {
                 const int s = probs[i];
-                a.q[i] = P.qkv[l][s]; a.q_pitch[i] = 3 * Cp;
-                a.k[i] = P.qkv[l][1 - s] + Cp; a.v[i] = P.qkv[l][1 - s] + 2 * Cp; a.kv_pitch[i] = 3 * Cp;
-                a.wq[i] = S.lca[s].wq; a.wk[i] = S.lca[s].wk; a.wv[i] = S.lca[s].wv;
-                a.v_out[i] = P.v[l][s];
-                a.gram[i] = P.gram[n - 1][s]; a.sq[i] = P.sq[n - 1][s]; a.sk[i] = P.sk[n - 1][s];
+                a.src[i][0] = P.qkv[l][s];                     // q of LCA s comes from its own tensor
+                a.src[i][1] = P.qkv[l][1 - s] + Cp;            // k, v from the sibling tensor
+                a.src[i][2] = P.qkv[l][1 - s] + 2 * Cp;
+                a.dst[i] = P.qkvdw[l][s];
+                a.w[i] = S.lca[s].wqkv;
+                a.sq[i] = P.sq[n - 1][s]; a.sk[i] = P.sk[n - 1][s];
+                gl.q[i] = P.qkvdw[l][s]; gl.k[i] = P.qkvdw[l][s] + Cp; gl.gram[i] = P.gram[n - 1][s];
             }
-            a.v_pitch = Cp; a.B = P.B; a.H = H; a.W = W; a.C = C; a.heads = heads; a.nprob = np;
-            mark("L" + std::to_string(l) + ".cab_dw3x3_gram", (double)np * P.B * H * W * 8.0 * C, (double)np * P.B * H * W * (2.0 * 27 * C + 2.0 * 18 * C));
-            if ((rc = launch_cab_dw_gram(a, st))) return rc;
+            a.src_pitch = 3 * Cp; a.dst_pitch = 3 * Cp; a.B = P.B; a.H = H; a.W = W;
+            a.nv = 3 * Cp / 8; a.seg_vecs = Cp / 8; a.nprob = np;
+            mark("L" + std::to_string(l) + ".cab_dw3x3_qkv", (double)np * P.B * H * W * 12.0 * C, (double)np * P.B * H * W * 2.0 * 27 * C);
+            if ((rc = launch_dw3(a, st))) return rc;
+            gl.pitch = 3 * Cp; gl.B = P.B; gl.H = H; gl.W = W; gl.C = C; gl.heads = heads; gl.nprob = np;
+            mark("L" + std::to_string(l) + ".cab_gram_tc", (double)np * P.B * H * W * 4.0 * C, (double)np * P.B * H * W * 2.0 * C * C);
+            if ((rc = launch_gram(gl, st))) return rc;
         }
         // 3. normalise + temperature + softmax + fold into project_out
         {
@@ -466,7 +477,7 @@ struct Fwd {
             // 4. x' = x + (W_o * blockdiag(attn_b)) v      (per-image 1x1)
             PackedWeights fw = Lw.fold_tmpl; fw.w = P.mfold[l][s]; fw.n_img = P.B > 1 ? P.B : 1;
             ConvGemmLaunch A;
-            A.mode = EPI_STORE; A.in = P.v[l][s]; A.B = P.B; A.H = H; A.W = W; A.in_pitch = Cp; A.flat = true;
+            A.mode = EPI_STORE; A.in = P.qkvdw[l][s] + 2 * Cp; A.B = P.B; A.H = H; A.W = W; A.in_pitch = 3 * Cp; A.flat = true;
             A.wt = &fw; A.out = P.xp[l][s]; A.out_pitch = Cp; A.res = x[s]; A.res_pitch = Cp;
             if (P.B == 1) fw.n_img = 1;
             if ((rc = gemm(A, "L" + std::to_string(l) + ".cab_attnv_proj_res"))) return rc;

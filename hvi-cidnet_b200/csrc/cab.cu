@@ -1,57 +1,197 @@
-// CAB (channel cross-attention, net/LCA.py:19-41) without ever materialising q or k:
+// CAB (channel cross-attention, net/LCA.py:19-41) in three kernels:
 //
-//   cab_dw_gram_kernel : depthwise 3x3 of q_pre / k_pre / v_pre (zero pad) on an 8x8-pixel tile
-//                        staged in shared memory; v is written out (NHWC), q and k are written
-//                        ONLY to shared memory, as K-major SWIZZLE_128B operand tiles
-//                        ([channel][64 pixels]), and contracted over the pixels on the tensor
-//                        cores:  G[Cq, Ck] += q[Cq, 64] * k[Ck, 64]^T   (tcgen05.mma, fp32 in TMEM,
-//                        accumulated over all tiles the CTA owns), together with sum(q^2), sum(k^2).
-//                        At the end the per-head 18x18 diagonal blocks are added to global memory.
-//   cab_fold_kernel    : L2-normalise (F.normalize eps 1e-12), temperature, softmax, and fold
-//                        attn into project_out:  M_b = W_o * blockdiag(attn_b)   (one CxC matrix per
-//                        image, written in the packed-weight layout of the conv GEMM), so that
-//                        project_out(attn @ v) becomes a single per-image 1x1 conv on v
-//                        (identity verified against the reference to 6e-7).
+//   dw3x3_kernel    : depthwise 3x3 (zero pad) of q_pre | k_pre | v_pre, NHWC in, NHWC out.
+//                     Sliding window down the rows: one thread owns (column x, 8 channels), keeps
+//                     the 3x3 neighbourhood and its 72 weights in registers and reads each new
+//                     row straight from global memory (the +-1 column neighbours are L1 hits).
+//                     Also accumulates sum(q^2), sum(k^2) per channel (F.normalize denominators).
+//   gram_kernel     : G[Cq, Ck] = sum_pixels q k^T on the tensor cores.  The NHWC tiles
+//                     [64 pixels][64 channels] land by TMA (SWIZZLE_128B) exactly in the UMMA
+//                     *MN-major* canonical layout, so the contraction over pixels needs no
+//                     transposition: tcgen05.mma kind::f16 with a_major = b_major = MN, fp32
+//                     accumulation in TMEM over the CTA's whole pixel range (split-K across CTAs),
+//                     then the per-head 18x18 diagonal blocks are atomically added to global.
+//   cab_fold_kernel : L2-normalise (eps 1e-12), temperature, softmax, and fold attn into
+//                     project_out:  M_b = W_o * blockdiag(attn_b)   (one CxC matrix per image, written
+//                     in the packed-weight layout of the conv GEMM), so project_out(attn @ v)
+//                     becomes a per-image 1x1 conv on v (identity verified to 6e-7).
 #include "cab.cuh"
 #include "ptx_sm100.cuh"
 
+#include <cstring>
+
 namespace cidnet {
 
-static constexpr int kT = 8;              // tile edge (64 pixels = one 128-byte swizzle row of fp16)
-static constexpr int kTH = kT + 2;        // with halo
-static constexpr int kCabThreads = 256;
+// ------------------------------------------------------------- depthwise ----
+static constexpr int kDwThreads = 256;
+static constexpr int kDwRows = 32;     // rows per CTA strip
 
-__device__ __forceinline__ void fence_proxy_async() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+__device__ __forceinline__ void unpack4(const uint2& raw, float* f) {
+#ifdef CIDNET_ACT_BF16
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+    const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+#else
+    const __half2 a = *reinterpret_cast<const __half2*>(&raw.x);
+    const __half2 b = *reinterpret_cast<const __half2*>(&raw.y);
+    const float2 fa = __half22float2(a), fb = __half22float2(b);
+#endif
+    f[0] = fa.x; f[1] = fa.y; f[2] = fb.x; f[3] = fb.y;
 }
 
-__global__ void __launch_bounds__(kCabThreads, 1)
-cab_dw_gram_kernel(const CabDwArgs a) {
+// one thread = (column x, 4 channels): 36 weights + a raw 3x3 window (18 registers)
+__global__ void __launch_bounds__(kDwThreads, 2)
+dw3x3_kernel(const Dw3Args a) {
+    __shared__ float s_ssq[2 * 144];
+    const int prob = blockIdx.z % a.nprob, b = blockIdx.z / a.nprob;
+    const int nv = a.nv * 2;                               // 8-byte vectors per pixel (all segments)
+    const int seg_v = a.seg_vecs * 2;
+    const int idx = blockIdx.x * kDwThreads + threadIdx.x; // vector index along the row
+    const int x = idx / nv, v = idx - x * nv;
+    const bool active = x < a.W;
+    const int seg = active ? v / seg_v : 0;                // 0 = q, 1 = k, 2 = v
+    const int c0 = (v - seg * seg_v) * 4;                  // channel within the segment
+    const long long hw = (long long)a.H * a.W;
+    const act_t* src = a.src[prob][seg] + (long long)b * hw * a.src_pitch + c0;
+    act_t* dst = a.dst[prob] + (long long)b * hw * a.dst_pitch + seg * seg_v * 4 + c0;
+    const int y0 = blockIdx.y * kDwRows;
+    const int y1 = min(y0 + kDwRows, a.H);
+
+    for (int i = threadIdx.x; i < 2 * 144; i += kDwThreads) s_ssq[i] = 0.f;
+    __syncthreads();
+
+    float w[9][4];
+    {
+        const float* wp = a.w[prob] + seg * seg_v * 4 + c0;   // [9][nv*4] tap major
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[t][e] = active ? __ldg(wp + t * nv * 4 + e) : 0.f;
+    }
+    float ssq[4] = {0.f, 0.f, 0.f, 0.f};
+
+    if (active) {
+        const bool has_l = x > 0, has_r = x + 1 < a.W;
+        uint2 win0[3], win1[3], win2[3];
+        auto load_row = [&](int y, uint2* r) {
+            r[0] = r[1] = r[2] = make_uint2(0, 0);
+            if (y < 0 || y >= a.H) return;
+            const act_t* p = src + ((long long)y * a.W + x) * a.src_pitch;
+            r[1] = *reinterpret_cast<const uint2*>(p);
+            if (has_l) r[0] = *reinterpret_cast<const uint2*>(p - a.src_pitch);
+            if (has_r) r[2] = *reinterpret_cast<const uint2*>(p + a.src_pitch);
+        };
+        auto step = [&](const uint2* r0, const uint2* r1, uint2* r2, int y) {
+            load_row(y + 1, r2);
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float f0[4], f1[4], f2[4];
+                unpack4(r0[c], f0); unpack4(r1[c], f1); unpack4(r2[c], f2);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    acc[e] = fmaf(f0[e], w[c][e], acc[e]);
+                    acc[e] = fmaf(f1[e], w[3 + c][e], acc[e]);
+                    acc[e] = fmaf(f2[e], w[6 + c][e], acc[e]);
+                }
+            }
+            uint2 raw;
+            act_t* ov = reinterpret_cast<act_t*>(&raw);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                ov[e] = f2act(acc[e]);
+                const float rf = act2f(ov[e]);
+                ssq[e] = fmaf(rf, rf, ssq[e]);
+            }
+            *reinterpret_cast<uint2*>(dst + ((long long)y * a.W + x) * a.dst_pitch) = raw;
+        };
+        load_row(y0 - 1, win0);
+        load_row(y0, win1);
+        for (int y = y0; y < y1; y += 3) {          // window roles rotate, no register moves
+            step(win0, win1, win2, y);
+            if (y + 1 < y1) step(win1, win2, win0, y + 1);
+            if (y + 2 < y1) step(win2, win0, win1, y + 2);
+        }
+        if (seg < 2) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) atomicAdd(&s_ssq[seg * 144 + c0 + e], ssq[e]);
+        }
+    }
+    __syncthreads();
+    // one global atomic per channel per CTA
+    const int Cp = a.seg_vecs * 8;
+    for (int i = threadIdx.x; i < 2 * Cp; i += kDwThreads) {
+        const int sg = i / Cp, c = i - sg * Cp;
+        const float val = s_ssq[sg * 144 + c];
+        if (val != 0.f) atomicAdd((sg == 0 ? a.sq[prob] : a.sk[prob]) + (long long)b * Cp + c, val);
+    }
+}
+
+int launch_dw3(const Dw3Args& a, cudaStream_t stream) {
+    CIDNET_CHECK(a.seg_vecs * 8 <= 144 && a.nv == 3 * a.seg_vecs, CIDNET_ERR_INVALID, "dw3: bad channel layout");
+    dim3 grid(ceil_div(a.W * a.nv * 2, kDwThreads), ceil_div(a.H, kDwRows), a.B * a.nprob);
+    dw3x3_kernel<<<grid, kDwThreads, 0, stream>>>(a);
+    CIDNET_CUDA_OK(cudaGetLastError());
+    return CIDNET_OK;
+}
+
+// ------------------------------------------------------------------ Gram ----
+struct GramArgs {
+    CUtensorMap tmQ[2];      // per problem: q  [B][HW][pitch] viewed {C, HW, B}
+    CUtensorMap tmK[2];
+    float* gram[2];          // [B][heads][18][18]
+    int C, heads, hw, chunks_per_cta, nchunks;
+};
+
+static constexpr int kGramThreads = 192;
+static constexpr uint32_t kBlk = 64 * 128;     // one [64 pixels][64 channels] swizzled block = 8 KB
+static constexpr int kGramStages = 3;
+
+// MN-major SWIZZLE_128B operand: 64 MN-elements (128 B) contiguous per K row, 8 K rows per
+// 1024-byte group (SBO), next 64 MN-elements LBO bytes further.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(kGramThreads, 1)
+gram_kernel(const __grid_constant__ GramArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int C = a.C, Cp = a.Cp;
-    const int nacc = (C > 72) ? 2 : 1;               // C=144: heads 0-3 and 4-7 in separate accumulators
-    const int rows_per_acc = (nacc == 2) ? 72 : C;
-    const int NB = (C == 36) ? 48 : 80;               // MMA N (k channels per accumulator, padded to %16)
-    uint8_t* opA = smem;                              // nacc x [128 rows][128 B]
-    uint8_t* opB = opA + nacc * 128 * 128;            // nacc x [NB rows][128 B]
-    act_t* s_in = reinterpret_cast<act_t*>(opB + nacc * NB * 128);   // [3][100][Cp]
-    uint64_t* mma_bar = reinterpret_cast<uint64_t*>(s_in + 3 * kTH * kTH * Cp);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+    const int C = a.C;
+    const int mtiles_ = (C + 127) / 128;
+    const int nA = 2 * mtiles_;                   // 64-channel blocks of q (blocks beyond C are TMA zero fill)
+    const int N = (C + 15) / 16 * 16;             // MMA N (k channels)
+    const int nB = (N + 63) / 64;
+    const int mtiles = (C + 127) / 128;
+    const uint32_t stage_bytes = (uint32_t)(nA + nB) * kBlk;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kGramStages * stage_bytes);
+    uint64_t* empty = full + kGramStages;
+    uint64_t* done = empty + kGramStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int prob = blockIdx.y, b = blockIdx.z;
-    const long long hw = (long long)a.H * a.W;
-    const int vecs = Cp / 8;                          // 16-byte vectors per pixel per tensor
+    const int c_begin = blockIdx.x * a.chunks_per_cta;
+    const int c_end = min(c_begin + a.chunks_per_cta, a.nchunks);
+    const int niter = c_end - c_begin;
+    if (niter <= 0) return;
 
     uint32_t ncols = 32;
-    while (ncols < (uint32_t)(nacc * NB)) ncols <<= 1;
+    while (ncols < (uint32_t)(mtiles * N)) ncols <<= 1;
 
-    // zero the operand buffers once: rows that no channel maps to must stay finite (zero)
-    for (int i = tid; i < (nacc * (128 + NB) * 128) / 16; i += kCabThreads)
-        reinterpret_cast<uint4*>(opA)[i] = make_uint4(0, 0, 0, 0);
-    if (warp == 0) {
-        if (lane == 0) { ptx::mbar_init(mma_bar, 1); ptx::fence_barrier_init(); }
+    if (warp == 0 && lane == 0) { ptx::prefetch_tensormap(&a.tmQ[prob]); ptx::prefetch_tensormap(&a.tmK[prob]); }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < kGramStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+            ptx::mbar_init(done, 1);
+            ptx::fence_barrier_init();
+        }
         __syncwarp();
         ptx::tmem_alloc(tmem_slot, ncols);
         ptx::tmem_relinquish();
@@ -61,160 +201,102 @@ cab_dw_gram_kernel(const CabDwArgs a) {
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // thread -> (tensor, 8-channel group); weights of that group live in registers
-    const int G = 3 * vecs;
-    const int nslots = kCabThreads / G;
-    const bool worker = tid < G * nslots;
-    const int g = tid % G, slot = tid / G;
-    const int which = g / vecs;                       // 0 = q, 1 = k, 2 = v
-    const int c0 = (g - which * vecs) * 8;
-    float w[9][8];
-    {
-        const float* wsrc = which == 0 ? a.wq[prob] : (which == 1 ? a.wk[prob] : a.wv[prob]);
-#pragma unroll
-        for (int t = 0; t < 9; ++t)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) w[t][e] = worker ? __ldg(wsrc + t * Cp + c0 + e) : 0.f;
-    }
-    float ssq[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) ssq[e] = 0.f;
-
-    const act_t* src[3] = {a.q[prob] + (long long)b * hw * a.q_pitch[prob],
-                           a.k[prob] + (long long)b * hw * a.kv_pitch[prob],
-                           a.v[prob] + (long long)b * hw * a.kv_pitch[prob]};
-    const int pitch[3] = {a.q_pitch[prob], a.kv_pitch[prob], a.kv_pitch[prob]};
-    act_t* vout = a.v_out[prob] + (long long)b * hw * a.v_pitch;
-
-    const int ntiles = a.tiles_x * a.tiles_y;
-    uint32_t phase = 0;
-    int iter = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
-        const int y0 = (tile / a.tiles_x) * kT, x0 = (tile % a.tiles_x) * kT;
-        // 1. stage the halo tiles (zero padding outside the image)
-        for (int i = tid; i < 3 * kTH * kTH * vecs; i += kCabThreads) {
-            const int t3 = i / (kTH * kTH * vecs);
-            const int r = i - t3 * (kTH * kTH * vecs);
-            const int p = r / vecs, v = r - p * vecs;
-            const int y = y0 + p / kTH - 1, x = x0 + p % kTH - 1;
-            uint4 val = make_uint4(0, 0, 0, 0);
-            if (y >= 0 && y < a.H && x >= 0 && x < a.W)
-                val = *reinterpret_cast<const uint4*>(src[t3] + ((long long)y * a.W + x) * pitch[t3] + v * 8);
-            *reinterpret_cast<uint4*>(s_in + ((size_t)t3 * kTH * kTH + p) * Cp + v * 8) = val;
-        }
-        // 2. the previous tile's MMAs must have finished reading opA/opB
-        if (iter > 0) { ptx::mbar_wait(mma_bar, phase); phase ^= 1u; }
-        __syncthreads();
-        // 3. depthwise 3x3; q,k -> swizzled operand tiles, v -> global
-        if (worker) {
-            const act_t* tin = s_in + (size_t)which * kTH * kTH * Cp + c0;
-            for (int px = slot; px < kT * kT; px += nslots) {
-                const int py = px >> 3, pxx = px & 7;
-                float acc[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-#pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    float f[8];
-                    load8(tin + ((py + t / 3) * kTH + pxx + t % 3) * Cp, f);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[e] = fmaf(f[e], w[t][e], acc[e]);
-                }
-                const int y = y0 + py, x = x0 + pxx;
-                const bool inside = (y < a.H) && (x < a.W);
-                if (which == 2) {
-                    if (inside) store8(vout + ((long long)y * a.W + x) * a.v_pitch + c0, acc);
-                } else {
-                    uint8_t* op = which == 0 ? opA : opB;
-                    const int op_rows = which == 0 ? 128 : NB;
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int c = c0 + e;
-                        const act_t r = f2act(inside ? acc[e] : 0.f);
-                        const float rf = act2f(r);
-                        ssq[e] = fmaf(rf, rf, ssq[e]);
-                        if (c < C) {
-                            const int ai = c / rows_per_acc, row = c - ai * rows_per_acc;
-                            uint8_t* dst = op + (size_t)ai * op_rows * 128 + row * 128 +
-                                           (((px >> 3) ^ (row & 7)) << 4) + (px & 7) * 2;
-                            *reinterpret_cast<act_t*>(dst) = r;
-                        }
-                    }
-                }
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < niter; ++i) {
+                const int s = i % kGramStages;
+                const uint32_t ph = (uint32_t)(i / kGramStages) & 1u;
+                ptx::mbar_wait(&empty[s], ph ^ 1u);
+                ptx::mbar_expect_tx(&full[s], stage_bytes);
+                uint8_t* st = smem + (size_t)s * stage_bytes;
+                const int p0 = (c_begin + i) * 64;
+                for (int j = 0; j < nA; ++j) ptx::tma_load_3d(st + j * kBlk, &a.tmQ[prob], &full[s], j * 64, p0, b);
+                for (int j = 0; j < nB; ++j) ptx::tma_load_3d(st + (nA + j) * kBlk, &a.tmK[prob], &full[s], j * 64, p0, b);
             }
         }
-        // 4. make the generic-proxy smem writes visible to the tensor core, then issue
-        fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
+    } else if (warp == 1) {
+        // instruction descriptor: fp32 accumulate, A and B MN-major (bits 15, 16), M = 128
+        const uint32_t idesc = ptx::umma_idesc_f16(CIDNET_UMMA_FMT, (uint32_t)N) | (1u << 15) | (1u << 16);
+        for (int i = 0; i < niter; ++i) {
+            const int s = i % kGramStages;
+            const uint32_t ph = (uint32_t)(i / kGramStages) & 1u;
+            ptx::mbar_wait(&full[s], ph);
             ptx::tc_fence_after();
-            const uint32_t idesc = ptx::umma_idesc_f16(CIDNET_UMMA_FMT, (uint32_t)NB);
-            for (int ai = 0; ai < nacc; ++ai) {
-                const uint64_t dA = ptx::umma_smem_desc_sw128(ptx::smem_u32(opA + (size_t)ai * 128 * 128));
-                const uint64_t dB = ptx::umma_smem_desc_sw128(ptx::smem_u32(opB + (size_t)ai * NB * 128));
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    ptx::umma_f16(tmem_base + ai * NB, dA + 2 * k, dB + 2 * k, idesc, (uint32_t)((iter | k) != 0));
-            }
-            ptx::umma_commit(mma_bar);
-        }
-    }
-    if (iter > 0) { ptx::mbar_wait(mma_bar, phase); }
-    ptx::tc_fence_after();
-
-    // epilogue: per-head diagonal blocks of the accumulators -> global (atomic, fp32)
-    if (iter > 0) {
-        if (warp < 4) {
-            const int r = warp * 32 + lane;
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-            float* gdst = a.gram[prob] + (long long)b * a.heads * 324;
-            for (int ai = 0; ai < nacc; ++ai) {
-                const int ch = ai * rows_per_acc + r;
-                const bool row_ok = (r < rows_per_acc) && (ch < C);
-                const int head = ch / 18, qi = ch - head * 18;
-                for (int cc = 0; cc < NB; cc += 16) {
-                    float v[16];
-                    ptx::tmem_ld16(taddr + ai * NB + cc, v);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int kc = ai * rows_per_acc + cc + j;      // global k channel
-                        if (row_ok && (cc + j) < rows_per_acc && kc < C && kc / 18 == head)
-                            atomicAdd(gdst + (head * 18 + qi) * 18 + (kc - head * 18), v[j]);
+            if (lane == 0) {
+                const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t sb = sa + nA * kBlk;
+                for (int mt = 0; mt < mtiles; ++mt) {
+                    const uint32_t lboA = kBlk;
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t dA = umma_desc_mn_sw128(sa + 2 * mt * kBlk + ks * 2048, lboA);
+                        const uint64_t dB = umma_desc_mn_sw128(sb + ks * 2048, kBlk);
+                        ptx::umma_f16(tmem_base + mt * N, dA, dB, idesc, (uint32_t)((i | ks) != 0));
                     }
                 }
+                ptx::umma_commit(&empty[s]);
+                if (i == niter - 1) ptx::umma_commit(done);
             }
+            __syncwarp();
         }
-        if (worker && which < 2) {
-            float* sdst = (which == 0 ? a.sq[prob] : a.sk[prob]) + (long long)b * Cp + c0;
+    } else {
+        const int q4 = warp & 3;
+        const int r = q4 * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        ptx::mbar_wait(done, 0);
+        ptx::tc_fence_after();
+        float* gdst = a.gram[prob] + (long long)b * a.heads * 324;
+        for (int mt = 0; mt < mtiles; ++mt) {
+            const int ch = mt * 128 + r;
+            const bool row_ok = ch < C;
+            const int head = ch / 18, qi = ch - head * 18;
+            for (int cc = 0; cc < N; cc += 16) {
+                float v[16];
+                ptx::tmem_ld16(taddr + mt * N + cc, v);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) atomicAdd(sdst + e, ssq[e]);
+                for (int j = 0; j < 16; ++j) {
+                    const int kc = cc + j;
+                    if (row_ok && kc < C && kc / 18 == head) atomicAdd(gdst + (head * 18 + qi) * 18 + (kc - head * 18), v[j]);
+                }
+            }
         }
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 0) ptx::tmem_dealloc(tmem_base, ncols);
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, ncols);
 }
 
-int launch_cab_dw_gram(CabDwArgs a, cudaStream_t stream) {
-    CIDNET_CHECK(a.C == 36 || a.C == 72 || a.C == 144, CIDNET_ERR_INVALID, "cab: C must be 36/72/144");
-    CIDNET_CHECK(a.heads * 18 == a.C, CIDNET_ERR_INVALID, "cab: heads*18 != C");
-    a.Cp = act_pitch(a.C);
-    a.tiles_x = ceil_div(a.W, kT);
-    a.tiles_y = ceil_div(a.H, kT);
-    const int ntiles = a.tiles_x * a.tiles_y;
-    const int nacc = a.C > 72 ? 2 : 1;
-    const int NB = a.C == 36 ? 48 : 80;
-    const size_t smem = 1024 + (size_t)nacc * (128 + NB) * 128 + (size_t)3 * kTH * kTH * a.Cp * sizeof(act_t) + 32;
+int encode_map_generic(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box);   // conv_gemm.cu
+
+int launch_gram(const GramLaunch& L, cudaStream_t stream) {
+    CIDNET_CHECK(L.C == 36 || L.C == 72 || L.C == 144, CIDNET_ERR_INVALID, "gram: C must be 36/72/144");
+    GramArgs a;
+    memset(&a, 0, sizeof a);
+    a.C = L.C; a.heads = L.heads; a.hw = L.H * L.W;
+    a.nchunks = ceil_div(a.hw, 64);
+    for (int p = 0; p < L.nprob; ++p) {
+        const uint64_t dims[3] = {(uint64_t)L.C, (uint64_t)a.hw, (uint64_t)L.B};
+        const uint64_t str[2] = {(uint64_t)L.pitch * sizeof(act_t), (uint64_t)L.pitch * sizeof(act_t) * a.hw};
+        const uint32_t box[3] = {64, 64, 1};
+        int rc = encode_map_generic(&a.tmQ[p], L.q[p], 3, dims, str, box);
+        if (rc) return rc;
+        if ((rc = encode_map_generic(&a.tmK[p], L.k[p], 3, dims, str, box))) return rc;
+        a.gram[p] = L.gram[p];
+    }
+    int nsplit = (148 * 2) / (L.nprob * L.B);
+    if (nsplit < 1) nsplit = 1;
+    if (nsplit > a.nchunks) nsplit = a.nchunks;
+    a.chunks_per_cta = ceil_div(a.nchunks, nsplit);
+    nsplit = ceil_div(a.nchunks, a.chunks_per_cta);
+    const int nA = 2 * ceil_div(L.C, 128), nB = ceil_div(round_up(L.C, 16), 64);
+    const size_t smem = 1024 + (size_t)kGramStages * (nA + nB) * kBlk + 64;
     static bool configured = false;
     if (!configured) {
-        CIDNET_CUDA_OK(cudaFuncSetAttribute(cab_dw_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CIDNET_CUDA_OK(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
-    int per_img = (148 * 3) / (a.nprob * a.B);
-    if (per_img < 1) per_img = 1;
-    if (per_img > ntiles) per_img = ntiles;
-    dim3 grid(per_img, a.nprob, a.B);
-    cab_dw_gram_kernel<<<grid, kCabThreads, smem, stream>>>(a);
+    dim3 grid(nsplit, L.nprob, L.B);
+    gram_kernel<<<grid, kGramThreads, smem, stream>>>(a);
     CIDNET_CUDA_OK(cudaGetLastError());
     return CIDNET_OK;
 }

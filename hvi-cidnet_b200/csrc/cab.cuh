@@ -3,18 +3,25 @@
 
 namespace cidnet {
 
-// One launch handles up to two independent CAB problems (the I_LCA / HV_LCA pair of a stage).
-struct CabDwArgs {
-    const act_t* q[2]; int q_pitch[2];          // q_pre (output of the folded q 1x1), channel 0 of q
-    const act_t* k[2]; const act_t* v[2]; int kv_pitch[2];
-    const float* wq[2]; const float* wk[2]; const float* wv[2];   // depthwise weights fp32 [9][Cp]
-    act_t* v_out[2]; int v_pitch;
-    float* gram[2];                              // [B][heads][18][18] fp32, pre-zeroed
-    float* sq[2]; float* sk[2];                  // [B][Cp] fp32, pre-zeroed
-    int B, H, W, C, Cp, heads, nprob;
-    int tiles_x, tiles_y;
+// depthwise 3x3 over the [q | k | v] pre-activations of up to two CAB problems
+struct Dw3Args {
+    const act_t* src[2][3];     // per problem: q_pre, k_pre, v_pre (channel 0 of each segment)
+    int src_pitch;
+    act_t* dst[2];              // per problem: [q | k | v] after the depthwise conv, pitch dst_pitch
+    int dst_pitch;
+    const float* w[2];          // fp32 [9][nv*8] tap major, segments in the same order
+    float* sq[2]; float* sk[2]; // [B][Cp] sum of squares of q / k (pre-zeroed)
+    int B, H, W, nv, seg_vecs, nprob;
 };
-int launch_cab_dw_gram(CabDwArgs a, cudaStream_t stream);
+int launch_dw3(const Dw3Args& a, cudaStream_t stream);
+
+struct GramLaunch {
+    const act_t* q[2]; const act_t* k[2];   // NHWC, channel 0 of q / k, common pitch
+    int pitch;
+    float* gram[2];                          // [B][heads][18][18] fp32, pre-zeroed
+    int B, H, W, C, heads, nprob;
+};
+int launch_gram(const GramLaunch& L, cudaStream_t stream);
 
 struct CabFoldArgs {
     const float* gram[2]; const float* sq[2]; const float* sk[2];

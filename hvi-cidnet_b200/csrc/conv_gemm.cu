@@ -353,6 +353,11 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t
     return CIDNET_OK;
 }
 
+int encode_map_generic(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box) {
+    return encode_map(m, base, rank, dims, strides_bytes, box);
+}
+
 static inline float ac_scale(int n_in, int n_out) {
     // torch area_pixel_compute_scale<float>(align_corners=True)
     return n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.f;

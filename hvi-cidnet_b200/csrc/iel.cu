@@ -1,126 +1,151 @@
-// IEL gate: the whole depthwise / tanh / product chain of the IEL block in ONE kernel,
-// staged in shared memory (replaces 3 depthwise convs, 2 tanh, 2 adds, 1 mul and the
-// two chunk() views of net/LCA.py:61-65).
+// IEL gate: the whole depthwise / tanh / product chain of the IEL block in ONE kernel
+// (replaces 3 depthwise convs, 2 tanh, 2 adds, 1 mul and the chunk() views of net/LCA.py:61-65):
 //
-// CTA = 16x16 output pixels x 16 hidden channels (of x1 AND the matching 16 of x2).
-//   t tile   (20x20, 2-pixel halo)  act_t  -> shared
-//   d tile   (18x18, 1-pixel halo)  fp32   -> shared   (d is ZERO outside the image: that is the
-//                                                        zero padding dwconv1/dwconv2 see)
-//   g        (16x16)                       -> global NHWC
+//   d  = dwconv(t)            (3x3 depthwise on [x1 | x2], zero pad)
+//   x1 = tanh(dwconv1(d1)) + d1 ;  x2 = tanh(dwconv2(d2)) + d2 ;  g = x1 * x2
+//
+// CTA = 32 columns of d (30 output columns) x 32 hidden channels of each half, walking DOWN a
+// strip of rows.  Stage 1: thread (half, 8-channel vector, column) slides a 3x3 window of t
+// (read straight from global, neighbours are L1 hits) and writes one row of d (fp32) into a
+// 4-row ring in shared memory -- d is ZERO outside the image, which is exactly the zero
+// padding dwconv1/dwconv2 see.  Stage 2: thread (4-channel sub-vector, vector, column) reads the
+// 3x3 neighbourhood of d for BOTH halves from the ring, applies dwconv1/2 + tanh + residual,
+// multiplies and stores g.  One __syncthreads per row.
 #include "iel.cuh"
 
 namespace cidnet {
 
-static constexpr int kIT = 16;
-static constexpr int kT2 = kIT + 4;   // t tile edge
-static constexpr int kT1 = kIT + 2;   // d tile edge
-static constexpr int kCG = 16;        // channels per CTA (per half)
+static constexpr int kCols = 32;       // d columns per CTA (outputs: kCols - 2)
+static constexpr int kRows = 32;       // output rows per CTA
+static constexpr int kCh = 32;         // channels per half per CTA
+static constexpr int kThreadsIel = 256;
 
-__global__ void __launch_bounds__(256)
+// tanh(x) = 1 - 2 / (exp(2x) + 1): two fast SFU ops, abs error ~1e-7 (vs ~5e-4 of tanh.approx)
+__device__ __forceinline__ float fast_tanh(float x) {
+    const float e = __expf(2.f * x);
+    return 1.f - __fdividef(2.f, e + 1.f);
+}
+
+__global__ void __launch_bounds__(kThreadsIel, 2)
 iel_gate_kernel(const IelGateArgs a) {
-    extern __shared__ __align__(16) uint8_t iel_smem[];
-    act_t* s_t = reinterpret_cast<act_t*>(iel_smem);                         // [2][400][16]
-    float* s_d = reinterpret_cast<float*>(s_t + 2 * kT2 * kT2 * kCG);        // [2][324][16]
-    float* s_w = s_d + 2 * kT1 * kT1 * kCG;                                  // [2][3 (w0,w1/w2 unused slot)][9][16]
+    // ring: [4 rows][2 halves][4 vecs][2 planes][32 cols] float4
+    __shared__ float4 s_d[4 * 2 * 4 * 2 * kCols];
+    __shared__ __align__(16) float s_w0[9 * 2 * kCh];     // dwconv   [tap][half][32]
+    __shared__ __align__(16) float s_w12[9 * 2 * kCh];    // dwconv1/2 [tap][half][32]
     const int tid = threadIdx.x;
-    const int hp = a.hp;
-    const int ngroups = hp / kCG;
-    const int prob = blockIdx.z % a.nprob;
-    const int b = blockIdx.z / a.nprob;
-    const int cg = blockIdx.y % ngroups;
-    const int tiles_x = (a.W + kIT - 1) / kIT;
-    const int y0 = (blockIdx.x / tiles_x) * kIT, x0 = (blockIdx.x % tiles_x) * kIT;
-    const int c0 = cg * kCG;
+    const int hp = a.hp, ngroups = hp / kCh;
+    const int prob = blockIdx.z % a.nprob, b = blockIdx.z / a.nprob;
+    const int cg = blockIdx.x % ngroups, strip = blockIdx.x / ngroups;
+    const int c0 = cg * kCh;
+    const int X0 = strip * (kCols - 2) - 1;                // image column of d column 0
+    const int y0 = blockIdx.y * kRows;
+    const int y1 = min(y0 + kRows, a.H);
     const int pitch_t = 2 * hp;
     const long long hw = (long long)a.H * a.W;
-    const act_t* t = a.t[prob] + (long long)b * hw * pitch_t;
 
-    // weights: s_w[half][0][tap][16] = dwconv, s_w[half][1][tap][16] = dwconv1 / dwconv2
-    for (int i = tid; i < 2 * 2 * 9 * kCG; i += 256) {
-        const int c = i % kCG, tap = (i / kCG) % 9, which = (i / (kCG * 9)) % 2, half = i / (kCG * 9 * 2);
-        float v;
-        if (which == 0) v = a.w0[prob][tap * 2 * hp + half * hp + c0 + c];
-        else v = (half == 0 ? a.w1[prob] : a.w2[prob])[tap * hp + c0 + c];
-        s_w[i] = v;
+    for (int i = tid; i < 9 * 2 * kCh; i += kThreadsIel) {
+        const int c = i % kCh, half = (i / kCh) & 1, tap = i / (2 * kCh);
+        s_w0[i] = a.w0[prob][tap * 2 * hp + half * hp + c0 + c];
+        s_w12[i] = (half == 0 ? a.w1[prob] : a.w2[prob])[tap * hp + c0 + c];
     }
-    // stage t: 400 pixels x 2 halves x 2 vectors of 8 channels
-    for (int i = tid; i < kT2 * kT2 * 4; i += 256) {
-        const int p = i >> 2, hv = i & 3, half = hv >> 1, v = hv & 1;
-        const int y = y0 + p / kT2 - 2, x = x0 + p % kT2 - 2;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (y >= 0 && y < a.H && x >= 0 && x < a.W)
-            val = *reinterpret_cast<const uint4*>(t + ((long long)y * a.W + x) * pitch_t + half * hp + c0 + v * 8);
-        *reinterpret_cast<uint4*>(s_t + ((size_t)half * kT2 * kT2 + p) * kCG + v * 8) = val;
-    }
+
+    const int dx = tid & 31;                  // column (lane): a warp shares (half|sub, vec) -> smem broadcasts
+    const int vec = (tid >> 5) & 3;           // 8-channel vector within the group
+    const int hs = tid >> 7;                  // stage 1: half;  stage 2: 4-channel sub-vector (plane)
+    const int xd = X0 + dx;                   // image column of this thread's d column
+    const bool col_in = xd >= 0 && xd < a.W;
+    const bool has_l = xd - 1 >= 0 && xd - 1 < a.W, has_r = xd + 1 >= 0 && xd + 1 < a.W;
+    const act_t* tsrc = a.t[prob] + (long long)b * hw * pitch_t + hs * hp + c0 + vec * 8;
+    act_t* gdst = a.g[prob] + (long long)b * hw * hp + c0 + vec * 8 + hs * 4;
+    const bool writer = dx >= 1 && dx <= kCols - 2 && col_in;
+
+    uint4 win0[3], win1[3], win2[3];          // raw 16-bit t values of three consecutive rows
+    auto load_row = [&](int y, uint4* r) {
+        r[0] = r[1] = r[2] = make_uint4(0, 0, 0, 0);
+        if (y < 0 || y >= a.H) return;
+        const act_t* p = tsrc + ((long long)y * a.W + xd) * pitch_t;
+        if (col_in) r[1] = *reinterpret_cast<const uint4*>(p);
+        if (has_l) r[0] = *reinterpret_cast<const uint4*>(p - pitch_t);
+        if (has_r) r[2] = *reinterpret_cast<const uint4*>(p + pitch_t);
+    };
+    auto fma_row = [&](const uint4* r, int tap0, float* acc) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const act_t* h = reinterpret_cast<const act_t*>(&r[c]);
+            const float4 wa = *reinterpret_cast<const float4*>(s_w0 + ((tap0 + c) * 2 + hs) * kCh + vec * 8);
+            const float4 wb = *reinterpret_cast<const float4*>(s_w0 + ((tap0 + c) * 2 + hs) * kCh + vec * 8 + 4);
+            acc[0] = fmaf(act2f(h[0]), wa.x, acc[0]); acc[1] = fmaf(act2f(h[1]), wa.y, acc[1]);
+            acc[2] = fmaf(act2f(h[2]), wa.z, acc[2]); acc[3] = fmaf(act2f(h[3]), wa.w, acc[3]);
+            acc[4] = fmaf(act2f(h[4]), wb.x, acc[4]); acc[5] = fmaf(act2f(h[5]), wb.y, acc[5]);
+            acc[6] = fmaf(act2f(h[6]), wb.z, acc[6]); acc[7] = fmaf(act2f(h[7]), wb.w, acc[7]);
+        }
+    };
+    // ring address of (row slot, half, vec, plane, col)
+    auto ring = [&](int slot, int half, int v, int plane, int col) -> float4* {
+        return s_d + ((((slot * 2 + half) * 4 + v) * 2 + plane) * kCols + col);
+    };
+
     __syncthreads();
-    // d = dwconv(t) on the 18x18 tile; zero outside the image
-    for (int i = tid; i < kT1 * kT1 * 4; i += 256) {
-        const int p = i >> 2, hv = i & 3, half = hv >> 1, v = hv & 1;
-        const int py = p / kT1, px = p % kT1;
-        const int y = y0 + py - 1, x = x0 + px - 1;
+    // one iteration: d(r) -> ring, then output row r-1.  (w0, w1, w2) = t rows r-1, r, r+1.
+    auto iter = [&](int r, uint4* w0, uint4* w1, uint4* w2) {
+        // ---- stage 1: d(r) for (half = hs, vec, column dx)
+        load_row(r + 1, w2);
         float acc[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-        if (y >= 0 && y < a.H && x >= 0 && x < a.W) {
-            const float* w = s_w + (half * 2 + 0) * 9 * kCG + v * 8;
-#pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-                float f[8];
-                load8(s_t + ((size_t)half * kT2 * kT2 + (py + tap / 3) * kT2 + px + tap % 3) * kCG + v * 8, f);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] = fmaf(f[e], w[tap * kCG + e], acc[e]);
-            }
+        if (r >= 0 && r < a.H && col_in) {
+            fma_row(w0, 0, acc);
+            fma_row(w1, 3, acc);
+            fma_row(w2, 6, acc);
         }
-        float* d = s_d + ((size_t)half * kT1 * kT1 + p) * kCG + v * 8;
-        *reinterpret_cast<float4*>(d) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        *reinterpret_cast<float4*>(d + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    }
-    __syncthreads();
-    // gate
-    act_t* g = a.g[prob] + (long long)b * hw * hp;
-    for (int i = tid; i < kIT * kIT * 2; i += 256) {
-        const int p = i >> 1, v = i & 1;
-        const int py = p / kIT, px = p % kIT;
-        const int y = y0 + py, x = x0 + px;
-        if (y >= a.H || x >= a.W) continue;
-        float out[8];
-        float xs[2][8];
+        *ring(r & 3, hs, vec, 0, dx) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *ring(r & 3, hs, vec, 1, dx) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        __syncthreads();
+        // ---- stage 2: output row yo = r - 1, channels [4*hs, 4*hs+4) of vec, both halves
+        const int yo = r - 1;
+        if (yo >= y0 && writer) {
+            float xs[2][4];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const float* w = s_w + (half * 2 + 1) * 9 * kCG + v * 8;
-            float acc[8];
+            for (int half = 0; half < 2; ++half) {
+                float o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+                for (int rr = 0; rr < 3; ++rr) {
+                    const int slot = (yo - 1 + rr) & 3;
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-                const float* d = s_d + ((size_t)half * kT1 * kT1 + (py + tap / 3) * kT1 + px + tap % 3) * kCG + v * 8;
-                const float4 d0 = *reinterpret_cast<const float4*>(d), d1 = *reinterpret_cast<const float4*>(d + 4);
-                const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] = fmaf(dv[e], w[tap * kCG + e], acc[e]);
+                    for (int cc = 0; cc < 3; ++cc) {
+                        const float4 dv = *ring(slot, half, vec, hs, dx - 1 + cc);
+                        const float4 wv = *reinterpret_cast<const float4*>(s_w12 + ((rr * 3 + cc) * 2 + half) * kCh + vec * 8 + hs * 4);
+                        o[0] = fmaf(dv.x, wv.x, o[0]); o[1] = fmaf(dv.y, wv.y, o[1]);
+                        o[2] = fmaf(dv.z, wv.z, o[2]); o[3] = fmaf(dv.w, wv.w, o[3]);
+                    }
+                }
+                const float4 dc = *ring(yo & 3, half, vec, hs, dx);
+                xs[half][0] = fast_tanh(o[0]) + dc.x; xs[half][1] = fast_tanh(o[1]) + dc.y;
+                xs[half][2] = fast_tanh(o[2]) + dc.z; xs[half][3] = fast_tanh(o[3]) + dc.w;
             }
-            const float* dc = s_d + ((size_t)half * kT1 * kT1 + (py + 1) * kT1 + px + 1) * kCG + v * 8;
+            uint2 raw;
+            act_t* ov = reinterpret_cast<act_t*>(&raw);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) xs[half][e] = tanhf(acc[e]) + dc[e];
+            for (int e = 0; e < 4; ++e) ov[e] = f2act(xs[0][e] * xs[1][e]);
+            *reinterpret_cast<uint2*>(gdst + ((long long)yo * a.W + xd) * hp) = raw;
         }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) out[e] = xs[0][e] * xs[1][e];
-        store8(g + ((long long)y * a.W + x) * hp + c0 + v * 8, out);
+        // the next iteration writes ring slot (r+1)&3, which the stage 2 above (rows r-2..r) never reads
+    };
+    // d rows r = y0-1 .. y1; the three window registers rotate roles (no register moves)
+    load_row(y0 - 2, win0);
+    load_row(y0 - 1, win1);
+    for (int r = y0 - 1; r <= y1; r += 3) {
+        iter(r, win0, win1, win2);
+        if (r + 1 <= y1) iter(r + 1, win1, win2, win0);
+        if (r + 2 <= y1) iter(r + 2, win2, win0, win1);
     }
 }
 
 int launch_iel_gate(const IelGateArgs& a, cudaStream_t stream) {
-    CIDNET_CHECK(a.hp % kCG == 0, CIDNET_ERR_INVALID, "iel: hp % 16");
-    const size_t smem = 2 * kT2 * kT2 * kCG * sizeof(act_t) + 2 * kT1 * kT1 * kCG * sizeof(float) +
-                        2 * 2 * 9 * kCG * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        CIDNET_CUDA_OK(cudaFuncSetAttribute(iel_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    const int tiles = ceil_div(a.W, kIT) * ceil_div(a.H, kIT);
-    dim3 grid(tiles, a.hp / kCG, a.B * a.nprob);
-    iel_gate_kernel<<<grid, 256, smem, stream>>>(a);
+    CIDNET_CHECK(a.hp % kCh == 0, CIDNET_ERR_INVALID, "iel: hp % 32");
+    const int strips = ceil_div(a.W, kCols - 2);
+    dim3 grid(strips * (a.hp / kCh), ceil_div(a.H, kRows), a.B * a.nprob);
+    iel_gate_kernel<<<grid, kThreadsIel, 0, stream>>>(a);
     CIDNET_CUDA_OK(cudaGetLastError());
     return CIDNET_OK;
 }

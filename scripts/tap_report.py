@@ -17,8 +17,8 @@ m = CIDNet().cuda().eval()
 m.load_state_dict(sd)
 y = m(x.cuda()).cpu()
 torch.cuda.synchronize()
-order = ["hvi", "i_enc0", "hv_0", "i_enc1", "hv_1", "I_LCA1.after_cab", "HV_LCA1.after_cab", "I_LCA1", "HV_LCA1",
-         "i_enc2", "hv_2", "I_LCA2", "HV_LCA2", "i_enc3", "hv_3", "I_LCA3.after_cab", "I_LCA3", "HV_LCA3", "I_LCA4", "HV_LCA4",
+order = ["hvi", "i_enc0", "hv_0", "i_enc1", "hv_1", "I_LCA1", "HV_LCA1",
+         "i_enc2", "hv_2", "I_LCA2", "HV_LCA2", "i_enc3", "hv_3", "I_LCA3", "HV_LCA3", "I_LCA4", "HV_LCA4",
          "hvd3", "id3", "HV_LCA5", "hvd2", "id2", "I_LCA6", "HV_LCA6", "id1", "hvd1", "out_hvi"]
 for name in order:
     a = m.read_tap(name).cpu()
