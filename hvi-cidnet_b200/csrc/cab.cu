@@ -331,8 +331,11 @@ cab_fold_kernel(const CabFoldArgs a) {
     // M[o][kin] = sum_{c' in head(kin)} Wo[o][head*18 + c'] * attn[head*18 + c'][kin - head*18]
     const float* wo = a.wo[prob];
     act_t* m = a.m_out[prob] + (long long)b * a.n_rows * a.kt;
-    const int total = a.n_rows * a.kt;
-    for (int i = tid; i < total; i += 256) {
+    // each CTA of the z dimension writes a slice of the rows (the softmax above is recomputed: cheap)
+    const int rows_per = (a.n_rows + gridDim.z - 1) / gridDim.z;
+    const int i_begin = blockIdx.z * rows_per * a.kt;
+    const int i_end = min((int)(blockIdx.z + 1) * rows_per, a.n_rows) * a.kt;
+    for (int i = i_begin + tid; i < i_end; i += 256) {
         const int o = i / a.kt, kin = i - o * a.kt;
         float acc = 0.f;
         if (o < C && kin < C) {
@@ -346,7 +349,7 @@ cab_fold_kernel(const CabFoldArgs a) {
 
 int launch_cab_fold(const CabFoldArgs& a, cudaStream_t stream) {
     CIDNET_CHECK(a.C <= 144, CIDNET_ERR_INVALID, "fold: C too large");
-    dim3 grid(a.nprob, a.B);
+    dim3 grid(a.nprob, a.B, 16);
     cab_fold_kernel<<<grid, 256, 0, stream>>>(a);
     CIDNET_CUDA_OK(cudaGetLastError());
     return CIDNET_OK;

@@ -51,10 +51,12 @@ static constexpr uint32_t kSubTileBytes = 128 * 128;   // 128 rows x 64 elements
 
 __device__ __forceinline__ float prelu_f(float v, float slope) { return v >= 0.f ? v : v * slope; }
 
-// store `n` (<=16) channels starting at p; n is rounded up to a multiple of 8 (the pitch is)
+// store `n` (<=32) channels starting at p; n is rounded up to a multiple of 8 (the pitch is)
 __device__ __forceinline__ void store_chunk(act_t* p, const float* v, int n) {
     if (n > 0) store8(p, v);
     if (n > 8) store8(p + 8, v + 8);
+    if (n > 16) store8(p + 16, v + 16);
+    if (n > 24) store8(p + 24, v + 24);
 }
 
 template <int kMode>
@@ -72,6 +74,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
     uint64_t* empty = full + stages;
     uint64_t* tmem_full = empty + stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);     // [block_n] bias, then [block_n] wsum (EPI_LN)
+    float* s_wsum = s_bias + a.block_n;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -174,6 +178,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
 
         float mean = 0.f, rstd = 1.f;
         if (kMode == EPI_LN) {
+            // bias / wsum of this channel block -> shared memory (read once per CTA instead of once
+            // per 16-column chunk from global); named barrier 1 = the 128 epilogue threads only
+            for (int i = row; i < a.block_n; i += 128) {
+                s_bias[i] = __ldg(a.bias + n0 + i);
+                s_wsum[i] = __ldg(a.wsum + n0 + i);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
             // per-pixel LayerNorm statistics from the A tile (all K chunks are still resident:
             // the host guarantees stages >= kchunks and taps == 1 for this mode)
             for (int kc = 0; kc < a.kchunks; ++kc) ptx::mbar_wait(&full[kc], 0);
@@ -203,6 +214,29 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
             }
         }
 
+        // pull the rows this thread will add (residual / low-res upsample taps) towards L1 while
+        // the MMAs are still running
+        if (kMode == EPI_STORE && a.res != nullptr && valid) {
+            const char* rp = reinterpret_cast<const char*>(a.res + (long long)img * a.res_img_stride +
+                                                           ((long long)y * a.Wv + x) * a.res_pitch + n0);
+            const int bytes = min(a.block_n, a.n_out - n0) * 2;
+            for (int o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L1 [%0];" :: "l"(rp + o));
+        }
+        if (kMode == EPI_UP && valid) {
+            const long long pix = (long long)y * a.Wv + x;
+            const int yr = (int)(pix / a.w_real), xr = (int)(pix - (long long)yr * a.w_real);
+            const int i0 = (int)(a.up_ry * (float)yr), j0 = (int)(a.up_rx * (float)xr);
+            const int i1 = i0 + (i0 < a.up_H - 1 ? 1 : 0), j1 = j0 + (j0 < a.up_W - 1 ? 1 : 0);
+            const char* tb = reinterpret_cast<const char*>(a.up + (long long)img * a.up_img_stride + n0);
+            const int bytes = min(a.block_n, a.n_out - n0) * 2;
+            for (int o = 0; o < bytes; o += 128) {
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(tb + ((long long)i0 * a.up_W + j0) * a.up_pitch * 2 + o));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(tb + ((long long)i0 * a.up_W + j1) * a.up_pitch * 2 + o));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(tb + ((long long)i1 * a.up_W + j0) * a.up_pitch * 2 + o));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(tb + ((long long)i1 * a.up_W + j1) * a.up_pitch * 2 + o));
+            }
+        }
+
         ptx::mbar_wait(tmem_full, 0);
         ptx::tc_fence_after();
 
@@ -220,13 +254,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
             const bool writer = valid && ((x & 1) == 0);
             act_t* outp = a.out + (long long)img * a.out_img_stride +
                           ((long long)oy * (a.Wv >> 1) + ox) * a.out_pitch + n0;
-            for (int c = 0; c < a.block_n; c += 16) {
+            for (int c = 0; c < a.block_n; c += 32) {
                 if (n0 + c >= a.n_out) break;
-                float e[16], o[16];
-                ptx::tmem_ld16(taddr + c, e);
-                ptx::tmem_ld16(taddr + a.block_n + c, o);
+                float e[32], o[32];
+                ptx::tmem_ld32(taddr + c, e);
+                ptx::tmem_ld32(taddr + a.block_n + c, o);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
+                for (int j = 0; j < 32; ++j) {
                     const float top = top_is_odd ? o[j] : e[j];
                     const float v = (1.f - ly) * top + ly * o[j];
                     const float vr = __shfl_down_sync(0xffffffffu, v, 1);
@@ -257,34 +291,38 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                 t10 = tb + ((long long)i1 * a.up_W + j0) * a.up_pitch;
                 t11 = tb + ((long long)i1 * a.up_W + j1) * a.up_pitch;
             }
-            for (int c = 0; c < a.block_n; c += 16) {
+            for (int c = 0; c < a.block_n; c += 32) {
                 if (n0 + c >= a.n_out) break;
-                float v[16];
-                ptx::tmem_ld16(taddr + c, v);
+                float v[32];
+                ptx::tmem_ld32(taddr + c, v);
                 const int nrem = a.n_out - (n0 + c);
                 if (kMode == EPI_LN) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int n = n0 + c + j;      // bias / wsum are padded to n_rows
-                        v[j] = rstd * (v[j] - mean * __ldg(a.wsum + n)) + __ldg(a.bias + n);
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = (c + j < a.block_n) ? c + j : 0;      // bias / wsum staged for block_n channels
+                        v[j] = rstd * (v[j] - mean * s_wsum[n]) + s_bias[n];
                     }
                 } else if (kMode == EPI_STORE) {
                     if (resp != nullptr && valid) {
-                        float r[16];
-                        load8(resp + c, r);
-                        if (nrem > 8) load8(resp + c + 8, r + 8);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) if (j < 8 || nrem > 8) v[j] += r[j];
+                        for (int h = 0; h < 4; ++h) {
+                            if (nrem > 8 * h) {
+                                float r[8];
+                                load8(resp + c + 8 * h, r);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[8 * h + j] += r[j];
+                            }
+                        }
                     }
                     if (a.use_prelu) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = prelu_f(v[j], a.prelu);
+                        for (int j = 0; j < 32; ++j) v[j] = prelu_f(v[j], a.prelu);
                     }
                 } else if (kMode == EPI_UP) {
                     if (valid) {
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            if (h == 0 || nrem > 8) {
+                        for (int h = 0; h < 4; ++h) {
+                            if (nrem > 8 * h) {
                                 float p00[8], p01[8], p10[8], p11[8];
                                 load8(t00 + c + 8 * h, p00); load8(t01 + c + 8 * h, p01);
                                 load8(t10 + c + 8 * h, p10); load8(t11 + c + 8 * h, p11);
@@ -449,7 +487,7 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
     if (stages > kiters) stages = kiters;
     if (stages > 8) stages = 8;
     a.stages = stages;
-    const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16;
+    const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 2 * wt.block_n * sizeof(float);
     CIDNET_CHECK(smem <= 227 * 1024, CIDNET_ERR_INVALID, "conv_gemm: shared memory budget exceeded");
 
     dim3 grid((unsigned)(a.tiles_x * a.tiles_y * L.B), (unsigned)wt.n_blocks, 1);
