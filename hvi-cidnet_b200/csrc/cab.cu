@@ -23,87 +23,94 @@
 namespace cidnet {
 
 // ------------------------------------------------------------- depthwise ----
-static constexpr int kDwThreads = 256;
+static constexpr int kDwThreads = 128;
 static constexpr int kDwRows = 32;     // rows per CTA strip
 
-__device__ __forceinline__ void unpack4(const uint2& raw, float* f) {
 #ifdef CIDNET_ACT_BF16
-    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
-    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
-    const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+#define CIDNET_FHFMA "fma.rn.f32.bf16"
 #else
-    const __half2 a = *reinterpret_cast<const __half2*>(&raw.x);
-    const __half2 b = *reinterpret_cast<const __half2*>(&raw.y);
-    const float2 fa = __half22float2(a), fb = __half22float2(b);
+#define CIDNET_FHFMA "fma.rn.f32.f16"
 #endif
-    f[0] = fa.x; f[1] = fa.y; f[2] = fb.x; f[3] = fb.y;
+// acc0/1 += lo/hi(a) * lo/hi(b): mixed-precision FMA (SASS FHFMA), operands stay packed 16-bit
+__device__ __forceinline__ void fhfma2(float& acc0, float& acc1, uint32_t a, uint32_t b) {
+    asm("{\n\t.reg .b16 al, ah, bl, bh;\n\t"
+        "mov.b32 {al, ah}, %2;\n\t"
+        "mov.b32 {bl, bh}, %3;\n\t"
+        CIDNET_FHFMA " %0, al, bl, %0;\n\t"
+        CIDNET_FHFMA " %1, ah, bh, %1;\n\t}"
+        : "+f"(acc0), "+f"(acc1) : "r"(a), "r"(b));
+}
+__device__ __forceinline__ void fhfma8(float* acc, const uint4& t, const uint4& w) {
+    fhfma2(acc[0], acc[1], t.x, w.x);
+    fhfma2(acc[2], acc[3], t.y, w.y);
+    fhfma2(acc[4], acc[5], t.z, w.z);
+    fhfma2(acc[6], acc[7], t.w, w.w);
 }
 
-// one thread = (column x, 4 channels): 36 weights + a raw 3x3 window (18 registers)
-__global__ void __launch_bounds__(kDwThreads, 2)
+// one thread = (column x, 8 channels): 9 packed weight vectors + a raw 3x3 window in registers,
+// FHFMA (16-bit x 16-bit + fp32) so no conversion instructions are needed
+__global__ void __launch_bounds__(kDwThreads, 3)
 dw3x3_kernel(const Dw3Args a) {
     __shared__ float s_ssq[2 * 144];
     const int prob = blockIdx.z % a.nprob, b = blockIdx.z / a.nprob;
-    const int nv = a.nv * 2;                               // 8-byte vectors per pixel (all segments)
-    const int seg_v = a.seg_vecs * 2;
+    const int nv = a.nv;                                   // 16-byte vectors per pixel (all segments)
     const int idx = blockIdx.x * kDwThreads + threadIdx.x; // vector index along the row
     const int x = idx / nv, v = idx - x * nv;
     const bool active = x < a.W;
-    const int seg = active ? v / seg_v : 0;                // 0 = q, 1 = k, 2 = v
-    const int c0 = (v - seg * seg_v) * 4;                  // channel within the segment
+    const int seg = active ? v / a.seg_vecs : 0;           // 0 = q, 1 = k, 2 = v
+    const int c0 = (v - seg * a.seg_vecs) * 8;             // channel within the segment
     const long long hw = (long long)a.H * a.W;
     const act_t* src = a.src[prob][seg] + (long long)b * hw * a.src_pitch + c0;
-    act_t* dst = a.dst[prob] + (long long)b * hw * a.dst_pitch + seg * seg_v * 4 + c0;
+    act_t* dst = a.dst[prob] + (long long)b * hw * a.dst_pitch + seg * a.seg_vecs * 8 + c0;
     const int y0 = blockIdx.y * kDwRows;
     const int y1 = min(y0 + kDwRows, a.H);
 
     for (int i = threadIdx.x; i < 2 * 144; i += kDwThreads) s_ssq[i] = 0.f;
     __syncthreads();
 
-    float w[9][4];
+    uint4 w[9];
     {
-        const float* wp = a.w[prob] + seg * seg_v * 4 + c0;   // [9][nv*4] tap major
+        const float* wp = a.w[prob] + seg * a.seg_vecs * 8 + c0;   // [9][nv*8] tap major
 #pragma unroll
-        for (int t = 0; t < 9; ++t)
+        for (int t = 0; t < 9; ++t) {
+            act_t* h = reinterpret_cast<act_t*>(&w[t]);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) w[t][e] = active ? __ldg(wp + t * nv * 4 + e) : 0.f;
+            for (int e = 0; e < 8; ++e) h[e] = f2act(active ? __ldg(wp + t * nv * 8 + e) : 0.f);
+        }
     }
-    float ssq[4] = {0.f, 0.f, 0.f, 0.f};
+    float ssq[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ssq[e] = 0.f;
 
     if (active) {
         const bool has_l = x > 0, has_r = x + 1 < a.W;
-        uint2 win0[3], win1[3], win2[3];
-        auto load_row = [&](int y, uint2* r) {
-            r[0] = r[1] = r[2] = make_uint2(0, 0);
+        const uint4 zero4 = make_uint4(0, 0, 0, 0);
+        uint4 win0[3], win1[3], win2[3];
+        auto load_row = [&](int y, uint4* r) {
+            r[0] = r[1] = r[2] = zero4;
             if (y < 0 || y >= a.H) return;
             const act_t* p = src + ((long long)y * a.W + x) * a.src_pitch;
-            r[1] = *reinterpret_cast<const uint2*>(p);
-            if (has_l) r[0] = *reinterpret_cast<const uint2*>(p - a.src_pitch);
-            if (has_r) r[2] = *reinterpret_cast<const uint2*>(p + a.src_pitch);
+            r[1] = *reinterpret_cast<const uint4*>(p);
+            if (has_l) r[0] = *reinterpret_cast<const uint4*>(p - a.src_pitch);
+            if (has_r) r[2] = *reinterpret_cast<const uint4*>(p + a.src_pitch);
         };
-        auto step = [&](const uint2* r0, const uint2* r1, uint2* r2, int y) {
+        auto step = [&](const uint4* r0, const uint4* r1, uint4* r2, int y) {
             load_row(y + 1, r2);
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            float acc[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = 0.f;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                float f0[4], f1[4], f2[4];
-                unpack4(r0[c], f0); unpack4(r1[c], f1); unpack4(r2[c], f2);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    acc[e] = fmaf(f0[e], w[c][e], acc[e]);
-                    acc[e] = fmaf(f1[e], w[3 + c][e], acc[e]);
-                    acc[e] = fmaf(f2[e], w[6 + c][e], acc[e]);
-                }
+                fhfma8(acc, r0[c], w[c]);
+                fhfma8(acc, r1[c], w[3 + c]);
+                fhfma8(acc, r2[c], w[6 + c]);
             }
-            uint2 raw;
+            uint4 raw;
             act_t* ov = reinterpret_cast<act_t*>(&raw);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                ov[e] = f2act(acc[e]);
-                const float rf = act2f(ov[e]);
-                ssq[e] = fmaf(rf, rf, ssq[e]);
-            }
-            *reinterpret_cast<uint2*>(dst + ((long long)y * a.W + x) * a.dst_pitch) = raw;
+            for (int e = 0; e < 8; ++e) ov[e] = f2act(acc[e]);
+            fhfma8(ssq, raw, raw);                                   // sum of squares of the ROUNDED values
+            *reinterpret_cast<uint4*>(dst + ((long long)y * a.W + x) * a.dst_pitch) = raw;
         };
         load_row(y0 - 1, win0);
         load_row(y0, win1);
@@ -114,7 +121,7 @@ dw3x3_kernel(const Dw3Args a) {
         }
         if (seg < 2) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) atomicAdd(&s_ssq[seg * 144 + c0 + e], ssq[e]);
+            for (int e = 0; e < 8; ++e) atomicAdd(&s_ssq[seg * 144 + c0 + e], ssq[e]);
         }
     }
     __syncthreads();
@@ -129,7 +136,7 @@ dw3x3_kernel(const Dw3Args a) {
 
 int launch_dw3(const Dw3Args& a, cudaStream_t stream) {
     CIDNET_CHECK(a.seg_vecs * 8 <= 144 && a.nv == 3 * a.seg_vecs, CIDNET_ERR_INVALID, "dw3: bad channel layout");
-    dim3 grid(ceil_div(a.W * a.nv * 2, kDwThreads), ceil_div(a.H, kDwRows), a.B * a.nprob);
+    dim3 grid(ceil_div(a.W * a.nv, kDwThreads), ceil_div(a.H, kDwRows), a.B * a.nprob);
     dw3x3_kernel<<<grid, kDwThreads, 0, stream>>>(a);
     CIDNET_CUDA_OK(cudaGetLastError());
     return CIDNET_OK;

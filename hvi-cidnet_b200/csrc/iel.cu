@@ -4,147 +4,192 @@
 //   d  = dwconv(t)            (3x3 depthwise on [x1 | x2], zero pad)
 //   x1 = tanh(dwconv1(d1)) + d1 ;  x2 = tanh(dwconv2(d2)) + d2 ;  g = x1 * x2
 //
-// CTA = 32 columns of d (30 output columns) x 32 hidden channels of each half, walking DOWN a
-// strip of rows.  Stage 1: thread (half, 8-channel vector, column) slides a 3x3 window of t
-// (read straight from global, neighbours are L1 hits) and writes one row of d (fp32) into a
-// 4-row ring in shared memory -- d is ZERO outside the image, which is exactly the zero
-// padding dwconv1/dwconv2 see.  Stage 2: thread (4-channel sub-vector, vector, column) reads the
-// 3x3 neighbourhood of d for BOTH halves from the ring, applies dwconv1/2 + tanh + residual,
-// multiplies and stores g.  One __syncthreads per row.
+// A warp = 32 image columns (lane = column) x 8 hidden channels of ONE half, walking down a strip
+// of rows; a CTA = 4 warps = {x1, x2} x 2 channel vectors.  Per row each thread issues ONE 16-byte
+// global load (its own column of t); the left/right neighbours of t and of d come from warp
+// shuffles (the two edge lanes fetch their outer neighbour themselves), so there is no shared
+// memory staging and no block-wide barrier.  The first depthwise runs on FHFMA (fp16 x fp16 + fp32,
+// `fma.rn.f32.f16`: no conversion instructions); d, the second depthwise, tanh and the product are
+// fp32.  d is ZERO outside the image (= the zero padding dwconv1/dwconv2 see).  The x2 warp hands
+// its tanh(..)+d to the x1 warp through 1 KB of shared memory and a 64-thread named barrier.
 #include "iel.cuh"
 
 namespace cidnet {
 
-static constexpr int kCols = 32;       // d columns per CTA (outputs: kCols - 2)
+static constexpr int kCols = 32;       // columns per warp (outputs: lanes 1..30)
 static constexpr int kRows = 32;       // output rows per CTA
-static constexpr int kCh = 32;         // channels per half per CTA
-static constexpr int kThreadsIel = 256;
+static constexpr int kThreadsIel = 128;
 
-// tanh(x) = 1 - 2 / (exp(2x) + 1): two fast SFU ops, abs error ~1e-7 (vs ~5e-4 of tanh.approx)
-__device__ __forceinline__ float fast_tanh(float x) {
-    const float e = __expf(2.f * x);
-    return 1.f - __fdividef(2.f, e + 1.f);
+#ifdef CIDNET_ACT_BF16
+#define CIDNET_FHFMA "fma.rn.f32.bf16"
+#else
+#define CIDNET_FHFMA "fma.rn.f32.f16"
+#endif
+
+// acc[0..1] += lo/hi(a) * lo/hi(b)   (two mixed-precision FMAs, operands stay packed)
+__device__ __forceinline__ void fhfma2(float& acc0, float& acc1, uint32_t a, uint32_t b) {
+    asm("{\n\t.reg .b16 al, ah, bl, bh;\n\t"
+        "mov.b32 {al, ah}, %2;\n\t"
+        "mov.b32 {bl, bh}, %3;\n\t"
+        CIDNET_FHFMA " %0, al, bl, %0;\n\t"
+        CIDNET_FHFMA " %1, ah, bh, %1;\n\t}"
+        : "+f"(acc0), "+f"(acc1) : "r"(a), "r"(b));
+}
+__device__ __forceinline__ void fhfma8(float* acc, const uint4& t, const uint4& w) {
+    fhfma2(acc[0], acc[1], t.x, w.x);
+    fhfma2(acc[2], acc[3], t.y, w.y);
+    fhfma2(acc[4], acc[5], t.z, w.z);
+    fhfma2(acc[6], acc[7], t.w, w.w);
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));    // one MUFU op, abs error < 2^-10.9
+    return y;
+}
+__device__ __forceinline__ uint4 shfl_up4(const uint4& v) {
+    return make_uint4(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1),
+                      __shfl_up_sync(0xffffffffu, v.z, 1), __shfl_up_sync(0xffffffffu, v.w, 1));
+}
+__device__ __forceinline__ uint4 shfl_down4(const uint4& v) {
+    return make_uint4(__shfl_down_sync(0xffffffffu, v.x, 1), __shfl_down_sync(0xffffffffu, v.y, 1),
+                      __shfl_down_sync(0xffffffffu, v.z, 1), __shfl_down_sync(0xffffffffu, v.w, 1));
 }
 
-__global__ void __launch_bounds__(kThreadsIel, 2)
+struct TRow { uint4 l, c, r; };          // raw 16-bit t values: left / centre / right column
+struct DRow { float l[8], c[8], r[8]; }; // d values (fp32)
+
+__global__ void __launch_bounds__(kThreadsIel, 3)
 iel_gate_kernel(const IelGateArgs a) {
-    // ring: [4 rows][2 halves][4 vecs][2 planes][32 cols] float4
-    __shared__ float4 s_d[4 * 2 * 4 * 2 * kCols];
-    __shared__ __align__(16) float s_w0[9 * 2 * kCh];     // dwconv   [tap][half][32]
-    __shared__ __align__(16) float s_w12[9 * 2 * kCh];    // dwconv1/2 [tap][half][32]
-    const int tid = threadIdx.x;
-    const int hp = a.hp, ngroups = hp / kCh;
+    __shared__ __align__(16) act_t s_w0[9 * 2 * 16];      // dwconv    [tap][half][16]  16-bit
+    __shared__ __align__(16) float s_w12[9 * 2 * 16];     // dwconv1/2 [tap][half][16]  fp32
+    __shared__ float4 s_x[2 * 2 * 2 * kCols];             // [vec][row parity][plane][lane]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int half = warp >> 1, vec = warp & 1;
+    const int hp = a.hp, ngroups = hp / 16;
     const int prob = blockIdx.z % a.nprob, b = blockIdx.z / a.nprob;
     const int cg = blockIdx.x % ngroups, strip = blockIdx.x / ngroups;
-    const int c0 = cg * kCh;
-    const int X0 = strip * (kCols - 2) - 1;                // image column of d column 0
+    const int c0 = cg * 16;
+    const int x = strip * (kCols - 2) - 1 + lane;         // image column of this lane
     const int y0 = blockIdx.y * kRows;
     const int y1 = min(y0 + kRows, a.H);
     const int pitch_t = 2 * hp;
     const long long hw = (long long)a.H * a.W;
 
-    for (int i = tid; i < 9 * 2 * kCh; i += kThreadsIel) {
-        const int c = i % kCh, half = (i / kCh) & 1, tap = i / (2 * kCh);
-        s_w0[i] = a.w0[prob][tap * 2 * hp + half * hp + c0 + c];
-        s_w12[i] = (half == 0 ? a.w1[prob] : a.w2[prob])[tap * hp + c0 + c];
+    for (int i = tid; i < 9 * 2 * 16; i += kThreadsIel) {
+        const int c = i & 15, hf = (i >> 4) & 1, tap = i >> 5;
+        s_w0[i] = f2act(a.w0[prob][tap * 2 * hp + hf * hp + c0 + c]);
+        s_w12[i] = (hf == 0 ? a.w1[prob] : a.w2[prob])[tap * hp + c0 + c];
     }
-
-    const int dx = tid & 31;                  // column (lane): a warp shares (half|sub, vec) -> smem broadcasts
-    const int vec = (tid >> 5) & 3;           // 8-channel vector within the group
-    const int hs = tid >> 7;                  // stage 1: half;  stage 2: 4-channel sub-vector (plane)
-    const int xd = X0 + dx;                   // image column of this thread's d column
-    const bool col_in = xd >= 0 && xd < a.W;
-    const bool has_l = xd - 1 >= 0 && xd - 1 < a.W, has_r = xd + 1 >= 0 && xd + 1 < a.W;
-    const act_t* tsrc = a.t[prob] + (long long)b * hw * pitch_t + hs * hp + c0 + vec * 8;
-    act_t* gdst = a.g[prob] + (long long)b * hw * hp + c0 + vec * 8 + hs * 4;
-    const bool writer = dx >= 1 && dx <= kCols - 2 && col_in;
-
-    uint4 win0[3], win1[3], win2[3];          // raw 16-bit t values of three consecutive rows
-    auto load_row = [&](int y, uint4* r) {
-        r[0] = r[1] = r[2] = make_uint4(0, 0, 0, 0);
-        if (y < 0 || y >= a.H) return;
-        const act_t* p = tsrc + ((long long)y * a.W + xd) * pitch_t;
-        if (col_in) r[1] = *reinterpret_cast<const uint4*>(p);
-        if (has_l) r[0] = *reinterpret_cast<const uint4*>(p - pitch_t);
-        if (has_r) r[2] = *reinterpret_cast<const uint4*>(p + pitch_t);
-    };
-    auto fma_row = [&](const uint4* r, int tap0, float* acc) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const act_t* h = reinterpret_cast<const act_t*>(&r[c]);
-            const float4 wa = *reinterpret_cast<const float4*>(s_w0 + ((tap0 + c) * 2 + hs) * kCh + vec * 8);
-            const float4 wb = *reinterpret_cast<const float4*>(s_w0 + ((tap0 + c) * 2 + hs) * kCh + vec * 8 + 4);
-            acc[0] = fmaf(act2f(h[0]), wa.x, acc[0]); acc[1] = fmaf(act2f(h[1]), wa.y, acc[1]);
-            acc[2] = fmaf(act2f(h[2]), wa.z, acc[2]); acc[3] = fmaf(act2f(h[3]), wa.w, acc[3]);
-            acc[4] = fmaf(act2f(h[4]), wb.x, acc[4]); acc[5] = fmaf(act2f(h[5]), wb.y, acc[5]);
-            acc[6] = fmaf(act2f(h[6]), wb.z, acc[6]); acc[7] = fmaf(act2f(h[7]), wb.w, acc[7]);
-        }
-    };
-    // ring address of (row slot, half, vec, plane, col)
-    auto ring = [&](int slot, int half, int v, int plane, int col) -> float4* {
-        return s_d + ((((slot * 2 + half) * 4 + v) * 2 + plane) * kCols + col);
-    };
-
     __syncthreads();
-    // one iteration: d(r) -> ring, then output row r-1.  (w0, w1, w2) = t rows r-1, r, r+1.
-    auto iter = [&](int r, uint4* w0, uint4* w1, uint4* w2) {
-        // ---- stage 1: d(r) for (half = hs, vec, column dx)
-        load_row(r + 1, w2);
-        float acc[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-        if (r >= 0 && r < a.H && col_in) {
-            fma_row(w0, 0, acc);
-            fma_row(w1, 3, acc);
-            fma_row(w2, 6, acc);
-        }
-        *ring(r & 3, hs, vec, 0, dx) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        *ring(r & 3, hs, vec, 1, dx) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-        __syncthreads();
-        // ---- stage 2: output row yo = r - 1, channels [4*hs, 4*hs+4) of vec, both halves
-        const int yo = r - 1;
-        if (yo >= y0 && writer) {
-            float xs[2][4];
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                float o[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int rr = 0; rr < 3; ++rr) {
-                    const int slot = (yo - 1 + rr) & 3;
-#pragma unroll
-                    for (int cc = 0; cc < 3; ++cc) {
-                        const float4 dv = *ring(slot, half, vec, hs, dx - 1 + cc);
-                        const float4 wv = *reinterpret_cast<const float4*>(s_w12 + ((rr * 3 + cc) * 2 + half) * kCh + vec * 8 + hs * 4);
-                        o[0] = fmaf(dv.x, wv.x, o[0]); o[1] = fmaf(dv.y, wv.y, o[1]);
-                        o[2] = fmaf(dv.z, wv.z, o[2]); o[3] = fmaf(dv.w, wv.w, o[3]);
-                    }
-                }
-                const float4 dc = *ring(yo & 3, half, vec, hs, dx);
-                xs[half][0] = fast_tanh(o[0]) + dc.x; xs[half][1] = fast_tanh(o[1]) + dc.y;
-                xs[half][2] = fast_tanh(o[2]) + dc.z; xs[half][3] = fast_tanh(o[3]) + dc.w;
-            }
-            uint2 raw;
-            act_t* ov = reinterpret_cast<act_t*>(&raw);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) ov[e] = f2act(xs[0][e] * xs[1][e]);
-            *reinterpret_cast<uint2*>(gdst + ((long long)yo * a.W + xd) * hp) = raw;
-        }
-        // the next iteration writes ring slot (r+1)&3, which the stage 2 above (rows r-2..r) never reads
+
+    const bool col_in = x >= 0 && x < a.W;
+    const bool left_in = x - 1 >= 0 && x - 1 < a.W, right_in = x + 1 >= 0 && x + 1 < a.W;
+    const act_t* tsrc = a.t[prob] + (long long)b * hw * pitch_t + half * hp + c0 + vec * 8;
+    act_t* gdst = a.g[prob] + (long long)b * hw * hp + c0 + vec * 8;
+    const bool writer = half == 0 && lane >= 1 && lane <= kCols - 2 && col_in;
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+
+    // global loads run ONE ROW AHEAD of their use: `pend_*` holds row r+2 while iteration r computes
+    uint4 pend_c = zero4, pend_e = zero4;      // own column; outer neighbour (edge lanes 0 / 31 only)
+    auto issue_load = [&](int y) {
+        pend_c = zero4; pend_e = zero4;
+        const bool row_in = y >= 0 && y < a.H;
+        const act_t* p = tsrc + ((long long)y * a.W + x) * pitch_t;
+        if (row_in && col_in) pend_c = *reinterpret_cast<const uint4*>(p);
+        if (lane == 0 && row_in && left_in) pend_e = *reinterpret_cast<const uint4*>(p - pitch_t);
+        if (lane == 31 && row_in && right_in) pend_e = *reinterpret_cast<const uint4*>(p + pitch_t);
     };
-    // d rows r = y0-1 .. y1; the three window registers rotate roles (no register moves)
-    load_row(y0 - 2, win0);
-    load_row(y0 - 1, win1);
+    auto take_trow = [&](TRow& t) {
+        t.c = pend_c;
+        t.l = shfl_up4(t.c);
+        t.r = shfl_down4(t.c);
+        if (lane == 0) t.l = pend_e;
+        if (lane == 31) t.r = pend_e;
+    };
+    auto dw0_row = [&](const TRow& t, int tap0, float* acc) {
+        const uint4* w = reinterpret_cast<const uint4*>(s_w0) + (half * 2 + vec);   // + tap * 4 uint4
+        fhfma8(acc, t.l, w[(tap0 + 0) * 4]);
+        fhfma8(acc, t.c, w[(tap0 + 1) * 4]);
+        fhfma8(acc, t.r, w[(tap0 + 2) * 4]);
+    };
+    auto dw12_row = [&](const DRow& d, int tap0, float* o) {
+        const float4* w = reinterpret_cast<const float4*>(s_w12) + (half * 4 + vec * 2);   // + tap * 8 float4
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+            const float* dv = cc == 0 ? d.l : (cc == 1 ? d.c : d.r);
+            const float4 wa = w[(tap0 + cc) * 8], wb = w[(tap0 + cc) * 8 + 1];
+            o[0] = fmaf(dv[0], wa.x, o[0]); o[1] = fmaf(dv[1], wa.y, o[1]);
+            o[2] = fmaf(dv[2], wa.z, o[2]); o[3] = fmaf(dv[3], wa.w, o[3]);
+            o[4] = fmaf(dv[4], wb.x, o[4]); o[5] = fmaf(dv[5], wb.y, o[5]);
+            o[6] = fmaf(dv[6], wb.z, o[6]); o[7] = fmaf(dv[7], wb.w, o[7]);
+        }
+    };
+
+    // one iteration: d(r) from t rows (r-1, r, r+1) = (t0, t1, t2); then output row r-1 from d rows
+    // (r-2, r-1, r) = (d0, d1, d2).  t2 and d2 are (re)filled here; the roles rotate in the caller.
+    auto iter = [&](int r, const TRow& t0, const TRow& t1, TRow& t2, const DRow& d0, const DRow& d1, DRow& d2) {
+        take_trow(t2);             // row r+1 (its load was issued one iteration ago)
+        issue_load(r + 2);         // in flight while this iteration computes
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d2.c[e] = 0.f;
+        if (r >= 0 && r < a.H && col_in) {
+            dw0_row(t0, 0, d2.c);
+            dw0_row(t1, 3, d2.c);
+            dw0_row(t2, 6, d2.c);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            d2.l[e] = __shfl_up_sync(0xffffffffu, d2.c[e], 1);
+            d2.r[e] = __shfl_down_sync(0xffffffffu, d2.c[e], 1);
+        }
+        const int yo = r - 1;
+        float xs[8];
+        {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = 0.f;
+            dw12_row(d0, 0, o);
+            dw12_row(d1, 3, o);
+            dw12_row(d2, 6, o);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) xs[e] = tanh_approx(o[e]) + d1.c[e];
+        }
+        // x2 warp -> shared -> x1 warp of the same channel vector (64-thread named barrier)
+        float4* slot = s_x + ((vec * 2 + (yo & 1)) * 2) * kCols + lane;
+        if (half == 1) {
+            slot[0] = make_float4(xs[0], xs[1], xs[2], xs[3]);
+            slot[kCols] = make_float4(xs[4], xs[5], xs[6], xs[7]);
+        }
+        asm volatile("bar.sync %0, 64;" :: "r"(1 + vec) : "memory");
+        if (writer && yo >= y0) {
+            const float4 pa = slot[0], pb = slot[kCols];
+            uint4 raw;
+            act_t* ov = reinterpret_cast<act_t*>(&raw);
+            ov[0] = f2act(xs[0] * pa.x); ov[1] = f2act(xs[1] * pa.y); ov[2] = f2act(xs[2] * pa.z); ov[3] = f2act(xs[3] * pa.w);
+            ov[4] = f2act(xs[4] * pb.x); ov[5] = f2act(xs[5] * pb.y); ov[6] = f2act(xs[6] * pb.z); ov[7] = f2act(xs[7] * pb.w);
+            *reinterpret_cast<uint4*>(gdst + ((long long)yo * a.W + x) * hp) = raw;
+        }
+    };
+
+    TRow tA, tB, tC;
+    DRow dA, dB, dC;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { dA.l[e] = dA.c[e] = dA.r[e] = 0.f; dB.l[e] = dB.c[e] = dB.r[e] = 0.f; }
+    issue_load(y0 - 2); take_trow(tA);
+    issue_load(y0 - 1); take_trow(tB);
+    issue_load(y0);
+    // d rows r = y0-1 .. y1; register roles rotate with period 3 (no register moves)
     for (int r = y0 - 1; r <= y1; r += 3) {
-        iter(r, win0, win1, win2);
-        if (r + 1 <= y1) iter(r + 1, win1, win2, win0);
-        if (r + 2 <= y1) iter(r + 2, win2, win0, win1);
+        iter(r, tA, tB, tC, dA, dB, dC);
+        if (r + 1 <= y1) iter(r + 1, tB, tC, tA, dB, dC, dA);
+        if (r + 2 <= y1) iter(r + 2, tC, tA, tB, dC, dA, dB);
     }
 }
 
 int launch_iel_gate(const IelGateArgs& a, cudaStream_t stream) {
-    CIDNET_CHECK(a.hp % kCh == 0, CIDNET_ERR_INVALID, "iel: hp % 32");
+    CIDNET_CHECK(a.hp % 16 == 0, CIDNET_ERR_INVALID, "iel: hp % 16");
     const int strips = ceil_div(a.W, kCols - 2);
-    dim3 grid(strips * (a.hp / kCh), ceil_div(a.H, kRows), a.B * a.nprob);
+    dim3 grid(strips * (a.hp / 16), ceil_div(a.H, kRows), a.B * a.nprob);
     iel_gate_kernel<<<grid, kThreadsIel, 0, stream>>>(a);
     CIDNET_CUDA_OK(cudaGetLastError());
     return CIDNET_OK;
