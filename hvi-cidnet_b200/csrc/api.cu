@@ -54,6 +54,7 @@ struct cidnet_ctx {
     DownWeights down[2][3];    // [branch 0=I,1=HV][block1..3]
     UpWeights up[2][3];        // [branch][block3, block2, block1]  (index 0 = block3)
     StageWeights stage[6];
+    PackedWeights eye[4];      // identity weights per level (residual adds inside the MMA)
     std::vector<void*> owned;  // every cudaMalloc'ed pointer (freed in destroy)
     std::map<std::string, Tap> taps;
     int last_B = 0;
@@ -229,7 +230,7 @@ int build_weights(cidnet_ctx* ctx) {
         for (int n = 1; n <= 3; ++n) {
             const std::string p = std::string(enc[br]) + "_block" + std::to_string(n);
             DownWeights& D = ctx->down[br][n - 1];
-            if ((rc = pack_conv_weights(&D.w, R[p + ".down.0.weight"].data(), kCh[n], kCh[n - 1], 9, nullptr, kCh[n], nullptr, nullptr))) return rc;
+            if ((rc = pack_conv_weights(&D.w, R[p + ".down.0.weight"].data(), kCh[n], kCh[n - 1], 9, nullptr, kCh[n], nullptr, nullptr, 128))) return rc;
             own(ctx, D.w);
             D.prelu = R[p + ".prelu.weight"][0];
         }
@@ -256,6 +257,10 @@ int build_weights(cidnet_ctx* ctx) {
             own(ctx, U.w1);
             U.prelu = R[p + ".prelu.weight"][0];
         }
+    }
+    for (int l = 1; l <= 3; ++l) {
+        if ((rc = pack_identity(&ctx->eye[l], kCh[l]))) return rc;
+        own(ctx, ctx->eye[l]);
     }
     for (int n = 1; n <= 6; ++n) {
         const int level = n <= 3 ? n : 7 - n;
@@ -391,7 +396,7 @@ struct Fwd {
         const double px_in = (double)L.B * L.H * L.W;
         const double px_out = L.mode == EPI_DOWN ? px_in / 4 : px_in;
         double bytes = px_in * w.cin * 2 + px_out * w.n_out * 2 + (double)w.n_out * w.cin * w.taps * 2 * (w.n_img > 1 ? L.B : 1);
-        if (L.res) bytes += px_out * w.n_out * 2;
+        if (L.in2) bytes += px_out * L.wt2->cin * 2;
         if (L.up) bytes += px_out / 4 * w.n_out * 2;
         mark(name, bytes, 2.0 * px_in * w.n_out * w.cin * w.taps);
         return launch_conv_gemm(L, st);
@@ -478,7 +483,7 @@ struct Fwd {
             PackedWeights fw = Lw.fold_tmpl; fw.w = P.mfold[l][s]; fw.n_img = P.B > 1 ? P.B : 1;
             ConvGemmLaunch A;
             A.mode = EPI_STORE; A.in = P.qkvdw[l][s] + 2 * Cp; A.B = P.B; A.H = H; A.W = W; A.in_pitch = 3 * Cp; A.flat = true;
-            A.wt = &fw; A.out = P.xp[l][s]; A.out_pitch = Cp; A.res = x[s]; A.res_pitch = Cp;
+            A.wt = &fw; A.out = P.xp[l][s]; A.out_pitch = Cp; A.in2 = x[s]; A.in2_pitch = Cp; A.wt2 = &ctx->eye[l];
             if (P.B == 1) fw.n_img = 1;
             if ((rc = gemm(A, "L" + std::to_string(l) + ".cab_attnv_proj_res"))) return rc;
             // 5. LayerNorm + project_in
@@ -506,7 +511,7 @@ struct Fwd {
             ConvGemmLaunch Cq;
             Cq.mode = EPI_STORE; Cq.in = P.g[l][s]; Cq.B = P.B; Cq.H = H; Cq.W = W; Cq.in_pitch = Lw.hp; Cq.flat = true;
             Cq.wt = &Lw.w_out; Cq.out = out[s]; Cq.out_pitch = Cp;
-            if (s == 0) { Cq.res = P.xp[l][s]; Cq.res_pitch = Cp; }
+            if (s == 0) { Cq.in2 = P.xp[l][s]; Cq.in2_pitch = Cp; Cq.wt2 = &ctx->eye[l]; }
             if ((rc = gemm(Cq, "L" + std::to_string(l) + ".iel_project_out"))) return rc;
             tap(std::string(s == 0 ? "I_LCA" : "HV_LCA") + std::to_string(n), out[s], C, l, Cp);
         }

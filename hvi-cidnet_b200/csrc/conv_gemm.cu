@@ -1,45 +1,47 @@
-// TMA-fed tcgen05 implicit-GEMM convolution for sm_100a.
+// Persistent TMA-fed tcgen05 implicit-GEMM convolution for sm_100a.
 //
 //   D[128 pixels, N] += A[128 pixels, K] * B[N, K]^T      (fp16/bf16 operands, fp32 accumulate in TMEM)
 //
-// One CTA = one tile of 128 output pixels (a TH x TW rectangle of one image, or 128
-// consecutive pixels for "flat" 1x1 layers) x one block of <=256 output channels.
-//   warp 0   : TMA producer.  For every (tap, 64-channel chunk) it issues ONE box load of the
-//              NHWC activation (shifted by the tap offset; TMA zero-fills out-of-image pixels,
-//              which IS the conv's zero padding, and channels >= Cin) and ONE box load of the
-//              packed weights, both landing in the canonical SWIZZLE_128B K-major layout.
-//   warp 1   : allocates TMEM, then a single thread issues tcgen05.mma (M=128, N=block_n, K=16).
-//   warps 2-5: epilogue.  tcgen05.ld the accumulator rows (thread == pixel), apply the fused
-//              tail and store NHWC act_t:
-//                EPI_STORE  (+residual, PReLU)                      CAB fold GEMM, IEL project_out, ...
-//                EPI_LN     LayerNorm folded in: rstd*(acc-mean*wsum)+bias, stats read from the
-//                           A tile that is still resident in shared memory
-//                EPI_DOWN   conv3x3 -> bilinear x0.5 (align_corners) -> PReLU; the tile is 16
-//                           columns x 8 ROW PAIRS, even rows in accumulator 0 and odd rows in
-//                           accumulator 1 (5-D TMA view), so the vertical lerp is thread-local
-//                           and the horizontal one is a single warp shuffle
+// One CTA per SM (per N block) loops over tiles of 128 output pixels (a TH x TW rectangle of one
+// image, or 128 consecutive pixels for "flat" 1x1 layers).
+//   warp 0   : TMA producer.  For every (tap, 64-channel chunk) ONE box load of the NHWC activation
+//              (shifted by the tap offset; TMA zero-fills out-of-image pixels -- that IS the conv's zero
+//              padding -- and channels >= Cin), landing in the canonical SWIZZLE_128B K-major layout.
+//              The packed weights are loaded ONCE per CTA and stay resident in shared memory when they
+//              fit; otherwise (and for per-image weights) they stream through the same ring.
+//              An optional second K source (in2 / wt2, e.g. identity weights) appends K chunks: that is
+//              how residual adds are done inside the MMA instead of in the epilogue.
+//   warp 1   : allocates TMEM (two accumulator buffers), a single thread issues tcgen05.mma
+//              (M=128, N=block_n, K=16); tcgen05.commit releases smem stages / publishes accumulators.
+//   warps 2-5: epilogue, overlapped with the next tile's MMAs through the TMEM double buffer:
+//              tcgen05.ld (thread == pixel row) -> fused tail -> 16-bit -> swizzled smem staging ->
+//              TMA store (64 channels x tile; channels >= Cout and out-of-image pixels are clipped).
+//                EPI_STORE  [-> PReLU]
+//                EPI_LN     LayerNorm folded in: rstd*(acc-mean*wsum)+bias, statistics read from the A
+//                           tile while it is resident (the epilogue warps co-own the stage's release)
+//                EPI_DOWN   conv3x3 -> bilinear x0.5 (align_corners) -> PReLU; the tile is 16 columns x
+//                           8 ROW PAIRS, even rows in accumulator 0 and odd rows in accumulator 1 (5-D
+//                           TMA view) -> thread-local vertical lerp + one shuffle for the horizontal
 //                EPI_UP     1x1 on the skip + bilinear x2 of the (pre-composed) low-res conv -> PReLU
 //
 // Replaces nn.Conv2d calls at net/LCA.py:13,15,17,51,57 and net/transformer_utils.py:39,58,60
-// together with the LayerNorm (:25-28), UpsamplingBilinear2d (:40,:59), cat (:64) and PReLU
-// (:43,:66) around them.
+// together with the LayerNorm (:25-28), UpsamplingBilinear2d (:40,:59), cat (:64), PReLU (:43,:66) and
+// the residual adds (LCA.py:79,91-92) around them.
 #include "conv_gemm.cuh"
 #include "ptx_sm100.cuh"
 
+#include <cstring>
 #include <mutex>
 
 namespace cidnet {
 
 // ------------------------------------------------------------------ params ---
 struct ConvGemmArgs {
-    CUtensorMap tmA;
-    CUtensorMap tmB;
-    int taps, kchunks, cin;
-    int Hv, Wv, TH, TW, tiles_x, tiles_y;
-    int n_out, block_n, stages, per_image_w;
-    int w_real;                      // real image width (pixels) of the OUTPUT grid of this launch
-    act_t* out; int out_pitch; long long out_img_stride;
-    const act_t* res; int res_pitch; long long res_img_stride;
+    CUtensorMap tmA, tmA2, tmB, tmB2, tmOut;
+    int taps, kchunks, kchunks2, cin, cin2;
+    int Hv, Wv, TH, TW, tiles_x, tiles_y, num_tiles;
+    int n_out, block_n, stages, per_image_w, b_resident;
+    int w_real;
     const float* bias; const float* wsum; float ln_eps;
     const act_t* up; int up_H, up_W, up_pitch; long long up_img_stride; float up_ry, up_rx;
     float prelu; int use_prelu;
@@ -48,15 +50,16 @@ struct ConvGemmArgs {
 
 static constexpr int kThreads = 192;
 static constexpr uint32_t kSubTileBytes = 128 * 128;   // 128 rows x 64 elements x 2 B
+static constexpr uint32_t kStagingBytes = 128 * 128;   // one 64-channel output block of a tile
 
 __device__ __forceinline__ float prelu_f(float v, float slope) { return v >= 0.f ? v : v * slope; }
 
-// store `n` (<=32) channels starting at p; n is rounded up to a multiple of 8 (the pitch is)
-__device__ __forceinline__ void store_chunk(act_t* p, const float* v, int n) {
-    if (n > 0) store8(p, v);
-    if (n > 8) store8(p + 8, v + 8);
-    if (n > 16) store8(p + 16, v + 16);
-    if (n > 24) store8(p + 24, v + 24);
+__device__ __forceinline__ uint4 pack8(const float* f) {
+    uint4 raw;
+    act_t* a = reinterpret_cast<act_t*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = f2act(f[i]);
+    return raw;
 }
 
 template <int kMode>
@@ -66,45 +69,55 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int kSub = (kMode == EPI_DOWN) ? 2 : 1;
     const uint32_t a_stage = kSub * kSubTileBytes;
-    const uint32_t b_stage = (uint32_t)a.block_n * 128u;
+    const uint32_t b_chunk = (uint32_t)a.block_n * 128u;
     const int stages = a.stages;
-    uint8_t* smA = smem;
-    uint8_t* smB = smem + (size_t)stages * a_stage;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smB + (size_t)stages * b_stage);
+    const int k1 = a.taps * a.kchunks;              // primary K iterations
+    const int kiters = k1 + a.kchunks2;
+    uint8_t* smBres = smem;                                                // resident weights (optional)
+    uint8_t* smA = smBres + (a.b_resident ? (size_t)kiters * b_chunk : 0);
+    uint8_t* smB = smA + (size_t)stages * a_stage;                         // streamed weights (optional)
+    uint8_t* smOut = smB + (a.b_resident ? 0 : (size_t)stages * b_chunk);  // 2 staging buffers
+    uint64_t* full = reinterpret_cast<uint64_t*>(smOut + 2 * kStagingBytes);
     uint64_t* empty = full + stages;
-    uint64_t* tmem_full = empty + stages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-    float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);     // [block_n] bias, then [block_n] wsum (EPI_LN)
+    uint64_t* bfull = empty + stages;
+    uint64_t* tmem_full = bfull + 1;      // [2]
+    uint64_t* tmem_empty = tmem_full + 2; // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);
     float* s_wsum = s_bias + a.block_n;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-
-    // tile decode
-    const int tiles_per_img = a.tiles_x * a.tiles_y;
-    const int img = blockIdx.x / tiles_per_img;
-    const int trem = blockIdx.x - img * tiles_per_img;
-    const int y0 = (trem / a.tiles_x) * a.TH;
-    const int x0 = (trem % a.tiles_x) * a.TW;
     const int n0 = blockIdx.y * a.block_n;
-    const int kiters = a.taps * a.kchunks;
+    const int tiles_per_img = a.tiles_x * a.tiles_y;
+    const uint32_t acc_cols = (uint32_t)(kSub * a.block_n);    // columns of one accumulator buffer
 
     uint32_t ncols = 32;
-    while (ncols < (uint32_t)(kSub * a.block_n)) ncols <<= 1;
+    while (ncols < 2 * acc_cols) ncols <<= 1;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&a.tmA);
         ptx::prefetch_tensormap(&a.tmB);
+        ptx::prefetch_tensormap(&a.tmOut);
+        if (a.kchunks2) { ptx::prefetch_tensormap(&a.tmA2); ptx::prefetch_tensormap(&a.tmB2); }
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
-            ptx::mbar_init(tmem_full, 1);
+            const uint32_t empty_count = (kMode == EPI_LN) ? 5u : 1u;   // MMA commit (+ 4 epilogue warps for LN)
+            for (int s = 0; s < stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], empty_count); }
+            ptx::mbar_init(bfull, 1);
+            for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], 4); }
             ptx::fence_barrier_init();
         }
         __syncwarp();
         ptx::tmem_alloc(tmem_slot, ncols);
         ptx::tmem_relinquish();
+    }
+    if (kMode == EPI_LN && warp >= 2) {
+        for (int i = threadIdx.x - 64; i < a.block_n; i += 128) {
+            s_bias[i] = __ldg(a.bias + n0 + i);
+            s_wsum[i] = __ldg(a.wsum + n0 + i);
+        }
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -114,56 +127,87 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
     if (warp == 0) {
         // ------------------------------------------------------- TMA producer
         if (lane == 0) {
-            for (int i = 0; i < kiters; ++i) {
-                const int s = i % stages;
-                const uint32_t ph = (uint32_t)(i / stages) & 1u;
-                ptx::mbar_wait(&empty[s], ph ^ 1u);
-                ptx::mbar_expect_tx(&full[s], a_stage + b_stage);
-                const int tap = i / a.kchunks;
-                const int kc = i - tap * a.kchunks;
-                int dy = 1, dx = 1;
-                if (a.taps == 9) { dy = tap / 3; dx = tap - dy * 3; }
-                uint8_t* dstA = smA + (size_t)s * a_stage;
-                if (kMode == EPI_DOWN) {
-#pragma unroll
-                    for (int sub = 0; sub < 2; ++sub) {
-                        const int srow = 2 * y0 + sub + dy - 1;     // first image row of this sub-tile
-                        ptx::tma_load_5d(dstA + sub * kSubTileBytes, &a.tmA, &full[s],
-                                         kc * 64, x0 + dx - 1, srow & 1, srow >> 1, img);
-                    }
-                } else {
-                    ptx::tma_load_4d(dstA, &a.tmA, &full[s], kc * 64, x0 + dx - 1, y0 + dy - 1, img);
+            if (a.b_resident) {
+                ptx::mbar_expect_tx(bfull, (uint32_t)kiters * b_chunk);
+                for (int i = 0; i < kiters; ++i) {
+                    if (i < k1) ptx::tma_load_3d(smBres + (size_t)i * b_chunk, &a.tmB, bfull, i * 64, n0, 0);
+                    else        ptx::tma_load_3d(smBres + (size_t)i * b_chunk, &a.tmB2, bfull, (i - k1) * 64, n0, 0);
                 }
-                ptx::tma_load_3d(smB + (size_t)s * b_stage, &a.tmB, &full[s], i * 64, n0,
-                                 a.per_image_w ? img : 0);
+            }
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+                const int img = t / tiles_per_img;
+                const int trem = t - img * tiles_per_img;
+                const int y0 = (trem / a.tiles_x) * a.TH;
+                const int x0 = (trem % a.tiles_x) * a.TW;
+                for (int i = 0; i < kiters; ++i, ++it) {
+                    const int s = it % stages;
+                    const uint32_t ph = (it / stages) & 1u;
+                    ptx::mbar_wait(&empty[s], ph ^ 1u);
+                    ptx::mbar_expect_tx(&full[s], a_stage + (a.b_resident ? 0u : b_chunk));
+                    uint8_t* dstA = smA + (size_t)s * a_stage;
+                    if (i < k1) {
+                        const int tap = i / a.kchunks;
+                        const int kc = i - tap * a.kchunks;
+                        int dy = 1, dx = 1;
+                        if (a.taps == 9) { dy = tap / 3; dx = tap - dy * 3; }
+                        if (kMode == EPI_DOWN) {
+#pragma unroll
+                            for (int sub = 0; sub < 2; ++sub) {
+                                const int srow = 2 * y0 + sub + dy - 1;     // first image row of this sub-tile
+                                ptx::tma_load_5d(dstA + sub * kSubTileBytes, &a.tmA, &full[s],
+                                                 kc * 64, x0 + dx - 1, srow & 1, srow >> 1, img);
+                            }
+                        } else {
+                            ptx::tma_load_4d(dstA, &a.tmA, &full[s], kc * 64, x0 + dx - 1, y0 + dy - 1, img);
+                        }
+                        if (!a.b_resident)
+                            ptx::tma_load_3d(smB + (size_t)s * b_chunk, &a.tmB, &full[s], i * 64, n0,
+                                             a.per_image_w ? img : 0);
+                    } else {
+                        const int kc = i - k1;
+                        ptx::tma_load_4d(dstA, &a.tmA2, &full[s], kc * 64, x0, y0, img);
+                        if (!a.b_resident)
+                            ptx::tma_load_3d(smB + (size_t)s * b_chunk, &a.tmB2, &full[s], kc * 64, n0, 0);
+                    }
+                }
             }
         }
     } else if (warp == 1) {
         // --------------------------------------------------------- MMA issuer
         const uint32_t idesc = ptx::umma_idesc_f16(CIDNET_UMMA_FMT, (uint32_t)a.block_n);
-        for (int i = 0; i < kiters; ++i) {
-            const int s = i % stages;
-            const uint32_t ph = (uint32_t)(i / stages) & 1u;
-            ptx::mbar_wait(&full[s], ph);
+        if (a.b_resident) { ptx::mbar_wait(bfull, 0); }
+        uint32_t it = 0, j = 0;
+        for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++j) {
+            const uint32_t buf = j & 1u;
+            ptx::mbar_wait(&tmem_empty[buf], ((j >> 1) & 1u) ^ 1u);      // epilogue drained this buffer
             ptx::tc_fence_after();
-            if (lane == 0) {
-                const int kc = i % a.kchunks;
-                int ksteps = (a.cin - kc * 64 + 15) >> 4;
-                if (ksteps > 4) ksteps = 4;
-                const uint64_t descB = ptx::umma_smem_desc_sw128(ptx::smem_u32(smB + (size_t)s * b_stage));
+            const uint32_t d_tmem = tmem_base + buf * acc_cols;
+            for (int i = 0; i < kiters; ++i, ++it) {
+                const int s = it % stages;
+                const uint32_t ph = (it / stages) & 1u;
+                ptx::mbar_wait(&full[s], ph);
+                ptx::tc_fence_after();
+                if (lane == 0) {
+                    int crem = (i < k1) ? a.cin - (i % a.kchunks) * 64 : a.cin2 - (i - k1) * 64;
+                    int ksteps = (crem + 15) >> 4;
+                    if (ksteps > 4) ksteps = 4;
+                    const uint8_t* bsrc = a.b_resident ? smBres + (size_t)i * b_chunk : smB + (size_t)s * b_chunk;
+                    const uint64_t descB = ptx::umma_smem_desc_sw128(ptx::smem_u32(bsrc));
 #pragma unroll
-                for (int sub = 0; sub < kSub; ++sub) {
-                    const uint64_t descA = ptx::umma_smem_desc_sw128(
-                        ptx::smem_u32(smA + (size_t)s * a_stage + sub * kSubTileBytes));
-                    for (int k = 0; k < ksteps; ++k) {
-                        ptx::umma_f16(tmem_base + sub * a.block_n, descA + 2 * k, descB + 2 * k, idesc,
-                                      (uint32_t)((i | k) != 0));
+                    for (int sub = 0; sub < kSub; ++sub) {
+                        const uint64_t descA = ptx::umma_smem_desc_sw128(
+                            ptx::smem_u32(smA + (size_t)s * a_stage + sub * kSubTileBytes));
+                        for (int k = 0; k < ksteps; ++k) {
+                            ptx::umma_f16(d_tmem + sub * a.block_n, descA + 2 * k, descB + 2 * k, idesc,
+                                          (uint32_t)((i | k) != 0));
+                        }
                     }
+                    ptx::umma_commit(&empty[s]);                           // frees the smem stage when the MMAs retire
+                    if (i == kiters - 1) ptx::umma_commit(&tmem_full[buf]); // accumulator complete
                 }
-                ptx::umma_commit(&empty[s]);                       // frees the smem slot when the MMAs retire
-                if (i == kiters - 1) ptx::umma_commit(tmem_full);  // accumulator complete
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else {
         // ----------------------------------------------------------- epilogue
@@ -171,113 +215,59 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
         const int row = q * 32 + lane;          // accumulator row == pixel within the tile
         const int ty = row / a.TW;
         const int tx = row - ty * a.TW;
-        const int y = y0 + ty;
-        const int x = x0 + tx;
-        const bool valid = (y < a.Hv) && (x < a.Wv);
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool issuer = (warp == 2 && lane == 0);
+        const int nblk64 = (min(a.block_n, a.n_out - n0) + 63) >> 6;     // 64-channel output blocks
+        uint32_t it = 0, j = 0, sb = 0;
+        for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++j) {
+            const int img = t / tiles_per_img;
+            const int trem = t - img * tiles_per_img;
+            const int y0 = (trem / a.tiles_x) * a.TH;
+            const int x0 = (trem % a.tiles_x) * a.TW;
+            const int y = y0 + ty, x = x0 + tx;
+            const bool valid = (y < a.Hv) && (x < a.Wv);
 
-        float mean = 0.f, rstd = 1.f;
-        if (kMode == EPI_LN) {
-            // bias / wsum of this channel block -> shared memory (read once per CTA instead of once
-            // per 16-column chunk from global); named barrier 1 = the 128 epilogue threads only
-            for (int i = row; i < a.block_n; i += 128) {
-                s_bias[i] = __ldg(a.bias + n0 + i);
-                s_wsum[i] = __ldg(a.wsum + n0 + i);
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            // per-pixel LayerNorm statistics from the A tile (all K chunks are still resident:
-            // the host guarantees stages >= kchunks and taps == 1 for this mode)
-            for (int kc = 0; kc < a.kchunks; ++kc) ptx::mbar_wait(&full[kc], 0);
-            float sum = 0.f;
-            for (int pass = 0; pass < 2; ++pass) {
-                float acc = 0.f;
-                for (int kc = 0; kc < a.kchunks; ++kc) {
-                    const uint8_t* rowp = smA + (size_t)kc * a_stage + row * 128;
-                    const int cbase = kc * 64;
+            float mean = 0.f, rstd = 1.f;
+            if (kMode == EPI_LN) {
+                // per-pixel LayerNorm statistics from the A tile (all K chunks of this tile are resident:
+                // the host guarantees stages >= kchunks + 1); then co-release the stages
+                for (int kc = 0; kc < a.kchunks; ++kc)
+                    ptx::mbar_wait(&full[(it + kc) % stages], ((it + kc) / stages) & 1u);
+                float sum = 0.f;
+                for (int pass = 0; pass < 2; ++pass) {
+                    float acc = 0.f;
+                    for (int kc = 0; kc < a.kchunks; ++kc) {
+                        const uint8_t* rowp = smA + (size_t)((it + kc) % stages) * a_stage + row * 128;
+                        const int cbase = kc * 64;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (cbase + j * 8 < a.cin) {
-                            float f[8];
-                            load8(reinterpret_cast<const act_t*>(rowp + ((j ^ (row & 7)) << 4)), f);
+                        for (int jv = 0; jv < 8; ++jv) {
+                            if (cbase + jv * 8 < a.cin) {
+                                float f[8];
+                                load8(reinterpret_cast<const act_t*>(rowp + ((jv ^ (row & 7)) << 4)), f);
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                if (cbase + j * 8 + e < a.cin) {
-                                    if (pass == 0) acc += f[e];
-                                    else { const float d = f[e] - mean; acc += d * d; }
+                                for (int e = 0; e < 8; ++e) {
+                                    if (cbase + jv * 8 + e < a.cin) {
+                                        if (pass == 0) acc += f[e];
+                                        else { const float d = f[e] - mean; acc += d * d; }
+                                    }
                                 }
                             }
                         }
                     }
+                    if (pass == 0) { sum = acc; mean = sum / (float)a.cin; }
+                    else rstd = 1.0f / sqrtf(acc / (float)a.cin + a.ln_eps);
                 }
-                if (pass == 0) { sum = acc; mean = sum / (float)a.cin; }
-                else rstd = 1.0f / sqrtf(acc / (float)a.cin + a.ln_eps);
+                __syncwarp();
+                if (lane == 0)
+                    for (int kc = 0; kc < a.kchunks; ++kc) ptx::mbar_arrive(&empty[(it + kc) % stages]);
             }
-        }
+            it += kiters;
 
-        // pull the rows this thread will add (residual / low-res upsample taps) towards L1 while
-        // the MMAs are still running
-        if (kMode == EPI_STORE && a.res != nullptr && valid) {
-            const char* rp = reinterpret_cast<const char*>(a.res + (long long)img * a.res_img_stride +
-                                                           ((long long)y * a.Wv + x) * a.res_pitch + n0);
-            const int bytes = min(a.block_n, a.n_out - n0) * 2;
-            for (int o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L1 [%0];" :: "l"(rp + o));
-        }
-        if (kMode == EPI_UP && valid) {
-            const long long pix = (long long)y * a.Wv + x;
-            const int yr = (int)(pix / a.w_real), xr = (int)(pix - (long long)yr * a.w_real);
-            const int i0 = (int)(a.up_ry * (float)yr), j0 = (int)(a.up_rx * (float)xr);
-            const int i1 = i0 + (i0 < a.up_H - 1 ? 1 : 0), j1 = j0 + (j0 < a.up_W - 1 ? 1 : 0);
-            const char* tb = reinterpret_cast<const char*>(a.up + (long long)img * a.up_img_stride + n0);
-            const int bytes = min(a.block_n, a.n_out - n0) * 2;
-            for (int o = 0; o < bytes; o += 128) {
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(tb + ((long long)i0 * a.up_W + j0) * a.up_pitch * 2 + o));
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(tb + ((long long)i0 * a.up_W + j1) * a.up_pitch * 2 + o));
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(tb + ((long long)i1 * a.up_W + j0) * a.up_pitch * 2 + o));
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(tb + ((long long)i1 * a.up_W + j1) * a.up_pitch * 2 + o));
-            }
-        }
-
-        ptx::mbar_wait(tmem_full, 0);
-        ptx::tc_fence_after();
-
-        if (kMode == EPI_DOWN) {
-            // y counts ROW PAIRS == output rows; x is the input column (even lanes own an output pixel)
-            const int oy = y, ox = x >> 1;
-            const float sy = a.down_ry * (float)oy;
-            const int i0 = (int)sy;
-            const float ly = sy - (float)i0;
-            const bool top_is_odd = (i0 - 2 * oy) != 0;      // only at the clamped last row
-            const float sx = a.down_rx * (float)ox;
-            const int j0 = (int)sx;
-            const float lx = sx - (float)j0;
-            const bool left_is_right = (j0 - 2 * ox) != 0;   // only at the clamped last column
-            const bool writer = valid && ((x & 1) == 0);
-            act_t* outp = a.out + (long long)img * a.out_img_stride +
-                          ((long long)oy * (a.Wv >> 1) + ox) * a.out_pitch + n0;
-            for (int c = 0; c < a.block_n; c += 32) {
-                if (n0 + c >= a.n_out) break;
-                float e[32], o[32];
-                ptx::tmem_ld32(taddr + c, e);
-                ptx::tmem_ld32(taddr + a.block_n + c, o);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float top = top_is_odd ? o[j] : e[j];
-                    const float v = (1.f - ly) * top + ly * o[j];
-                    const float vr = __shfl_down_sync(0xffffffffu, v, 1);
-                    const float left = left_is_right ? vr : v;
-                    e[j] = prelu_f((1.f - lx) * left + lx * vr, a.prelu);
-                }
-                if (writer) store_chunk(outp + c, e, a.n_out - (n0 + c));
-            }
-        } else {
-            const long long pix = (long long)y * a.Wv + x;
-            act_t* outp = a.out + (long long)img * a.out_img_stride + pix * a.out_pitch + n0;
-            const act_t* resp = (kMode == EPI_STORE && a.res != nullptr)
-                                    ? a.res + (long long)img * a.res_img_stride + pix * a.res_pitch + n0 : nullptr;
-            // EPI_UP: bilinear x2 taps of the low-res tensor (align_corners=True)
+            // EPI_UP: bilinear x2 taps of the low-res tensor (align_corners=True); pull them towards L1
+            // while the MMAs of this tile are still running
             const act_t *t00 = nullptr, *t01 = nullptr, *t10 = nullptr, *t11 = nullptr;
             float uly = 0.f, ulx = 0.f;
             if (kMode == EPI_UP && valid) {
+                const long long pix = (long long)y * a.Wv + x;
                 const int yr = (int)(pix / a.w_real), xr = (int)(pix - (long long)yr * a.w_real);
                 const float sy = a.up_ry * (float)yr;
                 const int i0 = (int)sy; uly = sy - (float)i0;
@@ -290,55 +280,116 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                 t01 = tb + ((long long)i0 * a.up_W + j1) * a.up_pitch;
                 t10 = tb + ((long long)i1 * a.up_W + j0) * a.up_pitch;
                 t11 = tb + ((long long)i1 * a.up_W + j1) * a.up_pitch;
+                const int bytes = min(a.block_n, a.n_out - n0) * 2;
+                for (int o = 0; o < bytes; o += 128) {
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(reinterpret_cast<const char*>(t00) + o));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(reinterpret_cast<const char*>(t01) + o));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(reinterpret_cast<const char*>(t10) + o));
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(reinterpret_cast<const char*>(t11) + o));
+                }
             }
-            for (int c = 0; c < a.block_n; c += 32) {
-                if (n0 + c >= a.n_out) break;
-                float v[32];
-                ptx::tmem_ld32(taddr + c, v);
-                const int nrem = a.n_out - (n0 + c);
-                if (kMode == EPI_LN) {
+            // EPI_DOWN geometry: y counts ROW PAIRS == output rows; even lanes own an output pixel
+            float dly = 0.f, dlx = 0.f;
+            bool top_is_odd = false, left_is_right = false;
+            if (kMode == EPI_DOWN) {
+                const int oy = y, ox = x >> 1;
+                const float sy = a.down_ry * (float)oy;
+                const int i0 = (int)sy;
+                dly = sy - (float)i0;
+                top_is_odd = (i0 - 2 * oy) != 0;          // only at the clamped last row
+                const float sx = a.down_rx * (float)ox;
+                const int j0 = (int)sx;
+                dlx = sx - (float)j0;
+                left_is_right = (j0 - 2 * ox) != 0;       // only at the clamped last column
+            }
+
+            const uint32_t buf = j & 1u;
+            ptx::mbar_wait(&tmem_full[buf], (j >> 1) & 1u);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + buf * acc_cols + ((uint32_t)(q * 32) << 16);
+
+            for (int cb = 0; cb < nblk64; ++cb, sb ^= 1u) {
+                uint8_t* stg = smOut + sb * kStagingBytes;
+                // the TMA store that used this staging buffer two blocks ago must have read it
+                if (issuer) ptx::tma_store_wait_read<1>();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int n = (c + j < a.block_n) ? c + j : 0;      // bias / wsum staged for block_n channels
-                        v[j] = rstd * (v[j] - mean * s_wsum[n]) + s_bias[n];
-                    }
-                } else if (kMode == EPI_STORE) {
-                    if (resp != nullptr && valid) {
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int c = cb * 64 + hh * 32;
+                    if (c >= a.block_n) break;                      // warp-uniform
+                    float v[32];
+                    if (kMode == EPI_DOWN) {
+                        float o[32];
+                        ptx::tmem_ld32(taddr + c, v);
+                        ptx::tmem_ld32(taddr + a.block_n + c, o);
 #pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            if (nrem > 8 * h) {
-                                float r[8];
-                                load8(resp + c + 8 * h, r);
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) v[8 * h + j] += r[j];
-                            }
+                        for (int e = 0; e < 32; ++e) {
+                            const float top = top_is_odd ? o[e] : v[e];
+                            const float vv = (1.f - dly) * top + dly * o[e];
+                            const float vr = __shfl_down_sync(0xffffffffu, vv, 1);
+                            const float left = left_is_right ? vr : vv;
+                            v[e] = prelu_f((1.f - dlx) * left + dlx * vr, a.prelu);
                         }
-                    }
-                    if (a.use_prelu) {
+                    } else {
+                        ptx::tmem_ld32(taddr + c, v);
+                        if (kMode == EPI_LN) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = prelu_f(v[j], a.prelu);
-                    }
-                } else if (kMode == EPI_UP) {
-                    if (valid) {
+                            for (int e = 0; e < 32; ++e) {
+                                const int n = (c + e < a.block_n) ? c + e : 0;
+                                v[e] = rstd * (v[e] - mean * s_wsum[n]) + s_bias[n];
+                            }
+                        } else if (kMode == EPI_STORE) {
+                            if (a.use_prelu) {
 #pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            if (nrem > 8 * h) {
-                                float p00[8], p01[8], p10[8], p11[8];
-                                load8(t00 + c + 8 * h, p00); load8(t01 + c + 8 * h, p01);
-                                load8(t10 + c + 8 * h, p10); load8(t11 + c + 8 * h, p11);
+                                for (int e = 0; e < 32; ++e) v[e] = prelu_f(v[e], a.prelu);
+                            }
+                        } else if (kMode == EPI_UP) {
+                            const int nrem = a.n_out - (n0 + c);
+                            if (valid) {
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const float up = (1.f - uly) * ((1.f - ulx) * p00[j] + ulx * p01[j]) +
-                                                     uly * ((1.f - ulx) * p10[j] + ulx * p11[j]);
-                                    v[8 * h + j] = prelu_f(v[8 * h + j] + up, a.prelu);
+                                for (int h = 0; h < 4; ++h) {
+                                    if (nrem > 8 * h) {
+                                        float p00[8], p01[8], p10[8], p11[8];
+                                        load8(t00 + c + 8 * h, p00); load8(t01 + c + 8 * h, p01);
+                                        load8(t10 + c + 8 * h, p10); load8(t11 + c + 8 * h, p11);
+#pragma unroll
+                                        for (int e = 0; e < 8; ++e) {
+                                            const float up = (1.f - uly) * ((1.f - ulx) * p00[e] + ulx * p01[e]) +
+                                                             uly * ((1.f - ulx) * p10[e] + ulx * p11[e]);
+                                            v[8 * h + e] = prelu_f(v[8 * h + e] + up, a.prelu);
+                                        }
+                                    }
                                 }
                             }
                         }
                     }
+                    // 16-bit, swizzled (SWIZZLE_128B) staging row; DOWN: only even lanes own an output pixel
+                    int srow = row;
+                    bool wr = true;
+                    if (kMode == EPI_DOWN) { srow = (row >> 4) * 8 + ((row & 15) >> 1); wr = (row & 1) == 0; }
+                    if (wr) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const int chunk = hh * 4 + g;       // 16-byte chunk within the 128-byte row
+                            *reinterpret_cast<uint4*>(stg + srow * 128 + ((chunk ^ (srow & 7)) << 4)) = pack8(v + 8 * g);
+                        }
+                    }
                 }
-                if (valid) store_chunk(outp + c, v, nrem);
+                ptx::fence_proxy_async_smem();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (issuer) {
+                    const int c0 = n0 + cb * 64;
+                    if (kMode == EPI_DOWN) ptx::tma_store_4d(&a.tmOut, stg, c0, x0 >> 1, y0, img);
+                    else                   ptx::tma_store_4d(&a.tmOut, stg, c0, x0, y0, img);
+                    ptx::tma_store_commit();
+                }
             }
+            // all TMEM reads of this buffer are done -> hand it back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
         }
+        if (issuer) ptx::tma_store_wait_all();
     }
 
     ptx::tc_fence_before();
@@ -401,6 +452,17 @@ static inline float ac_scale(int n_in, int n_out) {
     return n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.f;
 }
 
+static int num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
 template <int kMode>
 static int launch_mode(const ConvGemmArgs& args, dim3 grid, size_t smem, cudaStream_t stream) {
     static bool configured = false;   // per mode; attribute is sticky per function
@@ -423,40 +485,59 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
     CIDNET_CHECK(L.in_pitch % 8 == 0 && L.out_pitch % 8 == 0, CIDNET_ERR_INVALID, "conv_gemm: pitch % 8");
     CIDNET_CHECK(wt.taps == 1 || wt.taps == 9, CIDNET_ERR_INVALID, "conv_gemm: taps must be 1 or 9");
     CIDNET_CHECK(!(L.flat && wt.taps != 1), CIDNET_ERR_INVALID, "conv_gemm: flat tiling is for 1x1 only");
+    const int ksub = L.mode == EPI_DOWN ? 2 : 1;
+    CIDNET_CHECK(2 * ksub * wt.block_n <= 512, CIDNET_ERR_INVALID, "conv_gemm: accumulators exceed TMEM");
 
     ConvGemmArgs a;
     memset(&a, 0, sizeof a);
     a.taps = wt.taps; a.kchunks = wt.kchunks; a.cin = wt.cin;
     a.n_out = wt.n_out; a.block_n = wt.block_n; a.per_image_w = wt.n_img > 1 ? 1 : 0;
-    a.out = L.out; a.out_pitch = L.out_pitch;
-    a.res = L.res; a.res_pitch = L.res_pitch;
     a.bias = wt.bias; a.wsum = wt.wsum; a.ln_eps = L.ln_eps;
     a.prelu = L.prelu; a.use_prelu = L.use_prelu ? 1 : 0;
     a.w_real = L.W;
     const long long hw = (long long)L.H * L.W;
-    a.res_img_stride = hw * L.res_pitch;
+    int rc;
 
     const uint64_t pb = (uint64_t)L.in_pitch * sizeof(act_t);   // bytes per pixel row
+    const uint64_t ob = (uint64_t)L.out_pitch * sizeof(act_t);
     if (L.mode == EPI_DOWN) {
         CIDNET_CHECK(L.H % 2 == 0 && L.W % 2 == 0 && wt.taps == 9, CIDNET_ERR_INVALID, "conv_gemm: DOWN needs even H,W, 3x3");
         a.Hv = L.H / 2; a.Wv = L.W; a.TH = 8; a.TW = 16;
         a.in_H = L.H; a.in_W = L.W;
         a.down_ry = ac_scale(L.H, L.H / 2); a.down_rx = ac_scale(L.W, L.W / 2);
-        a.out_img_stride = (hw / 4) * L.out_pitch;
         const uint64_t dims[5] = {(uint64_t)wt.cin, (uint64_t)L.W, 2, (uint64_t)L.H / 2, (uint64_t)L.B};
         const uint64_t str[4] = {pb, pb * L.W, pb * L.W * 2, pb * hw};
         const uint32_t box[5] = {64, 16, 1, 8, 1};
-        int rc = encode_map(&a.tmA, L.in, 5, dims, str, box);
-        if (rc) return rc;
+        if ((rc = encode_map(&a.tmA, L.in, 5, dims, str, box))) return rc;
+        const uint64_t od[4] = {(uint64_t)wt.n_out, (uint64_t)L.W / 2, (uint64_t)L.H / 2, (uint64_t)L.B};
+        const uint64_t os[3] = {ob, ob * (L.W / 2), ob * (hw / 4)};
+        const uint32_t obox[4] = {64, 8, 8, 1};
+        if ((rc = encode_map(&a.tmOut, L.out, 4, od, os, obox))) return rc;
     } else {
         if (L.flat) { a.Hv = 1; a.Wv = (int)hw; a.TH = 1; a.TW = 128; }
         else        { a.Hv = L.H; a.Wv = L.W; a.TH = 8; a.TW = 16; }
-        a.out_img_stride = hw * L.out_pitch;
         const uint64_t dims[4] = {(uint64_t)wt.cin, (uint64_t)a.Wv, (uint64_t)a.Hv, (uint64_t)L.B};
         const uint64_t str[3] = {pb, pb * a.Wv, pb * hw};
         const uint32_t box[4] = {64, (uint32_t)a.TW, (uint32_t)a.TH, 1};
-        int rc = encode_map(&a.tmA, L.in, 4, dims, str, box);
-        if (rc) return rc;
+        if ((rc = encode_map(&a.tmA, L.in, 4, dims, str, box))) return rc;
+        const uint64_t od[4] = {(uint64_t)wt.n_out, (uint64_t)a.Wv, (uint64_t)a.Hv, (uint64_t)L.B};
+        const uint64_t os[3] = {ob, ob * a.Wv, ob * hw};
+        if ((rc = encode_map(&a.tmOut, L.out, 4, od, os, box))) return rc;
+        if (L.in2) {
+            CIDNET_CHECK(L.wt2 && L.wt2->w && L.wt2->taps == 1 && L.wt2->block_n == wt.block_n &&
+                             L.wt2->n_blocks == wt.n_blocks && L.wt2->n_img == 1 && L.in2_pitch % 8 == 0,
+                         CIDNET_ERR_INVALID, "conv_gemm: second K source must be a 1x1 with the same N blocking");
+            a.kchunks2 = L.wt2->kchunks; a.cin2 = L.wt2->cin;
+            const uint64_t pb2 = (uint64_t)L.in2_pitch * sizeof(act_t);
+            const uint64_t d2[4] = {(uint64_t)L.wt2->cin, (uint64_t)a.Wv, (uint64_t)a.Hv, (uint64_t)L.B};
+            const uint64_t s2[3] = {pb2, pb2 * a.Wv, pb2 * hw};
+            if ((rc = encode_map(&a.tmA2, L.in2, 4, d2, s2, box))) return rc;
+            const uint64_t kt2 = (uint64_t)L.wt2->ktot();
+            const uint64_t bd[3] = {kt2, (uint64_t)L.wt2->n_rows, 1};
+            const uint64_t bs[2] = {kt2 * sizeof(act_t), kt2 * sizeof(act_t) * L.wt2->n_rows};
+            const uint32_t bbox[3] = {64, (uint32_t)wt.block_n, 1};
+            if ((rc = encode_map(&a.tmB2, L.wt2->w, 3, bd, bs, bbox))) return rc;
+        }
         if (L.mode == EPI_UP) {
             CIDNET_CHECK(L.up != nullptr && L.H % 2 == 0 && L.W % 2 == 0, CIDNET_ERR_INVALID, "conv_gemm: UP needs t");
             a.up = L.up; a.up_H = L.H / 2; a.up_W = L.W / 2; a.up_pitch = L.up_pitch;
@@ -466,31 +547,47 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
     }
     a.tiles_x = ceil_div(a.Wv, a.TW);
     a.tiles_y = ceil_div(a.Hv, a.TH);
+    a.num_tiles = a.tiles_x * a.tiles_y * L.B;
     {
         const uint64_t kt = (uint64_t)wt.ktot();
         const uint64_t dims[3] = {kt, (uint64_t)wt.n_rows, (uint64_t)wt.n_img};
         const uint64_t str[2] = {kt * sizeof(act_t), kt * sizeof(act_t) * wt.n_rows};
         const uint32_t box[3] = {64, (uint32_t)wt.block_n, 1};
-        int rc = encode_map(&a.tmB, wt.w, 3, dims, str, box);
-        if (rc) return rc;
+        if ((rc = encode_map(&a.tmB, wt.w, 3, dims, str, box))) return rc;
     }
 
-    const int kiters = wt.taps * wt.kchunks;
-    const int ksub = L.mode == EPI_DOWN ? 2 : 1;
-    const size_t stage_bytes = (size_t)ksub * kSubTileBytes + (size_t)wt.block_n * 128;
-    int stages = (int)((96 * 1024) / stage_bytes);
-    if (stages < 2) stages = 2;
+    // shared-memory plan: [resident weights] [A ring] [streamed-weight ring] [2 staging] [barriers, bias]
+    const int kiters = wt.taps * wt.kchunks + a.kchunks2;
+    const size_t a_stage = (size_t)ksub * kSubTileBytes;
+    const size_t b_chunk = (size_t)wt.block_n * 128;
+    const size_t fixed = 1024 + 2 * kStagingBytes + 512 + 2 * wt.block_n * sizeof(float);
+    const size_t budget = 220 * 1024;
+    int min_stages = 2;
     if (L.mode == EPI_LN) {
-        CIDNET_CHECK(wt.taps == 1 && wt.kchunks <= 4 && wt.bias && wt.wsum, CIDNET_ERR_INVALID, "conv_gemm: LN needs 1x1, K<=256");
-        if (stages < wt.kchunks) stages = wt.kchunks;
+        CIDNET_CHECK(wt.taps == 1 && wt.kchunks <= 4 && wt.bias && wt.wsum && !L.in2, CIDNET_ERR_INVALID,
+                     "conv_gemm: LN needs a single-source 1x1 with K<=256");
+        min_stages = wt.kchunks + 1;
     }
-    if (stages > kiters) stages = kiters;
+    int stages;
+    const size_t bres = (size_t)kiters * b_chunk;
+    if (!a.per_image_w && fixed + bres + (size_t)(min_stages + 1) * a_stage <= budget) {
+        a.b_resident = 1;
+        stages = (int)((budget - fixed - bres) / a_stage);
+    } else {
+        a.b_resident = 0;
+        stages = (int)((budget - fixed) / (a_stage + b_chunk));
+    }
     if (stages > 8) stages = 8;
+    const int want = 2 * kiters > min_stages ? 2 * kiters : min_stages;   // two tiles in flight is plenty
+    if (stages > want) stages = want;
+    CIDNET_CHECK(stages >= min_stages, CIDNET_ERR_INVALID, "conv_gemm: shared memory budget exceeded");
     a.stages = stages;
-    const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 2 * wt.block_n * sizeof(float);
-    CIDNET_CHECK(smem <= 227 * 1024, CIDNET_ERR_INVALID, "conv_gemm: shared memory budget exceeded");
+    const size_t smem = fixed + (a.b_resident ? bres : 0) + (size_t)stages * (a_stage + (a.b_resident ? 0 : b_chunk));
 
-    dim3 grid((unsigned)(a.tiles_x * a.tiles_y * L.B), (unsigned)wt.n_blocks, 1);
+    int gx = num_sms() / wt.n_blocks;
+    if (gx < 1) gx = 1;
+    if (gx > a.num_tiles) gx = a.num_tiles;
+    dim3 grid((unsigned)gx, (unsigned)wt.n_blocks, 1);
     switch (L.mode) {
         case EPI_STORE: return launch_mode<EPI_STORE>(a, grid, smem, stream);
         case EPI_LN:    return launch_mode<EPI_LN>(a, grid, smem, stream);

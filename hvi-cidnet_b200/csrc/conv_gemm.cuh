@@ -5,7 +5,7 @@
 namespace cidnet {
 
 enum EpiMode {
-    EPI_STORE = 0,  // out = acc (+ residual) [-> PReLU]
+    EPI_STORE = 0,  // out = acc [-> PReLU]   (a residual is folded into the MMA: K-extension with identity weights)
     EPI_LN    = 1,  // out = rstd[p] * (acc - mean[p] * wsum[n]) + bias[n]   (LayerNorm folded into the 1x1)
     EPI_DOWN  = 2,  // out = PReLU(bilinear_x0.5(acc))                        (NormDownsample)
     EPI_UP    = 3,  // out = PReLU(acc + bilinear_x2(t)[p, n])                (NormUpsample tail)
@@ -28,9 +28,13 @@ struct PackedWeights {
     int ktot() const { return taps * kchunks * 64; }
 };
 
-static inline void choose_blocking(int n_out, int* block_n, int* n_blocks) {
-    int nb = ceil_div(n_out, 256);
-    int bn = round_up(ceil_div(n_out, nb), 16);
+// N blocking: <=256 accumulator columns per block (two TMEM buffers of block_n columns must fit the
+// 512-column TMEM; EPI_DOWN keeps two accumulators per buffer -> max_block 128)
+static inline void choose_blocking(int n_out, int* block_n, int* n_blocks, int max_block = 256) {
+    int nb = ceil_div(n_out, max_block);
+    // with several N blocks every block must end on a 64-channel boundary: the epilogue stores whole
+    // 64-channel boxes and only the tensor extent (not the neighbouring block) clips them
+    int bn = nb > 1 ? round_up(ceil_div(n_out, nb), 64) : round_up(n_out, 16);
     *block_n = bn;
     *n_blocks = nb;
 }
@@ -45,9 +49,11 @@ struct ConvGemmLaunch {
     // output
     act_t* out = nullptr;
     int out_pitch = 0;
-    // EPI_STORE extras
-    const act_t* res = nullptr;
-    int res_pitch = 0;
+    // optional second K source (same pixel grid, 1x1): acc += in2 * wt2^T.  Used with identity
+    // weights for residual adds (x + f(x)) so the epilogue never reads the residual from global.
+    const act_t* in2 = nullptr;
+    int in2_pitch = 0;
+    const PackedWeights* wt2 = nullptr;
     bool use_prelu = false;
     float prelu = 0.f;
     // EPI_LN

@@ -16,9 +16,10 @@ extern "C" CIDNET_API int cidnet_test_conv(const float* x, const float* w_host, 
     cudaStream_t stream = (cudaStream_t)stream_;
     CIDNET_CHECK(ksize == 1 || ksize == 3, CIDNET_ERR_INVALID, "ksize must be 1 or 3");
     const int taps = ksize * ksize;
-    PackedWeights pw;
+    PackedWeights pw, eye;
     int rc = pack_conv_weights(&pw, w_host, Cout, Cin, taps, nullptr, Cout,
-                               mode == EPI_LN ? ln_host : nullptr, mode == EPI_LN ? ln_host + Cin : nullptr);
+                               mode == EPI_LN ? ln_host : nullptr, mode == EPI_LN ? ln_host + Cin : nullptr,
+                               mode == EPI_DOWN ? 128 : 256);
     if (rc) return rc;
     const int pin = act_pitch(Cin), pout = act_pitch(Cout);
     const int Ho = mode == EPI_DOWN ? H / 2 : H, Wo = mode == EPI_DOWN ? W / 2 : W;
@@ -36,13 +37,17 @@ extern "C" CIDNET_API int cidnet_test_conv(const float* x, const float* w_host, 
         CIDNET_CUDA_OK(cudaMalloc(&xaux, (size_t)B * ah * aw * pout * sizeof(act_t)));
         rc = launch_nchw_to_nhwc(aux, xaux, B, Cout, ah, aw, pout, stream);
         if (mode == EPI_UP) { L.up = xaux; L.up_pitch = pout; }
-        else { L.res = xaux; L.res_pitch = pout; }
+        else {      // residual: second K source with identity weights
+            if ((rc = pack_identity(&eye, Cout))) return rc;
+            L.in2 = xaux; L.in2_pitch = pout; L.wt2 = &eye;
+        }
     }
     if (!rc) rc = launch_conv_gemm(L, stream);
     if (!rc) rc = launch_nhwc_to_nchw(xout, out, B, Cout, Ho, Wo, pout, stream);
     cudaError_t e = cudaStreamSynchronize(stream);
     cudaFree(xin); cudaFree(xout); if (xaux) cudaFree(xaux);
     free_packed(&pw);
+    free_packed(&eye);
     if (rc) return rc;
     CIDNET_CHECK(e == cudaSuccess, CIDNET_ERR_CUDA, std::string("test_conv: ") + cudaGetErrorString(e));
     return CIDNET_OK;

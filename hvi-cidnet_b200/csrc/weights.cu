@@ -21,10 +21,10 @@ int upload_act(act_t** dst, const std::vector<float>& v) {
 }
 
 int pack_conv_segments(PackedWeights* out, const std::vector<WeightSegment>& segs, int cin, int taps, int n_out,
-                       bool with_ln) {
+                       bool with_ln, int max_block) {
     PackedWeights p;
     p.cin = cin; p.taps = taps; p.kchunks = ceil_div(cin, 64); p.n_out = n_out; p.n_img = 1;
-    choose_blocking(n_out, &p.block_n, &p.n_blocks);
+    choose_blocking(n_out, &p.block_n, &p.n_blocks, max_block);
     p.n_rows = p.block_n * p.n_blocks;
     const int kt = p.ktot();
     std::vector<float> packed((size_t)p.n_rows * kt, 0.f);
@@ -59,10 +59,16 @@ int pack_conv_segments(PackedWeights* out, const std::vector<WeightSegment>& seg
 }
 
 int pack_conv_weights(PackedWeights* out, const float* w, int n_src, int cin, int taps, const int* row_of_src,
-                      int n_out, const float* ln_w, const float* ln_b) {
+                      int n_out, const float* ln_w, const float* ln_b, int max_block) {
     if (row_of_src != nullptr) return fail(CIDNET_ERR_INVALID, "pack_conv_weights: row maps go through segments");
     std::vector<WeightSegment> segs{{w, n_src, 0, ln_w, ln_b}};
-    return pack_conv_segments(out, segs, cin, taps, n_out, ln_w != nullptr);
+    return pack_conv_segments(out, segs, cin, taps, n_out, ln_w != nullptr, max_block);
+}
+
+int pack_identity(PackedWeights* out, int c) {
+    std::vector<float> eye((size_t)c * c, 0.f);
+    for (int i = 0; i < c; ++i) eye[(size_t)i * c + i] = 1.f;
+    return pack_conv_weights(out, eye.data(), c, c, 1, nullptr, c, nullptr, nullptr);
 }
 
 void free_packed(PackedWeights* p) {

@@ -21,9 +21,11 @@ struct WeightSegment {
 // Several row blocks (each with its own LayerNorm fold) into one GEMM weight, e.g.
 // [q of this LCA | k,v of the sibling LCA] sharing one A operand.
 int pack_conv_segments(PackedWeights* out, const std::vector<WeightSegment>& segs, int cin, int taps, int n_out,
-                       bool with_ln);
+                       bool with_ln, int max_block = 256);
 int pack_conv_weights(PackedWeights* out, const float* w, int n_src, int cin, int taps, const int* row_of_src,
-                      int n_out, const float* ln_w, const float* ln_b);
+                      int n_out, const float* ln_w, const float* ln_b, int max_block = 256);
+// identity [c][c] as a 1x1 weight: second K source of a GEMM == residual add inside the MMA
+int pack_identity(PackedWeights* out, int c);
 void free_packed(PackedWeights* p);
 
 // device buffer helpers
