@@ -33,6 +33,7 @@ SIGNATURES = {
                                  C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float, C.c_void_p]),
     "cidnet_forward_launches": (C.c_int, [C.c_void_p]),
     "cidnet_read_tap": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int), C.c_void_p]),
+    "cidnet_set_graphs": (C.c_int, [C.c_void_p, C.c_int]),
     "cidnet_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "cidnet_profile_count": (C.c_int, [C.c_void_p]),
     "cidnet_profile_get": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_float),

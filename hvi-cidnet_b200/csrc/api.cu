@@ -61,6 +61,24 @@ struct cidnet_ctx {
     int launches = 0;
     // optional per-launch profiling (bench.py roofline): event i is recorded BEFORE launch i,
     // one more after the last launch
+    // CUDA-graph replay of the forward: one entry per (shape, workspace, flags); the input / output
+    // image pointers are patched into the stem / head kernel nodes when they change
+    struct GraphEntry {
+        int B = 0, H = 0, W = 0, gated = 0, gated2 = 0; float alpha_s = 0, alpha = 0;
+        const void* ws = nullptr; const float* k_dev = nullptr;
+        int seen = 0;                         // eager runs with this key before capturing
+        cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+        cudaGraphNode_t stem_node = nullptr, head_node = nullptr;
+        cudaKernelNodeParams stem_p{}, head_p{};
+        void* stem_args[16]; void* head_args[16];
+        const float* cur_in = nullptr; float* cur_out = nullptr;
+        std::map<std::string, Tap> taps; int launches = 0;
+        uint64_t last_use = 0;
+    };
+    std::vector<GraphEntry*> graphs;
+    uint64_t use_clock = 0;
+    bool use_graphs = true;
+    cudaStream_t cap_stream = nullptr;   // capture happens on a private stream (the legacy default stream cannot be captured)
     bool profiling = false;
     std::vector<cudaEvent_t> events;
     struct Rec { std::string name; double bytes; double flops; };
@@ -584,6 +602,12 @@ extern "C" int cidnet_create(cidnet_ctx** out, int device) {
 }
 
 static void release_device(cidnet_ctx* ctx) {
+    for (auto* g : ctx->graphs) {
+        if (g->exec) cudaGraphExecDestroy(g->exec);
+        if (g->graph) cudaGraphDestroy(g->graph);
+        delete g;
+    }
+    ctx->graphs.clear();
     for (void* p : ctx->owned) cudaFree(p);
     ctx->owned.clear();
     ctx->finalized = false;
@@ -594,6 +618,7 @@ extern "C" int cidnet_destroy(cidnet_ctx* ctx) {
     cudaSetDevice(ctx->device);
     release_device(ctx);
     for (cudaEvent_t e : ctx->events) if (e) cudaEventDestroy(e);
+    if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
     delete ctx;
     return CIDNET_OK;
 }
@@ -641,16 +666,107 @@ extern "C" int cidnet_forward(cidnet_ctx* ctx, const float* rgb_in, float* rgb_o
     if (B == 0) return CIDNET_OK;
     CIDNET_CHECK(rgb_in && rgb_out && workspace, CIDNET_ERR_INVALID, "forward: null pointer");
     CIDNET_CHECK((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, CIDNET_ERR_INVALID, "forward: workspace must be 1024-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
     Fwd f;
-    f.ctx = ctx; f.st = (cudaStream_t)stream;
+    f.ctx = ctx; f.st = st;
     make_plan(&f.P, workspace, B, H, W);
     CIDNET_CHECK(workspace_bytes >= f.P.bytes, CIDNET_ERR_STATE,
                  "forward: workspace too small: need " + std::to_string(f.P.bytes) + " bytes");
+    ctx->last_B = B;
+
+    // ---- CUDA-graph path (skipped while profiling, inside somebody else's capture, or when disabled)
+    cidnet_ctx::GraphEntry* ge = nullptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (ctx->use_graphs && !ctx->profiling && cudaStreamIsCapturing(st, &cap) == cudaSuccess &&
+        cap == cudaStreamCaptureStatusNone) {
+        for (auto* g : ctx->graphs)
+            if (g->B == B && g->H == H && g->W == W && g->ws == workspace && g->k_dev == k_dev && g->gated == gated &&
+                g->gated2 == gated2 && g->alpha_s == alpha_s && g->alpha == alpha) { ge = g; break; }
+        if (!ge) {
+            if (ctx->graphs.size() >= 8) {                    // evict the least recently used entry
+                size_t lru = 0;
+                for (size_t i = 1; i < ctx->graphs.size(); ++i) if (ctx->graphs[i]->last_use < ctx->graphs[lru]->last_use) lru = i;
+                cidnet_ctx::GraphEntry* old = ctx->graphs[lru];
+                if (old->exec) cudaGraphExecDestroy(old->exec);
+                if (old->graph) cudaGraphDestroy(old->graph);
+                delete old;
+                ctx->graphs.erase(ctx->graphs.begin() + lru);
+            }
+            ge = new cidnet_ctx::GraphEntry();
+            ge->B = B; ge->H = H; ge->W = W; ge->ws = workspace; ge->k_dev = k_dev; ge->gated = gated; ge->gated2 = gated2;
+            ge->alpha_s = alpha_s; ge->alpha = alpha;
+            ctx->graphs.push_back(ge);
+        }
+        ge->last_use = ++ctx->use_clock;
+    }
+    if (ge && ge->exec) {
+        // replay; patch the external image pointers if they moved
+        if (ge->cur_in != rgb_in) {
+            ge->cur_in = rgb_in;
+            ge->stem_args[kStemArgIn] = &ge->cur_in;
+            ge->stem_p.kernelParams = ge->stem_args;
+            CIDNET_CUDA_OK(cudaGraphExecKernelNodeSetParams(ge->exec, ge->stem_node, &ge->stem_p));
+        }
+        if (ge->cur_out != rgb_out) {
+            ge->cur_out = rgb_out;
+            ge->head_args[kHeadArgOut] = &ge->cur_out;
+            ge->head_p.kernelParams = ge->head_args;
+            CIDNET_CUDA_OK(cudaGraphExecKernelNodeSetParams(ge->exec, ge->head_node, &ge->head_p));
+        }
+        CIDNET_CUDA_OK(cudaGraphLaunch(ge->exec, st));
+        ctx->taps = ge->taps;
+        ctx->launches = ge->launches;
+        return CIDNET_OK;
+    }
+    const bool capture = ge && ge->seen >= 1;     // first call with a new key runs eagerly (one-time setup)
+    if (ge) ge->seen++;
     ctx->taps.clear();
     ctx->recs.clear();
-    ctx->last_B = B;
+    if (capture) {
+        if (!ctx->cap_stream) CIDNET_CUDA_OK(cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking));
+        f.st = ctx->cap_stream;
+        CIDNET_CUDA_OK(cudaStreamBeginCapture(f.st, cudaStreamCaptureModeRelaxed));
+    }
     int rc = f.run(rgb_in, rgb_out, k_dev, gated, alpha_s, gated2, alpha);
     ctx->launches = f.launches;
+    if (capture) {
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(f.st, &graph);
+        f.st = st;
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        CIDNET_CHECK(e == cudaSuccess && graph, CIDNET_ERR_CUDA, std::string("forward: graph capture failed: ") + cudaGetErrorString(e));
+        // locate the stem / head kernel nodes
+        size_t nn = 0;
+        CIDNET_CUDA_OK(cudaGraphGetNodes(graph, nullptr, &nn));
+        std::vector<cudaGraphNode_t> nodes(nn);
+        CIDNET_CUDA_OK(cudaGraphGetNodes(graph, nodes.data(), &nn));
+        for (cudaGraphNode_t nd : nodes) {
+            cudaGraphNodeType ty;
+            if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+            cudaKernelNodeParams kp{};
+            if (cudaGraphKernelNodeGetParams(nd, &kp) != cudaSuccess) continue;
+            if (kp.func == stem_kernel_func()) {
+                ge->stem_node = nd; ge->stem_p = kp;
+                for (int i = 0; i < kStemNumArgs; ++i) ge->stem_args[i] = kp.kernelParams[i];
+            } else if (kp.func == head_kernel_func()) {
+                ge->head_node = nd; ge->head_p = kp;
+                for (int i = 0; i < kHeadNumArgs; ++i) ge->head_args[i] = kp.kernelParams[i];
+            }
+        }
+        cudaGraphExec_t exec = nullptr;
+        e = (ge->stem_node && ge->head_node) ? cudaGraphInstantiate(&exec, graph, 0) : cudaErrorUnknown;
+        if (e != cudaSuccess) {               // fall back to eager launches for this key
+            cudaGetLastError();
+            cudaGraphDestroy(graph);
+            ge->seen = -1000000;
+            return f.run(rgb_in, rgb_out, k_dev, gated, alpha_s, gated2, alpha);
+        }
+        ge->graph = graph; ge->exec = exec;
+        ge->cur_in = rgb_in; ge->cur_out = rgb_out;
+        ge->taps = ctx->taps; ge->launches = f.launches;
+        CIDNET_CUDA_OK(cudaGraphLaunch(exec, st));
+        return CIDNET_OK;
+    }
     return rc;
 }
 
@@ -689,5 +805,12 @@ extern "C" int cidnet_profile_get(cidnet_ctx* ctx, int i, char* name, int name_c
     if (alg_bytes) *alg_bytes = r.bytes;
     if (flops) *flops = r.flops;
     if (ms) CIDNET_CUDA_OK(cudaEventElapsedTime(ms, ctx->events[i], ctx->events[i + 1]));
+    return CIDNET_OK;
+}
+
+// CUDA-graph replay of cidnet_forward is on by default; 0 turns it off (every call launches eagerly)
+extern "C" int cidnet_set_graphs(cidnet_ctx* ctx, int enable) {
+    CIDNET_CHECK(ctx, CIDNET_ERR_INVALID, "set_graphs: null ctx");
+    ctx->use_graphs = enable != 0;
     return CIDNET_OK;
 }

@@ -40,7 +40,7 @@ struct ConvGemmArgs {
     CUtensorMap tmA, tmA2, tmB, tmB2, tmOut;
     int taps, kchunks, kchunks2, cin, cin2;
     int Hv, Wv, TH, TW, tiles_x, tiles_y, num_tiles;
-    int n_out, block_n, stages, per_image_w, b_resident;
+    int n_out, block_n, stages, per_image_w, b_resident, stg_bufs;
     int w_real;
     const float* bias; const float* wsum; float ln_eps;
     const act_t* up; int up_H, up_W, up_pitch; long long up_img_stride; float up_ry, up_rx;
@@ -48,7 +48,8 @@ struct ConvGemmArgs {
     float down_ry, down_rx; int in_H, in_W;
 };
 
-static constexpr int kThreads = 192;
+static constexpr int kEpiGroups = 2;                    // epilogue warpgroups; group g owns TMEM buffer g (tiles j with j&1 == g)
+static constexpr int kThreads = 64 + 128 * kEpiGroups;
 static constexpr uint32_t kSubTileBytes = 128 * 128;   // 128 rows x 64 elements x 2 B
 static constexpr uint32_t kStagingBytes = 128 * 128;   // one 64-channel output block of a tile
 
@@ -76,15 +77,16 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
     uint8_t* smBres = smem;                                                // resident weights (optional)
     uint8_t* smA = smBres + (a.b_resident ? (size_t)kiters * b_chunk : 0);
     uint8_t* smB = smA + (size_t)stages * a_stage;                         // streamed weights (optional)
-    uint8_t* smOut = smB + (a.b_resident ? 0 : (size_t)stages * b_chunk);  // 2 staging buffers
-    uint64_t* full = reinterpret_cast<uint64_t*>(smOut + 2 * kStagingBytes);
+    uint8_t* smOut = smB + (a.b_resident ? 0 : (size_t)stages * b_chunk);  // 2 staging buffers per epilogue group
+    uint64_t* full = reinterpret_cast<uint64_t*>(smOut + (size_t)a.stg_bufs * kEpiGroups * kStagingBytes);
     uint64_t* empty = full + stages;
     uint64_t* bfull = empty + stages;
     uint64_t* tmem_full = bfull + 1;      // [2]
     uint64_t* tmem_empty = tmem_full + 2; // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);
-    float* s_wsum = s_bias + a.block_n;
+    const int bn32 = (a.block_n + 31) & ~31;
+    float* s_wsum = s_bias + bn32;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -114,9 +116,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
         ptx::tmem_relinquish();
     }
     if (kMode == EPI_LN && warp >= 2) {
-        for (int i = threadIdx.x - 64; i < a.block_n; i += 128) {
-            s_bias[i] = __ldg(a.bias + n0 + i);
-            s_wsum[i] = __ldg(a.wsum + n0 + i);
+        for (int i = threadIdx.x - 64; i < bn32; i += 128 * kEpiGroups) {
+            s_bias[i] = i < a.block_n ? __ldg(a.bias + n0 + i) : 0.f;
+            s_wsum[i] = i < a.block_n ? __ldg(a.wsum + n0 + i) : 0.f;
         }
     }
     ptx::tc_fence_before();
@@ -212,13 +214,18 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
     } else {
         // ----------------------------------------------------------- epilogue
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int grp = (warp - 2) >> 2;        // epilogue group == TMEM buffer it drains
         const int row = q * 32 + lane;          // accumulator row == pixel within the tile
         const int ty = row / a.TW;
         const int tx = row - ty * a.TW;
-        const bool issuer = (warp == 2 && lane == 0);
+        const bool issuer = (((warp - 2) & 3) == 0 && lane == 0);
+        uint8_t* const stg_base = smOut + (size_t)grp * a.stg_bufs * kStagingBytes;
+        const uint32_t sb_toggle = a.stg_bufs - 1;
+        const uint32_t bar_id = 1 + grp;
         const int nblk64 = (min(a.block_n, a.n_out - n0) + 63) >> 6;     // 64-channel output blocks
         uint32_t it = 0, j = 0, sb = 0;
         for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++j) {
+            if ((int)(j & 1u) != grp) { it += kiters; continue; }      // the other group's tile
             const int img = t / tiles_per_img;
             const int trem = t - img * tiles_per_img;
             const int y0 = (trem / a.tiles_x) * a.TH;
@@ -308,11 +315,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + buf * acc_cols + ((uint32_t)(q * 32) << 16);
 
-            for (int cb = 0; cb < nblk64; ++cb, sb ^= 1u) {
-                uint8_t* stg = smOut + sb * kStagingBytes;
+            for (int cb = 0; cb < nblk64; ++cb, sb ^= sb_toggle) {
+                uint8_t* stg = stg_base + sb * kStagingBytes;
                 // the TMA store that used this staging buffer two blocks ago must have read it
-                if (issuer) ptx::tma_store_wait_read<1>();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (issuer) { if (a.stg_bufs == 2) ptx::tma_store_wait_read<1>(); else ptx::tma_store_wait_read<0>(); }
+                asm volatile("bar.sync %0, 128;" :: "r"(bar_id) : "memory");
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     const int c = cb * 64 + hh * 32;
@@ -333,10 +340,15 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                     } else {
                         ptx::tmem_ld32(taddr + c, v);
                         if (kMode == EPI_LN) {
+                            const float nm = -mean * rstd;                  // rstd*(v - mean*ws) + b = rstd*v + nm*ws + b
 #pragma unroll
-                            for (int e = 0; e < 32; ++e) {
-                                const int n = (c + e < a.block_n) ? c + e : 0;
-                                v[e] = rstd * (v[e] - mean * s_wsum[n]) + s_bias[n];
+                            for (int e4 = 0; e4 < 8; ++e4) {
+                                const float4 ws = *reinterpret_cast<const float4*>(s_wsum + c + 4 * e4);
+                                const float4 bs = *reinterpret_cast<const float4*>(s_bias + c + 4 * e4);
+                                v[4 * e4 + 0] = fmaf(rstd, v[4 * e4 + 0], fmaf(nm, ws.x, bs.x));
+                                v[4 * e4 + 1] = fmaf(rstd, v[4 * e4 + 1], fmaf(nm, ws.y, bs.y));
+                                v[4 * e4 + 2] = fmaf(rstd, v[4 * e4 + 2], fmaf(nm, ws.z, bs.z));
+                                v[4 * e4 + 3] = fmaf(rstd, v[4 * e4 + 3], fmaf(nm, ws.w, bs.w));
                             }
                         } else if (kMode == EPI_STORE) {
                             if (a.use_prelu) {
@@ -376,7 +388,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                     }
                 }
                 ptx::fence_proxy_async_smem();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" :: "r"(bar_id) : "memory");
                 if (issuer) {
                     const int c0 = n0 + cb * 64;
                     if (kMode == EPI_DOWN) ptx::tma_store_4d(&a.tmOut, stg, c0, x0 >> 1, y0, img);
@@ -560,25 +572,33 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
     const int kiters = wt.taps * wt.kchunks + a.kchunks2;
     const size_t a_stage = (size_t)ksub * kSubTileBytes;
     const size_t b_chunk = (size_t)wt.block_n * 128;
-    const size_t fixed = 1024 + 2 * kStagingBytes + 512 + 2 * wt.block_n * sizeof(float);
-    const size_t budget = 220 * 1024;
+    const size_t budget = 226 * 1024;
     int min_stages = 2;
     if (L.mode == EPI_LN) {
         CIDNET_CHECK(wt.taps == 1 && wt.kchunks <= 4 && wt.bias && wt.wsum && !L.in2, CIDNET_ERR_INVALID,
                      "conv_gemm: LN needs a single-source 1x1 with K<=256");
         min_stages = wt.kchunks + 1;
     }
-    int stages;
     const size_t bres = (size_t)kiters * b_chunk;
-    if (!a.per_image_w && fixed + bres + (size_t)(min_stages + 1) * a_stage <= budget) {
-        a.b_resident = 1;
-        stages = (int)((budget - fixed - bres) / a_stage);
-    } else {
-        a.b_resident = 0;
-        stages = (int)((budget - fixed) / (a_stage + b_chunk));
+    const int want = 2 * kiters > min_stages ? 2 * kiters : min_stages;   // two tiles in flight is plenty
+    int stages = 0;
+    size_t fixed = 0;
+    // preference: resident weights (2 staging buffers, then 1), else streamed weights (2, then 1)
+    for (int pass = 0; pass < 4 && stages < min_stages; ++pass) {
+        const int bufs = (pass & 1) ? 1 : 2;
+        const bool resident = pass < 2;
+        fixed = 1024 + (size_t)bufs * kEpiGroups * kStagingBytes + 512 + 2 * round_up(wt.block_n, 32) * sizeof(float);
+        if (resident) {
+            if (a.per_image_w || fixed + bres + (size_t)min_stages * a_stage > budget) continue;
+            a.b_resident = 1; a.stg_bufs = bufs;
+            stages = (int)((budget - fixed - bres) / a_stage);
+        } else {
+            if (fixed + (size_t)min_stages * (a_stage + b_chunk) > budget) continue;
+            a.b_resident = 0; a.stg_bufs = bufs;
+            stages = (int)((budget - fixed) / (a_stage + b_chunk));
+        }
     }
     if (stages > 8) stages = 8;
-    const int want = 2 * kiters > min_stages ? 2 * kiters : min_stages;   // two tiles in flight is plenty
     if (stages > want) stages = want;
     CIDNET_CHECK(stages >= min_stages, CIDNET_ERR_INVALID, "conv_gemm: shared memory budget exceeded");
     a.stages = stages;

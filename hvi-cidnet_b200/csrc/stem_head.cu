@@ -105,6 +105,8 @@ stem_kernel(const float* __restrict__ rgb, float* __restrict__ hvi, act_t* __res
     }
 }
 
+const void* stem_kernel_func() { return reinterpret_cast<const void*>(&stem_kernel); }
+
 int launch_stem(const StemArgs& a, cudaStream_t stream) {
     CIDNET_CHECK(a.pitch == 40, CIDNET_ERR_INVALID, "stem: pitch must be 40");
     dim3 grid(ceil_div(a.W, kTile), ceil_div(a.H, kTile), a.B);
@@ -183,6 +185,8 @@ head_kernel(const act_t* __restrict__ i_dec1, const act_t* __restrict__ hv_1, co
     float* o = rgb + (long long)b * 3 * hw + pix;
     o[0] = r; o[hw] = g; o[2 * hw] = bl;
 }
+
+const void* head_kernel_func() { return reinterpret_cast<const void*>(&head_kernel); }
 
 int launch_head(const HeadArgs& a, cudaStream_t stream) {
     CIDNET_CHECK(a.pitch == 40, CIDNET_ERR_INVALID, "head: pitch must be 40");

@@ -23,4 +23,11 @@ struct HeadArgs {
 };
 int launch_head(const HeadArgs& a, cudaStream_t stream);
 
+// kernel entry addresses (CUDA-graph node identification: argument 0 of the stem is the input image,
+// argument 3 of the head is the output image)
+const void* stem_kernel_func();
+const void* head_kernel_func();
+static constexpr int kStemNumArgs = 11, kStemArgIn = 0;
+static constexpr int kHeadNumArgs = 12, kHeadArgOut = 3;
+
 }  // namespace cidnet

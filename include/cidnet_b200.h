@@ -75,6 +75,10 @@ CIDNET_API int64_t cidnet_workspace_bytes(int B, int H, int W);
 CIDNET_API int cidnet_forward(cidnet_ctx* ctx, const float* rgb_in, float* rgb_out, int B, int H, int W,
                    void* workspace, int64_t workspace_bytes, const float* k_dev,
                    int gated, float alpha_s, int gated2, float alpha, void* stream);
+/* cidnet_forward replays a CUDA graph of its ~90 kernel launches from the second call with the same
+ * (shape, workspace, flags) on (the image pointers may change freely: they are patched into the
+ * graph).  cidnet_set_graphs(ctx, 0) turns this off. */
+CIDNET_API int cidnet_set_graphs(cidnet_ctx* ctx, int enable);
 /* number of kernels one cidnet_forward launches (for bench.py's gpu_launches) */
 CIDNET_API int cidnet_forward_launches(cidnet_ctx* ctx);
 

@@ -15,8 +15,12 @@ taps = {}
 ref = O.forward(x, sd, taps=taps)
 m = CIDNet().cuda().eval()
 m.load_state_dict(sd)
-y = m(x.cuda()).cpu()
+xc = x.cuda()
+y = m(xc).cpu()            # eager (first call with this shape)
+y2 = m(xc).cpu()           # captured into a CUDA graph
+y3 = m(xc.clone()).cpu()   # graph replay with a patched input pointer
 torch.cuda.synchronize()
+print('graph replay vs eager max diff:', float((y2 - y).abs().max()), float((y3 - y).abs().max()))
 order = ["hvi", "i_enc0", "hv_0", "i_enc1", "hv_1", "I_LCA1", "HV_LCA1",
          "i_enc2", "hv_2", "I_LCA2", "HV_LCA2", "i_enc3", "hv_3", "I_LCA3", "HV_LCA3", "I_LCA4", "HV_LCA4",
          "hvd3", "id3", "HV_LCA5", "hvd2", "id2", "I_LCA6", "HV_LCA6", "id1", "hvd1", "out_hvi"]
