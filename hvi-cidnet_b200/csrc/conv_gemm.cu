@@ -30,6 +30,7 @@
 #include "conv_gemm.cuh"
 #include "ptx_sm100.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -41,6 +42,7 @@ struct ConvGemmArgs {
     int taps, kchunks, kchunks2, cin, cin2;
     int Hv, Wv, TH, TW, tiles_x, tiles_y, num_tiles;
     int n_out, block_n, stages, per_image_w, b_resident, stg_bufs;
+    int halo, halo_baseoff;          // 3x3: tile + halo loaded once per channel chunk, taps = row-shifted views
     int w_real;
     const float* bias; const float* wsum; float ln_eps;
     const act_t* up; int up_H, up_W, up_pitch; long long up_img_stride; float up_ry, up_rx;
@@ -52,6 +54,7 @@ static constexpr int kEpiGroups = 2;                    // epilogue warpgroups; 
 static constexpr int kThreads = 64 + 128 * kEpiGroups;
 static constexpr uint32_t kSubTileBytes = 128 * 128;   // 128 rows x 64 elements x 2 B
 static constexpr uint32_t kStagingBytes = 128 * 128;   // one 64-channel output block of a tile
+static constexpr uint32_t kHaloTileBytes = 11 * 16 * 128;   // halo mode: 11 rows x 16 columns x 64 channels
 
 __device__ __forceinline__ float prelu_f(float v, float slope) { return v >= 0.f ? v : v * slope; }
 
@@ -69,13 +72,14 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int kSub = (kMode == EPI_DOWN) ? 2 : 1;
-    const uint32_t a_stage = kSub * kSubTileBytes;
+    const uint32_t a_stage = kSub * (a.halo ? kHaloTileBytes : kSubTileBytes);
     const uint32_t b_chunk = (uint32_t)a.block_n * 128u;
     const int stages = a.stages;
-    const int k1 = a.taps * a.kchunks;              // primary K iterations
-    const int kiters = k1 + a.kchunks2;
+    const int k1 = a.taps * a.kchunks;              // primary K chunks (weight chunks)
+    const int nbchunks = k1 + a.kchunks2;           // weight chunks resident / streamed
+    const int kiters = a.halo ? a.kchunks : nbchunks;   // pipeline iterations (A stages) per tile
     uint8_t* smBres = smem;                                                // resident weights (optional)
-    uint8_t* smA = smBres + (a.b_resident ? (size_t)kiters * b_chunk : 0);
+    uint8_t* smA = smBres + (a.b_resident ? (size_t)nbchunks * b_chunk : 0);
     uint8_t* smB = smA + (size_t)stages * a_stage;                         // streamed weights (optional)
     uint8_t* smOut = smB + (a.b_resident ? 0 : (size_t)stages * b_chunk);  // 2 staging buffers per epilogue group
     uint64_t* full = reinterpret_cast<uint64_t*>(smOut + (size_t)a.stg_bufs * kEpiGroups * kStagingBytes);
@@ -130,8 +134,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
         // ------------------------------------------------------- TMA producer
         if (lane == 0) {
             if (a.b_resident) {
-                ptx::mbar_expect_tx(bfull, (uint32_t)kiters * b_chunk);
-                for (int i = 0; i < kiters; ++i) {
+                ptx::mbar_expect_tx(bfull, (uint32_t)nbchunks * b_chunk);
+                for (int i = 0; i < nbchunks; ++i) {
                     if (i < k1) ptx::tma_load_3d(smBres + (size_t)i * b_chunk, &a.tmB, bfull, i * 64, n0, 0);
                     else        ptx::tma_load_3d(smBres + (size_t)i * b_chunk, &a.tmB2, bfull, (i - k1) * 64, n0, 0);
                 }
@@ -148,7 +152,15 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                     ptx::mbar_wait(&empty[s], ph ^ 1u);
                     ptx::mbar_expect_tx(&full[s], a_stage + (a.b_resident ? 0u : b_chunk));
                     uint8_t* dstA = smA + (size_t)s * a_stage;
-                    if (i < k1) {
+                    if (a.halo) {
+                        // i == channel chunk; one (DOWN: two, even / odd rows) halo box serves all 9 taps
+                        if (kMode == EPI_DOWN) {
+                            ptx::tma_load_5d(dstA, &a.tmA, &full[s], i * 64, x0 - 1, 0, y0 - 1, img);
+                            ptx::tma_load_5d(dstA + kHaloTileBytes, &a.tmA, &full[s], i * 64, x0 - 1, 1, y0 - 1, img);
+                        } else {
+                            ptx::tma_load_4d(dstA, &a.tmA, &full[s], i * 64, x0 - 1, y0 - 1, img);
+                        }
+                    } else if (i < k1) {
                         const int tap = i / a.kchunks;
                         const int kc = i - tap * a.kchunks;
                         int dy = 1, dx = 1;
@@ -190,7 +202,33 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                 const uint32_t ph = (it / stages) & 1u;
                 ptx::mbar_wait(&full[s], ph);
                 ptx::tc_fence_after();
-                if (lane == 0) {
+                if (lane == 0 && a.halo) {
+                    int ksteps = (a.cin - i * 64 + 15) >> 4;
+                    if (ksteps > 4) ksteps = 4;
+                    const uint32_t abase = ptx::smem_u32(smA + (size_t)s * a_stage);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int dy = tap / 3, dx = tap - dy * 3;
+                        const uint64_t descB = ptx::umma_smem_desc_sw128(
+                            ptx::smem_u32(smBres + (size_t)(tap * a.kchunks + i) * b_chunk));
+#pragma unroll
+                        for (int sub = 0; sub < kSub; ++sub) {
+                            // which halo tile and which first row this (accumulator, tap) reads
+                            uint32_t tile = 0, rowoff = (uint32_t)(dy * 16 + dx);
+                            if (kMode == EPI_DOWN) {
+                                // tiles hold even (0) / odd (1) image rows of row pairs [y0-1, y0+9]
+                                if (sub == 0) { tile = (dy == 1) ? 0u : 1u; rowoff = (uint32_t)((dy == 0 ? 0 : 16) + dx); }
+                                else          { tile = (dy == 1) ? 1u : 0u; rowoff = (uint32_t)((dy == 2 ? 32 : 16) + dx); }
+                            }
+                            const uint64_t descA = ptx::umma_smem_desc_sw128_rowshift(
+                                abase + tile * kHaloTileBytes + rowoff * 128u, (uint32_t)a.halo_baseoff);
+                            for (int k = 0; k < ksteps; ++k)
+                                ptx::umma_f16(d_tmem + sub * a.block_n, descA + 2 * k, descB + 2 * k, idesc,
+                                              (uint32_t)((i | tap | k) != 0));
+                        }
+                    }
+                    ptx::umma_commit(&empty[s]);
+                    if (i == kiters - 1) ptx::umma_commit(&tmem_full[buf]);
+                } else if (lane == 0) {
                     int crem = (i < k1) ? a.cin - (i % a.kchunks) * 64 : a.cin2 - (i - k1) * 64;
                     int ksteps = (crem + 15) >> 4;
                     if (ksteps > 4) ksteps = 4;
@@ -216,8 +254,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int grp = (warp - 2) >> 2;        // epilogue group == TMEM buffer it drains
         const int row = q * 32 + lane;          // accumulator row == pixel within the tile
-        const int ty = row / a.TW;
-        const int tx = row - ty * a.TW;
+        const int pw = a.halo ? 16 : a.TW;      // halo mode: rows are 16 wide, the last 2 columns are wrap-around garbage
+        const int ty = row / pw;
+        const int tx = row - ty * pw;
+        const bool col_ok = tx < a.TW;
         const bool issuer = (((warp - 2) & 3) == 0 && lane == 0);
         uint8_t* const stg_base = smOut + (size_t)grp * a.stg_bufs * kStagingBytes;
         const uint32_t sb_toggle = a.stg_bufs - 1;
@@ -231,7 +271,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
             const int y0 = (trem / a.tiles_x) * a.TH;
             const int x0 = (trem % a.tiles_x) * a.TW;
             const int y = y0 + ty, x = x0 + tx;
-            const bool valid = (y < a.Hv) && (x < a.Wv);
+            const bool valid = col_ok && (y < a.Hv) && (x < a.Wv);
 
             float mean = 0.f, rstd = 1.f;
             if (kMode == EPI_LN) {
@@ -376,9 +416,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                         }
                     }
                     // 16-bit, swizzled (SWIZZLE_128B) staging row; DOWN: only even lanes own an output pixel
-                    int srow = row;
-                    bool wr = true;
-                    if (kMode == EPI_DOWN) { srow = (row >> 4) * 8 + ((row & 15) >> 1); wr = (row & 1) == 0; }
+                    int srow = a.halo ? ty * a.TW + tx : row;      // halo mode: drop the 2 garbage columns
+                    bool wr = col_ok;
+                    if (kMode == EPI_DOWN) { srow = ty * (a.TW >> 1) + (tx >> 1); wr = col_ok && (tx & 1) == 0; }
                     if (wr) {
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
@@ -510,28 +550,42 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
     const long long hw = (long long)L.H * L.W;
     int rc;
 
+    // 3x3 halo mode: possible when all 9 taps' weights stay resident next to >= 2 halo stages
+    {
+        static const bool no_halo = getenv("CIDNET_NO_HALO") != nullptr;
+        // measured on B200: the SWIZZLE_128B XOR is applied to ABSOLUTE shared-memory address bits, so a
+        // descriptor that starts on an arbitrary 128-byte row of a 1024-byte aligned TMA tile reads the
+        // right data with base_offset = 0 (setting (addr >> 7) & 7 there gives wrong results)
+        static const bool no_baseoff = getenv("CIDNET_HALO_BASEOFF") == nullptr;
+        const size_t fixed1 = 1024 + (size_t)kEpiGroups * kStagingBytes + 512 + 2 * round_up(wt.block_n, 32) * sizeof(float);
+        const size_t need = fixed1 + (size_t)9 * wt.kchunks * wt.block_n * 128 + (size_t)2 * ksub * kHaloTileBytes;
+        a.halo = (wt.taps == 9 && !L.in2 && !a.per_image_w && !no_halo && need <= 226 * 1024) ? 1 : 0;
+        a.halo_baseoff = no_baseoff ? 0 : 1;
+    }
+    const int tw = a.halo ? 14 : 16;                            // halo mode: 16-wide smem rows, 14 valid columns
     const uint64_t pb = (uint64_t)L.in_pitch * sizeof(act_t);   // bytes per pixel row
     const uint64_t ob = (uint64_t)L.out_pitch * sizeof(act_t);
     if (L.mode == EPI_DOWN) {
         CIDNET_CHECK(L.H % 2 == 0 && L.W % 2 == 0 && wt.taps == 9, CIDNET_ERR_INVALID, "conv_gemm: DOWN needs even H,W, 3x3");
-        a.Hv = L.H / 2; a.Wv = L.W; a.TH = 8; a.TW = 16;
+        a.Hv = L.H / 2; a.Wv = L.W; a.TH = 8; a.TW = tw;
         a.in_H = L.H; a.in_W = L.W;
         a.down_ry = ac_scale(L.H, L.H / 2); a.down_rx = ac_scale(L.W, L.W / 2);
         const uint64_t dims[5] = {(uint64_t)wt.cin, (uint64_t)L.W, 2, (uint64_t)L.H / 2, (uint64_t)L.B};
         const uint64_t str[4] = {pb, pb * L.W, pb * L.W * 2, pb * hw};
-        const uint32_t box[5] = {64, 16, 1, 8, 1};
+        const uint32_t box[5] = {64, 16, 1, (uint32_t)(a.halo ? 11 : 8), 1};
         if ((rc = encode_map(&a.tmA, L.in, 5, dims, str, box))) return rc;
         const uint64_t od[4] = {(uint64_t)wt.n_out, (uint64_t)L.W / 2, (uint64_t)L.H / 2, (uint64_t)L.B};
         const uint64_t os[3] = {ob, ob * (L.W / 2), ob * (hw / 4)};
-        const uint32_t obox[4] = {64, 8, 8, 1};
+        const uint32_t obox[4] = {64, (uint32_t)(tw / 2), 8, 1};
         if ((rc = encode_map(&a.tmOut, L.out, 4, od, os, obox))) return rc;
     } else {
         if (L.flat) { a.Hv = 1; a.Wv = (int)hw; a.TH = 1; a.TW = 128; }
-        else        { a.Hv = L.H; a.Wv = L.W; a.TH = 8; a.TW = 16; }
+        else        { a.Hv = L.H; a.Wv = L.W; a.TH = 8; a.TW = tw; }
         const uint64_t dims[4] = {(uint64_t)wt.cin, (uint64_t)a.Wv, (uint64_t)a.Hv, (uint64_t)L.B};
         const uint64_t str[3] = {pb, pb * a.Wv, pb * hw};
         const uint32_t box[4] = {64, (uint32_t)a.TW, (uint32_t)a.TH, 1};
-        if ((rc = encode_map(&a.tmA, L.in, 4, dims, str, box))) return rc;
+        const uint32_t hbox[4] = {64, 16, 11, 1};
+        if ((rc = encode_map(&a.tmA, L.in, 4, dims, str, a.halo ? hbox : box))) return rc;
         const uint64_t od[4] = {(uint64_t)wt.n_out, (uint64_t)a.Wv, (uint64_t)a.Hv, (uint64_t)L.B};
         const uint64_t os[3] = {ob, ob * a.Wv, ob * hw};
         if ((rc = encode_map(&a.tmOut, L.out, 4, od, os, box))) return rc;
@@ -569,8 +623,9 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
     }
 
     // shared-memory plan: [resident weights] [A ring] [streamed-weight ring] [2 staging] [barriers, bias]
-    const int kiters = wt.taps * wt.kchunks + a.kchunks2;
-    const size_t a_stage = (size_t)ksub * kSubTileBytes;
+    const int nbchunks = wt.taps * wt.kchunks + a.kchunks2;
+    const int kiters = a.halo ? wt.kchunks : nbchunks;
+    const size_t a_stage = (size_t)ksub * (a.halo ? kHaloTileBytes : kSubTileBytes);
     const size_t b_chunk = (size_t)wt.block_n * 128;
     const size_t budget = 226 * 1024;
     int min_stages = 2;
@@ -579,7 +634,7 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
                      "conv_gemm: LN needs a single-source 1x1 with K<=256");
         min_stages = wt.kchunks + 1;
     }
-    const size_t bres = (size_t)kiters * b_chunk;
+    const size_t bres = (size_t)nbchunks * b_chunk;
     const int want = 2 * kiters > min_stages ? 2 * kiters : min_stages;   // two tiles in flight is plenty
     int stages = 0;
     size_t fixed = 0;
@@ -593,7 +648,7 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
             a.b_resident = 1; a.stg_bufs = bufs;
             stages = (int)((budget - fixed - bres) / a_stage);
         } else {
-            if (fixed + (size_t)min_stages * (a_stage + b_chunk) > budget) continue;
+            if (a.halo || fixed + (size_t)min_stages * (a_stage + b_chunk) > budget) continue;
             a.b_resident = 0; a.stg_bufs = bufs;
             stages = (int)((budget - fixed) / (a_stage + b_chunk));
         }
