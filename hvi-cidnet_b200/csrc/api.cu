@@ -5,10 +5,12 @@
 // is kept as fp32 NCHW for the global residual (:119).
 #include "cab.cuh"
 #include "conv_gemm.cuh"
+#include "dwtc.cuh"
 #include "iel.cuh"
 #include "stem_head.cuh"
 #include "weights.cuh"
 
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -24,6 +26,7 @@ struct LcaWeights {
     bool live = true;
     int C = 0, Cp = 0, heads = 0, h = 0, hp = 0;
     float* wqkv = nullptr;                               // depthwise weights [9][3*Cp]: q_dwconv | kv_dwconv (k) | (v)
+    DwtcWeights dw_q, dw_kv;                              // the same, as diagonal tensor-core tiles
     float* temp = nullptr;                               // [heads]
     float* wo = nullptr;                                 // [C][C]
     PackedWeights fold_tmpl;                             // geometry of the per-image folded weights
@@ -188,6 +191,10 @@ int build_lca(cidnet_ctx* ctx, const std::string& pfx, int level, LcaWeights* L)
         dw_tapmajor(R[pfx + ".ffn.kv_dwconv.weight"], 0, C, 3 * Cp, Cp, &wqkv);
         dw_tapmajor(R[pfx + ".ffn.kv_dwconv.weight"], C, C, 3 * Cp, 2 * Cp, &wqkv);
         if ((rc = dev_f32(ctx, &L->wqkv, wqkv))) return rc;
+        if ((rc = pack_dwtc_weights(&L->dw_q, wqkv.data(), 3 * Cp, 0, C))) return rc;
+        ctx->owned.push_back(L->dw_q.w);
+        if ((rc = pack_dwtc_weights(&L->dw_kv, wqkv.data(), 3 * Cp, Cp, Cp + C))) return rc;
+        ctx->owned.push_back(L->dw_kv.w);
     }
     if ((rc = dev_f32(ctx, &L->temp, R[pfx + ".ffn.temperature"]))) return rc;
     if ((rc = dev_f32(ctx, &L->wo, R[pfx + ".ffn.project_out.weight"]))) return rc;
@@ -476,7 +483,25 @@ struct Fwd {
             a.src_pitch = 3 * Cp; a.dst_pitch = 3 * Cp; a.B = P.B; a.H = H; a.W = W;
             a.nv = 3 * Cp / 8; a.seg_vecs = Cp / 8; a.nprob = np;
             mark("L" + std::to_string(l) + ".cab_dw3x3_qkv", (double)np * P.B * H * W * 12.0 * C, (double)np * P.B * H * W * 2.0 * 27 * C);
-            if ((rc = launch_dw3(a, st))) return rc;
+            // default: FHFMA sliding-window kernel.  CIDNET_DW_TENSOR_CORES=1 selects the tcgen05 variant
+            // (dwtc.cu: correct, but per-tile latencies make it ~2x slower in its current form)
+            static const bool cuda_core_dw = getenv("CIDNET_DW_TENSOR_CORES") == nullptr;
+            if (cuda_core_dw) {
+                if ((rc = launch_dw3(a, st))) return rc;
+            } else {
+                DwtcLaunch D;
+                D.B = P.B; D.H = H; D.W = W;
+                for (int i = 0; i < np; ++i) {
+                    const int s = probs[i];
+                    DwtcSeg& q = D.seg[D.nseg++];
+                    q.in = P.qkv[l][s]; q.in_pitch = 3 * Cp; q.out = P.qkvdw[l][s]; q.out_pitch = 3 * Cp;
+                    q.wt = &S.lca[s].dw_q; q.ssq = P.sq[n - 1][s]; q.ssq_pitch = Cp; q.ssq_channels = C;
+                    DwtcSeg& kv = D.seg[D.nseg++];
+                    kv.in = P.qkv[l][1 - s] + Cp; kv.in_pitch = 3 * Cp; kv.out = P.qkvdw[l][s] + Cp; kv.out_pitch = 3 * Cp;
+                    kv.wt = &S.lca[s].dw_kv; kv.ssq = P.sk[n - 1][s]; kv.ssq_pitch = Cp; kv.ssq_channels = C;
+                }
+                if ((rc = launch_dwtc(D, st))) return rc;
+            }
             gl.pitch = 3 * Cp; gl.B = P.B; gl.H = H; gl.W = W; gl.C = C; gl.heads = heads; gl.nprob = np;
             mark("L" + std::to_string(l) + ".cab_gram_tc", (double)np * P.B * H * W * 4.0 * C, (double)np * P.B * H * W * 2.0 * C * C);
             if ((rc = launch_gram(gl, st))) return rc;
@@ -597,6 +622,7 @@ extern "C" int cidnet_create(cidnet_ctx** out, int device) {
                      std::to_string(prop.minor) + "; this library contains sm_100a code only (no fallback)");
     cidnet_ctx* c = new cidnet_ctx();
     c->device = device;
+    if (getenv("CIDNET_NO_GRAPH")) c->use_graphs = false;   // e.g. under ncu: profile plain launches
     *out = c;
     return CIDNET_OK;
 }
