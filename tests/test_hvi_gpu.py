@@ -80,12 +80,22 @@ def test_empty_and_errors(trans):
 
 
 def test_full_hd_round_trip_properties(trans):
-    """Size-independent properties at BASELINE cfg-3 frame size: PHVIT(HVIT(x)) ~= x
-    (grey pixels come back within 1e-4 by construction, App. A) and I == max(rgb)."""
+    """Size-independent properties at BASELINE cfg-3 frame size: I == max(rgb), |H|,|V| <= 1 and
+    PHVIT(HVIT(x)) ~= x (grey pixels come back within 1e-4 by construction, App. A).  The reference has a
+    `h % 1 == 1.0 -> hi == 6 -> black pixel` hole (~1 pixel in 1e7 for random input): a pixel that fails
+    the round trip here must fail it in the oracle too."""
     trans.density_k.data.fill_(0.2)
-    x = torch.rand(4, 3, 1080, 1920, device="cuda")
-    hvi = trans.HVIT(x)
-    assert torch.equal(hvi[:, 2], x.amax(dim=1))
-    assert float(hvi[:, :2].abs().max()) <= 1.0 + 1e-6
-    back = trans.PHVIT(hvi)
-    assert float((back - x).abs().max()) <= 2e-4
+    k = np.float32(0.2).item()
+    for seed in range(3):
+        gen = torch.Generator(device="cuda").manual_seed(seed)
+        x = torch.rand(4, 3, 1080, 1920, device="cuda", generator=gen)
+        hvi = trans.HVIT(x)
+        assert torch.equal(hvi[:, 2], x.amax(dim=1))
+        assert float(hvi[:, :2].abs().max()) <= 1.0 + 1e-6
+        back = trans.PHVIT(hvi)
+        bad = ((back - x).abs().amax(dim=1) > 2e-4).nonzero()
+        assert bad.shape[0] <= 8, f"{bad.shape[0]} pixels fail the round trip"
+        for b, yy, xx in bad.tolist():
+            px = x[b, :, yy, xx].cpu().reshape(1, 3, 1, 1)
+            ref_back = O.phvit(O.hvit(px, k), k)
+            assert float((ref_back - px).abs().max()) > 2e-4, f"round trip fails only in the CUDA path: {px.flatten().tolist()}"
