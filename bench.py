@@ -32,6 +32,7 @@ WORKLOADS = {
     "cfg2": (1, 640, 1120, "CIDNet 1x3x640x1120 (BASELINE.json configs[1])"),
     "cfg4": (64, 400, 600, "CIDNet 64x3x400x600 batch (per rank: 64/N images)"),
     "cfg5": (1, 2160, 3840, "CIDNet 1x3x2160x3840 single 4K image on one GPU"),
+    "cfg3": (32, 1080, 1920, "standalone PHVIT(HVIT(x)) round trip, 32x3x1080x1920 (HBM roofline check)"),
 }
 METRIC = "CIDNet inference megapixels/s"
 UNIT = "MP/s"
@@ -144,7 +145,7 @@ def run_reference(args):
     torch.set_grad_enabled(False)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    B, H, W, desc = WORKLOADS[args.workload]
+    B, H, W, desc = WORKLOADS[args.workload if args.workload != "cfg3" else "cfg2"]
     sd, wdesc = make_weights()
     sd = {k: v.float() for k, v in sd.items()}
     sample_B, sample_H, sample_W = 1, H, W
@@ -316,6 +317,85 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_hvi(args):
+    """--workload cfg3: the standalone RGB<->HVI transform (BASELINE.json configs[2]).  A step = HVIT then
+    PHVIT over the whole batch (48 B/pixel algorithmic: 24 per direction, fp32 planar)."""
+    import torch
+    import torch.distributed as dist
+    from hvi_cidnet_b200.net.HVI_transform import RGB_HVI
+    from oracle import cidnet_oracle as O
+    torch.set_grad_enabled(False)
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    B, H, W, desc = WORKLOADS["cfg3"]
+    t = RGB_HVI().to(dev)
+    x = torch.rand(B, 3, H, W, device=dev)          # 796 MB >> L2: every step streams from HBM
+    nbytes = x.numel() * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    nwarm, t0 = 0, time.perf_counter()
+    while nwarm < max(3, args.warmup) or time.perf_counter() - t0 < 0.4:
+        y = t.PHVIT(t.HVIT(x)); nwarm += 1
+        torch.cuda.synchronize()
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+    ev[0].record()
+    for i in range(args.steps):
+        hvi = t.HVIT(x); ev[2 * i + 1].record()
+        y = t.PHVIT(hvi); ev[2 * i + 2].record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = ev[0].elapsed_time(ev[-1])
+    ms_h = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)) / args.steps
+    ms_p = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)) / args.steps
+    hx = torch.rand(B, 3, H, W).pin_memory(); hy = torch.empty(B, 3, H, W).pin_memory()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(max(2, args.steps // 4)):
+        hy.copy_(t.PHVIT(t.HVIT(hx.to(dev, non_blocking=True))), non_blocking=True)
+    f1.record(); barrier()
+    ms_e2e = f0.elapsed_time(f1) / max(2, args.steps // 4)
+    if world > 1:
+        tt = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms_total, ms_e2e = float(tt[0]), float(tt[1])
+    if rank == 0:
+        mp = B * H * W * world / 1e6
+        xs = O.make_input("uniform", 2, H, W, seed=1)
+        t1 = time.perf_counter(); n = 0
+        while time.perf_counter() - t1 < 8.0:
+            O.phvit(O.hvit(xs, 0.2), 0.2); n += 1
+        cpu_v = 2 * H * W * n / (time.perf_counter() - t1) / 1e6
+        gb_h, gb_p = nbytes * 2 / ms_h / 1e6, nbytes * 2 / ms_p / 1e6
+        worst = min(gb_h, gb_p)
+        line = {"metric": "RGB<->HVI round trip megapixels/s", "value": mp * args.steps / (ms_total / 1e3), "unit": UNIT,
+                "n_gpus": world, "steps": args.steps, "warmup": nwarm, "ms_per_step": ms_total / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "cfg3: " + desc, "per_rank_batch": B, "l2": "796 MB per tensor, far larger than L2"},
+                "e2e": {"value": mp / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
+                "gpu_launches": 2 * args.steps,
+                "roofline": {"kernel": "hvi_vec4_kernel<PHVIT>" if gb_p < gb_h else "hvi_vec4_kernel<HVIT>", "bound": "hbm",
+                             "achieved": worst, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": worst / peaks["hbm_gbs"],
+                             "traffic": None, "peak_source": peaks["source"],
+                             "hvit_GBps": gb_h, "phvit_GBps": gb_p, "algorithmic_bytes_per_px": 24},
+                "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                 "sample": f"{n} round trips of 2x3x{H}x{W}, torch CPU fp32 (oracle port)"},
+                "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -326,6 +406,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "cfg3":
+        run_hvi(args)
     else:
         run_ours(args)
 
