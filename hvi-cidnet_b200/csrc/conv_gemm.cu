@@ -58,12 +58,32 @@ static constexpr uint32_t kHaloTileBytes = 11 * 16 * 128;   // halo mode: 11 row
 
 __device__ __forceinline__ float prelu_f(float v, float slope) { return v >= 0.f ? v : v * slope; }
 
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {      // one F2FP instruction
+#ifdef CIDNET_ACT_BF16
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+#else
+    __half2 h = __floats2half2_rn(lo, hi);
+#endif
+    return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ uint4 pack8(const float* f) {
-    uint4 raw;
-    act_t* a = reinterpret_cast<act_t*>(&raw);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = f2act(f[i]);
-    return raw;
+    return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+}
+#ifdef CIDNET_ACT_BF16
+#define CIDNET_FHFMA "fma.rn.f32.bf16"
+#define CIDNET_ONE_ONE 0x3F803F80u
+#else
+#define CIDNET_FHFMA "fma.rn.f32.f16"
+#define CIDNET_ONE_ONE 0x3C003C00u
+#endif
+// acc0/1 += lo/hi(a) * lo/hi(b): mixed-precision FMA (SASS FHFMA), 16-bit operands stay packed
+__device__ __forceinline__ void fhfma2(float& acc0, float& acc1, uint32_t a, uint32_t b) {
+    asm("{\n\t.reg .b16 al, ah, bl, bh;\n\t"
+        "mov.b32 {al, ah}, %2;\n\t"
+        "mov.b32 {bl, bh}, %3;\n\t"
+        CIDNET_FHFMA " %0, al, bl, %0;\n\t"
+        CIDNET_FHFMA " %1, ah, bh, %1;\n\t}"
+        : "+f"(acc0), "+f"(acc1) : "r"(a), "r"(b));
 }
 
 template <int kMode>
@@ -279,30 +299,24 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                 // the host guarantees stages >= kchunks + 1); then co-release the stages
                 for (int kc = 0; kc < a.kchunks; ++kc)
                     ptx::mbar_wait(&full[(it + kc) % stages], ((it + kc) / stages) & 1u);
-                float sum = 0.f;
-                for (int pass = 0; pass < 2; ++pass) {
-                    float acc = 0.f;
-                    for (int kc = 0; kc < a.kchunks; ++kc) {
-                        const uint8_t* rowp = smA + (size_t)((it + kc) % stages) * a_stage + row * 128;
-                        const int cbase = kc * 64;
-#pragma unroll
-                        for (int jv = 0; jv < 8; ++jv) {
-                            if (cbase + jv * 8 < a.cin) {
-                                float f[8];
-                                load8(reinterpret_cast<const act_t*>(rowp + ((jv ^ (row & 7)) << 4)), f);
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) {
-                                    if (cbase + jv * 8 + e < a.cin) {
-                                        if (pass == 0) acc += f[e];
-                                        else { const float d = f[e] - mean; acc += d * d; }
-                                    }
-                                }
-                            }
-                        }
+                // one pass: sum and sum of squares with FHFMA (x*1 and x*x, exact 16-bit products, fp32
+                // accumulation; channels >= Cin are TMA zero fill and contribute nothing)
+                float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                for (int kc = 0; kc < a.kchunks; ++kc) {
+                    const uint8_t* rowp = smA + (size_t)((it + kc) % stages) * a_stage + row * 128;
+                    const int nvec = min(8, (a.cin - kc * 64 + 7) >> 3);
+                    for (int jv = 0; jv < nvec; ++jv) {
+                        const uint4 raw = *reinterpret_cast<const uint4*>(rowp + ((jv ^ (row & 7)) << 4));
+                        fhfma2(s0, s1, raw.x, CIDNET_ONE_ONE); fhfma2(q0, q1, raw.x, raw.x);
+                        fhfma2(s0, s1, raw.y, CIDNET_ONE_ONE); fhfma2(q0, q1, raw.y, raw.y);
+                        fhfma2(s0, s1, raw.z, CIDNET_ONE_ONE); fhfma2(q0, q1, raw.z, raw.z);
+                        fhfma2(s0, s1, raw.w, CIDNET_ONE_ONE); fhfma2(q0, q1, raw.w, raw.w);
                     }
-                    if (pass == 0) { sum = acc; mean = sum / (float)a.cin; }
-                    else rstd = 1.0f / sqrtf(acc / (float)a.cin + a.ln_eps);
                 }
+                const float inv_c = 1.0f / (float)a.cin;
+                mean = (s0 + s1) * inv_c;
+                const float var = fmaxf((q0 + q1) * inv_c - mean * mean, 0.f);
+                rstd = 1.0f / sqrtf(var + a.ln_eps);
                 __syncwarp();
                 if (lane == 0)
                     for (int kc = 0; kc < a.kchunks; ++kc) ptx::mbar_arrive(&empty[(it + kc) % stages]);

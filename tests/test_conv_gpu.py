@@ -93,6 +93,20 @@ def test_conv1x1_layernorm_folded(cin, cout):
     assert _rel(out, ref) < 4e-3
 
 
+def test_layernorm_folded_large_mean():
+    """the folded LayerNorm uses E[x^2] - mean^2 and corrects the mean after the GEMM: check a
+    |mean| / std ratio of ~10 (far beyond what the network produces) still holds the tolerance."""
+    g = torch.Generator().manual_seed(5)
+    cin, cout = 72, 216
+    x = torch.randn(1, cin, 16, 24, generator=g) + 10.0
+    w = torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5
+    lw = 1.0 + 0.3 * torch.randn(cin, generator=g)
+    lb = 0.2 * torch.randn(cin, generator=g)
+    ref = F.conv2d(O.layer_norm_cf(_r(x), lw, lb), w)
+    out = run_conv(x, w, ln=torch.cat([lw, lb]), mode=1, flat=1)
+    assert _rel(out, ref) < 1e-2
+
+
 @pytest.mark.parametrize("cin,cout,hw", [(36, 36, (32, 48)), (36, 72, (16, 32)), (72, 144, (24, 40)), (36, 36, (400, 600))])
 def test_conv3x3_down(cin, cout, hw):
     g = torch.Generator().manual_seed(cin + 7)
