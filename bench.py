@@ -115,11 +115,32 @@ class ClockSampler:
         self.thread = threading.Thread(target=self._loop, daemon=True)
         self.thread.start()
 
+    def poll_until(self, event):
+        """Sample from the CALLING thread while `event` (a recorded torch.cuda.Event) is pending: the
+        work is already enqueued, so the samples are taken under load without a second thread
+        competing with the launch loop."""
+        if self.nv is None:
+            event.synchronize()
+            return
+        nv = self.nv
+        self.thread = True
+        while not event.query():
+            try:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h),
+                                  nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+            except Exception as e:  # pragma: no cover
+                self.err = repr(e)
+                break
+            time.sleep(0.002)
+
     def stop(self):
         if self.nv is None or self.thread is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % self.err]}
         self.stop_flag = True
-        self.thread.join(timeout=1.0)
+        if self.thread is not True:
+            self.thread.join(timeout=1.0)
         nv = self.nv
         names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
                  "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
@@ -243,12 +264,12 @@ def run_ours(args):
             torch.cuda.synchronize()
     barrier()
     sampler = ClockSampler(local)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
         y = model(xs[i % ring])
     e1.record()
+    sampler.poll_until(e1)          # clocks / throttle reasons while the timed steps execute
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = model.num_launches() * args.steps
@@ -347,12 +368,13 @@ def run_hvi(args):
         y = t.PHVIT(t.HVIT(x)); nwarm += 1
         torch.cuda.synchronize()
     barrier()
-    sampler = ClockSampler(local); sampler.start()
+    sampler = ClockSampler(local)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
     ev[0].record()
     for i in range(args.steps):
         hvi = t.HVIT(x); ev[2 * i + 1].record()
         y = t.PHVIT(hvi); ev[2 * i + 2].record()
+    sampler.poll_until(ev[-1])
     barrier()
     clocks = sampler.stop()
     ms_total = ev[0].elapsed_time(ev[-1])

@@ -483,7 +483,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box) {
+                      const uint32_t* box, int swizzle_bytes = 128) {
     EncodeTiledFn fn = get_encode_fn();
     CIDNET_CHECK(fn != nullptr, CIDNET_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t gdim[5], gstr[4];
@@ -496,7 +496,9 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t
     const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
 #endif
     CUresult r = fn(m, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char buf[256];
@@ -511,6 +513,11 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t
 int encode_map_generic(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                        const uint32_t* box) {
     return encode_map(m, base, rank, dims, strides_bytes, box);
+}
+
+int encode_map_generic_swz(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                           const uint32_t* box, int swizzle_bytes) {
+    return encode_map(m, base, rank, dims, strides_bytes, box, swizzle_bytes);
 }
 
 static inline float ac_scale(int n_in, int n_out) {

@@ -13,6 +13,10 @@
 // fp32.  d is ZERO outside the image (= the zero padding dwconv1/dwconv2 see).  The x2 warp hands
 // its tanh(..)+d to the x1 warp through 1 KB of shared memory and a 64-thread named barrier.
 #include "iel.cuh"
+#include "ptx_sm100.cuh"
+
+#include <cstdlib>
+#include <cstring>
 
 namespace cidnet {
 
@@ -56,12 +60,12 @@ __device__ __forceinline__ uint4 shfl_down4(const uint4& v) {
 }
 
 struct TRow { uint4 l, c, r; };          // raw 16-bit t values: left / centre / right column
-struct DRow { float l[8], c[8], r[8]; }; // d values (fp32)
+struct DRow { uint4 l, c, r; float cf[8]; };   // d: 16-bit packed left / centre / right (dwconv1/2 operands) + fp32 centre (residual)
 
-__global__ void __launch_bounds__(kThreadsIel, 3)
-iel_gate_kernel(const IelGateArgs a) {
+__global__ void __launch_bounds__(kThreadsIel, 4)
+iel_gate_v3_kernel(const IelGateArgs a) {
     __shared__ __align__(16) act_t s_w0[9 * 2 * 16];      // dwconv    [tap][half][16]  16-bit
-    __shared__ __align__(16) float s_w12[9 * 2 * 16];     // dwconv1/2 [tap][half][16]  fp32
+    __shared__ __align__(16) act_t s_w12[9 * 2 * 16];     // dwconv1/2 [tap][half][16]  16-bit
     __shared__ float4 s_x[2 * 2 * 2 * kCols];             // [vec][row parity][plane][lane]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int half = warp >> 1, vec = warp & 1;
@@ -78,7 +82,7 @@ iel_gate_kernel(const IelGateArgs a) {
     for (int i = tid; i < 9 * 2 * 16; i += kThreadsIel) {
         const int c = i & 15, hf = (i >> 4) & 1, tap = i >> 5;
         s_w0[i] = f2act(a.w0[prob][tap * 2 * hp + hf * hp + c0 + c]);
-        s_w12[i] = (hf == 0 ? a.w1[prob] : a.w2[prob])[tap * hp + c0 + c];
+        s_w12[i] = f2act((hf == 0 ? a.w1[prob] : a.w2[prob])[tap * hp + c0 + c]);
     }
     __syncthreads();
 
@@ -113,16 +117,17 @@ iel_gate_kernel(const IelGateArgs a) {
         fhfma8(acc, t.r, w[(tap0 + 2) * 4]);
     };
     auto dw12_row = [&](const DRow& d, int tap0, float* o) {
-        const float4* w = reinterpret_cast<const float4*>(s_w12) + (half * 4 + vec * 2);   // + tap * 8 float4
+        const uint4* w = reinterpret_cast<const uint4*>(s_w12) + (half * 2 + vec);   // + tap * 4 uint4
+        fhfma8(o, d.l, w[(tap0 + 0) * 4]);
+        fhfma8(o, d.c, w[(tap0 + 1) * 4]);
+        fhfma8(o, d.r, w[(tap0 + 2) * 4]);
+    };
+    auto pack8h = [](const float* f) -> uint4 {
+        uint4 raw;
+        act_t* o = reinterpret_cast<act_t*>(&raw);
 #pragma unroll
-        for (int cc = 0; cc < 3; ++cc) {
-            const float* dv = cc == 0 ? d.l : (cc == 1 ? d.c : d.r);
-            const float4 wa = w[(tap0 + cc) * 8], wb = w[(tap0 + cc) * 8 + 1];
-            o[0] = fmaf(dv[0], wa.x, o[0]); o[1] = fmaf(dv[1], wa.y, o[1]);
-            o[2] = fmaf(dv[2], wa.z, o[2]); o[3] = fmaf(dv[3], wa.w, o[3]);
-            o[4] = fmaf(dv[4], wb.x, o[4]); o[5] = fmaf(dv[5], wb.y, o[5]);
-            o[6] = fmaf(dv[6], wb.z, o[6]); o[7] = fmaf(dv[7], wb.w, o[7]);
-        }
+        for (int e = 0; e < 8; ++e) o[e] = f2act(f[e]);
+        return raw;
     };
 
     // one iteration: d(r) from t rows (r-1, r, r+1) = (t0, t1, t2); then output row r-1 from d rows
@@ -131,17 +136,15 @@ iel_gate_kernel(const IelGateArgs a) {
         take_trow(t2);             // row r+1 (its load was issued one iteration ago)
         issue_load(r + 2);         // in flight while this iteration computes
 #pragma unroll
-        for (int e = 0; e < 8; ++e) d2.c[e] = 0.f;
+        for (int e = 0; e < 8; ++e) d2.cf[e] = 0.f;
         if (r >= 0 && r < a.H && col_in) {
-            dw0_row(t0, 0, d2.c);
-            dw0_row(t1, 3, d2.c);
-            dw0_row(t2, 6, d2.c);
+            dw0_row(t0, 0, d2.cf);
+            dw0_row(t1, 3, d2.cf);
+            dw0_row(t2, 6, d2.cf);
         }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            d2.l[e] = __shfl_up_sync(0xffffffffu, d2.c[e], 1);
-            d2.r[e] = __shfl_down_sync(0xffffffffu, d2.c[e], 1);
-        }
+        d2.c = pack8h(d2.cf);              // 16-bit copy: operand of dwconv1/2 (and what the neighbours see)
+        d2.l = shfl_up4(d2.c);
+        d2.r = shfl_down4(d2.c);
         const int yo = r - 1;
         float xs[8];
         {
@@ -152,7 +155,7 @@ iel_gate_kernel(const IelGateArgs a) {
             dw12_row(d1, 3, o);
             dw12_row(d2, 6, o);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) xs[e] = tanh_approx(o[e]) + d1.c[e];
+            for (int e = 0; e < 8; ++e) xs[e] = tanh_approx(o[e]) + d1.cf[e];
         }
         // x2 warp -> shared -> x1 warp of the same channel vector (64-thread named barrier)
         float4* slot = s_x + ((vec * 2 + (yo & 1)) * 2) * kCols + lane;
@@ -173,8 +176,9 @@ iel_gate_kernel(const IelGateArgs a) {
 
     TRow tA, tB, tC;
     DRow dA, dB, dC;
+    dA.l = dA.c = dA.r = zero4; dB.l = dB.c = dB.r = zero4;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { dA.l[e] = dA.c[e] = dA.r[e] = 0.f; dB.l[e] = dB.c[e] = dB.r[e] = 0.f; }
+    for (int e = 0; e < 8; ++e) { dA.cf[e] = 0.f; dB.cf[e] = 0.f; }
     issue_load(y0 - 2); take_trow(tA);
     issue_load(y0 - 1); take_trow(tB);
     issue_load(y0);
@@ -186,11 +190,211 @@ iel_gate_kernel(const IelGateArgs a) {
     }
 }
 
-int launch_iel_gate(const IelGateArgs& a, cudaStream_t stream) {
+static int launch_iel_gate_v3(const IelGateArgs& a, cudaStream_t stream) {
     CIDNET_CHECK(a.hp % 16 == 0, CIDNET_ERR_INVALID, "iel: hp % 16");
     const int strips = ceil_div(a.W, kCols - 2);
     dim3 grid(strips * (a.hp / 16), ceil_div(a.H, kRows), a.B * a.nprob);
-    iel_gate_kernel<<<grid, kThreadsIel, 0, stream>>>(a);
+    iel_gate_v3_kernel<<<grid, kThreadsIel, 0, stream>>>(a);
+    CIDNET_CUDA_OK(cudaGetLastError());
+    return CIDNET_OK;
+}
+
+// ================================================================================================
+// v4: TMA-fed.  A producer warp streams row blocks of t -- {16 channels, 34 columns (1-column halo),
+// 4 rows} per half, zero-filled outside the image -- into a SWIZZLE_32B shared-memory ring; the four
+// compute warps (x1/x2 x 2 channel vectors, lane = column) read their own column and both neighbours
+// with conflict-free LDS.128.  No global loads, edge-lane special cases or prefetch registers in the
+// compute warps; d still moves between lanes by shuffle and between the x1/x2 warps by 1 KB of smem.
+// ================================================================================================
+static constexpr int kRB = 4;                         // rows per TMA box
+static constexpr int kV4Stages = 6;
+static constexpr int kBoxCols = kCols + 2;            // 34
+static constexpr uint32_t kHalfBoxBytes = kRB * kBoxCols * 32;      // 4352
+static constexpr uint32_t kV4StageBytes = 2 * 4608;   // two halves, each padded to a 512-byte multiple
+static constexpr int kV4Threads = 160;
+
+struct IelV4Args {
+    CUtensorMap tmT[2];         // per problem: t viewed {2*hp channels, W, H, B}, box {16, 34, 4, 1}, SWIZZLE_32B
+    IelGateArgs g;
+};
+
+__global__ void __launch_bounds__(kV4Threads, 2)
+iel_gate_v4_kernel(const __grid_constant__ IelV4Args A) {
+    const IelGateArgs& a = A.g;
+    extern __shared__ uint8_t v4_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(v4_smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ring = smem;                                                  // kV4Stages x kV4StageBytes
+    act_t* s_w0 = reinterpret_cast<act_t*>(ring + kV4Stages * kV4StageBytes);   // [9][2][16]
+    act_t* s_w12 = s_w0 + 9 * 2 * 16;
+    float4* s_x = reinterpret_cast<float4*>(s_w12 + 9 * 2 * 16);          // [vec][parity][plane][lane]
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_x + 2 * 2 * 2 * kCols);
+    uint64_t* empty = full + kV4Stages;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int hp = a.hp, ngroups = hp / 16;
+    const int prob = blockIdx.z % a.nprob, b = blockIdx.z / a.nprob;
+    const int cg = blockIdx.x % ngroups, strip = blockIdx.x / ngroups;
+    const int c0 = cg * 16;
+    const int X0 = strip * (kCols - 2) - 1;               // image column of lane 0
+    const int y0 = blockIdx.y * kRows;
+    const int y1 = min(y0 + kRows, a.H);
+    const int nrows = (y1 - y0) + 4;                      // t rows y0-2 .. y1+1
+    const int nblocks = (nrows + kRB - 1) / kRB;
+
+    for (int i = tid; i < 9 * 2 * 16; i += kV4Threads) {
+        const int c = i & 15, hf = (i >> 4) & 1, tap = i >> 5;
+        s_w0[i] = f2act(a.w0[prob][tap * 2 * hp + hf * hp + c0 + c]);
+        s_w12[i] = f2act((hf == 0 ? a.w1[prob] : a.w2[prob])[tap * hp + c0 + c]);
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kV4Stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 4); }
+        ptx::fence_barrier_init();
+        ptx::prefetch_tensormap(&A.tmT[prob]);
+    }
+    __syncthreads();
+
+    if (warp == 4) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            for (int k = 0; k < nblocks; ++k) {
+                const int s = k % kV4Stages;
+                ptx::mbar_wait(&empty[s], ((k / kV4Stages) & 1u) ^ 1u);
+                ptx::mbar_expect_tx(&full[s], 2 * kHalfBoxBytes);
+                uint8_t* dst = ring + (size_t)s * kV4StageBytes;
+                const int yb = y0 - 2 + k * kRB;
+                ptx::tma_load_4d(dst, &A.tmT[prob], &full[s], c0, X0 - 1, yb, b);
+                ptx::tma_load_4d(dst + 4608, &A.tmT[prob], &full[s], hp + c0, X0 - 1, yb, b);
+            }
+        }
+        return;
+    }
+    // ---------------------------------------------------------------- compute warps
+    const int half = warp >> 1, vec = warp & 1;
+    const int x = X0 + lane;
+    const bool col_in = x >= 0 && x < a.W;
+    const long long hw = (long long)a.H * a.W;
+    act_t* gdst = a.g[prob] + (long long)b * hw * hp + c0 + vec * 8;
+    const bool writer = half == 0 && lane >= 1 && lane <= kCols - 2 && col_in;
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+
+    // t row (relative index j = row - (y0-2)) -> left / centre / right 16-byte vectors from the ring
+    auto lds_trow = [&](int j, TRow& t) {
+        const int k = j / kRB, rr = j - k * kRB;
+        const int s = k % kV4Stages;
+        if (rr == 0) ptx::mbar_wait(&full[s], (k / kV4Stages) & 1u);       // first row of a block: wait for the TMA
+        const uint8_t* base = ring + (size_t)s * kV4StageBytes + half * 4608;
+        const uint32_t row0 = (uint32_t)(rr * kBoxCols + lane) * 32u;        // box column = lane (image column x-1)
+        auto ld = [&](uint32_t off) {
+            const uint32_t o = off + (uint32_t)vec * 16u;
+            return *reinterpret_cast<const uint4*>(base + (o ^ (((o >> 7) & 1u) << 4)));   // SWIZZLE_32B
+        };
+        t.l = ld(row0); t.c = ld(row0 + 32u); t.r = ld(row0 + 64u);
+        if (rr == kRB - 1 || j == nrows - 1) {        // last row of the block consumed: release the stage
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&empty[s]);
+        }
+    };
+    auto dw0_row = [&](const TRow& t, int tap0, float* acc) {
+        const uint4* w = reinterpret_cast<const uint4*>(s_w0) + (half * 2 + vec);
+        fhfma8(acc, t.l, w[(tap0 + 0) * 4]);
+        fhfma8(acc, t.c, w[(tap0 + 1) * 4]);
+        fhfma8(acc, t.r, w[(tap0 + 2) * 4]);
+    };
+    auto dw12_row = [&](const DRow& d, int tap0, float* o) {
+        const uint4* w = reinterpret_cast<const uint4*>(s_w12) + (half * 2 + vec);
+        fhfma8(o, d.l, w[(tap0 + 0) * 4]);
+        fhfma8(o, d.c, w[(tap0 + 1) * 4]);
+        fhfma8(o, d.r, w[(tap0 + 2) * 4]);
+    };
+    auto pack8h = [](const float* f) -> uint4 {
+        uint4 raw;
+        act_t* o = reinterpret_cast<act_t*>(&raw);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = f2act(f[e]);
+        return raw;
+    };
+    auto iter = [&](int r, const TRow& t0, const TRow& t1, TRow& t2, const DRow& d0, const DRow& d1, DRow& d2) {
+        lds_trow(r + 1 - (y0 - 2), t2);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d2.cf[e] = 0.f;
+        if (r >= 0 && r < a.H && col_in) {             // d is zero outside the image
+            dw0_row(t0, 0, d2.cf);
+            dw0_row(t1, 3, d2.cf);
+            dw0_row(t2, 6, d2.cf);
+        }
+        d2.c = pack8h(d2.cf);
+        d2.l = shfl_up4(d2.c);
+        d2.r = shfl_down4(d2.c);
+        const int yo = r - 1;
+        float xs[8];
+        {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = 0.f;
+            dw12_row(d0, 0, o);
+            dw12_row(d1, 3, o);
+            dw12_row(d2, 6, o);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) xs[e] = tanh_approx(o[e]) + d1.cf[e];
+        }
+        float4* slot = s_x + ((vec * 2 + (yo & 1)) * 2) * kCols + lane;
+        if (half == 1) {
+            slot[0] = make_float4(xs[0], xs[1], xs[2], xs[3]);
+            slot[kCols] = make_float4(xs[4], xs[5], xs[6], xs[7]);
+        }
+        asm volatile("bar.sync %0, 64;" :: "r"(1 + vec) : "memory");
+        if (writer && yo >= y0) {
+            const float4 pa = slot[0], pb = slot[kCols];
+            uint4 raw;
+            act_t* ov = reinterpret_cast<act_t*>(&raw);
+            ov[0] = f2act(xs[0] * pa.x); ov[1] = f2act(xs[1] * pa.y); ov[2] = f2act(xs[2] * pa.z); ov[3] = f2act(xs[3] * pa.w);
+            ov[4] = f2act(xs[4] * pb.x); ov[5] = f2act(xs[5] * pb.y); ov[6] = f2act(xs[6] * pb.z); ov[7] = f2act(xs[7] * pb.w);
+            *reinterpret_cast<uint4*>(gdst + ((long long)yo * a.W + x) * hp) = raw;
+        }
+    };
+    TRow tA, tB, tC;
+    DRow dA, dB, dC;
+    dA.l = dA.c = dA.r = zero4; dB.l = dB.c = dB.r = zero4;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { dA.cf[e] = 0.f; dB.cf[e] = 0.f; }
+    lds_trow(0, tA);
+    lds_trow(1, tB);
+    for (int r = y0 - 1; r <= y1; r += 3) {
+        iter(r, tA, tB, tC, dA, dB, dC);
+        if (r + 1 <= y1) iter(r + 1, tB, tC, tA, dB, dC, dA);
+        if (r + 2 <= y1) iter(r + 2, tC, tA, tB, dC, dA, dB);
+    }
+}
+
+int encode_map_generic_swz(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                           const uint32_t* box, int swizzle_bytes);   // conv_gemm.cu
+
+int launch_iel_gate(const IelGateArgs& a, cudaStream_t stream) {
+    static const bool use_v3 = getenv("CIDNET_IEL_V3") != nullptr;
+    if (use_v3) return launch_iel_gate_v3(a, stream);
+    CIDNET_CHECK(a.hp % 16 == 0, CIDNET_ERR_INVALID, "iel: hp % 16");
+    IelV4Args A;
+    memset(&A, 0, sizeof A);
+    A.g = a;
+    const long long hw = (long long)a.H * a.W;
+    for (int p = 0; p < a.nprob; ++p) {
+        const uint64_t pb = (uint64_t)2 * a.hp * sizeof(act_t);
+        const uint64_t dims[4] = {(uint64_t)2 * a.hp, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
+        const uint64_t str[3] = {pb, pb * a.W, pb * hw};
+        const uint32_t box[4] = {16, (uint32_t)kBoxCols, (uint32_t)kRB, 1};
+        int rc = encode_map_generic_swz(&A.tmT[p], a.t[p], 4, dims, str, box, 32);
+        if (rc) return rc;
+    }
+    const size_t smem = 1024 + (size_t)kV4Stages * kV4StageBytes + 2 * 9 * 2 * 16 * sizeof(act_t) +
+                        2 * 2 * 2 * kCols * sizeof(float4) + 2 * kV4Stages * sizeof(uint64_t) + 64;
+    static bool configured = false;
+    if (!configured) {
+        CIDNET_CUDA_OK(cudaFuncSetAttribute(iel_gate_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int strips = ceil_div(a.W, kCols - 2);
+    dim3 grid(strips * (a.hp / 16), ceil_div(a.H, kRows), a.B * a.nprob);
+    iel_gate_v4_kernel<<<grid, kV4Threads, smem, stream>>>(A);
     CIDNET_CUDA_OK(cudaGetLastError());
     return CIDNET_OK;
 }
