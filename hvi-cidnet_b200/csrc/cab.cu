@@ -168,8 +168,10 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
 
 __global__ void __launch_bounds__(kGramThreads, 1)
 gram_kernel(const __grid_constant__ GramArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment is required by the SWIZZLE_128B TMA / UMMA tiles; using the array directly
+    // (no integer round trip) keeps the accesses in the shared state space (LDS / STS, not generic LD / ST)
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
     const int C = a.C;
     const int mtiles_ = (C + 127) / 128;
     const int nA = 2 * mtiles_;                   // 64-channel blocks of q (blocks beyond C are TMA zero fill)

@@ -89,8 +89,10 @@ __device__ __forceinline__ void fhfma2(float& acc0, float& acc1, uint32_t a, uin
 template <int kMode>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment is required by the SWIZZLE_128B TMA / UMMA tiles; using the array directly
+    // (no integer round trip) keeps the accesses in the shared state space (LDS / STS, not generic LD / ST)
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
     constexpr int kSub = (kMode == EPI_DOWN) ? 2 : 1;
     const uint32_t a_stage = kSub * (a.halo ? kHaloTileBytes : kSubTileBytes);
     const uint32_t b_chunk = (uint32_t)a.block_n * 128u;

@@ -44,8 +44,10 @@ struct DwtcArgs {
 
 __global__ void __launch_bounds__(kDwtcThreads, 1)
 dwtc_kernel(const __grid_constant__ DwtcArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment is required by the SWIZZLE_128B TMA / UMMA tiles; using the array directly
+    // (no integer round trip) keeps the accesses in the shared state space (LDS / STS, not generic LD / ST)
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
     const int stages = a.stages;
     uint8_t* smW = smem;                                        // 9 taps x 2 KB (padded to 18 KB)
     uint8_t* smA = smW + 9 * kWTapBytes;                        // halo ring

@@ -208,9 +208,9 @@ static int launch_iel_gate_v3(const IelGateArgs& a, cudaStream_t stream) {
 // ================================================================================================
 static constexpr int kRB = 4;                         // rows per TMA box
 static constexpr int kV4Stages = 6;
-static constexpr int kBoxCols = kCols + 2;            // 34
-static constexpr uint32_t kHalfBoxBytes = kRB * kBoxCols * 32;      // 4352
-static constexpr uint32_t kV4StageBytes = 2 * 4608;   // two halves, each padded to a 512-byte multiple
+static constexpr int kBoxCols = 40;                   // 34 needed; 40 makes the row pitch (1280 B) a multiple of the 256-byte swizzle period
+static constexpr uint32_t kHalfBoxBytes = kRB * kBoxCols * 32;      // 5120
+static constexpr uint32_t kV4StageBytes = 2 * kHalfBoxBytes;
 static constexpr int kV4Threads = 160;
 
 struct IelV4Args {
@@ -221,8 +221,8 @@ struct IelV4Args {
 __global__ void __launch_bounds__(kV4Threads, 2)
 iel_gate_v4_kernel(const __grid_constant__ IelV4Args A) {
     const IelGateArgs& a = A.g;
-    extern __shared__ uint8_t v4_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(v4_smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
     uint8_t* ring = smem;                                                  // kV4Stages x kV4StageBytes
     act_t* s_w0 = reinterpret_cast<act_t*>(ring + kV4Stages * kV4StageBytes);   // [9][2][16]
     act_t* s_w12 = s_w0 + 9 * 2 * 16;
@@ -263,7 +263,7 @@ iel_gate_v4_kernel(const __grid_constant__ IelV4Args A) {
                 uint8_t* dst = ring + (size_t)s * kV4StageBytes;
                 const int yb = y0 - 2 + k * kRB;
                 ptx::tma_load_4d(dst, &A.tmT[prob], &full[s], c0, X0 - 1, yb, b);
-                ptx::tma_load_4d(dst + 4608, &A.tmT[prob], &full[s], hp + c0, X0 - 1, yb, b);
+                ptx::tma_load_4d(dst + kHalfBoxBytes, &A.tmT[prob], &full[s], hp + c0, X0 - 1, yb, b);
             }
         }
         return;
@@ -277,18 +277,21 @@ iel_gate_v4_kernel(const __grid_constant__ IelV4Args A) {
     const bool writer = half == 0 && lane >= 1 && lane <= kCols - 2 && col_in;
     const uint4 zero4 = make_uint4(0, 0, 0, 0);
 
+    // SWIZZLE_32B: byte offset o -> o ^ (bit 7 of o) << 4.  Row pitch and stage size are multiples of 256 B,
+    // so the swizzled offsets of the three columns this lane reads are constants
+    auto swz = [](uint32_t o) { return o ^ (((o >> 7) & 1u) << 4); };
+    const uint32_t off_l = swz((uint32_t)lane * 32u + (uint32_t)vec * 16u);
+    const uint32_t off_c = swz((uint32_t)(lane + 1) * 32u + (uint32_t)vec * 16u);
+    const uint32_t off_r = swz((uint32_t)(lane + 2) * 32u + (uint32_t)vec * 16u);
     // t row (relative index j = row - (y0-2)) -> left / centre / right 16-byte vectors from the ring
     auto lds_trow = [&](int j, TRow& t) {
         const int k = j / kRB, rr = j - k * kRB;
         const int s = k % kV4Stages;
         if (rr == 0) ptx::mbar_wait(&full[s], (k / kV4Stages) & 1u);       // first row of a block: wait for the TMA
-        const uint8_t* base = ring + (size_t)s * kV4StageBytes + half * 4608;
-        const uint32_t row0 = (uint32_t)(rr * kBoxCols + lane) * 32u;        // box column = lane (image column x-1)
-        auto ld = [&](uint32_t off) {
-            const uint32_t o = off + (uint32_t)vec * 16u;
-            return *reinterpret_cast<const uint4*>(base + (o ^ (((o >> 7) & 1u) << 4)));   // SWIZZLE_32B
-        };
-        t.l = ld(row0); t.c = ld(row0 + 32u); t.r = ld(row0 + 64u);
+        const uint8_t* base = ring + (size_t)s * kV4StageBytes + half * kHalfBoxBytes + rr * (kBoxCols * 32);
+        t.l = *reinterpret_cast<const uint4*>(base + off_l);
+        t.c = *reinterpret_cast<const uint4*>(base + off_c);
+        t.r = *reinterpret_cast<const uint4*>(base + off_r);
         if (rr == kRB - 1 || j == nrows - 1) {        // last row of the block consumed: release the stage
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&empty[s]);
