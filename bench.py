@@ -31,7 +31,7 @@ WORKLOADS = {
     "cfg1": (1, 400, 600, "CIDNet 1x3x400x600 (LOLv1 shape)"),
     "cfg2": (1, 640, 1120, "CIDNet 1x3x640x1120 (BASELINE.json configs[1])"),
     "cfg4": (64, 400, 600, "CIDNet 64x3x400x600 batch (per rank: 64/N images)"),
-    "cfg5": (1, 2160, 3840, "CIDNet 1x3x2160x3840 single 4K image on one GPU"),
+    "cfg5": (1, 2160, 3840, "CIDNet 1x3x2160x3840 single 4K image (N>1: rows sharded over the GPUs)"),
     "cfg3": (32, 1080, 1920, "standalone PHVIT(HVIT(x)) round trip, 32x3x1080x1920 (HBM roofline check)"),
 }
 METRIC = "CIDNet inference megapixels/s"
@@ -240,6 +240,8 @@ def run_ours(args):
     sd, wdesc = make_weights()
     model = CIDNet().to(dev).eval()
     model.load_state_dict(sd, strict=True)
+    if args.workload == "cfg5" and world > 1:
+        return run_cfg5_sharded(args, model, sd, wdesc, dev, world, rank, peaks)
 
     # inputs: a ring of distinct images whose total size exceeds L2, so no step finds its input
     # (or the previous step's intermediates, which are rewritten every step) in cache
@@ -298,12 +300,27 @@ def run_ours(args):
         hy.copy_(model(xin), non_blocking=True)
     f1.record()
     barrier()
+    ms_e2e_sync = f0.elapsed_time(f1)
+    # the same through the streamed driver (hvi-cidnet_b200/stream.py): H2D / forward / D2H of consecutive
+    # steps overlap on three streams; every step still uploads its input and downloads its result
+    from hvi_cidnet_b200.stream import StreamedCIDNet
+    drv = StreamedCIDNet(model, depth=3)
+    for _ in drv.run(hx[i % len(hx)] for i in range(3)):
+        pass
+    barrier()
+    f0.record()
+    nres = 0
+    for res in drv.run(hx[i % len(hx)] for i in range(args.steps)):
+        nres += 1
+    f1.record()
+    barrier()
+    assert nres == args.steps
     ms_e2e = f0.elapsed_time(f1)
 
     if world > 1:
-        t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_total, ms_e2e, ms_e2e_sync], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_e2e = float(t[0]), float(t[1])
+        ms_total, ms_e2e, ms_e2e_sync = float(t[0]), float(t[1]), float(t[2])
     mp_step_all = B * H * W * world / 1e6
     value = mp_step_all * args.steps / (ms_total / 1e3)
     e2e_value = mp_step_all * args.steps / (ms_e2e / 1e3)
@@ -331,11 +348,87 @@ def run_ours(args):
                                  "all intermediates are rewritten every step",
                            "accumulate": "fp32", "parallelism": f"dp{world} (independent images, no collective)"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": img_bytes, "d2h_bytes_per_step": img_bytes,
-                        "ms_per_step": ms_e2e / args.steps},
+                        "ms_per_step": ms_e2e / args.steps, "api": "StreamedCIDNet(model).run(pinned host batches) -> pinned host results",
+                        "sync_loop_value": mp_step_all * args.steps / (ms_e2e_sync / 1e3),
+                        "sync_loop_note": "reference-style loop: x.cuda() -> model(x) -> .cpu() per step on one stream"},
                 "gpu_launches": launches, "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_cfg5_sharded(args, model, sd, wdesc, dev, world, rank, peaks):
+    """--workload cfg5 --gpus N>1 (BASELINE.json configs[4]): ONE 4K image, rows sharded over the ranks
+    (hvi-cidnet_b200/dist.py RowShardedCIDNet -> cidnet_forward_sharded); conv halos and the partial Gram
+    sums cross the GPUs over NCCL.  value: every rank's strip (+halo) resident in HBM; e2e: each rank
+    uploads its strip from pinned host memory and downloads its owned output rows every step."""
+    import torch
+    import torch.distributed as dist
+    from hvi_cidnet_b200.dist import RowShardedCIDNet, strip_plan, strip_local_range
+    B, H, W, desc = WORKLOADS["cfg5"]
+    net = RowShardedCIDNet(model, halo=16)
+    sh = strip_plan(H, world, rank, 16)
+    a, b = strip_local_range(sh)
+    g = torch.Generator().manual_seed(1234)
+    nimg = 3
+    hfull = [torch.rand(1, 3, H, W, generator=g) for _ in range(nimg)]           # same images on every rank
+    hloc = [t[:, :, a:b, :].contiguous().pin_memory() for t in hfull]
+    xs = [t.to(dev) for t in hloc]
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    nwarm, t0 = 0, time.perf_counter()
+    while nwarm < max(3, args.warmup) or time.perf_counter() - t0 < 0.4:
+        net.forward_strip(xs[nwarm % nimg], H)
+        nwarm += 1
+    barrier()
+    sampler = ClockSampler(dev.index)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        y, _ = net.forward_strip(xs[i % nimg], H)
+    e1.record()
+    sampler.poll_until(e1)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    launches = model.num_launches() * args.steps
+    halo_calls = sum(1 for e in net.comm.log if e[0] == "halo")
+    ar_calls = sum(1 for e in net.comm.log if e[0] == "allreduce")
+    sent = net.comm.bytes_sent
+    # end to end: pinned strip -> H2D -> sharded forward -> D2H of the owned rows
+    hy = torch.empty(1, 3, sh.row_end - sh.row_begin, W).pin_memory()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        y, _ = net.forward_strip(hloc[i % nimg].to(dev, non_blocking=True), H)
+        hy.copy_(y[:, :, sh.row_begin - a:sh.row_end - a, :], non_blocking=True)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(t[0]), float(t[1])
+    if rank == 0:
+        mp_step = H * W / 1e6
+        act = "fp16" if __import__("hvi_cidnet_b200._lib", fromlist=["lib"]).lib().cidnet_act_dtype() == 0 else "bf16"
+        line = {"metric": METRIC, "value": mp_step * args.steps / (ms_total / 1e3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": nwarm, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": act, "data": "synthetic",
+                "config": {"workload": f"cfg5: CIDNet 1x3x{H}x{W}, rows sharded over {world} GPUs (halo 16 rows)", "H": H, "W": W,
+                           "weights": wdesc, "local_rows_rank0": b - a,
+                           "l2": f"{nimg} distinct images in rotation; all intermediates are rewritten every step",
+                           "parallelism": f"spatial row strips x{world}: {halo_calls} halo exchanges + {ar_calls} Gram all-reduces "
+                                          f"per forward over NCCL, {sent} halo bytes sent per rank per forward"},
+                "e2e": {"value": mp_step * args.steps / (ms_e2e / 1e3), "unit": UNIT,
+                        "h2d_bytes_per_step": hloc[0].numel() * 4, "d2h_bytes_per_step": hy.numel() * 4,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "roofline": None, "cpu_baseline": None, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
 
 
 def run_hvi(args):

@@ -14,6 +14,21 @@ class CidnetError(RuntimeError):
         self.code = code
 
 
+class Shard(C.Structure):
+    """cidnet_shard (include/cidnet_b200.h)"""
+    _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("H_global", C.c_int32),
+                ("row_begin", C.c_int32), ("row_end", C.c_int32), ("halo", C.c_int32)]
+
+
+class HaloReq(C.Structure):
+    """cidnet_halo_req"""
+    _fields_ = [("base", C.c_void_p), ("row_bytes", C.c_int64), ("rows", C.c_int32),
+                ("halo_top", C.c_int32), ("halo_bot", C.c_int32), ("reserved", C.c_int32)]
+
+
+HALO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(HaloReq), C.c_int)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
+
 _lib = None
 
 # name -> (restype, argtypes); must list every symbol include/cidnet_b200.h declares
@@ -32,6 +47,13 @@ SIGNATURES = {
     "cidnet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                  C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float, C.c_void_p]),
     "cidnet_forward_launches": (C.c_int, [C.c_void_p]),
+    "cidnet_shard_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Shard)]),
+    "cidnet_shard_local_rows": (C.c_int, [C.POINTER(Shard)]),
+    "cidnet_forward_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Shard), C.c_void_p, C.c_int64,
+                                         C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float,
+                                         HALO_FN, ALLREDUCE_FN, C.c_void_p, C.c_void_p]),
+    "cidnet_forward_sharded_dry": (C.c_int, [C.c_int, C.POINTER(Shard), C.c_void_p, C.c_int64, HALO_FN, ALLREDUCE_FN,
+                                             C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cidnet_read_tap": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int), C.c_void_p]),
     "cidnet_set_graphs": (C.c_int, [C.c_void_p, C.c_int]),
     "cidnet_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),

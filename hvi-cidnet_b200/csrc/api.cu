@@ -394,8 +394,61 @@ void make_plan(Plan* P, void* ws, int B, int H, int W) {
 }
 
 // ---------------------------------------------------------------- forward ---
+// Row-strip sharding of one image over the ranks of a node (cidnet_forward_sharded).  The local image
+// = owned rows + `halo` rows of the neighbours on every interior side; all kernels run over the whole
+// local image exactly as in the unsharded forward, so every 3x3 stage leaves one more outermost halo
+// row invalid.  `margin[t]` = number of halo rows of tensor t (at t's own level) that still hold the
+// true values; when a stage needs more than is left, the halo is refreshed from the neighbours.
+struct ShardState {
+    bool on = false, dry = false;
+    int rank = 0, nranks = 1, gH = 0, row0 = 0, halo_top = 0, halo_bot = 0;
+    cidnet_halo_fn halo_fn = nullptr; cidnet_allreduce_fn ar_fn = nullptr; void* user = nullptr;
+    std::map<const void*, int> margin;
+    int halo_calls = 0, allreduce_calls = 0;
+};
+struct HaloT { const void* p; int level; int pitch; };
+static const int kNoLimit = 1 << 28;
+
 struct Fwd {
     cidnet_ctx* ctx; Plan P; cudaStream_t st; int launches = 0;
+    ShardState sh;
+
+    bool live() const { return !sh.dry; }
+    bool split() const { return sh.on && sh.nranks > 1; }
+    int ht(int l) const { return sh.halo_top >> l; }
+    int hb(int l) const { return sh.halo_bot >> l; }
+    int own_rows(int l) const { return P.H[l] - ht(l) - hb(l); }
+    int mg(const void* p) {
+        if (!split()) return kNoLimit;
+        auto it = sh.margin.find(p);
+        return it == sh.margin.end() ? 0 : it->second;
+    }
+    void setm(const void* p, int m) { if (split()) sh.margin[p] = m < kNoLimit ? m : kNoLimit; }
+    // make sure every listed tensor has at least `need` valid halo rows: one halo callback for all of
+    // those that do not (the callback refreshes the whole halo -> margin = halo rows of the level)
+    int ensure(const std::vector<HaloT>& ts, int need) {
+        if (!split()) return CIDNET_OK;
+        std::vector<cidnet_halo_req> reqs;
+        for (const HaloT& t : ts) {
+            if (!t.p || mg(t.p) >= need) continue;
+            bool dup = false;
+            for (const auto& r : reqs) dup |= (r.base == t.p);
+            if (dup) continue;
+            cidnet_halo_req r;
+            r.base = const_cast<void*>(t.p);
+            r.row_bytes = (int64_t)P.W[t.level] * t.pitch * (int64_t)sizeof(act_t);
+            r.rows = P.H[t.level]; r.halo_top = ht(t.level); r.halo_bot = hb(t.level);
+            reqs.push_back(r);
+            const int full = (sh.halo_top > 0 ? sh.halo_top : sh.halo_bot) >> t.level;
+            CIDNET_CHECK(full >= need, CIDNET_ERR_INVALID, "forward_sharded: halo too small for this stage");
+            sh.margin[t.p] = full;
+        }
+        if (reqs.empty()) return CIDNET_OK;
+        ++sh.halo_calls;
+        const int rc = sh.halo_fn(sh.user, reqs.data(), (int)reqs.size());
+        CIDNET_CHECK(rc == 0, CIDNET_ERR_STATE, "forward_sharded: halo exchange callback failed (" + std::to_string(rc) + ")");
+        return CIDNET_OK;
+    }
 
     void tap(const std::string& name, const void* p, int C, int l, int pitch, bool f32 = false) {
         ctx->taps[name] = Tap{p, C, P.H[l], P.W[l], pitch, f32};
@@ -424,7 +477,7 @@ struct Fwd {
         if (L.in2) bytes += px_out * L.wt2->cin * 2;
         if (L.up) bytes += px_out / 4 * w.n_out * 2;
         mark(name, bytes, 2.0 * px_in * w.n_out * w.cin * w.taps);
-        return launch_conv_gemm(L, st);
+        return live() ? launch_conv_gemm(L, st) : CIDNET_OK;
     }
 
     int down(int br, int n, const act_t* in, act_t* out) {   // level n-1 -> n
@@ -432,6 +485,10 @@ struct Fwd {
         ConvGemmLaunch L;
         L.mode = EPI_DOWN; L.in = in; L.B = P.B; L.H = P.H[n - 1]; L.W = P.W[n - 1]; L.in_pitch = act_pitch(kCh[n - 1]);
         L.wt = &D.w; L.out = out; L.out_pitch = act_pitch(kCh[n]); L.prelu = D.prelu;
+        if (sh.on) { L.gH = sh.gH >> (n - 1); L.grow = sh.row0 >> (n - 1); }
+        // conv rows 2y, 2y+1 feed output row y: an input margin m leaves (m - 1) / 2 valid output halo rows
+        CIDNET_CHECK(mg(in) >= 1, CIDNET_ERR_STATE, "forward_sharded: down block without a valid input halo");
+        setm(out, mg(in) >= kNoLimit ? kNoLimit : (mg(in) - 1) / 2);
         return gemm(L, "down" + std::to_string(n) + ".conv3x3_bilinear_prelu");
     }
     int up(int br, int n, const act_t* x, const act_t* skip, act_t* t, act_t* out) {   // level n -> n-1
@@ -439,12 +496,18 @@ struct Fwd {
         ConvGemmLaunch A;
         A.mode = EPI_STORE; A.in = x; A.B = P.B; A.H = P.H[n]; A.W = P.W[n]; A.in_pitch = act_pitch(kCh[n]);
         A.wt = &U.w3; A.out = t; A.out_pitch = act_pitch(kCh[n - 1]);
+        // output row Y reads low-res rows floor(Y*r), +1 with r < 1/2: a low-res margin m_t gives
+        // 2 (m_t - 1) valid output halo rows; m_t = margin(x) - 1 after the 3x3
+        CIDNET_CHECK(mg(x) >= 2, CIDNET_ERR_STATE, "forward_sharded: up block without a valid input halo");
+        setm(t, mg(x) - 1);
+        setm(out, std::min(mg(x) >= kNoLimit ? kNoLimit : 2 * (mg(x) - 2), mg(skip)));
         int rc = gemm(A, "up" + std::to_string(n) + ".conv3x3_composed");
         if (rc) return rc;
         ConvGemmLaunch Bq;
         Bq.mode = EPI_UP; Bq.in = skip; Bq.B = P.B; Bq.H = P.H[n - 1]; Bq.W = P.W[n - 1]; Bq.in_pitch = act_pitch(kCh[n - 1]);
         Bq.flat = true; Bq.wt = &U.w1; Bq.out = out; Bq.out_pitch = act_pitch(kCh[n - 1]);
         Bq.up = t; Bq.up_pitch = act_pitch(kCh[n - 1]); Bq.prelu = U.prelu;
+        if (sh.on) { Bq.gH = sh.gH >> (n - 1); Bq.grow = sh.row0 >> (n - 1); }
         return gemm(Bq, "up" + std::to_string(n) + ".skip1x1_bilinear_prelu");
     }
 
@@ -457,6 +520,9 @@ struct Fwd {
         const act_t* x[2] = {x_i, x_hv};
         act_t* out[2] = {out_i, out_hv};
         int rc;
+        // the depthwise 3x3 of q|k|v needs one valid halo row of both inputs
+        if ((rc = ensure({{x_i, l, Cp}, {x_hv, l, Cp}}, 1))) return rc;
+        const int m_dw = split() ? std::min(mg(x_i), mg(x_hv)) - 1 : kNoLimit;
         // 1. LayerNorm + q / kv 1x1 of both branches: one GEMM per input tensor
         for (int s = 0; s < 2; ++s) {
             ConvGemmLaunch L;
@@ -482,11 +548,16 @@ struct Fwd {
             }
             a.src_pitch = 3 * Cp; a.dst_pitch = 3 * Cp; a.B = P.B; a.H = H; a.W = W;
             a.nv = 3 * Cp / 8; a.seg_vecs = Cp / 8; a.nprob = np;
+            // sharded: sum q^2, sum k^2 and the Gram run over the OWNED rows only (partial sums, all-reduced below)
+            const int own0 = sh.on ? ht(l) : 0, own_n = sh.on ? own_rows(l) : H;
+            a.stat_y0 = own0; a.stat_y1 = own0 + own_n;
+            for (int i = 0; i < np; ++i) { gl.q[i] += (long long)own0 * W * 3 * Cp; gl.k[i] += (long long)own0 * W * 3 * Cp; }
             mark("L" + std::to_string(l) + ".cab_dw3x3_qkv", (double)np * P.B * H * W * 12.0 * C, (double)np * P.B * H * W * 2.0 * 27 * C);
             // default: FHFMA sliding-window kernel.  CIDNET_DW_TENSOR_CORES=1 selects the tcgen05 variant
             // (dwtc.cu: correct, but per-tile latencies make it ~2x slower in its current form)
             static const bool cuda_core_dw = getenv("CIDNET_DW_TENSOR_CORES") == nullptr;
-            if (cuda_core_dw) {
+            if (!live()) {
+            } else if (cuda_core_dw || sh.on) {
                 if ((rc = launch_dw3(a, st))) return rc;
             } else {
                 DwtcLaunch D;
@@ -502,9 +573,19 @@ struct Fwd {
                 }
                 if ((rc = launch_dwtc(D, st))) return rc;
             }
-            gl.pitch = 3 * Cp; gl.B = P.B; gl.H = H; gl.W = W; gl.C = C; gl.heads = heads; gl.nprob = np;
-            mark("L" + std::to_string(l) + ".cab_gram_tc", (double)np * P.B * H * W * 4.0 * C, (double)np * P.B * H * W * 2.0 * C * C);
-            if ((rc = launch_gram(gl, st))) return rc;
+            gl.pitch = 3 * Cp; gl.B = P.B; gl.H = own_n; gl.W = W; gl.C = C; gl.heads = heads; gl.nprob = np;
+            gl.img_stride_px = (long long)H * W;
+            mark("L" + std::to_string(l) + ".cab_gram_tc", (double)np * P.B * own_n * W * 4.0 * C, (double)np * P.B * own_n * W * 2.0 * C * C);
+            if (live() && (rc = launch_gram(gl, st))) return rc;
+            if (split()) {
+                // one all-reduce (sum, fp32) of the raw partial [Gram | sum q^2 | sum k^2] of the live problems;
+                // normalisation, temperature and softmax then run identically on every rank
+                float* lo = P.gram[n - 1][probs[0]];
+                float* hi = P.sk[n - 1][probs[np - 1]] + (int64_t)P.B * Cp;
+                ++sh.allreduce_calls;
+                const int arc = sh.ar_fn(sh.user, lo, (int64_t)(hi - lo));
+                CIDNET_CHECK(arc == 0, CIDNET_ERR_STATE, "forward_sharded: all-reduce callback failed (" + std::to_string(arc) + ")");
+            }
         }
         // 3. normalise + temperature + softmax + fold into project_out
         {
@@ -517,7 +598,7 @@ struct Fwd {
             const PackedWeights& t = S.lca[probs[0]].fold_tmpl;
             f.B = P.B; f.C = C; f.Cp = Cp; f.heads = heads; f.nprob = np; f.n_rows = t.n_rows; f.kt = t.ktot();
             mark("L" + std::to_string(l) + ".cab_softmax_fold", (double)np * P.B * (C * C * 6.0), (double)np * P.B * 36.0 * C * C);
-            if ((rc = launch_cab_fold(f, st))) return rc;
+            if (live() && (rc = launch_cab_fold(f, st))) return rc;
         }
         for (int i = 0; i < np; ++i) {
             const int s = probs[i];
@@ -529,6 +610,13 @@ struct Fwd {
             A.wt = &fw; A.out = P.xp[l][s]; A.out_pitch = Cp; A.in2 = x[s]; A.in2_pitch = Cp; A.wt2 = &ctx->eye[l];
             if (P.B == 1) fw.n_img = 1;
             if ((rc = gemm(A, "L" + std::to_string(l) + ".cab_attnv_proj_res"))) return rc;
+            setm(P.xp[l][s], m_dw);
+        }
+        // the IEL gate chains two depthwise 3x3: two valid halo rows of x' (project_in is recomputed on them)
+        if ((rc = ensure({{S.lca[0].live ? P.xp[l][0] : nullptr, l, Cp}, {P.xp[l][1], l, Cp}}, 2))) return rc;
+        for (int i = 0; i < np; ++i) {
+            const int s = probs[i];
+            LcaWeights& Lw = S.lca[s];
             // 5. LayerNorm + project_in
             ConvGemmLaunch Bq;
             Bq.mode = EPI_LN; Bq.in = P.xp[l][s]; Bq.B = P.B; Bq.H = H; Bq.W = W; Bq.in_pitch = Cp; Bq.flat = true;
@@ -545,7 +633,7 @@ struct Fwd {
             }
             g.B = P.B; g.H = H; g.W = W; g.hp = S.lca[probs[0]].hp; g.nprob = np;
             mark("L" + std::to_string(l) + ".iel_gate", (double)np * P.B * H * W * 6.0 * S.lca[probs[0]].h, (double)np * P.B * H * W * 2.0 * 36 * S.lca[probs[0]].h);
-            if ((rc = launch_iel_gate(g, st))) return rc;
+            if (live() && (rc = launch_iel_gate(g, st))) return rc;
         }
         // 7. project_out (+ residual for I_LCA only)
         for (int i = 0; i < np; ++i) {
@@ -556,6 +644,7 @@ struct Fwd {
             Cq.wt = &Lw.w_out; Cq.out = out[s]; Cq.out_pitch = Cp;
             if (s == 0) { Cq.in2 = P.xp[l][s]; Cq.in2_pitch = Cp; Cq.wt2 = &ctx->eye[l]; }
             if ((rc = gemm(Cq, "L" + std::to_string(l) + ".iel_project_out"))) return rc;
+            setm(out[s], mg(P.xp[l][s]) >= kNoLimit ? kNoLimit : mg(P.xp[l][s]) - 2);
             tap(std::string(s == 0 ? "I_LCA" : "HV_LCA") + std::to_string(n), out[s], C, l, Cp);
         }
         return CIDNET_OK;
@@ -563,43 +652,53 @@ struct Fwd {
 
     int run(const float* rgb_in, float* rgb_out, const float* k_dev, int gated, float alpha_s, int gated2, float alpha) {
         int rc;
-        CIDNET_CUDA_OK(cudaMemsetAsync(P.stats, 0, (size_t)P.stats_bytes, st));
+        if (live()) CIDNET_CUDA_OK(cudaMemsetAsync(P.stats, 0, (size_t)P.stats_bytes, st));
         StemArgs sa{rgb_in, P.hvi, P.i_enc0, P.hv_0, ctx->stem_whv, ctx->stem_wi, k_dev ? k_dev : ctx->k_dev,
                     ctx->k_host, P.B, P.H[0], P.W[0], 40};
         mark("L0.stem_hvit_block0", (double)P.B * P.H[0] * P.W[0] * 168.0, (double)P.B * P.H[0] * P.W[0] * 2.0 * 1296);
-        if ((rc = launch_stem(sa, st))) return rc;
+        if (live() && (rc = launch_stem(sa, st))) return rc;
+        // the local input image carries the neighbours' rows: the replicate-padded 3x3 spoils the outermost one
+        setm(P.i_enc0, (sh.halo_top > 0 ? sh.halo_top : sh.halo_bot) - 1);
+        setm(P.hv_0, (sh.halo_top > 0 ? sh.halo_top : sh.halo_bot) - 1);
         tap("hvi", P.hvi, 3, 0, 0, true); tap("i_enc0", P.i_enc0, 36, 0, 40); tap("hv_0", P.hv_0, 36, 0, 40);
+        if ((rc = ensure({{P.i_enc0, 0, 40}, {P.hv_0, 0, 40}}, 1))) return rc;
         if ((rc = down(0, 1, P.i_enc0, P.enc_i[1]))) return rc;
         if ((rc = down(1, 1, P.hv_0, P.enc_hv[1]))) return rc;
         tap("i_enc1", P.enc_i[1], 36, 1, 40); tap("hv_1", P.enc_hv[1], 36, 1, 40);
         if ((rc = lca_stage(1, P.enc_i[1], P.enc_hv[1], P.lca_i[1], P.lca_hv[1]))) return rc;
+        if ((rc = ensure({{P.lca_i[1], 1, 40}, {P.lca_hv[1], 1, 40}}, 1))) return rc;
         if ((rc = down(0, 2, P.lca_i[1], P.enc_i[2]))) return rc;
         if ((rc = down(1, 2, P.lca_hv[1], P.enc_hv[2]))) return rc;
         tap("i_enc2", P.enc_i[2], 72, 2, 72); tap("hv_2", P.enc_hv[2], 72, 2, 72);
         if ((rc = lca_stage(2, P.enc_i[2], P.enc_hv[2], P.lca_i[2], P.lca_hv[2]))) return rc;
         // block3 consumes the PRE-LCA2 tensors (CIDNet.py:94-95)
+        if ((rc = ensure({{P.enc_i[2], 2, 72}, {P.enc_hv[2], 2, 72}}, 1))) return rc;
         if ((rc = down(0, 3, P.enc_i[2], P.enc_i[3]))) return rc;
         if ((rc = down(1, 3, P.enc_hv[2], P.enc_hv[3]))) return rc;
         tap("i_enc3", P.enc_i[3], 144, 3, 144); tap("hv_3", P.enc_hv[3], 144, 3, 144);
         if ((rc = lca_stage(3, P.enc_i[3], P.enc_hv[3], P.lca_i[3], P.lca_hv[3]))) return rc;
         // LCA4: both consume the LCA3 outputs (HV_LCA4 sees i_enc4, CIDNet.py:101)
         if ((rc = lca_stage(4, P.lca_i[3], P.lca_hv[3], P.lca_i[4], P.lca_hv[4]))) return rc;
+        if ((rc = ensure({{P.lca_hv[4], 3, 144}, {P.lca_i[4], 3, 144}}, 2))) return rc;
         if ((rc = up(1, 3, P.lca_hv[4], P.lca_hv[2], P.tup_hv[3], P.dec_hv[2]))) return rc;
         if ((rc = up(0, 3, P.lca_i[4], P.lca_i[2], P.tup_i[3], P.dec_i[2]))) return rc;
         tap("hvd3", P.dec_hv[2], 72, 2, 72); tap("id3", P.dec_i[2], 72, 2, 72);
         // stage 5: I_LCA5 is dead, only HV_LCA5(hv_3, i_dec3)
         if ((rc = lca_stage(5, P.dec_i[2], P.dec_hv[2], nullptr, P.lca_hv[5]))) return rc;
+        if ((rc = ensure({{P.lca_hv[5], 2, 72}, {P.dec_i[2], 2, 72}}, 2))) return rc;
         if ((rc = up(1, 2, P.lca_hv[5], P.lca_hv[1], P.tup_hv[2], P.dec_hv[1]))) return rc;
         if ((rc = up(0, 2, P.dec_i[2], P.lca_i[1], P.tup_i[2], P.dec_i[1]))) return rc;   // takes i_dec3 (:109)
         tap("hvd2", P.dec_hv[1], 36, 1, 40); tap("id2", P.dec_i[1], 36, 1, 40);
         if ((rc = lca_stage(6, P.dec_i[1], P.dec_hv[1], P.lca_i[6], P.lca_hv[6]))) return rc;
+        if ((rc = ensure({{P.lca_i[6], 1, 40}, {P.lca_hv[6], 1, 40}}, 2))) return rc;
         if ((rc = up(0, 1, P.lca_i[6], P.i_enc0, P.tup_i[1], P.id1))) return rc;
         if ((rc = up(1, 1, P.lca_hv[6], P.hv_0, P.tup_hv[1], P.hvd1))) return rc;
         tap("id1", P.id1, 36, 0, 40); tap("hvd1", P.hvd1, 36, 0, 40);
+        if ((rc = ensure({{P.id1, 0, 40}, {P.hvd1, 0, 40}}, 1))) return rc;
         HeadArgs ha{P.id1, P.hvd1, P.hvi, rgb_out, P.out_hvi, ctx->head_wi, ctx->head_whv,
                     k_dev ? k_dev : ctx->k_dev, ctx->k_host, alpha_s, alpha, gated, gated2, P.B, P.H[0], P.W[0], 40};
         mark("L0.head_block0_phvit", (double)P.B * P.H[0] * P.W[0] * 168.0, (double)P.B * P.H[0] * P.W[0] * 2.0 * 972);
-        if ((rc = launch_head(ha, st))) return rc;
+        if (live() && (rc = launch_head(ha, st))) return rc;
         finish_marks();
         tap("out_hvi", P.out_hvi, 3, 0, 0, true);
         return CIDNET_OK;
@@ -793,6 +892,106 @@ extern "C" int cidnet_forward(cidnet_ctx* ctx, const float* rgb_in, float* rgb_o
         CIDNET_CUDA_OK(cudaGraphLaunch(exec, st));
         return CIDNET_OK;
     }
+    return rc;
+}
+
+// ---- row-strip sharded forward (single image over the GPUs of one node) -------------------
+static int check_shard(const cidnet_shard* sh, int W) {
+    CIDNET_CHECK(sh != nullptr, CIDNET_ERR_INVALID, "forward_sharded: null shard descriptor");
+    CIDNET_CHECK(sh->nranks >= 1 && sh->rank >= 0 && sh->rank < sh->nranks, CIDNET_ERR_INVALID, "forward_sharded: bad rank");
+    CIDNET_CHECK(W > 0 && W % 8 == 0 && sh->H_global > 0 && sh->H_global % 8 == 0, CIDNET_ERR_INVALID,
+                 "forward_sharded: H and W must be multiples of 8");
+    CIDNET_CHECK(sh->row_begin % 8 == 0 && sh->row_end % 8 == 0 && sh->row_begin >= 0 && sh->row_begin < sh->row_end &&
+                     sh->row_end <= sh->H_global, CIDNET_ERR_INVALID, "forward_sharded: bad owned row range");
+    CIDNET_CHECK((sh->rank == 0) == (sh->row_begin == 0) && (sh->rank == sh->nranks - 1) == (sh->row_end == sh->H_global),
+                 CIDNET_ERR_INVALID, "forward_sharded: the first / last rank must own the first / last rows");
+    if (sh->nranks > 1)
+        CIDNET_CHECK(sh->halo >= 16 && sh->halo % 16 == 0 && sh->halo <= sh->row_end - sh->row_begin, CIDNET_ERR_INVALID,
+                     "forward_sharded: halo must be a multiple of 16, >= 16 and <= the owned rows");
+    return CIDNET_OK;
+}
+static void shard_state(const cidnet_shard* sh, ShardState* s) {
+    s->on = true; s->rank = sh->rank; s->nranks = sh->nranks; s->gH = sh->H_global;
+    s->halo_top = (sh->nranks > 1 && sh->rank > 0) ? sh->halo : 0;
+    s->halo_bot = (sh->nranks > 1 && sh->rank < sh->nranks - 1) ? sh->halo : 0;
+    s->row0 = sh->row_begin - s->halo_top;
+}
+
+extern "C" int cidnet_shard_plan(int H, int nranks, int rank, int halo, cidnet_shard* out) {
+    CIDNET_CHECK(out != nullptr && H > 0 && H % 8 == 0 && nranks >= 1 && rank >= 0 && rank < nranks, CIDNET_ERR_INVALID,
+                 "shard_plan: bad arguments");
+    const int rows3 = H / 8, base = rows3 / nranks, extra = rows3 % nranks;
+    CIDNET_CHECK(base >= 1, CIDNET_ERR_INVALID, "shard_plan: more ranks than coarsest-level rows");
+    const int b3 = rank * base + (rank < extra ? rank : extra);
+    const int n3 = base + (rank < extra ? 1 : 0);
+    out->rank = rank; out->nranks = nranks; out->H_global = H;
+    out->row_begin = 8 * b3; out->row_end = 8 * (b3 + n3); out->halo = nranks > 1 ? halo : 0;
+    return check_shard(out, 8);
+}
+
+extern "C" int cidnet_shard_local_rows(const cidnet_shard* sh) {
+    if (!sh) return 0;
+    ShardState s; shard_state(sh, &s);
+    return sh->row_end - sh->row_begin + s.halo_top + s.halo_bot;
+}
+
+extern "C" int cidnet_forward_sharded(cidnet_ctx* ctx, const float* rgb_local, float* rgb_out_local, int W,
+                                      const cidnet_shard* sh, void* workspace, int64_t workspace_bytes,
+                                      const float* k_dev, int gated, float alpha_s, int gated2, float alpha,
+                                      cidnet_halo_fn halo_fn, cidnet_allreduce_fn allreduce_fn, void* user,
+                                      void* stream) {
+    CIDNET_CHECK(ctx, CIDNET_ERR_INVALID, "forward_sharded: null ctx");
+    CIDNET_CHECK(ctx->finalized, CIDNET_ERR_STATE, "forward_sharded: weights not finalized (call cidnet_finalize_weights)");
+    int rc = check_shard(sh, W);
+    if (rc) return rc;
+    CIDNET_CHECK(sh->nranks == 1 || (halo_fn && allreduce_fn), CIDNET_ERR_INVALID, "forward_sharded: callbacks required");
+    CIDNET_CHECK(rgb_local && rgb_out_local && workspace, CIDNET_ERR_INVALID, "forward_sharded: null pointer");
+    CIDNET_CHECK((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, CIDNET_ERR_INVALID, "forward_sharded: workspace must be 1024-byte aligned");
+    Fwd f;
+    f.ctx = ctx; f.st = (cudaStream_t)stream;
+    shard_state(sh, &f.sh);
+    f.sh.halo_fn = halo_fn; f.sh.ar_fn = allreduce_fn; f.sh.user = user;
+    const int H = cidnet_shard_local_rows(sh);
+    make_plan(&f.P, workspace, 1, H, W);
+    CIDNET_CHECK(workspace_bytes >= f.P.bytes, CIDNET_ERR_STATE,
+                 "forward_sharded: workspace too small: need " + std::to_string(f.P.bytes) + " bytes");
+    ctx->last_B = 1;
+    ctx->taps.clear();
+    ctx->recs.clear();
+    rc = f.run(rgb_local, rgb_out_local, k_dev, gated, alpha_s, gated2, alpha);
+    ctx->launches = f.launches;
+    return rc;
+}
+
+extern "C" int cidnet_forward_sharded_dry(int W, const cidnet_shard* sh, void* workspace, int64_t workspace_bytes,
+                                          cidnet_halo_fn halo_fn, cidnet_allreduce_fn allreduce_fn, void* user,
+                                          int* n_halo_calls, int* n_allreduce_calls) {
+    int rc = check_shard(sh, W);
+    if (rc) return rc;
+    CIDNET_CHECK(sh->nranks == 1 || (halo_fn && allreduce_fn), CIDNET_ERR_INVALID, "forward_sharded_dry: callbacks required");
+    CIDNET_CHECK(workspace && (reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, CIDNET_ERR_INVALID,
+                 "forward_sharded_dry: workspace must be 1024-byte aligned");
+    cidnet_ctx dummy;                      // weights are only dereferenced by the (skipped) launches
+    for (int n = 0; n < 6; ++n) {
+        const int l = n < 3 ? n + 1 : 6 - n;
+        for (int s = 0; s < 2; ++s) {
+            LcaWeights& L = dummy.stage[n].lca[s];
+            L.live = !(n == 4 && s == 0);
+            L.C = kCh[l]; L.Cp = act_pitch(kCh[l]); L.heads = kHeads[l]; L.h = (int)(kCh[l] * 2.66); L.hp = round_up(L.h, 16);
+            choose_blocking(L.C, &L.fold_tmpl.block_n, &L.fold_tmpl.n_blocks);
+            L.fold_tmpl.n_rows = L.fold_tmpl.block_n * L.fold_tmpl.n_blocks;
+        }
+    }
+    Fwd f;
+    f.ctx = &dummy; f.st = nullptr;
+    shard_state(sh, &f.sh);
+    f.sh.dry = true;
+    f.sh.halo_fn = halo_fn; f.sh.ar_fn = allreduce_fn; f.sh.user = user;
+    make_plan(&f.P, workspace, 1, cidnet_shard_local_rows(sh), W);
+    CIDNET_CHECK(workspace_bytes >= f.P.bytes, CIDNET_ERR_STATE, "forward_sharded_dry: workspace too small");
+    rc = f.run(nullptr, nullptr, nullptr, 0, 1.f, 0, 1.f);
+    if (n_halo_calls) *n_halo_calls = f.sh.halo_calls;
+    if (n_allreduce_calls) *n_allreduce_calls = f.sh.allreduce_calls;
     return rc;
 }
 

@@ -109,7 +109,7 @@ dw3x3_kernel(const Dw3Args a) {
             act_t* ov = reinterpret_cast<act_t*>(&raw);
 #pragma unroll
             for (int e = 0; e < 8; ++e) ov[e] = f2act(acc[e]);
-            fhfma8(ssq, raw, raw);                                   // sum of squares of the ROUNDED values
+            if (y >= a.stat_y0 && y < a.stat_y1) fhfma8(ssq, raw, raw);   // sum of squares of the ROUNDED values
             *reinterpret_cast<uint4*>(dst + ((long long)y * a.W + x) * a.dst_pitch) = raw;
         };
         load_row(y0 - 1, win0);
@@ -134,7 +134,9 @@ dw3x3_kernel(const Dw3Args a) {
     }
 }
 
-int launch_dw3(const Dw3Args& a, cudaStream_t stream) {
+int launch_dw3(const Dw3Args& a_in, cudaStream_t stream) {
+    Dw3Args a = a_in;
+    if (a.stat_y1 <= 0) { a.stat_y0 = 0; a.stat_y1 = a.H; }
     CIDNET_CHECK(a.seg_vecs * 8 <= 144 && a.nv == 3 * a.seg_vecs, CIDNET_ERR_INVALID, "dw3: bad channel layout");
     dim3 grid(ceil_div(a.W * a.nv, kDwThreads), ceil_div(a.H, kDwRows), a.B * a.nprob);
     dw3x3_kernel<<<grid, kDwThreads, 0, stream>>>(a);
@@ -285,7 +287,8 @@ int launch_gram(const GramLaunch& L, cudaStream_t stream) {
     a.nchunks = ceil_div(a.hw, 64);
     for (int p = 0; p < L.nprob; ++p) {
         const uint64_t dims[3] = {(uint64_t)L.C, (uint64_t)a.hw, (uint64_t)L.B};
-        const uint64_t str[2] = {(uint64_t)L.pitch * sizeof(act_t), (uint64_t)L.pitch * sizeof(act_t) * a.hw};
+        const uint64_t img_px = L.img_stride_px > 0 ? (uint64_t)L.img_stride_px : (uint64_t)a.hw;
+        const uint64_t str[2] = {(uint64_t)L.pitch * sizeof(act_t), (uint64_t)L.pitch * sizeof(act_t) * img_px};
         const uint32_t box[3] = {64, 64, 1};
         int rc = encode_map_generic(&a.tmQ[p], L.q[p], 3, dims, str, box);
         if (rc) return rc;

@@ -12,6 +12,7 @@ struct Dw3Args {
     const float* w[2];          // fp32 [9][nv*8] tap major, segments in the same order
     float* sq[2]; float* sk[2]; // [B][Cp] sum of squares of q / k (pre-zeroed)
     int B, H, W, nv, seg_vecs, nprob;
+    int stat_y0, stat_y1;       // rows whose squares enter sq / sk (row-strip sharding: the owned rows); 0,0 = all
 };
 int launch_dw3(const Dw3Args& a, cudaStream_t stream);
 
@@ -20,6 +21,7 @@ struct GramLaunch {
     int pitch;
     float* gram[2];                          // [B][heads][18][18] fp32, pre-zeroed
     int B, H, W, C, heads, nprob;
+    long long img_stride_px;                 // pixels between images (0 = H*W; larger when H covers only the owned rows)
 };
 int launch_gram(const GramLaunch& L, cudaStream_t stream);
 

@@ -48,6 +48,10 @@ struct ConvGemmArgs {
     const act_t* up; int up_H, up_W, up_pitch; long long up_img_stride; float up_ry, up_rx;
     float prelu; int use_prelu;
     float down_ry, down_rx; int in_H, in_W;
+    // row-strip sharding: global row index of local output row 0 (DOWN: on the half-resolution grid,
+    // UP: on the full-resolution grid), global row of local row 0 of the low-res UP source and its
+    // global row count.  All zero / == local sizes when the image is not sharded.
+    int down_row0, up_row0, up_src_row0, up_Hg;
 };
 
 static constexpr int kEpiGroups = 2;                    // epilogue warpgroups; group g owns TMEM buffer g (tiles j with j&1 == g)
@@ -332,9 +336,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
             if (kMode == EPI_UP && valid) {
                 const long long pix = (long long)y * a.Wv + x;
                 const int yr = (int)(pix / a.w_real), xr = (int)(pix - (long long)yr * a.w_real);
-                const float sy = a.up_ry * (float)yr;
-                const int i0 = (int)sy; uly = sy - (float)i0;
-                const int i1 = i0 + (i0 < a.up_H - 1 ? 1 : 0);
+                const float sy = a.up_ry * (float)(yr + a.up_row0);          // GLOBAL source row
+                const int i0g = (int)sy; uly = sy - (float)i0g;
+                const int i1g = i0g + (i0g < a.up_Hg - 1 ? 1 : 0);
+                // local rows of the strip (clamped: rows outside it only feed halo rows that are invalid anyway)
+                const int i0 = min(max(i0g - a.up_src_row0, 0), a.up_H - 1);
+                const int i1 = min(max(i1g - a.up_src_row0, 0), a.up_H - 1);
                 const float sx = a.up_rx * (float)xr;
                 const int j0 = (int)sx; ulx = sx - (float)j0;
                 const int j1 = j0 + (j0 < a.up_W - 1 ? 1 : 0);
@@ -355,7 +362,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
             float dly = 0.f, dlx = 0.f;
             bool top_is_odd = false, left_is_right = false;
             if (kMode == EPI_DOWN) {
-                const int oy = y, ox = x >> 1;
+                const int oy = y + a.down_row0, ox = x >> 1;                 // GLOBAL output row
                 const float sy = a.down_ry * (float)oy;
                 const int i0 = (int)sy;
                 dly = sy - (float)i0;
@@ -592,7 +599,10 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
         CIDNET_CHECK(L.H % 2 == 0 && L.W % 2 == 0 && wt.taps == 9, CIDNET_ERR_INVALID, "conv_gemm: DOWN needs even H,W, 3x3");
         a.Hv = L.H / 2; a.Wv = L.W; a.TH = 8; a.TW = tw;
         a.in_H = L.H; a.in_W = L.W;
-        a.down_ry = ac_scale(L.H, L.H / 2); a.down_rx = ac_scale(L.W, L.W / 2);
+        const int gH = L.gH ? L.gH : L.H;
+        CIDNET_CHECK(gH % 2 == 0 && L.grow % 2 == 0 && L.grow + L.H <= gH, CIDNET_ERR_INVALID, "conv_gemm: bad row strip");
+        a.down_ry = ac_scale(gH, gH / 2); a.down_rx = ac_scale(L.W, L.W / 2);
+        a.down_row0 = L.grow / 2;
         const uint64_t dims[5] = {(uint64_t)wt.cin, (uint64_t)L.W, 2, (uint64_t)L.H / 2, (uint64_t)L.B};
         const uint64_t str[4] = {pb, pb * L.W, pb * L.W * 2, pb * hw};
         const uint32_t box[5] = {64, 16, 1, (uint32_t)(a.halo ? 11 : 8), 1};
@@ -631,7 +641,10 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
             CIDNET_CHECK(L.up != nullptr && L.H % 2 == 0 && L.W % 2 == 0, CIDNET_ERR_INVALID, "conv_gemm: UP needs t");
             a.up = L.up; a.up_H = L.H / 2; a.up_W = L.W / 2; a.up_pitch = L.up_pitch;
             a.up_img_stride = (hw / 4) * L.up_pitch;
-            a.up_ry = ac_scale(L.H / 2, L.H); a.up_rx = ac_scale(L.W / 2, L.W);
+            const int gH = L.gH ? L.gH : L.H;
+            CIDNET_CHECK(gH % 2 == 0 && L.grow % 2 == 0 && L.grow + L.H <= gH, CIDNET_ERR_INVALID, "conv_gemm: bad row strip");
+            a.up_ry = ac_scale(gH / 2, gH); a.up_rx = ac_scale(L.W / 2, L.W);
+            a.up_row0 = L.grow; a.up_src_row0 = L.grow / 2; a.up_Hg = gH / 2;
         }
     }
     a.tiles_x = ceil_div(a.Wv, a.TW);

@@ -61,6 +61,11 @@ struct ConvGemmLaunch {
     // EPI_UP: low-resolution tensor t [B, H/2, W/2, up_pitch] to be upsampled x2 and added
     const act_t* up = nullptr;
     int up_pitch = 0;
+    // Row-strip sharding of ONE image (cidnet_forward_sharded): this launch covers local rows
+    // [0, H) = global rows [grow, grow + H) of an image with gH rows on this launch's INPUT pixel
+    // grid (gH == 0: not sharded).  Only the align_corners bilinear weights of EPI_DOWN / EPI_UP
+    // depend on it (they are functions of the GLOBAL row index and size); grow must be even.
+    int gH = 0, grow = 0;
 };
 
 int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream);

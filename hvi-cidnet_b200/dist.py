@@ -34,3 +34,196 @@ def forward_sharded(model, x_full, group=None, gather=True):
     bufs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(bufs, pad, group=group)
     return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+
+
+# ----------------------------------------------------------------------------------------------
+# Single image, rows sharded over the GPUs of one node (BASELINE.json configs[4]).
+# The C library drives the schedule (cidnet_forward_sharded) and calls back into the two
+# functions below whenever data has to cross ranks: halo rows of NHWC activations to / from the
+# two neighbours, and one all-reduce of the raw [Gram | sum q^2 | sum k^2] per LCA stage.
+# ----------------------------------------------------------------------------------------------
+import ctypes as _C
+
+
+class StripComm:
+    """Transport of the halo / all-reduce callbacks over a torch.distributed process group.
+
+    `buffer` is the torch tensor (uint8, 1-D) the library's pointers point into (the workspace).
+      * NCCL group, CUDA buffer: P2P send/recv and all_reduce act directly on views of the
+        workspace -- rows are contiguous in NHWC, nothing is packed or staged; NVLink carries them.
+      * any other combination (gloo group; CPU buffer in the dry-run tests; two ranks sharing one
+        GPU in the single-GPU parity test): the same rows are staged through host memory.
+    """
+
+    def __init__(self, buffer, group=None):
+        self.buf = buffer
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.direct = buffer.is_cuda and dist.get_backend(group) == "nccl"
+        self.error = None
+        self.log = []                                   # ("halo", [(offset, row_bytes, rows, top, bot)...]) / ("allreduce", offset, count)
+        self.bytes_sent = 0
+        self.halo_cb = _clib().HALO_FN(self._halo)
+        self.allreduce_cb = _clib().ALLREDUCE_FN(self._allreduce)
+
+    def _peer(self, r):
+        return dist.get_global_rank(self.group, r) if self.group is not None else r
+
+    def _view(self, ptr, nbytes):
+        off = ptr - self.buf.data_ptr()
+        if off < 0 or off + nbytes > self.buf.numel():
+            raise RuntimeError("callback pointer outside the registered workspace")
+        return self.buf[off:off + nbytes]
+
+    def _halo(self, user, reqs, n):
+        try:
+            sends, recvs, entry = [], [], []
+            for i in range(n):
+                q = reqs[i]
+                t = self._view(q.base, q.rows * q.row_bytes).view(q.rows, q.row_bytes)
+                entry.append((q.base - self.buf.data_ptr(), q.row_bytes, q.rows, q.halo_top, q.halo_bot))
+                if q.halo_top > 0:                       # neighbour above: rank - 1
+                    sends.append((t[q.halo_top:2 * q.halo_top], self.rank - 1))
+                    recvs.append((t[:q.halo_top], self.rank - 1))
+                if q.halo_bot > 0:                       # neighbour below: rank + 1
+                    sends.append((t[q.rows - 2 * q.halo_bot:q.rows - q.halo_bot], self.rank + 1))
+                    recvs.append((t[q.rows - q.halo_bot:], self.rank + 1))
+            self.log.append(("halo", entry))
+            self.bytes_sent += sum(s.numel() for s, _ in sends)
+            if self.direct:
+                ops = [dist.P2POp(dist.isend, s, self._peer(p), self.group) for s, p in sends]
+                ops += [dist.P2POp(dist.irecv, r, self._peer(p), self.group) for r, p in recvs]
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()                             # stream-ordered for NCCL (no host sync)
+            else:
+                hs = [s.cpu().contiguous() for s, _ in sends]
+                hr = [torch.empty(r.shape, dtype=r.dtype) for r, _ in recvs]
+                ops = [dist.P2POp(dist.isend, s, self._peer(p), self.group) for s, (_, p) in zip(hs, sends)]
+                ops += [dist.P2POp(dist.irecv, r, self._peer(p), self.group) for r, (_, p) in zip(hr, recvs)]
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+                for h, (r, _) in zip(hr, recvs):
+                    r.copy_(h)
+            return 0
+        except BaseException as e:                       # never let an exception cross the C boundary
+            self.error = e
+            return -1
+
+    def _allreduce(self, user, ptr, count):
+        try:
+            t = self._view(ptr, 4 * count).view(torch.float32)
+            self.log.append(("allreduce", ptr - self.buf.data_ptr(), int(count)))
+            if self.direct:
+                dist.all_reduce(t, group=self.group)
+            else:
+                h = t.cpu()
+                dist.all_reduce(h, group=self.group)
+                t.copy_(h)
+            return 0
+        except BaseException as e:
+            self.error = e
+            return -1
+
+
+def _clib():
+    from . import _lib
+    return _lib
+
+
+def strip_plan(H, world_size, rank, halo=16):
+    """cidnet_shard for `rank`: balanced split of the H/8 coarsest rows (no device needed)."""
+    L = _clib()
+    sh = L.Shard()
+    L.check(L.lib().cidnet_shard_plan(int(H), int(world_size), int(rank), int(halo), _C.byref(sh)))
+    return sh
+
+
+def strip_local_range(sh):
+    """(first, last+1) global rows of the LOCAL image of shard `sh` (owned rows + halos)."""
+    top = sh.halo if (sh.nranks > 1 and sh.rank > 0) else 0
+    bot = sh.halo if (sh.nranks > 1 and sh.rank < sh.nranks - 1) else 0
+    return sh.row_begin - top, sh.row_end + bot
+
+
+class RowShardedCIDNet:
+    """One image, rows partitioned over the ranks of `group` (one process per GPU).
+
+        net = RowShardedCIDNet(model)            # model: hvi_cidnet_b200 CIDNet on this rank's GPU
+        y = net(x)                               # x: [1,3,H,W] full image (CPU pinned or CUDA), same on every rank
+                                                 # y: full [1,3,H,W] result on every rank (gather=True)
+
+    Each rank uploads / computes only its strip (+ halo); conv halos and the partial Gram sums
+    travel over NCCL (NVLink) -- see include/cidnet_b200.h, "rows sharded over the GPUs of one node".
+    """
+
+    def __init__(self, model, group=None, halo=16):
+        self.model, self.group, self.halo = model, group, int(halo)
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._ws = {}
+        self.comm = None
+
+    def _workspace(self, rows, W, device):
+        key = (rows, W, str(device))
+        if key not in self._ws:
+            L = _clib()
+            n = L.lib().cidnet_workspace_bytes(1, rows, W)
+            ws = torch.empty(n + 1024, dtype=torch.uint8, device=device)
+            self._ws = {key: (ws, StripComm(ws, self.group) if self.world > 1 else None)}
+        return self._ws[key]
+
+    def forward_strip(self, x_local, H_global):
+        """x_local: CUDA fp32 [1,3,local_rows,W] = this rank's local image.  Returns the local output
+        [1,3,local_rows,W]; only the owned rows (see strip_plan / strip_local_range) are meaningful."""
+        L = _clib()
+        m = self.model
+        dev = x_local.device
+        sh = strip_plan(H_global, self.world, self.rank, self.halo)
+        rows = L.lib().cidnet_shard_local_rows(_C.byref(sh))
+        if tuple(x_local.shape) != (1, 3, rows, x_local.shape[3]) or x_local.dtype != torch.float32 or not x_local.is_cuda:
+            raise RuntimeError(f"forward_strip expects a CUDA fp32 [1,3,{rows},W] local image, got {tuple(x_local.shape)} on {dev}")
+        W = x_local.shape[3]
+        x_local = x_local.contiguous()
+        out = torch.empty_like(x_local)
+        with torch.cuda.device(dev):
+            ctx = m._ensure_ctx(dev)
+            ws, comm = self._workspace(rows, W, dev)
+            self.comm = comm
+            if comm is not None:
+                comm.log, comm.bytes_sent = [], 0            # per-forward record of the exchanges
+            off = (-ws.data_ptr()) % 1024
+            t = m.trans
+            kd = t.density_k.detach()
+            t._note_hvit_called()
+            rc = L.lib().cidnet_forward_sharded(
+                ctx, x_local.data_ptr(), out.data_ptr(), W, _C.byref(sh), ws.data_ptr() + off, ws.numel() - off,
+                kd.data_ptr() if kd.dtype == torch.float32 else None,
+                int(bool(t.gated)), float(t.alpha_s), int(bool(t.gated2)), float(t.alpha),
+                comm.halo_cb if comm else L.HALO_FN(), comm.allreduce_cb if comm else L.ALLREDUCE_FN(), None,
+                L.stream_ptr(dev))
+            if comm is not None and comm.error is not None:
+                err, comm.error = comm.error, None
+                raise err
+            L.check(rc)
+        return out, sh
+
+    def __call__(self, x, gather=True):
+        if x.dim() != 4 or x.shape[0] != 1 or x.shape[1] != 3:
+            raise RuntimeError(f"RowShardedCIDNet expects one image [1,3,H,W], got {tuple(x.shape)}")
+        H, W = int(x.shape[2]), int(x.shape[3])
+        dev = self.model.trans.density_k.device
+        sh = strip_plan(H, self.world, self.rank, self.halo)
+        a, b = strip_local_range(sh)
+        x_local = x[:, :, a:b, :].to(dev, torch.float32, non_blocking=True).contiguous()
+        out, sh = self.forward_strip(x_local, H)
+        own = out[:, :, sh.row_begin - a:sh.row_end - a, :]
+        if not gather or self.world == 1:
+            return own.contiguous()
+        plans = [strip_plan(H, self.world, r, self.halo) for r in range(self.world)]
+        nmax = max(p.row_end - p.row_begin for p in plans)
+        pad = own.new_zeros((1, 3, nmax, W))
+        pad[:, :, :own.shape[2]] = own
+        bufs = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(bufs, pad, group=self.group)
+        return torch.cat([bf[:, :, :p.row_end - p.row_begin] for bf, p in zip(bufs, plans)], dim=2)

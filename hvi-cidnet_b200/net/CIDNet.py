@@ -168,7 +168,9 @@ class CIDNet(nn.Module, PyTorchModelHubMixin):
         return ws, ws.data_ptr() + off, ws.numel() - off
 
     # ------------------------------------------------------------------ reference surface
-    def forward(self, x):
+    def forward(self, x, out=None):
+        """`out` (optional, extension): a CUDA fp32 tensor of x's shape to write the result into (the
+        streamed driver keeps a ring of them); by default a fresh tensor is returned like the reference."""
         dtypes = x.dtype
         if not isinstance(x, torch.Tensor) or not x.is_cuda:
             raise RuntimeError(f"CIDNet.forward: input is on {getattr(x, 'device', None)}; the B200-native path has no "
@@ -183,7 +185,11 @@ class CIDNet(nn.Module, PyTorchModelHubMixin):
         if k.device != x.device:
             raise RuntimeError(f"model parameters are on {k.device} but the input is on {x.device}")
         xin = x.contiguous() if dtypes == torch.float32 else x.float().contiguous()
-        out = torch.empty_like(xin)
+        if out is None:
+            out = torch.empty_like(xin)
+        elif (out.shape != xin.shape or out.dtype != torch.float32 or out.device != xin.device
+              or not out.is_contiguous() or dtypes != torch.float32):
+            raise RuntimeError("CIDNet.forward: `out` must be a contiguous fp32 tensor of the input's shape and device")
         if B == 0:
             return out.to(dtypes)
         with torch.cuda.device(x.device):

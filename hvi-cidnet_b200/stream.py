@@ -1,0 +1,78 @@
+"""Streamed inference driver: replaces the reference's synchronous batch-1 loops
+(eval_SID_blur.py:25-40, eval.py:56-75: `.cuda()` -> model -> `.cpu()` per image, each a full
+host<->device round trip on the default stream) by a 3-stage pipeline
+
+    copy-in stream  : pinned host batch  -> device ring slot          (H2D)
+    compute stream  : CIDNet.forward(slot) -> device output ring slot (C ABI / CUDA-graph replay)
+    copy-out stream : device output slot -> pinned host ring slot     (D2H)
+
+so the PCIe copies of step i+1 / i-1 overlap the kernels of step i.  Results are yielded in input
+order, `depth - 1` steps behind the submissions.  All arithmetic is the unchanged CIDNet.forward."""
+import torch
+
+
+class StreamedCIDNet:
+    def __init__(self, model, depth=3):
+        if depth < 2:
+            raise ValueError("depth must be >= 2")
+        self.model, self.depth = model, int(depth)
+        self._shape = None
+
+    def _setup(self, shape, dev):
+        if self._shape == (tuple(shape), dev):
+            return
+        d = self.depth
+        self.dev = dev
+        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.x = [torch.empty(shape, device=dev) for _ in range(d)]
+        self.y = [torch.empty(shape, device=dev) for _ in range(d)]
+        self.hy = [torch.empty(shape).pin_memory() for _ in range(d)]
+        self.in_ready = [torch.cuda.Event() for _ in range(d)]
+        self.in_free = [torch.cuda.Event() for _ in range(d)]      # compute has consumed x[slot]
+        self.out_ready = [torch.cuda.Event() for _ in range(d)]
+        self.out_done = [torch.cuda.Event() for _ in range(d)]     # D2H of y[slot] -> hy[slot] finished
+        self._shape = (tuple(shape), dev)
+
+    def run(self, host_batches):
+        """host_batches: iterable of fp32 [B,3,H,W] host tensors of ONE shape (pinned memory for real
+        overlap).  Yields the enhanced batches as pinned host tensors, in order; a yielded tensor is
+        valid until `depth` further results have been produced (copy it if it must live longer)."""
+        m = self.model
+        dev = m.trans.density_k.device
+        if dev.type != "cuda":
+            raise RuntimeError("StreamedCIDNet: the model must live on an sm_100 CUDA device (no CPU fallback)")
+        main = torch.cuda.current_stream(dev)
+        pending = []                                               # slots submitted, not yet yielded
+        n = 0
+        with torch.no_grad():
+            for hx in host_batches:
+                if hx.dtype != torch.float32 or hx.is_cuda:
+                    raise RuntimeError("StreamedCIDNet.run expects fp32 host tensors")
+                self._setup(hx.shape, dev)
+                slot = n % self.depth
+                if n >= self.depth:                                # the slot's previous result must have been handed out
+                    while slot in pending:
+                        done = pending.pop(0)
+                        self.out_done[done].synchronize()
+                        yield self.hy[done]
+                with torch.cuda.stream(self.s_in):
+                    if n >= self.depth:
+                        self.s_in.wait_event(self.in_free[slot])
+                    self.x[slot].copy_(hx, non_blocking=True)
+                    self.in_ready[slot].record(self.s_in)
+                main.wait_event(self.in_ready[slot])
+                if n >= self.depth:
+                    main.wait_event(self.out_done[slot])           # y[slot] no longer being copied out
+                m(self.x[slot], out=self.y[slot])
+                self.in_free[slot].record(main)
+                self.out_ready[slot].record(main)
+                with torch.cuda.stream(self.s_out):
+                    self.s_out.wait_event(self.out_ready[slot])
+                    self.hy[slot].copy_(self.y[slot], non_blocking=True)
+                    self.out_done[slot].record(self.s_out)
+                pending.append(slot)
+                n += 1
+            while pending:
+                done = pending.pop(0)
+                self.out_done[done].synchronize()
+                yield self.hy[done]

@@ -82,6 +82,66 @@ CIDNET_API int cidnet_set_graphs(cidnet_ctx* ctx, int enable);
 /* number of kernels one cidnet_forward launches (for bench.py's gpu_launches) */
 CIDNET_API int cidnet_forward_launches(cidnet_ctx* ctx);
 
+/* ---- single image, rows sharded over the GPUs of one node ---------------------
+ * BASELINE.json configs[4] (1x3x2160x3840 over 8 B200): the reference has no multi-GPU path
+ * at all; this is the spatial partition of CIDNet.forward (net/CIDNet.py:71-122).
+ * Rank r owns the image rows [row_begin, row_end) (multiples of 8) and works on a LOCAL image
+ * = those rows plus `halo` rows of each existing neighbour (rank-1 above, rank+1 below), laid
+ * out contiguously: [halo_top | owned | halo_bot] with halo_top = (rank > 0 ? halo : 0),
+ * halo_bot = (rank < nranks-1 ? halo : 0).
+ *
+ * Two things cross the ranks, both through callbacks the HOST supplies (torch.distributed /
+ * NCCL over NVLink in hvi-cidnet_b200/dist.py) so that the library itself stays free of any
+ * communication dependency:
+ *   halo      every 3x3 stage invalidates one more outermost halo row; before a stage that needs
+ *             more valid halo rows than are left, the library asks for the halos of a list of
+ *             local tensors to be refreshed.  For request q the rank must (stream-ordered)
+ *               send  its first owned  q.halo_top rows to rank-1   (if halo_top > 0)
+ *               send  its last  owned  q.halo_bot rows to rank+1   (if halo_bot > 0)
+ *               receive rank-1's rows into local rows [0, halo_top)
+ *               receive rank+1's rows into local rows [rows-halo_bot, rows)
+ *             rows are contiguous (NHWC): row i starts at base + i*row_bytes.
+ *   allreduce sum over all ranks, in place, of `count` fp32 values: the raw partial per-head Gram
+ *             and the partial sums of q^2, k^2 of one LCA stage (CAB, net/LCA.py:30-33);
+ *             normalisation, temperature and softmax then run identically on every rank.
+ * Every rank issues the same sequence of callbacks (the schedule depends only on `halo`).
+ * The callbacks must enqueue their work on `stream` (or make `stream` wait for it) and return 0.
+ */
+typedef struct cidnet_shard {
+    int32_t rank, nranks;
+    int32_t H_global;            /* rows of the whole image (multiple of 8) */
+    int32_t row_begin, row_end;  /* owned rows [row_begin, row_end), multiples of 8 */
+    int32_t halo;                /* halo rows per interior side: multiple of 16, >= 16, <= owned rows of every rank */
+} cidnet_shard;
+typedef struct cidnet_halo_req {
+    void* base;                  /* local tensor (dev), row 0 of the local image at the tensor's level */
+    int64_t row_bytes;           /* bytes of one image row of this tensor */
+    int32_t rows;                /* local rows = halo_top + owned + halo_bot */
+    int32_t halo_top, halo_bot;  /* halo rows of this tensor above / below the owned rows (0 at an image border) */
+    int32_t reserved;
+} cidnet_halo_req;
+typedef int (*cidnet_halo_fn)(void* user, const cidnet_halo_req* reqs, int n);
+typedef int (*cidnet_allreduce_fn)(void* user, float* buf, int64_t count);
+
+/* balanced partition of the H/8 coarsest-level rows over nranks (first H/8 % nranks ranks get one more) */
+CIDNET_API int cidnet_shard_plan(int H, int nranks, int rank, int halo, cidnet_shard* out);
+/* rows of the local image of `sh` (what rgb_local / rgb_out_local and the workspace are sized for) */
+CIDNET_API int cidnet_shard_local_rows(const cidnet_shard* sh);
+/* rgb_local / rgb_out_local: dev fp32 [1,3,local_rows,W]; only the owned rows of rgb_out_local are
+ * meaningful.  workspace >= cidnet_workspace_bytes(1, local_rows, W).  With nranks == 1 this is
+ * cidnet_forward (the callbacks are never called and may be NULL). */
+CIDNET_API int cidnet_forward_sharded(cidnet_ctx* ctx, const float* rgb_local, float* rgb_out_local, int W,
+                                      const cidnet_shard* sh, void* workspace, int64_t workspace_bytes,
+                                      const float* k_dev, int gated, float alpha_s, int gated2, float alpha,
+                                      cidnet_halo_fn halo_fn, cidnet_allreduce_fn allreduce_fn, void* user,
+                                      void* stream);
+/* host-only dry run of the same schedule (no device, no kernels): calls the callbacks exactly as
+ * cidnet_forward_sharded would, with `workspace` any host buffer of the same size -- used by the
+ * CPU (gloo) tests of the exchange logic.  Needs no weights. */
+CIDNET_API int cidnet_forward_sharded_dry(int W, const cidnet_shard* sh, void* workspace, int64_t workspace_bytes,
+                                          cidnet_halo_fn halo_fn, cidnet_allreduce_fn allreduce_fn, void* user,
+                                          int* n_halo_calls, int* n_allreduce_calls);
+
 /* ---- parity taps ----------------------------------------------------------
  * After a forward, copy a named internal activation (NHWC, 16-bit) out as fp32
  * NCHW so tests can compare every stage with the oracle.  Names are those of

@@ -54,3 +54,101 @@ def test_forward_sharded_gloo_world2():
     assert len(ret) == world
     for r in range(world):
         assert ret[r] <= 1e-6, ret[r]
+
+
+# ---------------------------------------------------------------------------------------------
+# Row-strip sharding of ONE image (cfg 5): the library's exchange schedule, dry-run on CPU.
+# cidnet_forward_sharded_dry walks the same schedule as the CUDA forward (no kernels) and calls the
+# halo / all-reduce callbacks with pointers into a host workspace; StripComm moves the rows over gloo.
+# ---------------------------------------------------------------------------------------------
+def test_strip_plan_covers_image():
+    import hvi_cidnet_b200  # noqa: F401
+    from hvi_cidnet_b200.dist import strip_plan, strip_local_range
+    from hvi_cidnet_b200 import _lib
+    for H, world in ((2160, 8), (2160, 1), (64, 3), (400, 2), (640, 4)):
+        pos = 0
+        for r in range(world):
+            sh = strip_plan(H, world, r, 16)
+            assert sh.row_begin == pos and sh.row_begin % 8 == 0 and sh.row_end % 8 == 0
+            a, b = strip_local_range(sh)
+            assert a == max(0, sh.row_begin - (16 if world > 1 else 0)) and b == min(H, sh.row_end + (16 if world > 1 else 0))
+            import ctypes
+            assert _lib.lib().cidnet_shard_local_rows(ctypes.byref(sh)) == b - a
+            pos = sh.row_end
+        assert pos == H
+    with pytest.raises(_lib.CidnetError):
+        strip_plan(64, 16, 0, 16)            # more ranks than coarsest rows
+    with pytest.raises(_lib.CidnetError):
+        strip_plan(64, 4, 0, 32)             # halo larger than the owned rows
+
+
+def _pattern(rank, nfloats):
+    return (torch.arange(nfloats, dtype=torch.float32) % 997.0) + 1000.0 * (rank + 1)
+
+
+def _dry_worker(rank, world, port, H, W, ret):
+    import ctypes
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import hvi_cidnet_b200  # noqa: F401
+    from hvi_cidnet_b200 import _lib
+    from hvi_cidnet_b200.dist import StripComm, strip_plan
+    L = _lib.lib()
+    sh = strip_plan(H, world, rank, 16)
+    rows = L.cidnet_shard_local_rows(ctypes.byref(sh))
+    nbytes = L.cidnet_workspace_bytes(1, rows, W)
+    raw = torch.zeros(nbytes + 2048, dtype=torch.uint8)
+    off = (-raw.data_ptr()) % 1024
+    ws = raw[off:off + (nbytes // 4) * 4]
+    ws.view(torch.float32).copy_(_pattern(rank, ws.numel() // 4))
+    comm = StripComm(ws)
+    nh, na = ctypes.c_int(), ctypes.c_int()
+    rc = L.cidnet_forward_sharded_dry(W, ctypes.byref(sh), ws.data_ptr(), ws.numel(), comm.halo_cb, comm.allreduce_cb,
+                                      None, ctypes.byref(nh), ctypes.byref(na))
+    assert rc == 0 and comm.error is None, (rc, comm.error, L.cidnet_last_error())
+    logs = [None] * world
+    dist.all_gather_object(logs, comm.log)
+    f = ws.view(torch.float32)
+    bad = 0
+    kinds = [[e[0] for e in lg] for lg in logs]
+    assert all(k == kinds[0] for k in kinds), "ranks disagree on the callback sequence"
+    for i, e in enumerate(comm.log):
+        if e[0] == "halo":
+            assert all(len(lg[i][1]) == len(e[1]) for lg in logs)
+            for j, (o, rb, nr, top, bot) in enumerate(e[1]):
+                t = f[o // 4:(o + nr * rb) // 4].view(nr, rb // 4)
+                if top:
+                    po, prb, pnr, ptop, pbot = logs[rank - 1][i][1][j]
+                    assert prb == rb and pbot == top
+                    src = _pattern(rank - 1, po // 4 + pnr * prb // 4)[po // 4:].view(pnr, prb // 4)
+                    bad += int(not torch.equal(t[:top], src[pnr - 2 * pbot:pnr - pbot]))
+                if bot:
+                    po, prb, pnr, ptop, pbot = logs[rank + 1][i][1][j]
+                    assert prb == rb and ptop == bot
+                    src = _pattern(rank + 1, po // 4 + pnr * prb // 4)[po // 4:].view(pnr, prb // 4)
+                    bad += int(not torch.equal(t[nr - bot:], src[ptop:2 * ptop]))
+                # owned rows untouched
+                own = _pattern(rank, o // 4 + nr * rb // 4)[o // 4:].view(nr, rb // 4)
+                bad += int(not torch.equal(t[top:nr - bot], own[top:nr - bot]))
+        else:
+            _, o, cnt = e
+            want = sum(_pattern(r, logs[r][i][1] // 4 + cnt)[logs[r][i][1] // 4:] for r in range(world))
+            assert all(lg[i][2] == cnt for lg in logs)
+            bad += int(not torch.equal(f[o // 4:o // 4 + cnt], want))
+    ret[rank] = (bad, nh.value, na.value, len(comm.log), comm.bytes_sent)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,H,W", [(2, 64, 16), (3, 64, 24)])
+def test_strip_schedule_dry_run_gloo(world, H, W):
+    port = 31000 + (os.getpid() % 2000) + world
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_dry_worker, args=(world, port, H, W, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(world):
+        bad, nh, na, nlog, sent = ret[r]
+        assert bad == 0, f"rank {r}: {bad} halo / all-reduce regions hold the wrong data"
+        assert na == 6 and nh >= 6 and nlog == nh + na     # one all-reduce per LCA stage
+        assert sent > 0

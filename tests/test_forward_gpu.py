@@ -101,3 +101,19 @@ def test_batch_independence(model):
         ys = torch.cat([model(x[i:i + 1]) for i in range(3)])
     # fp32 atomics accumulate the Gram partial sums in a run-dependent order -> ~1e-5 noise
     assert float((yb - ys).abs().max()) <= 1e-4
+
+
+def test_streamed_driver_matches_plain_forward(model):
+    """hvi-cidnet_b200/stream.py: 3-stream pipelined host->device->host loop == model(x) per batch, in order."""
+    from hvi_cidnet_b200.stream import StreamedCIDNet
+    sd = O.make_state_dict(5, True)
+    model.load_state_dict(sd, strict=True)
+    xs = [O.make_input("uniform", 2, 64, 96, seed=100 + i).pin_memory() for i in range(7)]
+    with torch.no_grad():
+        want = [model(x.cuda()).cpu() for x in xs]
+        got = [y.clone() for y in StreamedCIDNet(model, depth=3).run(iter(xs))]
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert torch.equal(g, w)
+    with pytest.raises(RuntimeError):
+        model(xs[0].cuda(), out=torch.empty(1, 3, 8, 8, device="cuda"))

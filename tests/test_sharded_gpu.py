@@ -1,0 +1,87 @@
+"""Row-strip sharded forward of ONE image (BASELINE.json configs[4]; include/cidnet_b200.h
+cidnet_forward_sharded) against the unsharded CUDA forward and the fp32 oracle.
+
+The ranks are real processes.  With >= world GPUs every rank takes its own GPU and the halos /
+Gram sums travel over NCCL (NVLink); on a single-GPU box the ranks share cuda:0 and the very same
+callbacks are staged through gloo -- the schedule, the kernels and the row arithmetic under test
+are identical.  Tolerances: owned rows equal the unsharded forward up to the summation order of the
+Gram (fp32 atomics) -> 2e-4; against the oracle the usual 2e-3 / 50 dB contract."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, H, W, use_nccl, ret):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dev = torch.device("cuda", rank if use_nccl else 0)
+    torch.cuda.set_device(dev)
+    if use_nccl:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    import hvi_cidnet_b200  # noqa: F401
+    from hvi_cidnet_b200.net.CIDNet import CIDNet
+    from hvi_cidnet_b200.dist import RowShardedCIDNet
+    from oracle import cidnet_oracle as O
+    torch.set_grad_enabled(False)
+    torch.set_num_threads(4)
+    sd = O.make_state_dict(5, True)
+    model = CIDNet().to(dev).eval()
+    model.load_state_dict(sd, strict=True)
+    x = O.make_input("uniform", 1, H, W, seed=33)
+    net = RowShardedCIDNet(model, halo=16)
+    y = net(x.pin_memory(), gather=True).cpu()           # full image on every rank
+    y2 = net(x.to(dev), gather=True).cpu()               # second call: same workspace, device input
+    full = model(x.to(dev)).cpu()                        # unsharded CUDA forward on this rank's GPU
+    out = {"vs_full": float((y - full).abs().max()), "repeat": float((y - y2).abs().max()),
+           "halo_calls": sum(1 for e in net.comm.log if e[0] == "halo"),
+           "allreduce_calls": sum(1 for e in net.comm.log if e[0] == "allreduce"),
+           "direct": bool(net.comm.direct)}
+    if rank == 0:
+        ref = O.forward(x, sd)
+        out["vs_oracle"] = float((y.clamp(0, 1) - ref.clamp(0, 1)).abs().max())
+        out["psnr"] = float(O.psnr(y.clamp(0, 1), ref.clamp(0, 1)))
+    ret[rank] = out
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,H,W", [(2, 128, 64), (3, 192, 40), (2, 400, 600)])
+def test_row_sharded_forward_matches_unsharded(world, H, W):
+    use_nccl = torch.cuda.device_count() >= world
+    port = 33000 + (os.getpid() % 2000) + world
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, H, W, use_nccl, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(world):
+        o = ret[r]
+        assert o["vs_full"] <= 2e-4, (r, o)
+        assert o["repeat"] <= 2e-4, (r, o)
+        assert o["allreduce_calls"] == 6 and o["halo_calls"] >= 6, (r, o)
+        assert o["direct"] == use_nccl
+    assert ret[0]["vs_oracle"] <= 2e-3 and ret[0]["psnr"] >= 50.0, ret[0]
+
+
+def test_sharded_entry_with_one_rank_is_the_plain_forward():
+    """nranks == 1: no callbacks, same kernels -> bit-identical to cidnet_forward."""
+    from hvi_cidnet_b200.net.CIDNet import CIDNet
+    from hvi_cidnet_b200.dist import RowShardedCIDNet
+    from oracle import cidnet_oracle as O
+    torch.set_grad_enabled(False)
+    sd = O.make_state_dict(2, True)
+    model = CIDNet().cuda().eval()
+    model.load_state_dict(sd, strict=True)
+    x = O.make_input("uniform", 1, 64, 96, seed=4).cuda()
+    y = RowShardedCIDNet(model)(x)
+    full = model(x)
+    assert float((y - full).abs().max()) <= 2e-4
