@@ -18,6 +18,7 @@
 #include "cab.cuh"
 #include "ptx_sm100.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace cidnet {
@@ -50,7 +51,7 @@ __device__ __forceinline__ void fhfma8(float* acc, const uint4& t, const uint4& 
 // one thread = (column x, 8 channels): 9 packed weight vectors + a raw 3x3 window in registers,
 // FHFMA (16-bit x 16-bit + fp32) so no conversion instructions are needed
 __global__ void __launch_bounds__(kDwThreads, 3)
-dw3x3_kernel(const Dw3Args a) {
+dw3x3_f32acc_kernel(const Dw3Args a) {
     __shared__ float s_ssq[2 * 144];
     const int prob = blockIdx.z % a.nprob, b = blockIdx.z / a.nprob;
     const int nv = a.nv;                                   // 16-byte vectors per pixel (all segments)
@@ -134,12 +135,136 @@ dw3x3_kernel(const Dw3Args a) {
     }
 }
 
+
+#ifndef CIDNET_ACT_BF16
+// fp16 build: the same sliding window with PACKED fp16 math (HFMA2: two multiply-adds per issue slot,
+// accumulators are the packed output vector -> no conversions, ~100 registers instead of 162 so five
+// CTAs fit an SM and hide the global-load latency the fp32-accumulate kernel was bound by).  The 9-tap
+// sum is rounded to fp16 after every tap (two chains); end-to-end effect measured against the fp32
+// oracle: max-abs 1.0e-4 -> 1.2e-4 (see iel.cu v5).  sum q^2 / sum k^2 stay fp32 (FHFMA).
+__device__ __forceinline__ uint32_t hfma2u(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t hmul2u(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t hadd2u(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint4 hmul8(const uint4& t, const uint4& w) {
+    return make_uint4(hmul2u(t.x, w.x), hmul2u(t.y, w.y), hmul2u(t.z, w.z), hmul2u(t.w, w.w));
+}
+__device__ __forceinline__ void hfma8(uint4& acc, const uint4& t, const uint4& w) {
+    acc.x = hfma2u(t.x, w.x, acc.x); acc.y = hfma2u(t.y, w.y, acc.y);
+    acc.z = hfma2u(t.z, w.z, acc.z); acc.w = hfma2u(t.w, w.w, acc.w);
+}
+
+template <bool kPrefetch, int kMinBlocks>
+__global__ void __launch_bounds__(kDwThreads, kMinBlocks)
+dw3x3_kernel(const Dw3Args a) {
+    __shared__ float s_ssq[2 * 144];
+    const int prob = blockIdx.z % a.nprob, b = blockIdx.z / a.nprob;
+    const int nv = a.nv;                                   // 16-byte vectors per pixel (all segments)
+    const int idx = blockIdx.x * kDwThreads + threadIdx.x; // vector index along the row
+    const int x = idx / nv, v = idx - x * nv;
+    const bool active = x < a.W;
+    const int seg = active ? v / a.seg_vecs : 0;           // 0 = q, 1 = k, 2 = v
+    const int c0 = (v - seg * a.seg_vecs) * 8;             // channel within the segment
+    const long long hw = (long long)a.H * a.W;
+    const act_t* src = a.src[prob][seg] + (long long)b * hw * a.src_pitch + c0;
+    act_t* dst = a.dst[prob] + (long long)b * hw * a.dst_pitch + seg * a.seg_vecs * 8 + c0;
+    const int y0 = blockIdx.y * kDwRows;
+    const int y1 = min(y0 + kDwRows, a.H);
+
+    for (int i = threadIdx.x; i < 2 * 144; i += kDwThreads) s_ssq[i] = 0.f;
+    __syncthreads();
+
+    uint4 w[9];
+    {
+        const float* wp = a.w[prob] + seg * a.seg_vecs * 8 + c0;   // [9][nv*8] tap major
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            act_t* h = reinterpret_cast<act_t*>(&w[t]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) h[e] = f2act(active ? __ldg(wp + t * nv * 8 + e) : 0.f);
+        }
+    }
+    float ssq[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ssq[e] = 0.f;
+
+    if (active) {
+        const bool has_l = x > 0, has_r = x + 1 < a.W;
+        const uint4 zero4 = make_uint4(0, 0, 0, 0);
+        uint4 win0[3], win1[3], win2[3], pend[3];
+        // loads run one row ahead of their use
+        auto issue = [&](int y) {
+            pend[0] = pend[1] = pend[2] = zero4;
+            if (y < 0 || y >= a.H) return;
+            const act_t* p = src + ((long long)y * a.W + x) * a.src_pitch;
+            pend[1] = *reinterpret_cast<const uint4*>(p);
+            if (has_l) pend[0] = *reinterpret_cast<const uint4*>(p - a.src_pitch);
+            if (has_r) pend[2] = *reinterpret_cast<const uint4*>(p + a.src_pitch);
+        };
+        auto step = [&](const uint4* r0, const uint4* r1, uint4* r2, int y) {
+            if (kPrefetch) { r2[0] = pend[0]; r2[1] = pend[1]; r2[2] = pend[2]; issue(y + 2); }   // row y+1 arrives, y+2 leaves
+            else           { issue(y + 1); r2[0] = pend[0]; r2[1] = pend[1]; r2[2] = pend[2]; }
+            uint4 pa = hmul8(r0[0], w[0]);
+            uint4 pb = hmul8(r2[0], w[6]);
+            hfma8(pa, r0[1], w[1]); hfma8(pb, r2[1], w[7]);
+            hfma8(pa, r0[2], w[2]); hfma8(pb, r2[2], w[8]);
+            hfma8(pa, r1[0], w[3]);
+            hfma8(pa, r1[1], w[4]);
+            hfma8(pa, r1[2], w[5]);
+            const uint4 raw = make_uint4(hadd2u(pa.x, pb.x), hadd2u(pa.y, pb.y), hadd2u(pa.z, pb.z), hadd2u(pa.w, pb.w));
+            if (y >= a.stat_y0 && y < a.stat_y1) fhfma8(ssq, raw, raw);   // sum of squares of the STORED values
+            *reinterpret_cast<uint4*>(dst + ((long long)y * a.W + x) * a.dst_pitch) = raw;
+        };
+        issue(y0 - 1); win0[0] = pend[0]; win0[1] = pend[1]; win0[2] = pend[2];
+        issue(y0);     win1[0] = pend[0]; win1[1] = pend[1]; win1[2] = pend[2];
+        if (kPrefetch) issue(y0 + 1);
+        for (int y = y0; y < y1; y += 3) {          // window roles rotate, no register moves
+            step(win0, win1, win2, y);
+            if (y + 1 < y1) step(win1, win2, win0, y + 1);
+            if (y + 2 < y1) step(win2, win0, win1, y + 2);
+        }
+        if (seg < 2) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(&s_ssq[seg * 144 + c0 + e], ssq[e]);
+        }
+    }
+    __syncthreads();
+    // one global atomic per channel per CTA
+    const int Cp = a.seg_vecs * 8;
+    for (int i = threadIdx.x; i < 2 * Cp; i += kDwThreads) {
+        const int sg = i / Cp, c = i - sg * Cp;
+        const float val = s_ssq[sg * 144 + c];
+        if (val != 0.f) atomicAdd((sg == 0 ? a.sq[prob] : a.sk[prob]) + (long long)b * Cp + c, val);
+    }
+}
+#endif
+
 int launch_dw3(const Dw3Args& a_in, cudaStream_t stream) {
     Dw3Args a = a_in;
     if (a.stat_y1 <= 0) { a.stat_y0 = 0; a.stat_y1 = a.H; }
     CIDNET_CHECK(a.seg_vecs * 8 <= 144 && a.nv == 3 * a.seg_vecs, CIDNET_ERR_INVALID, "dw3: bad channel layout");
     dim3 grid(ceil_div(a.W * a.nv, kDwThreads), ceil_div(a.H, kDwRows), a.B * a.nprob);
-    dw3x3_kernel<<<grid, kDwThreads, 0, stream>>>(a);
+#ifndef CIDNET_ACT_BF16
+    // 0 (default): packed fp16, no prefetch, 4 CTAs / SM; 1: packed fp16, one-row prefetch, 3 CTAs / SM;
+    // 2: fp32-accumulate FHFMA kernel
+    static const int variant = getenv("CIDNET_DW_VARIANT") ? atoi(getenv("CIDNET_DW_VARIANT")) : 0;
+    if (variant == 0)      dw3x3_kernel<false, 4><<<grid, kDwThreads, 0, stream>>>(a);
+    else if (variant == 1) dw3x3_kernel<true, 3><<<grid, kDwThreads, 0, stream>>>(a);
+    else                   dw3x3_f32acc_kernel<<<grid, kDwThreads, 0, stream>>>(a);
+#else
+    dw3x3_f32acc_kernel<<<grid, kDwThreads, 0, stream>>>(a);
+#endif
     CIDNET_CUDA_OK(cudaGetLastError());
     return CIDNET_OK;
 }

@@ -412,7 +412,8 @@ __device__ __forceinline__ uint4 hadd8(const uint4& a, const uint4& b) {
 
 static constexpr int kV5Stages = 4;
 
-__global__ void __launch_bounds__(kV4Threads, 4)
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kV4Threads, kMinBlocks)
 iel_gate_v5_kernel(const __grid_constant__ IelV4Args A) {
     const IelGateArgs& a = A.g;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -555,10 +556,13 @@ int launch_iel_gate(const IelGateArgs& a, cudaStream_t stream) {
                              2 * 2 * kCols * sizeof(uint4) + 2 * kV5Stages * sizeof(uint64_t) + 64;
         static bool configured5 = false;
         if (!configured5) {
-            CIDNET_CUDA_OK(cudaFuncSetAttribute(iel_gate_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+            CIDNET_CUDA_OK(cudaFuncSetAttribute(iel_gate_v5_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+            CIDNET_CUDA_OK(cudaFuncSetAttribute(iel_gate_v5_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
             configured5 = true;
         }
-        iel_gate_v5_kernel<<<grid, kV4Threads, smem5, stream>>>(A);
+        static const bool three = getenv("CIDNET_IEL_3CTA") != nullptr;    // 3 CTAs / SM, no register spills
+        if (three) iel_gate_v5_kernel<3><<<grid, kV4Threads, smem5, stream>>>(A);
+        else       iel_gate_v5_kernel<4><<<grid, kV4Threads, smem5, stream>>>(A);
         CIDNET_CUDA_OK(cudaGetLastError());
         return CIDNET_OK;
     }

@@ -113,7 +113,7 @@ def test_streamed_driver_matches_plain_forward(model):
         want = [model(x.cuda()).cpu() for x in xs]
         got = [y.clone() for y in StreamedCIDNet(model, depth=3).run(iter(xs))]
     assert len(got) == len(want)
-    for g, w in zip(got, want):
-        assert torch.equal(g, w)
+    for g, w in zip(got, want):        # not bit-equal: the Gram's fp32 atomics are order dependent run to run
+        assert float((g - w).abs().max()) <= 2e-4
     with pytest.raises(RuntimeError):
         model(xs[0].cuda(), out=torch.empty(1, 3, 8, 8, device="cuda"))
