@@ -526,6 +526,145 @@ iel_gate_v5_kernel(const __grid_constant__ IelV4Args A) {
         if (r + 2 <= y1) iter(r + 2, tC, tA, tB, dC, dA, dB);
     }
 }
+
+// ================================================================================================
+// v6 (fp16 build): v5's data path, but the 18 weight vectors (dwconv + dwconv1/2, 8 channels) live in
+// REGISTERS -- ncu on v5 showed the shared-memory data pipe as the top unit (66 %: two wavefronts per
+// warp-uniform LDS.128, 36 of the 52 wavefronts per warp-row were weight re-loads).  To pay for the
+// 72 weight registers the two 3x3 stages are evaluated in SCATTER form: an arriving row updates the
+// three output rows it touches (three running partial sums) instead of three input rows being kept, so
+// only the arriving (l, c, r) vectors are live.  Same arithmetic, same fp16 rounding points as v5 up to
+// the summation order (row-major chains).
+// ================================================================================================
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kV4Threads, kMinBlocks)
+iel_gate_v6_kernel(const __grid_constant__ IelV4Args A) {
+    const IelGateArgs& a = A.g;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
+    uint8_t* ring = smem;                                                  // kV5Stages x kV4StageBytes
+    uint4* s_x = reinterpret_cast<uint4*>(ring + kV5Stages * kV4StageBytes);   // [vec][slot 0..3][lane] packed x2
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_x + 2 * 4 * kCols);
+    uint64_t* empty = full + kV5Stages;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int hp = a.hp, ngroups = hp / 16;
+    const int prob = blockIdx.z % a.nprob, b = blockIdx.z / a.nprob;
+    const int cg = blockIdx.x % ngroups, strip = blockIdx.x / ngroups;
+    const int c0 = cg * 16;
+    const int X0 = strip * (kCols - 2) - 1;               // image column of lane 0
+    const int y0 = blockIdx.y * kRows;
+    const int y1 = min(y0 + kRows, a.H);
+    const int nrows = (y1 - y0) + 4;                      // t rows y0-2 .. y1+1
+    const int nblocks = (nrows + kRB - 1) / kRB;
+
+    if (tid == 0) {
+        for (int s = 0; s < kV5Stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 4); }
+        ptx::fence_barrier_init();
+        ptx::prefetch_tensormap(&A.tmT[prob]);
+    }
+    __syncthreads();
+
+    if (warp == 4) {
+        if (lane == 0) {
+            for (int k = 0; k < nblocks; ++k) {
+                const int s = k % kV5Stages;
+                ptx::mbar_wait(&empty[s], ((k / kV5Stages) & 1u) ^ 1u);
+                ptx::mbar_expect_tx(&full[s], 2 * kHalfBoxBytes);
+                uint8_t* dst = ring + (size_t)s * kV4StageBytes;
+                const int yb = y0 - 2 + k * kRB;
+                ptx::tma_load_4d(dst, &A.tmT[prob], &full[s], c0, X0 - 1, yb, b);
+                ptx::tma_load_4d(dst + kHalfBoxBytes, &A.tmT[prob], &full[s], hp + c0, X0 - 1, yb, b);
+            }
+        }
+        return;
+    }
+    const int half = warp >> 1, vec = warp & 1;
+    const int x = X0 + lane;
+    const bool col_in = x >= 0 && x < a.W;
+    const long long hw = (long long)a.H * a.W;
+    act_t* gdst = a.g[prob] + (long long)b * hw * hp + c0 + vec * 8;
+    const bool writer = half == 0 && lane >= 1 && lane <= kCols - 2 && col_in;
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+
+    // the 18 weight vectors of this thread's 8 channels, packed fp16, in registers for the whole strip
+    uint4 w0[9], w12[9];
+    {
+        const float* p0 = a.w0[prob] + half * hp + c0 + vec * 8;                     // [tap][2*hp]
+        const float* p1 = (half == 0 ? a.w1[prob] : a.w2[prob]) + c0 + vec * 8;      // [tap][hp]
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const float4 a0 = __ldg(reinterpret_cast<const float4*>(p0 + t * 2 * hp));
+            const float4 a1 = __ldg(reinterpret_cast<const float4*>(p0 + t * 2 * hp) + 1);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p1 + t * hp));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p1 + t * hp) + 1);
+            __half2 h;
+            h = __floats2half2_rn(a0.x, a0.y); w0[t].x = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2half2_rn(a0.z, a0.w); w0[t].y = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2half2_rn(a1.x, a1.y); w0[t].z = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2half2_rn(a1.z, a1.w); w0[t].w = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2half2_rn(b0.x, b0.y); w12[t].x = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2half2_rn(b0.z, b0.w); w12[t].y = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2half2_rn(b1.x, b1.y); w12[t].z = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2half2_rn(b1.z, b1.w); w12[t].w = *reinterpret_cast<uint32_t*>(&h);
+        }
+    }
+
+    auto swz = [](uint32_t o) { return o ^ (((o >> 7) & 1u) << 4); };
+    const uint32_t off_l = swz((uint32_t)lane * 32u + (uint32_t)vec * 16u);
+    const uint32_t off_c = swz((uint32_t)(lane + 1) * 32u + (uint32_t)vec * 16u);
+    const uint32_t off_r = swz((uint32_t)(lane + 2) * 32u + (uint32_t)vec * 16u);
+    auto lds_trow = [&](int j, TRow& t) {
+        const int k = j / kRB, rr = j - k * kRB;
+        const int s = k % kV5Stages;
+        if (rr == 0) ptx::mbar_wait(&full[s], (k / kV5Stages) & 1u);
+        const uint8_t* base = ring + (size_t)s * kV4StageBytes + half * kHalfBoxBytes + rr * (kBoxCols * 32);
+        t.l = *reinterpret_cast<const uint4*>(base + off_l);
+        t.c = *reinterpret_cast<const uint4*>(base + off_c);
+        t.r = *reinterpret_cast<const uint4*>(base + off_r);
+        if (rr == kRB - 1 || j == nrows - 1) {
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&empty[s]);
+        }
+    };
+    // scatter step of one 3x3 stage: the arriving row R is the top row of `n` (new), the middle row of `m`
+    // and the bottom row of `f` (finished after this call)
+    auto scatter = [&](const uint4* w, const TRow& R, uint4& n, uint4& m, uint4& f) {
+        n = hmul8(R.l, w[0]); hfma8(m, R.l, w[3]); hfma8(f, R.l, w[6]);
+        hfma8(n, R.c, w[1]);  hfma8(m, R.c, w[4]); hfma8(f, R.c, w[7]);
+        hfma8(n, R.r, w[2]);  hfma8(m, R.r, w[5]); hfma8(f, R.r, w[8]);
+    };
+    // iteration j (= arriving t row y0-2+j): finishes d(row y0-3+j) and output row y0-4+j
+    //   pn/pm/pf, qn/qm/qf: running sums of the two stages (roles rotate in the caller); dprev = centre of
+    //   the previous d row (the residual of the output row finished here)
+    auto iter = [&](int j, uint4& pn, uint4& pm, uint4& pf, uint4& qn, uint4& qm, uint4& qf, uint4& dprev) {
+        TRow T;
+        lds_trow(j, T);
+        scatter(w0, T, pn, pm, pf);
+        const int rd = y0 - 3 + j;                                    // the d row finished now
+        TRow D;
+        D.c = (rd >= 0 && rd < a.H && col_in) ? pf : zero4;           // d is zero outside the image
+        D.l = shfl_up4(D.c);
+        D.r = shfl_down4(D.c);
+        scatter(w12, D, qn, qm, qf);
+        const int yo = rd - 1;                                         // the output row finished now
+        const uint4 xs = make_uint4(hadd2u(htanh2u(qf.x), dprev.x), hadd2u(htanh2u(qf.y), dprev.y),
+                                    hadd2u(htanh2u(qf.z), dprev.z), hadd2u(htanh2u(qf.w), dprev.w));
+        dprev = D.c;
+        uint4* slot = s_x + (vec * 4 + (j & 3)) * kCols + lane;
+        if (half == 1) *slot = xs;
+        asm volatile("bar.sync %0, 64;" :: "r"(1 + vec) : "memory");
+        if (writer && yo >= y0 && yo < y1)
+            *reinterpret_cast<uint4*>(gdst + ((long long)yo * a.W + x) * hp) = hmul8(xs, *slot);
+    };
+    uint4 pA = zero4, pB = zero4, pC = zero4, qA = zero4, qB = zero4, qC = zero4, dprev = zero4;
+    // rows j = 0 .. nrows-1; the running-sum roles rotate with period 3 (no register moves)
+    for (int j = 0; j < nrows; j += 3) {
+        iter(j, pA, pB, pC, qA, qB, qC, dprev);
+        if (j + 1 < nrows) iter(j + 1, pC, pA, pB, qC, qA, qB, dprev);
+        if (j + 2 < nrows) iter(j + 2, pB, pC, pA, qB, qC, qA, dprev);
+    }
+}
 #endif  // !CIDNET_ACT_BF16
 
 int encode_map_generic_swz(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
@@ -551,6 +690,21 @@ int launch_iel_gate(const IelGateArgs& a, cudaStream_t stream) {
     dim3 grid(strips * (a.hp / 16), ceil_div(a.H, kRows), a.B * a.nprob);
 #ifndef CIDNET_ACT_BF16
     static const bool use_v4 = getenv("CIDNET_IEL_V4") != nullptr;      // fp32-accumulate variant (FHFMA)
+    static const int v6 = getenv("CIDNET_IEL_V6") ? atoi(getenv("CIDNET_IEL_V6")) : 2;   // weights in registers, 2 (default) / 3 CTAs per SM; 0 = v5
+    if (!use_v4 && v6) {
+        const size_t smem6 = 1024 + (size_t)kV5Stages * kV4StageBytes + 2 * 4 * kCols * sizeof(uint4) +
+                             2 * kV5Stages * sizeof(uint64_t) + 64;
+        static bool configured6 = false;
+        if (!configured6) {
+            CIDNET_CUDA_OK(cudaFuncSetAttribute(iel_gate_v6_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
+            CIDNET_CUDA_OK(cudaFuncSetAttribute(iel_gate_v6_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
+            configured6 = true;
+        }
+        if (v6 == 2) iel_gate_v6_kernel<2><<<grid, kV4Threads, smem6, stream>>>(A);
+        else         iel_gate_v6_kernel<3><<<grid, kV4Threads, smem6, stream>>>(A);
+        CIDNET_CUDA_OK(cudaGetLastError());
+        return CIDNET_OK;
+    }
     if (!use_v4) {
         const size_t smem5 = 1024 + (size_t)kV5Stages * kV4StageBytes + 2 * 9 * 2 * 16 * sizeof(act_t) +
                              2 * 2 * kCols * sizeof(uint4) + 2 * kV5Stages * sizeof(uint64_t) + 64;
