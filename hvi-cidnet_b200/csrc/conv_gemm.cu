@@ -671,7 +671,11 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
         min_stages = wt.kchunks + 1;
     }
     const size_t bres = (size_t)nbchunks * b_chunk;
-    const int want = 2 * kiters > min_stages ? 2 * kiters : min_stages;   // two tiles in flight is plenty
+    // A tiles in flight.  Measured on B200 (cfg2 / cfg4): 2, 4 and 6 tiles give the same step time -- the
+    // per-tile cost (~3000-3900 cycles whatever N and K) is the epilogue's dependent-latency chain, not the
+    // load pipeline -- so the ring stays at 2 tiles.  CIDNET_GEMM_DEPTH overrides (tiles).
+    static const int depth = getenv("CIDNET_GEMM_DEPTH") ? atoi(getenv("CIDNET_GEMM_DEPTH")) : 2;
+    const int want = depth * kiters > min_stages ? depth * kiters : min_stages;
     int stages = 0;
     size_t fixed = 0;
     // preference: resident weights (2 staging buffers, then 1), else streamed weights (2, then 1)
@@ -689,7 +693,7 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
             stages = (int)((budget - fixed) / (a_stage + b_chunk));
         }
     }
-    if (stages > 8) stages = 8;
+    if (stages > 12) stages = 12;
     if (stages > want) stages = want;
     CIDNET_CHECK(stages >= min_stages, CIDNET_ERR_INVALID, "conv_gemm: shared memory budget exceeded");
     a.stages = stages;
