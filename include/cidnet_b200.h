@@ -142,6 +142,17 @@ CIDNET_API int cidnet_forward_sharded_dry(int W, const cidnet_shard* sh, void* w
                                           cidnet_halo_fn halo_fn, cidnet_allreduce_fn allreduce_fn, void* user,
                                           int* n_halo_calls, int* n_allreduce_calls);
 
+/* ---- 8-bit image I/O (the callers' pre / post-processing, one kernel each) ------------------
+ * cidnet_pre_u8 : src dev u8 [B,h,w,3] (HWC, what PIL / a decoder yields) -> dst dev fp32 [B,3,H,W]:
+ *                 transforms.ToTensor (x/255, HWC->CHW), reflect padding on the bottom / right up to
+ *                 (H,W) (data/eval_sets.py:22-27, demo.py:47-52: H,W = h,w rounded up to multiples of 8)
+ *                 and input**gamma (eval.py:64, demo.py:57).
+ * cidnet_post_u8: src dev fp32 [B,3,H,W] -> dst dev u8 [B,h,w,3]: clamp(0,1) (eval.py:69), crop to
+ *                 [:h,:w] (eval.py:71), transforms.ToPILImage (mul(255).byte(), i.e. truncation). */
+CIDNET_API int cidnet_pre_u8(const uint8_t* src_hwc, float* dst_nchw, int B, int h, int w, int H, int W, float gamma,
+                             void* stream);
+CIDNET_API int cidnet_post_u8(const float* src_nchw, uint8_t* dst_hwc, int B, int h, int w, int H, int W, void* stream);
+
 /* ---- parity taps ----------------------------------------------------------
  * After a forward, copy a named internal activation (NHWC, 16-bit) out as fp32
  * NCHW so tests can compare every stage with the oracle.  Names are those of

@@ -384,6 +384,28 @@ def make_input(kind: str, B: int, H: int, W: int, seed: int = 1234) -> torch.Ten
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
 
 
+def pre_u8(img_u8_hwc: torch.Tensor, gamma: float = 1.0) -> torch.Tensor:
+    """Caller-side pre-processing of the reference's eval loops, restated with the same torch calls:
+    transforms.ToTensor (uint8 HWC -> float CHW / 255), reflect padding of the bottom / right edge to a
+    multiple of 8 (data/eval_sets.py:22-27, demo.py:47-52) and `input ** gamma` (eval.py:64, demo.py:57).
+    img_u8_hwc: [B,h,w,3] uint8 -> [B,3,H,W] float32."""
+    x = img_u8_hwc.permute(0, 3, 1, 2).to(torch.float32).div(255)
+    factor = 8
+    h, w = x.shape[2], x.shape[3]
+    H, W = ((h + factor) // factor) * factor, ((w + factor) // factor) * factor
+    padh = H - h if h % factor != 0 else 0
+    padw = W - w if w % factor != 0 else 0
+    x = F.pad(x, (0, padw, 0, padh), "reflect")
+    return x ** gamma
+
+
+def post_u8(out: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    """clamp(0,1) (eval.py:69), crop (eval.py:71), transforms.ToPILImage on a float tensor
+    (= mul(255).byte(), truncation).  [B,3,H,W] float32 -> [B,h,w,3] uint8."""
+    o = torch.clamp(out, 0, 1)[:, :, :h, :w]
+    return o.mul(255).byte().permute(0, 2, 3, 1).contiguous()
+
+
 def psnr(a: torch.Tensor, b: torch.Tensor) -> float:
     mse = torch.mean((a.double() - b.double()) ** 2).item()
     return float("inf") if mse == 0 else 10.0 * math.log10(1.0 / mse)

@@ -117,3 +117,39 @@ def test_streamed_driver_matches_plain_forward(model):
         assert float((g - w).abs().max()) <= 2e-4
     with pytest.raises(RuntimeError):
         model(xs[0].cuda(), out=torch.empty(1, 3, 8, 8, device="cuda"))
+
+
+@pytest.mark.parametrize("h,w,gamma", [(61, 93, 1.0), (64, 96, 1.0), (50, 77, 0.8)])
+def test_u8_pre_post_and_enhance(model, h, w, gamma):
+    """8-bit I/O path (cidnet_pre_u8 / cidnet_post_u8 / CIDNet.enhance_u8) against the oracle's restatement
+    of the reference's caller code (ToTensor, reflect pad to x8, **gamma; clamp, crop, ToPILImage)."""
+    import ctypes as C
+    from hvi_cidnet_b200 import _lib
+    sd = O.make_state_dict(5, True)
+    model.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(7)
+    img = torch.randint(0, 256, (2, h, w, 3), generator=g, dtype=torch.uint8)
+    ref_x = O.pre_u8(img, gamma)
+    H, W = ref_x.shape[2], ref_x.shape[3]
+    lib = _lib.lib()
+    d_img = img.cuda()
+    x = torch.empty(2, 3, H, W, device="cuda")
+    _lib.check(lib.cidnet_pre_u8(d_img.data_ptr(), x.data_ptr(), 2, h, w, H, W, float(gamma), _lib.stream_ptr(x.device)))
+    if gamma == 1.0:
+        assert torch.equal(x.cpu(), ref_x)                        # bit exact: same division, pure data movement
+    else:
+        assert float((x.cpu() - ref_x).abs().max()) <= 2e-6       # powf vs torch.pow
+    # post on identical fp32 input: exact (integer result of the same fp32 multiply + truncation)
+    yy = (torch.rand(2, 3, H, W, generator=g) * 1.4 - 0.2)
+    ref_o = O.post_u8(yy, h, w)
+    o = torch.empty(2, h, w, 3, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.cidnet_post_u8(yy.cuda().data_ptr(), o.data_ptr(), 2, h, w, H, W, _lib.stream_ptr(o.device)))
+    assert torch.equal(o.cpu(), ref_o)
+    # end to end: 8-bit in, 8-bit out; the forward's 2e-3 tolerance is < 1 LSB (1/255), truncation can flip one level
+    with torch.no_grad():
+        got = model.enhance_u8(d_img, gamma).cpu()
+        want = O.post_u8(O.forward(ref_x, sd), h, w)
+    diff = (got.int() - want.int()).abs()
+    assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 0.1
+    with pytest.raises(RuntimeError):
+        model.enhance_u8(img)                                     # CPU tensor: no fallback
