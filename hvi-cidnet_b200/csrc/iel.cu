@@ -536,7 +536,7 @@ iel_gate_v5_kernel(const __grid_constant__ IelV4Args A) {
 // only the arriving (l, c, r) vectors are live.  Same arithmetic, same fp16 rounding points as v5 up to
 // the summation order (row-major chains).
 // ================================================================================================
-template <int kMinBlocks>
+template <int kMinBlocks, bool kW12Smem>
 __global__ void __launch_bounds__(kV4Threads, kMinBlocks)
 iel_gate_v6_kernel(const __grid_constant__ IelV4Args A) {
     const IelGateArgs& a = A.g;
@@ -546,6 +546,7 @@ iel_gate_v6_kernel(const __grid_constant__ IelV4Args A) {
     uint4* s_x = reinterpret_cast<uint4*>(ring + kV5Stages * kV4StageBytes);   // [vec][slot 0..3][lane] packed x2
     uint64_t* full = reinterpret_cast<uint64_t*>(s_x + 2 * 4 * kCols);
     uint64_t* empty = full + kV5Stages;
+    act_t* s_w12 = reinterpret_cast<act_t*>(empty + kV5Stages);               // kW12Smem: [9][2][16] dwconv1/2 weights
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int hp = a.hp, ngroups = hp / 16;
@@ -558,6 +559,12 @@ iel_gate_v6_kernel(const __grid_constant__ IelV4Args A) {
     const int nrows = (y1 - y0) + 4;                      // t rows y0-2 .. y1+1
     const int nblocks = (nrows + kRB - 1) / kRB;
 
+    if (kW12Smem) {
+        for (int i = tid; i < 9 * 2 * 16; i += kV4Threads) {
+            const int c = i & 15, hf = (i >> 4) & 1, tap = i >> 5;
+            s_w12[i] = f2act((hf == 0 ? a.w1[prob] : a.w2[prob])[tap * hp + c0 + c]);
+        }
+    }
     if (tid == 0) {
         for (int s = 0; s < kV5Stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 4); }
         ptx::fence_barrier_init();
@@ -587,8 +594,11 @@ iel_gate_v6_kernel(const __grid_constant__ IelV4Args A) {
     const bool writer = half == 0 && lane >= 1 && lane <= kCols - 2 && col_in;
     const uint4 zero4 = make_uint4(0, 0, 0, 0);
 
-    // the 18 weight vectors of this thread's 8 channels, packed fp16, in registers for the whole strip
-    uint4 w0[9], w12[9];
+    // the weight vectors of this thread's 8 channels, packed fp16, in registers for the whole strip
+    // (kW12Smem: only dwconv's; dwconv1/2's are re-read from shared memory -> 36 registers less, 3 CTAs / SM)
+    uint4 w0[9], w12[kW12Smem ? 1 : 9];
+    const uint4* w12p = kW12Smem ? reinterpret_cast<const uint4*>(s_w12) + (half * 2 + vec) : w12;
+    constexpr int kW12Stride = kW12Smem ? 4 : 1;
     {
         const float* p0 = a.w0[prob] + half * hp + c0 + vec * 8;                     // [tap][2*hp]
         const float* p1 = (half == 0 ? a.w1[prob] : a.w2[prob]) + c0 + vec * 8;      // [tap][hp]
@@ -596,17 +606,22 @@ iel_gate_v6_kernel(const __grid_constant__ IelV4Args A) {
         for (int t = 0; t < 9; ++t) {
             const float4 a0 = __ldg(reinterpret_cast<const float4*>(p0 + t * 2 * hp));
             const float4 a1 = __ldg(reinterpret_cast<const float4*>(p0 + t * 2 * hp) + 1);
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p1 + t * hp));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p1 + t * hp) + 1);
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+            if (!kW12Smem) {
+                b0 = __ldg(reinterpret_cast<const float4*>(p1 + t * hp));
+                b1 = __ldg(reinterpret_cast<const float4*>(p1 + t * hp) + 1);
+            }
             __half2 h;
             h = __floats2half2_rn(a0.x, a0.y); w0[t].x = *reinterpret_cast<uint32_t*>(&h);
             h = __floats2half2_rn(a0.z, a0.w); w0[t].y = *reinterpret_cast<uint32_t*>(&h);
             h = __floats2half2_rn(a1.x, a1.y); w0[t].z = *reinterpret_cast<uint32_t*>(&h);
             h = __floats2half2_rn(a1.z, a1.w); w0[t].w = *reinterpret_cast<uint32_t*>(&h);
-            h = __floats2half2_rn(b0.x, b0.y); w12[t].x = *reinterpret_cast<uint32_t*>(&h);
-            h = __floats2half2_rn(b0.z, b0.w); w12[t].y = *reinterpret_cast<uint32_t*>(&h);
-            h = __floats2half2_rn(b1.x, b1.y); w12[t].z = *reinterpret_cast<uint32_t*>(&h);
-            h = __floats2half2_rn(b1.z, b1.w); w12[t].w = *reinterpret_cast<uint32_t*>(&h);
+            if (!kW12Smem) {
+                h = __floats2half2_rn(b0.x, b0.y); w12[t].x = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2half2_rn(b0.z, b0.w); w12[t].y = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2half2_rn(b1.x, b1.y); w12[t].z = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2half2_rn(b1.z, b1.w); w12[t].w = *reinterpret_cast<uint32_t*>(&h);
+            }
         }
     }
 
@@ -629,10 +644,10 @@ iel_gate_v6_kernel(const __grid_constant__ IelV4Args A) {
     };
     // scatter step of one 3x3 stage: the arriving row R is the top row of `n` (new), the middle row of `m`
     // and the bottom row of `f` (finished after this call)
-    auto scatter = [&](const uint4* w, const TRow& R, uint4& n, uint4& m, uint4& f) {
-        n = hmul8(R.l, w[0]); hfma8(m, R.l, w[3]); hfma8(f, R.l, w[6]);
-        hfma8(n, R.c, w[1]);  hfma8(m, R.c, w[4]); hfma8(f, R.c, w[7]);
-        hfma8(n, R.r, w[2]);  hfma8(m, R.r, w[5]); hfma8(f, R.r, w[8]);
+    auto scatter = [&](const uint4* w, const int ws, const TRow& R, uint4& n, uint4& m, uint4& f) {
+        n = hmul8(R.l, w[0 * ws]); hfma8(m, R.l, w[3 * ws]); hfma8(f, R.l, w[6 * ws]);
+        hfma8(n, R.c, w[1 * ws]);  hfma8(m, R.c, w[4 * ws]); hfma8(f, R.c, w[7 * ws]);
+        hfma8(n, R.r, w[2 * ws]);  hfma8(m, R.r, w[5 * ws]); hfma8(f, R.r, w[8 * ws]);
     };
     // iteration j (= arriving t row y0-2+j): finishes d(row y0-3+j) and output row y0-4+j
     //   pn/pm/pf, qn/qm/qf: running sums of the two stages (roles rotate in the caller); dprev = centre of
@@ -640,13 +655,13 @@ iel_gate_v6_kernel(const __grid_constant__ IelV4Args A) {
     auto iter = [&](int j, uint4& pn, uint4& pm, uint4& pf, uint4& qn, uint4& qm, uint4& qf, uint4& dprev) {
         TRow T;
         lds_trow(j, T);
-        scatter(w0, T, pn, pm, pf);
+        scatter(w0, 1, T, pn, pm, pf);
         const int rd = y0 - 3 + j;                                    // the d row finished now
         TRow D;
         D.c = (rd >= 0 && rd < a.H && col_in) ? pf : zero4;           // d is zero outside the image
         D.l = shfl_up4(D.c);
         D.r = shfl_down4(D.c);
-        scatter(w12, D, qn, qm, qf);
+        scatter(w12p, kW12Stride, D, qn, qm, qf);
         const int yo = rd - 1;                                         // the output row finished now
         const uint4 xs = make_uint4(hadd2u(htanh2u(qf.x), dprev.x), hadd2u(htanh2u(qf.y), dprev.y),
                                     hadd2u(htanh2u(qf.z), dprev.z), hadd2u(htanh2u(qf.w), dprev.w));
@@ -690,18 +705,19 @@ int launch_iel_gate(const IelGateArgs& a, cudaStream_t stream) {
     dim3 grid(strips * (a.hp / 16), ceil_div(a.H, kRows), a.B * a.nprob);
 #ifndef CIDNET_ACT_BF16
     static const bool use_v4 = getenv("CIDNET_IEL_V4") != nullptr;      // fp32-accumulate variant (FHFMA)
-    static const int v6 = getenv("CIDNET_IEL_V6") ? atoi(getenv("CIDNET_IEL_V6")) : 2;   // weights in registers, 2 (default) / 3 CTAs per SM; 0 = v5
+    static const int v6 = getenv("CIDNET_IEL_V6") ? atoi(getenv("CIDNET_IEL_V6")) : 3;   // 3 (default): dwconv weights in registers, 3 CTAs / SM; 2: all weights in registers, 2 CTAs / SM; 0 = v5
     if (!use_v4 && v6) {
         const size_t smem6 = 1024 + (size_t)kV5Stages * kV4StageBytes + 2 * 4 * kCols * sizeof(uint4) +
-                             2 * kV5Stages * sizeof(uint64_t) + 64;
+                             2 * kV5Stages * sizeof(uint64_t) + 9 * 2 * 16 * sizeof(act_t) + 64;
         static bool configured6 = false;
         if (!configured6) {
-            CIDNET_CUDA_OK(cudaFuncSetAttribute(iel_gate_v6_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
-            CIDNET_CUDA_OK(cudaFuncSetAttribute(iel_gate_v6_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
+            CIDNET_CUDA_OK(cudaFuncSetAttribute(iel_gate_v6_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
+            CIDNET_CUDA_OK(cudaFuncSetAttribute(iel_gate_v6_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
             configured6 = true;
         }
-        if (v6 == 2) iel_gate_v6_kernel<2><<<grid, kV4Threads, smem6, stream>>>(A);
-        else         iel_gate_v6_kernel<3><<<grid, kV4Threads, smem6, stream>>>(A);
+        // 2: all 18 weight vectors in registers, 2 CTAs / SM;  3: dwconv1/2 weights from shared memory, 3 CTAs / SM
+        if (v6 == 2) iel_gate_v6_kernel<2, false><<<grid, kV4Threads, smem6, stream>>>(A);
+        else         iel_gate_v6_kernel<3, true><<<grid, kV4Threads, smem6, stream>>>(A);
         CIDNET_CUDA_OK(cudaGetLastError());
         return CIDNET_OK;
     }
