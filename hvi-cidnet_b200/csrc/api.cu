@@ -82,6 +82,8 @@ struct cidnet_ctx {
     uint64_t use_clock = 0;
     bool use_graphs = true;
     cudaStream_t cap_stream = nullptr;   // capture happens on a private stream (the legacy default stream cannot be captured)
+    cudaStream_t cap_stream2 = nullptr;  // second branch of the captured graph: the I and HV halves of a stage run concurrently
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool profiling = false;
     std::vector<cudaEvent_t> events;
     struct Rec { std::string name; double bytes; double flops; };
@@ -413,6 +415,12 @@ struct Fwd {
     cidnet_ctx* ctx; Plan P; cudaStream_t st; int launches = 0;
     ShardState sh;
 
+    // two-branch mode (only while the forward is being captured into a CUDA graph): the I and the HV launch
+    // of a pair go to two streams = two parallel graph branches, each on half of the SMs
+    bool par = false; cudaStream_t st2 = nullptr;
+    cudaStream_t S(int br) const { return (par && br == 1) ? st2 : st; }
+    void fork() { if (par) { cudaEventRecord(ctx->ev_fork, st); cudaStreamWaitEvent(st2, ctx->ev_fork, 0); } }
+    void join() { if (par) { cudaEventRecord(ctx->ev_join, st2); cudaStreamWaitEvent(st, ctx->ev_join, 0); } }
     bool live() const { return !sh.dry; }
     bool split() const { return sh.on && sh.nranks > 1; }
     int ht(int l) const { return sh.halo_top >> l; }
@@ -469,7 +477,7 @@ struct Fwd {
     void finish_marks() {
         if (ctx->profiling && !ctx->recs.empty()) cudaEventRecord(ctx->events[ctx->recs.size()], st);
     }
-    int gemm(ConvGemmLaunch& L, const std::string& name) {
+    int gemm(ConvGemmLaunch& L, const std::string& name, int br = 0, bool paired = true) {
         const PackedWeights& w = *L.wt;
         const double px_in = (double)L.B * L.H * L.W;
         const double px_out = L.mode == EPI_DOWN ? px_in / 4 : px_in;
@@ -477,7 +485,8 @@ struct Fwd {
         if (L.in2) bytes += px_out * L.wt2->cin * 2;
         if (L.up) bytes += px_out / 4 * w.n_out * 2;
         mark(name, bytes, 2.0 * px_in * w.n_out * w.cin * w.taps);
-        return live() ? launch_conv_gemm(L, st) : CIDNET_OK;
+        if (par && paired) L.max_ctas = device_sm_count() / 2;
+        return live() ? launch_conv_gemm(L, S(br)) : CIDNET_OK;
     }
 
     int down(int br, int n, const act_t* in, act_t* out) {   // level n-1 -> n
@@ -489,7 +498,7 @@ struct Fwd {
         // conv rows 2y, 2y+1 feed output row y: an input margin m leaves (m - 1) / 2 valid output halo rows
         CIDNET_CHECK(mg(in) >= 1, CIDNET_ERR_STATE, "forward_sharded: down block without a valid input halo");
         setm(out, mg(in) >= kNoLimit ? kNoLimit : (mg(in) - 1) / 2);
-        return gemm(L, "down" + std::to_string(n) + ".conv3x3_bilinear_prelu");
+        return gemm(L, "down" + std::to_string(n) + ".conv3x3_bilinear_prelu", br);
     }
     int up(int br, int n, const act_t* x, const act_t* skip, act_t* t, act_t* out) {   // level n -> n-1
         const UpWeights& U = ctx->up[br][3 - n];
@@ -501,14 +510,14 @@ struct Fwd {
         CIDNET_CHECK(mg(x) >= 2, CIDNET_ERR_STATE, "forward_sharded: up block without a valid input halo");
         setm(t, mg(x) - 1);
         setm(out, std::min(mg(x) >= kNoLimit ? kNoLimit : 2 * (mg(x) - 2), mg(skip)));
-        int rc = gemm(A, "up" + std::to_string(n) + ".conv3x3_composed");
+        int rc = gemm(A, "up" + std::to_string(n) + ".conv3x3_composed", br);
         if (rc) return rc;
         ConvGemmLaunch Bq;
         Bq.mode = EPI_UP; Bq.in = skip; Bq.B = P.B; Bq.H = P.H[n - 1]; Bq.W = P.W[n - 1]; Bq.in_pitch = act_pitch(kCh[n - 1]);
         Bq.flat = true; Bq.wt = &U.w1; Bq.out = out; Bq.out_pitch = act_pitch(kCh[n - 1]);
         Bq.up = t; Bq.up_pitch = act_pitch(kCh[n - 1]); Bq.prelu = U.prelu;
         if (sh.on) { Bq.gH = sh.gH >> (n - 1); Bq.grow = sh.row0 >> (n - 1); }
-        return gemm(Bq, "up" + std::to_string(n) + ".skip1x1_bilinear_prelu");
+        return gemm(Bq, "up" + std::to_string(n) + ".skip1x1_bilinear_prelu", br);
     }
 
     // one LCA stage: I_LCA(x_i, x_hv) and HV_LCA(x_hv, x_i)   (net/LCA.py:78-81, 90-93)
@@ -524,12 +533,14 @@ struct Fwd {
         if ((rc = ensure({{x_i, l, Cp}, {x_hv, l, Cp}}, 1))) return rc;
         const int m_dw = split() ? std::min(mg(x_i), mg(x_hv)) - 1 : kNoLimit;
         // 1. LayerNorm + q / kv 1x1 of both branches: one GEMM per input tensor
+        fork();
         for (int s = 0; s < 2; ++s) {
             ConvGemmLaunch L;
             L.mode = EPI_LN; L.in = x[s]; L.B = P.B; L.H = H; L.W = W; L.in_pitch = Cp; L.flat = true;
             L.wt = &S.qkv[s]; L.out = P.qkv[l][s]; L.out_pitch = 3 * Cp;
-            if ((rc = gemm(L, "L" + std::to_string(l) + ".ln_qkv_1x1"))) return rc;
+            if ((rc = gemm(L, "L" + std::to_string(l) + ".ln_qkv_1x1", s))) return rc;
         }
+        join();
         // 2. depthwise 3x3 of [q | k | v] (+ sum q^2, sum k^2), then the Gram on the tensor cores
         int probs[2], np = 0;
         for (int s = 0; s < 2; ++s) if (S.lca[s].live) probs[np++] = s;
@@ -600,6 +611,8 @@ struct Fwd {
             mark("L" + std::to_string(l) + ".cab_softmax_fold", (double)np * P.B * (C * C * 6.0), (double)np * P.B * 36.0 * C * C);
             if (live() && (rc = launch_cab_fold(f, st))) return rc;
         }
+        const bool both = np == 2;        // stage 5 has a single live problem: it keeps all the SMs
+        fork();
         for (int i = 0; i < np; ++i) {
             const int s = probs[i];
             LcaWeights& Lw = S.lca[s];
@@ -609,7 +622,7 @@ struct Fwd {
             A.mode = EPI_STORE; A.in = P.qkvdw[l][s] + 2 * Cp; A.B = P.B; A.H = H; A.W = W; A.in_pitch = 3 * Cp; A.flat = true;
             A.wt = &fw; A.out = P.xp[l][s]; A.out_pitch = Cp; A.in2 = x[s]; A.in2_pitch = Cp; A.wt2 = &ctx->eye[l];
             if (P.B == 1) fw.n_img = 1;
-            if ((rc = gemm(A, "L" + std::to_string(l) + ".cab_attnv_proj_res"))) return rc;
+            if ((rc = gemm(A, "L" + std::to_string(l) + ".cab_attnv_proj_res", s, both))) return rc;
             setm(P.xp[l][s], m_dw);
         }
         // the IEL gate chains two depthwise 3x3: two valid halo rows of x' (project_in is recomputed on them)
@@ -621,8 +634,9 @@ struct Fwd {
             ConvGemmLaunch Bq;
             Bq.mode = EPI_LN; Bq.in = P.xp[l][s]; Bq.B = P.B; Bq.H = H; Bq.W = W; Bq.in_pitch = Cp; Bq.flat = true;
             Bq.wt = &Lw.w_in; Bq.out = P.tin[l][s]; Bq.out_pitch = 2 * Lw.hp;
-            if ((rc = gemm(Bq, "L" + std::to_string(l) + ".ln_iel_project_in"))) return rc;
+            if ((rc = gemm(Bq, "L" + std::to_string(l) + ".ln_iel_project_in", s, both))) return rc;
         }
+        join();
         // 6. IEL gate (dw 3x3 -> dw 3x3 + tanh + residual -> product)
         {
             IelGateArgs g; memset(&g, 0, sizeof g);
@@ -636,6 +650,7 @@ struct Fwd {
             if (live() && (rc = launch_iel_gate(g, st))) return rc;
         }
         // 7. project_out (+ residual for I_LCA only)
+        fork();
         for (int i = 0; i < np; ++i) {
             const int s = probs[i];
             LcaWeights& Lw = S.lca[s];
@@ -643,10 +658,11 @@ struct Fwd {
             Cq.mode = EPI_STORE; Cq.in = P.g[l][s]; Cq.B = P.B; Cq.H = H; Cq.W = W; Cq.in_pitch = Lw.hp; Cq.flat = true;
             Cq.wt = &Lw.w_out; Cq.out = out[s]; Cq.out_pitch = Cp;
             if (s == 0) { Cq.in2 = P.xp[l][s]; Cq.in2_pitch = Cp; Cq.wt2 = &ctx->eye[l]; }
-            if ((rc = gemm(Cq, "L" + std::to_string(l) + ".iel_project_out"))) return rc;
+            if ((rc = gemm(Cq, "L" + std::to_string(l) + ".iel_project_out", s, both))) return rc;
             setm(out[s], mg(P.xp[l][s]) >= kNoLimit ? kNoLimit : mg(P.xp[l][s]) - 2);
             tap(std::string(s == 0 ? "I_LCA" : "HV_LCA") + std::to_string(n), out[s], C, l, Cp);
         }
+        join();
         return CIDNET_OK;
     }
 
@@ -662,37 +678,49 @@ struct Fwd {
         setm(P.hv_0, (sh.halo_top > 0 ? sh.halo_top : sh.halo_bot) - 1);
         tap("hvi", P.hvi, 3, 0, 0, true); tap("i_enc0", P.i_enc0, 36, 0, 40); tap("hv_0", P.hv_0, 36, 0, 40);
         if ((rc = ensure({{P.i_enc0, 0, 40}, {P.hv_0, 0, 40}}, 1))) return rc;
+        fork();
         if ((rc = down(0, 1, P.i_enc0, P.enc_i[1]))) return rc;
         if ((rc = down(1, 1, P.hv_0, P.enc_hv[1]))) return rc;
+        join();
         tap("i_enc1", P.enc_i[1], 36, 1, 40); tap("hv_1", P.enc_hv[1], 36, 1, 40);
         if ((rc = lca_stage(1, P.enc_i[1], P.enc_hv[1], P.lca_i[1], P.lca_hv[1]))) return rc;
         if ((rc = ensure({{P.lca_i[1], 1, 40}, {P.lca_hv[1], 1, 40}}, 1))) return rc;
+        fork();
         if ((rc = down(0, 2, P.lca_i[1], P.enc_i[2]))) return rc;
         if ((rc = down(1, 2, P.lca_hv[1], P.enc_hv[2]))) return rc;
+        join();
         tap("i_enc2", P.enc_i[2], 72, 2, 72); tap("hv_2", P.enc_hv[2], 72, 2, 72);
         if ((rc = lca_stage(2, P.enc_i[2], P.enc_hv[2], P.lca_i[2], P.lca_hv[2]))) return rc;
         // block3 consumes the PRE-LCA2 tensors (CIDNet.py:94-95)
         if ((rc = ensure({{P.enc_i[2], 2, 72}, {P.enc_hv[2], 2, 72}}, 1))) return rc;
+        fork();
         if ((rc = down(0, 3, P.enc_i[2], P.enc_i[3]))) return rc;
         if ((rc = down(1, 3, P.enc_hv[2], P.enc_hv[3]))) return rc;
+        join();
         tap("i_enc3", P.enc_i[3], 144, 3, 144); tap("hv_3", P.enc_hv[3], 144, 3, 144);
         if ((rc = lca_stage(3, P.enc_i[3], P.enc_hv[3], P.lca_i[3], P.lca_hv[3]))) return rc;
         // LCA4: both consume the LCA3 outputs (HV_LCA4 sees i_enc4, CIDNet.py:101)
         if ((rc = lca_stage(4, P.lca_i[3], P.lca_hv[3], P.lca_i[4], P.lca_hv[4]))) return rc;
         if ((rc = ensure({{P.lca_hv[4], 3, 144}, {P.lca_i[4], 3, 144}}, 2))) return rc;
+        fork();
         if ((rc = up(1, 3, P.lca_hv[4], P.lca_hv[2], P.tup_hv[3], P.dec_hv[2]))) return rc;
         if ((rc = up(0, 3, P.lca_i[4], P.lca_i[2], P.tup_i[3], P.dec_i[2]))) return rc;
+        join();
         tap("hvd3", P.dec_hv[2], 72, 2, 72); tap("id3", P.dec_i[2], 72, 2, 72);
         // stage 5: I_LCA5 is dead, only HV_LCA5(hv_3, i_dec3)
         if ((rc = lca_stage(5, P.dec_i[2], P.dec_hv[2], nullptr, P.lca_hv[5]))) return rc;
         if ((rc = ensure({{P.lca_hv[5], 2, 72}, {P.dec_i[2], 2, 72}}, 2))) return rc;
+        fork();
         if ((rc = up(1, 2, P.lca_hv[5], P.lca_hv[1], P.tup_hv[2], P.dec_hv[1]))) return rc;
         if ((rc = up(0, 2, P.dec_i[2], P.lca_i[1], P.tup_i[2], P.dec_i[1]))) return rc;   // takes i_dec3 (:109)
+        join();
         tap("hvd2", P.dec_hv[1], 36, 1, 40); tap("id2", P.dec_i[1], 36, 1, 40);
         if ((rc = lca_stage(6, P.dec_i[1], P.dec_hv[1], P.lca_i[6], P.lca_hv[6]))) return rc;
         if ((rc = ensure({{P.lca_i[6], 1, 40}, {P.lca_hv[6], 1, 40}}, 2))) return rc;
+        fork();
         if ((rc = up(0, 1, P.lca_i[6], P.i_enc0, P.tup_i[1], P.id1))) return rc;
         if ((rc = up(1, 1, P.lca_hv[6], P.hv_0, P.tup_hv[1], P.hvd1))) return rc;
+        join();
         tap("id1", P.id1, 36, 0, 40); tap("hvd1", P.hvd1, 36, 0, 40);
         if ((rc = ensure({{P.id1, 0, 40}, {P.hvd1, 0, 40}}, 1))) return rc;
         HeadArgs ha{P.id1, P.hvd1, P.hvi, rgb_out, P.out_hvi, ctx->head_wi, ctx->head_whv,
@@ -744,6 +772,9 @@ extern "C" int cidnet_destroy(cidnet_ctx* ctx) {
     release_device(ctx);
     for (cudaEvent_t e : ctx->events) if (e) cudaEventDestroy(e);
     if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
+    if (ctx->cap_stream2) cudaStreamDestroy(ctx->cap_stream2);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
     return CIDNET_OK;
 }
@@ -850,6 +881,13 @@ extern "C" int cidnet_forward(cidnet_ctx* ctx, const float* rgb_in, float* rgb_o
     if (capture) {
         if (!ctx->cap_stream) CIDNET_CUDA_OK(cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking));
         f.st = ctx->cap_stream;
+        static const bool one_branch = getenv("CIDNET_ONE_BRANCH") != nullptr;
+        if (!one_branch) {
+            if (!ctx->cap_stream2) CIDNET_CUDA_OK(cudaStreamCreateWithFlags(&ctx->cap_stream2, cudaStreamNonBlocking));
+            if (!ctx->ev_fork) CIDNET_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+            if (!ctx->ev_join) CIDNET_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+            f.par = true; f.st2 = ctx->cap_stream2;
+        }
         CIDNET_CUDA_OK(cudaStreamBeginCapture(f.st, cudaStreamCaptureModeRelaxed));
     }
     int rc = f.run(rgb_in, rgb_out, k_dev, gated, alpha_s, gated2, alpha);
@@ -884,6 +922,7 @@ extern "C" int cidnet_forward(cidnet_ctx* ctx, const float* rgb_in, float* rgb_o
             cudaGetLastError();
             cudaGraphDestroy(graph);
             ge->seen = -1000000;
+            f.par = false;
             return f.run(rgb_in, rgb_out, k_dev, gated, alpha_s, gated2, alpha);
         }
         ge->graph = graph; ge->exec = exec;

@@ -558,6 +558,8 @@ static int launch_mode(const ConvGemmArgs& args, dim3 grid, size_t smem, cudaStr
     return CIDNET_OK;
 }
 
+int device_sm_count() { return num_sms(); }
+
 int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
     const PackedWeights& wt = *L.wt;
     CIDNET_CHECK(L.in && L.out && wt.w, CIDNET_ERR_INVALID, "conv_gemm: null pointer");
@@ -699,7 +701,7 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
     a.stages = stages;
     const size_t smem = fixed + (a.b_resident ? bres : 0) + (size_t)stages * (a_stage + (a.b_resident ? 0 : b_chunk));
 
-    int gx = num_sms() / wt.n_blocks;
+    int gx = (L.max_ctas > 0 ? L.max_ctas : num_sms()) / wt.n_blocks;
     if (gx < 1) gx = 1;
     if (gx > a.num_tiles) gx = a.num_tiles;
     dim3 grid((unsigned)gx, (unsigned)wt.n_blocks, 1);

@@ -66,9 +66,13 @@ struct ConvGemmLaunch {
     // grid (gH == 0: not sharded).  Only the align_corners bilinear weights of EPI_DOWN / EPI_UP
     // depend on it (they are functions of the GLOBAL row index and size); grow must be even.
     int gH = 0, grow = 0;
+    // persistent grid size limit (0 = one CTA per SM): two independent launches that run concurrently on
+    // two streams take half the SMs each, so their fixed prologue / tail costs overlap
+    int max_ctas = 0;
 };
 
 int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream);
+int device_sm_count();
 
 // layout helpers (tests / taps only)
 int launch_nchw_to_nhwc(const float* src, act_t* dst, int B, int C, int H, int W, int pitch, cudaStream_t s);
