@@ -229,13 +229,20 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                 ptx::mbar_wait(&full[s], ph);
                 ptx::tc_fence_after();
                 if (lane == 0 && a.halo) {
+                    // One thread issues every tcgen05.mma; ncu showed the tensor pipe busy only ~55 % of the time
+                    // behind this loop (~150 cycles of uniform-datapath descriptor arithmetic per MMA), so the
+                    // loops are fully unrolled: tap / sub-tile offsets are compile-time constants added to two base
+                    // descriptors, the accumulate flag is an immediate and only `k < ksteps` stays a uniform branch.
                     int ksteps = (a.cin - i * 64 + 15) >> 4;
                     if (ksteps > 4) ksteps = 4;
-                    const uint32_t abase = ptx::smem_u32(smA + (size_t)s * a_stage);
+                    const uint64_t dA0 = ptx::umma_smem_desc_sw128_rowshift(ptx::smem_u32(smA + (size_t)s * a_stage),
+                                                                            0u);
+                    uint64_t descB = ptx::umma_smem_desc_sw128(ptx::smem_u32(smBres + (size_t)i * b_chunk));
+                    const uint64_t b_tap = (uint64_t)(((uint32_t)a.kchunks * b_chunk) >> 4);   // next tap's weights
+                    const uint32_t d0 = d_tmem, d1 = d_tmem + (uint32_t)a.block_n;
+#pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         const int dy = tap / 3, dx = tap - dy * 3;
-                        const uint64_t descB = ptx::umma_smem_desc_sw128(
-                            ptx::smem_u32(smBres + (size_t)(tap * a.kchunks + i) * b_chunk));
 #pragma unroll
                         for (int sub = 0; sub < kSub; ++sub) {
                             // which halo tile and which first row this (accumulator, tap) reads
@@ -245,12 +252,19 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                                 if (sub == 0) { tile = (dy == 1) ? 0u : 1u; rowoff = (uint32_t)((dy == 0 ? 0 : 16) + dx); }
                                 else          { tile = (dy == 1) ? 1u : 0u; rowoff = (uint32_t)((dy == 2 ? 32 : 16) + dx); }
                             }
-                            const uint64_t descA = ptx::umma_smem_desc_sw128_rowshift(
-                                abase + tile * kHaloTileBytes + rowoff * 128u, (uint32_t)a.halo_baseoff);
-                            for (int k = 0; k < ksteps; ++k)
-                                ptx::umma_f16(d_tmem + sub * a.block_n, descA + 2 * k, descB + 2 * k, idesc,
-                                              (uint32_t)((i | tap | k) != 0));
+                            const uint64_t descA = dA0 + (uint64_t)((tile * kHaloTileBytes + rowoff * 128u) >> 4);
+                            const uint32_t dt = sub == 0 ? d0 : d1;
+                            if (tap == 0) {
+                                if (i == 0) ptx::umma_f16_c<false>(dt, descA, descB, idesc);
+                                else        ptx::umma_f16_c<true>(dt, descA, descB, idesc);
+                            } else {
+                                ptx::umma_f16_c<true>(dt, descA, descB, idesc);
+                            }
+                            if (ksteps > 1) ptx::umma_f16_c<true>(dt, descA + 2, descB + 2, idesc);
+                            if (ksteps > 2) ptx::umma_f16_c<true>(dt, descA + 4, descB + 4, idesc);
+                            if (ksteps > 3) ptx::umma_f16_c<true>(dt, descA + 6, descB + 6, idesc);
                         }
+                        descB += b_tap;
                     }
                     ptx::umma_commit(&empty[s]);
                     if (i == kiters - 1) ptx::umma_commit(&tmem_full[buf]);
@@ -264,10 +278,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                     for (int sub = 0; sub < kSub; ++sub) {
                         const uint64_t descA = ptx::umma_smem_desc_sw128(
                             ptx::smem_u32(smA + (size_t)s * a_stage + sub * kSubTileBytes));
-                        for (int k = 0; k < ksteps; ++k) {
-                            ptx::umma_f16(d_tmem + sub * a.block_n, descA + 2 * k, descB + 2 * k, idesc,
-                                          (uint32_t)((i | k) != 0));
-                        }
+                        const uint32_t dt = d_tmem + sub * a.block_n;
+                        if (i == 0) ptx::umma_f16_c<false>(dt, descA, descB, idesc);
+                        else        ptx::umma_f16_c<true>(dt, descA, descB, idesc);
+                        if (ksteps > 1) ptx::umma_f16_c<true>(dt, descA + 2, descB + 2, idesc);
+                        if (ksteps > 2) ptx::umma_f16_c<true>(dt, descA + 4, descB + 4, idesc);
+                        if (ksteps > 3) ptx::umma_f16_c<true>(dt, descA + 6, descB + 6, idesc);
                     }
                     ptx::umma_commit(&empty[s]);                           // frees the smem stage when the MMAs retire
                     if (i == kiters - 1) ptx::umma_commit(&tmem_full[buf]); // accumulator complete
