@@ -217,6 +217,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
         // --------------------------------------------------------- MMA issuer
         const uint32_t idesc = ptx::umma_idesc_f16(CIDNET_UMMA_FMT, (uint32_t)a.block_n);
         if (a.b_resident) { ptx::mbar_wait(bfull, 0); }
+        const uint32_t leader = ptx::elect_one() ? 1u : 0u;     // the one lane whose tcgen05.mma / commit take effect
         uint32_t it = 0, j = 0;
         for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++j) {
             const uint32_t buf = j & 1u;
@@ -228,8 +229,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                 const uint32_t ph = (it / stages) & 1u;
                 ptx::mbar_wait(&full[s], ph);
                 ptx::tc_fence_after();
-                if (lane == 0 && a.halo) {
-                    // One thread issues every tcgen05.mma; ncu showed the tensor pipe busy only ~55 % of the time
+                if (a.halo) {
+                    // One (elected) lane issues every tcgen05.mma, the whole warp runs the loop convergently; ncu showed the tensor pipe busy only ~55 % of the time
                     // behind this loop (~150 cycles of uniform-datapath descriptor arithmetic per MMA), so the
                     // loops are fully unrolled: tap / sub-tile offsets are compile-time constants added to two base
                     // descriptors, the accumulate flag is an immediate and only `k < ksteps` stays a uniform branch.
@@ -255,20 +256,20 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                             const uint64_t descA = dA0 + (uint64_t)((tile * kHaloTileBytes + rowoff * 128u) >> 4);
                             const uint32_t dt = sub == 0 ? d0 : d1;
                             if (tap == 0) {
-                                if (i == 0) ptx::umma_f16_c<false>(dt, descA, descB, idesc);
-                                else        ptx::umma_f16_c<true>(dt, descA, descB, idesc);
+                                if (i == 0) ptx::umma_f16_lead<false>(leader, dt, descA, descB, idesc);
+                                else        ptx::umma_f16_lead<true>(leader, dt, descA, descB, idesc);
                             } else {
-                                ptx::umma_f16_c<true>(dt, descA, descB, idesc);
+                                ptx::umma_f16_lead<true>(leader, dt, descA, descB, idesc);
                             }
-                            if (ksteps > 1) ptx::umma_f16_c<true>(dt, descA + 2, descB + 2, idesc);
-                            if (ksteps > 2) ptx::umma_f16_c<true>(dt, descA + 4, descB + 4, idesc);
-                            if (ksteps > 3) ptx::umma_f16_c<true>(dt, descA + 6, descB + 6, idesc);
+                            if (ksteps > 1) ptx::umma_f16_lead<true>(leader, dt, descA + 2, descB + 2, idesc);
+                            if (ksteps > 2) ptx::umma_f16_lead<true>(leader, dt, descA + 4, descB + 4, idesc);
+                            if (ksteps > 3) ptx::umma_f16_lead<true>(leader, dt, descA + 6, descB + 6, idesc);
                         }
                         descB += b_tap;
                     }
-                    ptx::umma_commit(&empty[s]);
-                    if (i == kiters - 1) ptx::umma_commit(&tmem_full[buf]);
-                } else if (lane == 0) {
+                    ptx::umma_commit_lead(leader, &empty[s]);
+                    if (i == kiters - 1) ptx::umma_commit_lead(leader, &tmem_full[buf]);
+                } else {
                     int crem = (i < k1) ? a.cin - (i % a.kchunks) * 64 : a.cin2 - (i - k1) * 64;
                     int ksteps = (crem + 15) >> 4;
                     if (ksteps > 4) ksteps = 4;
@@ -279,14 +280,14 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                         const uint64_t descA = ptx::umma_smem_desc_sw128(
                             ptx::smem_u32(smA + (size_t)s * a_stage + sub * kSubTileBytes));
                         const uint32_t dt = d_tmem + sub * a.block_n;
-                        if (i == 0) ptx::umma_f16_c<false>(dt, descA, descB, idesc);
-                        else        ptx::umma_f16_c<true>(dt, descA, descB, idesc);
-                        if (ksteps > 1) ptx::umma_f16_c<true>(dt, descA + 2, descB + 2, idesc);
-                        if (ksteps > 2) ptx::umma_f16_c<true>(dt, descA + 4, descB + 4, idesc);
-                        if (ksteps > 3) ptx::umma_f16_c<true>(dt, descA + 6, descB + 6, idesc);
+                        if (i == 0) ptx::umma_f16_lead<false>(leader, dt, descA, descB, idesc);
+                        else        ptx::umma_f16_lead<true>(leader, dt, descA, descB, idesc);
+                        if (ksteps > 1) ptx::umma_f16_lead<true>(leader, dt, descA + 2, descB + 2, idesc);
+                        if (ksteps > 2) ptx::umma_f16_lead<true>(leader, dt, descA + 4, descB + 4, idesc);
+                        if (ksteps > 3) ptx::umma_f16_lead<true>(leader, dt, descA + 6, descB + 6, idesc);
                     }
-                    ptx::umma_commit(&empty[s]);                           // frees the smem stage when the MMAs retire
-                    if (i == kiters - 1) ptx::umma_commit(&tmem_full[buf]); // accumulator complete
+                    ptx::umma_commit_lead(leader, &empty[s]);                           // frees the smem stage when the MMAs retire
+                    if (i == kiters - 1) ptx::umma_commit_lead(leader, &tmem_full[buf]); // accumulator complete
                 }
                 __syncwarp();
             }

@@ -125,6 +125,27 @@ __device__ __forceinline__ void umma_f16_c(uint32_t d_tmem, uint64_t a_desc, uin
                      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                      :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
 }
+// Warp-convergent forms: EVERY lane of the issuing warp executes the statement, the instruction itself is
+// predicated on `leader` (true in exactly one lane, from elect_one()).  Keeping the control flow convergent lets
+// the compiler hold descriptors in uniform registers without the per-instruction ELECT / BRA.U.ANY retry loop
+// it emits for uniform-operand instructions under a divergent `if (lane == 0)`.
+template <bool kAccumulate>
+__device__ __forceinline__ void umma_f16_lead(uint32_t leader, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                              uint32_t idesc) {
+    if (kAccumulate)
+        asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 q, %4, 0;\n\tsetp.eq.b32 p, 0, 0;\n\t"
+                     "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(leader) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 q, %4, 0;\n\tsetp.ne.b32 p, 0, 0;\n\t"
+                     "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void umma_commit_lead(uint32_t leader, uint64_t* bar) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+                 :: "r"(smem_u32(bar)), "r"(leader) : "memory");
+}
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread retire
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
