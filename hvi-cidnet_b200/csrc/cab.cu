@@ -353,26 +353,30 @@ gram_kernel(const __grid_constant__ GramArgs a) {
     } else if (warp == 1) {
         // instruction descriptor: fp32 accumulate, A and B MN-major (bits 15, 16), M = 128
         const uint32_t idesc = ptx::umma_idesc_f16(CIDNET_UMMA_FMT, (uint32_t)N) | (1u << 15) | (1u << 16);
+        // the whole warp runs the loop convergently, one elected lane's tcgen05.mma / commit take effect
+        // (see conv_gemm.cu: a divergent `if (lane == 0)` costs an ELECT retry loop per instruction)
+        const uint32_t leader = ptx::elect_one() ? 1u : 0u;
         for (int i = 0; i < niter; ++i) {
             const int s = i % kGramStages;
             const uint32_t ph = (uint32_t)(i / kGramStages) & 1u;
             ptx::mbar_wait(&full[s], ph);
             ptx::tc_fence_after();
-            if (lane == 0) {
-                const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
-                const uint32_t sb = sa + nA * kBlk;
-                for (int mt = 0; mt < mtiles; ++mt) {
-                    const uint32_t lboA = kBlk;
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t dA = umma_desc_mn_sw128(sa + 2 * mt * kBlk + ks * 2048, lboA);
-                        const uint64_t dB = umma_desc_mn_sw128(sb + ks * 2048, kBlk);
-                        ptx::umma_f16(tmem_base + mt * N, dA, dB, idesc, (uint32_t)((i | ks) != 0));
-                    }
+            const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
+            const uint64_t dB0 = umma_desc_mn_sw128(sa + nA * kBlk, kBlk);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                if (mt < mtiles) {
+                    const uint64_t dA0 = umma_desc_mn_sw128(sa + 2 * mt * kBlk, kBlk);
+                    const uint32_t dt = tmem_base + mt * N;
+                    if (i == 0) ptx::umma_f16_lead<false>(leader, dt, dA0, dB0, idesc);
+                    else        ptx::umma_f16_lead<true>(leader, dt, dA0, dB0, idesc);
+                    ptx::umma_f16_lead<true>(leader, dt, dA0 + (2048 >> 4), dB0 + (2048 >> 4), idesc);
+                    ptx::umma_f16_lead<true>(leader, dt, dA0 + (4096 >> 4), dB0 + (4096 >> 4), idesc);
+                    ptx::umma_f16_lead<true>(leader, dt, dA0 + (6144 >> 4), dB0 + (6144 >> 4), idesc);
                 }
-                ptx::umma_commit(&empty[s]);
-                if (i == niter - 1) ptx::umma_commit(done);
             }
-            __syncwarp();
+            ptx::umma_commit_lead(leader, &empty[s]);
+            if (i == niter - 1) ptx::umma_commit_lead(leader, done);
         }
     } else {
         const int q4 = warp & 3;

@@ -536,7 +536,12 @@ iel_gate_v5_kernel(const __grid_constant__ IelV4Args A) {
 // only the arriving (l, c, r) vectors are live.  Same arithmetic, same fp16 rounding points as v5 up to
 // the summation order (row-major chains).
 // ================================================================================================
-template <int kMinBlocks, bool kW12Smem>
+// kCpAsync (experiment, CIDNET_IEL_V6=4): the producer warp fills the ring with 16-byte cp.async copies (all 32
+// lanes, zero fill outside the image, completion through cp.async.mbarrier.arrive) instead of TMA boxes, same
+// shared-memory layout (the 32-byte swizzle applied by hand).  Written to test whether the 32-byte box rows
+// (320 TMA requests per 4-row block) limit the kernel: they do not -- measured 15 % SLOWER than the TMA producer
+// (cfg4 L1: 4.24 vs 3.67 ms), so TMA stays the default.
+template <int kMinBlocks, bool kW12Smem, bool kCpAsync>
 __global__ void __launch_bounds__(kV4Threads, kMinBlocks)
 iel_gate_v6_kernel(const __grid_constant__ IelV4Args A) {
     const IelGateArgs& a = A.g;
@@ -566,13 +571,54 @@ iel_gate_v6_kernel(const __grid_constant__ IelV4Args A) {
         }
     }
     if (tid == 0) {
-        for (int s = 0; s < kV5Stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 4); }
+        for (int s = 0; s < kV5Stages; ++s) { ptx::mbar_init(&full[s], kCpAsync ? 32 : 1); ptx::mbar_init(&empty[s], 4); }
         ptx::fence_barrier_init();
-        ptx::prefetch_tensormap(&A.tmT[prob]);
+        if (!kCpAsync) ptx::prefetch_tensormap(&A.tmT[prob]);
     }
     __syncthreads();
 
     if (warp == 4) {
+        if (kCpAsync) {
+            // chunk q = 0..79 of a box row: column c = q >> 1, 16-byte half h = q & 1; lanes take q = lane + 32 m
+            const long long hwp = (long long)a.H * a.W;
+            const act_t* tbase = a.t[prob] + (long long)b * hwp * (2 * hp) + c0;
+            for (int k = 0; k < nblocks; ++k) {
+                const int s = k % kV5Stages;
+                ptx::mbar_wait(&empty[s], ((k / kV5Stages) & 1u) ^ 1u);
+                const uint32_t dst0 = ptx::smem_u32(ring + (size_t)s * kV4StageBytes);
+                const int yb = y0 - 2 + k * kRB;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+                    for (int rr = 0; rr < kRB; ++rr) {
+                        const int y = yb + rr;
+                        const bool row_in = y >= 0 && y < a.H;
+                        const act_t* rowp = tbase + (long long)(row_in ? y : 0) * a.W * (2 * hp) + hf * hp;
+#pragma unroll
+                        for (int m = 0; m < 3; ++m) {
+                            const int q = lane + 32 * m;
+                            if (q < 2 * kBoxCols) {
+                                const int c = q >> 1, h = q & 1;
+                                const int x = X0 - 1 + c;
+                                const bool in = row_in && x >= 0 && x < a.W;
+                                const act_t* src = rowp + (long long)(in ? x : 0) * (2 * hp) + h * 8;
+                                uint32_t o = (uint32_t)(rr * (kBoxCols * 32) + c * 32 + h * 16);
+                                o ^= ((o >> 7) & 1u) << 4;                       // SWIZZLE_32B
+                                const uint32_t dst = dst0 + hf * kHalfBoxBytes + o;
+                                const uint32_t nbytes = in ? 16u : 0u;           // 0 -> the 16 bytes are zero filled
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                                             :: "r"(dst), "l"(src), "r"(nbytes) : "memory");
+                            }
+                        }
+                    }
+                }
+                // this lane's copies of the stage -> one of the 32 arrivals the full barrier expects
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];"
+                             :: "r"(ptx::smem_u32(&full[s])) : "memory");
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            return;
+        }
         if (lane == 0) {
             for (int k = 0; k < nblocks; ++k) {
                 const int s = k % kV5Stages;
@@ -711,13 +757,16 @@ int launch_iel_gate(const IelGateArgs& a, cudaStream_t stream) {
                              2 * kV5Stages * sizeof(uint64_t) + 9 * 2 * 16 * sizeof(act_t) + 64;
         static bool configured6 = false;
         if (!configured6) {
-            CIDNET_CUDA_OK(cudaFuncSetAttribute(iel_gate_v6_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
-            CIDNET_CUDA_OK(cudaFuncSetAttribute(iel_gate_v6_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
+            CIDNET_CUDA_OK(cudaFuncSetAttribute(iel_gate_v6_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
+            CIDNET_CUDA_OK(cudaFuncSetAttribute(iel_gate_v6_kernel<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
+            CIDNET_CUDA_OK(cudaFuncSetAttribute(iel_gate_v6_kernel<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
             configured6 = true;
         }
-        // 2: all 18 weight vectors in registers, 2 CTAs / SM;  3: dwconv1/2 weights from shared memory, 3 CTAs / SM
-        if (v6 == 2) iel_gate_v6_kernel<2, false><<<grid, kV4Threads, smem6, stream>>>(A);
-        else         iel_gate_v6_kernel<3, true><<<grid, kV4Threads, smem6, stream>>>(A);
+        // 2: all 18 weight vectors in registers, 2 CTAs / SM;  3: dwconv1/2 weights from shared memory, 3 CTAs / SM;
+        // 4: as 3 with the cp.async producer instead of TMA
+        if (v6 == 2)      iel_gate_v6_kernel<2, false, false><<<grid, kV4Threads, smem6, stream>>>(A);
+        else if (v6 == 3) iel_gate_v6_kernel<3, true, false><<<grid, kV4Threads, smem6, stream>>>(A);
+        else              iel_gate_v6_kernel<3, true, true><<<grid, kV4Threads, smem6, stream>>>(A);
         CIDNET_CUDA_OK(cudaGetLastError());
         return CIDNET_OK;
     }
