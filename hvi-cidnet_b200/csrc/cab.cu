@@ -250,6 +250,190 @@ dw3x3_kernel(const Dw3Args a) {
 }
 #endif
 
+#ifndef CIDNET_ACT_BF16
+// ------------------------------------------------------------------------------------------------
+// dw3x3 v2 (fp16 build, CIDNET_DW_VARIANT=3): the IEL gate's data path applied to the q|k|v depthwise conv.
+// A producer warp streams {16 channels, 34 columns, 4 rows} TMA boxes (SWIZZLE_32B, zero fill = the conv's
+// padding) of two 16-channel groups into a shared-memory ring; four compute warps (group x 8-channel vector,
+// lane = image column) read their column and both neighbours with conflict-free LDS.128, keep the 9 weight
+// vectors in registers and evaluate the 3x3 in scatter form (three running sums).  Compared with the
+// register-window kernel above nothing waits on a global load: the ring keeps kDw2Stages x 4 rows in flight.
+// ------------------------------------------------------------------------------------------------
+static constexpr int kDw2Cols = 32;          // output columns per warp (all 32 lanes produce one)
+static constexpr int kDw2BoxCols = 40;       // 34 needed; 40 keeps the row pitch (1280 B) a multiple of the swizzle period
+static constexpr int kDw2RB = 4;             // rows per box
+static constexpr int kDw2Stages = 4;
+static constexpr int kDw2Rows = 32;          // output rows per CTA
+static constexpr uint32_t kDw2GroupBytes = kDw2RB * kDw2BoxCols * 32;   // one 16-channel group box
+static constexpr uint32_t kDw2StageBytes = 2 * kDw2GroupBytes;
+static constexpr int kDw2Threads = 160;
+
+struct Dw2Args {
+    CUtensorMap tm[2][3];       // per problem, per segment: {C channels, W, H, B}, box {16, 40, 4, 1}, SWIZZLE_32B
+    Dw3Args g;
+    int groups_per_seg;         // 16-channel groups per segment = ceil(Cp / 16)
+};
+
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kDw2Threads, kMinBlocks)
+dw3x3_v2_kernel(const __grid_constant__ Dw2Args A) {
+    const Dw3Args& a = A.g;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
+    uint8_t* ring = smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + kDw2Stages * kDw2StageBytes);
+    uint64_t* empty = full + kDw2Stages;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Cp = a.seg_vecs * 8;
+    const int gps = A.groups_per_seg, ngroups = 3 * gps, npairs = (ngroups + 1) / 2;
+    const int prob = blockIdx.z % a.nprob, b = blockIdx.z / a.nprob;
+    const int pair = blockIdx.x % npairs, strip = blockIdx.x / npairs;
+    const int X0 = strip * kDw2Cols;                         // image column of lane 0
+    const int y0 = blockIdx.y * kDw2Rows;
+    const int y1 = min(y0 + kDw2Rows, a.H);
+    const int nrows = (y1 - y0) + 2;                         // input rows y0-1 .. y1
+    const int nblocks = (nrows + kDw2RB - 1) / kDw2RB;
+
+    if (tid == 0) {
+        for (int s = 0; s < kDw2Stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 4); }
+        ptx::fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == 4) {
+        if (lane == 0) {
+            int gseg[2], gc0[2];
+            for (int g = 0; g < 2; ++g) {
+                const int grp = 2 * pair + g;
+                gseg[g] = grp < ngroups ? grp / gps : -1;
+                gc0[g] = grp < ngroups ? (grp - gseg[g] * gps) * 16 : 0;
+            }
+            const uint32_t bytes = (gseg[0] >= 0 ? kDw2GroupBytes : 0u) + (gseg[1] >= 0 ? kDw2GroupBytes : 0u);
+            for (int k = 0; k < nblocks; ++k) {
+                const int s = k % kDw2Stages;
+                ptx::mbar_wait(&empty[s], ((k / kDw2Stages) & 1u) ^ 1u);
+                ptx::mbar_expect_tx(&full[s], bytes);
+                uint8_t* dst = ring + (size_t)s * kDw2StageBytes;
+                const int yb = y0 - 1 + k * kDw2RB;
+                for (int g = 0; g < 2; ++g)
+                    if (gseg[g] >= 0)
+                        ptx::tma_load_4d(dst + g * kDw2GroupBytes, &A.tm[prob][gseg[g]], &full[s], gc0[g], X0 - 1, yb, b);
+            }
+        }
+        return;
+    }
+    const int g = warp >> 1, vec = warp & 1;
+    const int grp = 2 * pair + g;
+    const int seg = grp < ngroups ? grp / gps : 0;
+    const int c0 = (grp - seg * gps) * 16 + vec * 8;           // channel within the segment
+    const bool ch_live = grp < ngroups && c0 < Cp;             // whole-vector granularity (Cp is a multiple of 8)
+    const int x = X0 + lane;
+    const bool col_in = x < a.W;
+    const long long hw = (long long)a.H * a.W;
+    act_t* dst = a.dst[prob] + (long long)b * hw * a.dst_pitch + seg * Cp + c0;
+
+    uint4 w[9];
+    {
+        const float* wp = a.w[prob] + seg * Cp + c0;             // [9][3*Cp] tap major
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
+            if (ch_live) {
+                f0 = __ldg(reinterpret_cast<const float4*>(wp + t * 3 * Cp));
+                f1 = __ldg(reinterpret_cast<const float4*>(wp + t * 3 * Cp) + 1);
+            }
+            __half2 h;
+            h = __floats2half2_rn(f0.x, f0.y); w[t].x = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2half2_rn(f0.z, f0.w); w[t].y = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2half2_rn(f1.x, f1.y); w[t].z = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2half2_rn(f1.z, f1.w); w[t].w = *reinterpret_cast<uint32_t*>(&h);
+        }
+    }
+    auto swz = [](uint32_t o) { return o ^ (((o >> 7) & 1u) << 4); };
+    const uint32_t off_l = swz((uint32_t)lane * 32u + (uint32_t)vec * 16u);
+    const uint32_t off_c = swz((uint32_t)(lane + 1) * 32u + (uint32_t)vec * 16u);
+    const uint32_t off_r = swz((uint32_t)(lane + 2) * 32u + (uint32_t)vec * 16u);
+    float ssq[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ssq[e] = 0.f;
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+
+    // iteration j (= arriving input row y0-1+j): finishes output row y0-2+j.  pn / pm / pf: running sums
+    auto iter = [&](int j, uint4& pn, uint4& pm, uint4& pf) {
+        const int k = j / kDw2RB, rr = j - k * kDw2RB;
+        const int s = k % kDw2Stages;
+        if (rr == 0) ptx::mbar_wait(&full[s], (k / kDw2Stages) & 1u);
+        const uint8_t* base = ring + (size_t)s * kDw2StageBytes + g * kDw2GroupBytes + rr * (kDw2BoxCols * 32);
+        const uint4 tl = *reinterpret_cast<const uint4*>(base + off_l);
+        const uint4 tc = *reinterpret_cast<const uint4*>(base + off_c);
+        const uint4 tr = *reinterpret_cast<const uint4*>(base + off_r);
+        if (rr == kDw2RB - 1 || j == nrows - 1) {
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&empty[s]);
+        }
+        pn = hmul8(tl, w[0]); hfma8(pm, tl, w[3]); hfma8(pf, tl, w[6]);
+        hfma8(pn, tc, w[1]);  hfma8(pm, tc, w[4]); hfma8(pf, tc, w[7]);
+        hfma8(pn, tr, w[2]);  hfma8(pm, tr, w[5]); hfma8(pf, tr, w[8]);
+        const int yo = y0 - 2 + j;
+        if (ch_live && col_in && yo >= y0 && yo < y1) {
+            if (seg < 2 && yo >= a.stat_y0 && yo < a.stat_y1) fhfma8(ssq, pf, pf);     // squares of the STORED values
+            *reinterpret_cast<uint4*>(dst + ((long long)yo * a.W + x) * a.dst_pitch) = pf;
+        }
+    };
+    uint4 pA = zero4, pB = zero4, pC = zero4;
+    for (int j = 0; j < nrows; j += 3) {
+        iter(j, pA, pB, pC);
+        if (j + 1 < nrows) iter(j + 1, pC, pA, pB);
+        if (j + 2 < nrows) iter(j + 2, pB, pC, pA);
+    }
+    if (seg < 2 && ch_live) {
+        // sum over the warp's 32 columns, one global atomic per channel per warp
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float v = ssq[e];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0 && v != 0.f) atomicAdd((seg == 0 ? a.sq[prob] : a.sk[prob]) + (long long)b * Cp + c0 + e, v);
+        }
+    }
+}
+
+int encode_map_generic_swz(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                           const uint32_t* box, int swizzle_bytes);   // conv_gemm.cu
+
+static int launch_dw3_v2(const Dw3Args& a, cudaStream_t stream, int min_blocks) {
+    Dw2Args A;
+    memset(&A, 0, sizeof A);
+    A.g = a;
+    const int Cp = a.seg_vecs * 8;
+    A.groups_per_seg = ceil_div(Cp, 16);
+    const long long hw = (long long)a.H * a.W;
+    for (int p = 0; p < a.nprob; ++p)
+        for (int sg = 0; sg < 3; ++sg) {
+            const uint64_t pb = (uint64_t)a.src_pitch * sizeof(act_t);
+            const uint64_t dims[4] = {(uint64_t)Cp, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
+            const uint64_t str[3] = {pb, pb * a.W, pb * hw};
+            const uint32_t box[4] = {16, (uint32_t)kDw2BoxCols, (uint32_t)kDw2RB, 1};
+            int rc = encode_map_generic_swz(&A.tm[p][sg], a.src[p][sg], 4, dims, str, box, 32);
+            if (rc) return rc;
+        }
+    const size_t smem = 1024 + (size_t)kDw2Stages * kDw2StageBytes + 2 * kDw2Stages * sizeof(uint64_t) + 64;
+    static bool configured = false;
+    if (!configured) {
+        CIDNET_CUDA_OK(cudaFuncSetAttribute(dw3x3_v2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CIDNET_CUDA_OK(cudaFuncSetAttribute(dw3x3_v2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int npairs = (3 * A.groups_per_seg + 1) / 2;
+    dim3 grid(ceil_div(a.W, kDw2Cols) * npairs, ceil_div(a.H, kDw2Rows), a.B * a.nprob);
+    if (min_blocks == 4) dw3x3_v2_kernel<4><<<grid, kDw2Threads, smem, stream>>>(A);
+    else                 dw3x3_v2_kernel<3><<<grid, kDw2Threads, smem, stream>>>(A);
+    CIDNET_CUDA_OK(cudaGetLastError());
+    return CIDNET_OK;
+}
+#endif
+
 int launch_dw3(const Dw3Args& a_in, cudaStream_t stream) {
     Dw3Args a = a_in;
     if (a.stat_y1 <= 0) { a.stat_y0 = 0; a.stat_y1 = a.H; }
@@ -259,6 +443,7 @@ int launch_dw3(const Dw3Args& a_in, cudaStream_t stream) {
     // 0 (default): packed fp16, no prefetch, 4 CTAs / SM; 1: packed fp16, one-row prefetch, 3 CTAs / SM;
     // 2: fp32-accumulate FHFMA kernel
     static const int variant = getenv("CIDNET_DW_VARIANT") ? atoi(getenv("CIDNET_DW_VARIANT")) : 0;
+    if (variant == 3 || variant == 4) return launch_dw3_v2(a, stream, variant == 3 ? 4 : 3);   // v2 (TMA ring), 4 / 3 CTAs per SM
     if (variant == 0)      dw3x3_kernel<false, 4><<<grid, kDwThreads, 0, stream>>>(a);
     else if (variant == 1) dw3x3_kernel<true, 3><<<grid, kDwThreads, 0, stream>>>(a);
     else                   dw3x3_f32acc_kernel<<<grid, kDwThreads, 0, stream>>>(a);
@@ -321,6 +506,16 @@ gram_kernel(const __grid_constant__ GramArgs a) {
     uint32_t ncols = 32;
     while (ncols < (uint32_t)(mtiles * N)) ncols <<= 1;
 
+    // q blocks that lie entirely beyond C (C = 36 / 72: the upper 64 of the M = 128 rows) are never loaded: every
+    // TMA row request costs the same whether it moves data or zero fill, so they are zeroed once here instead
+    const int nA_load = min(nA, (C + 63) / 64);
+    if (nA_load < nA) {
+        for (int s = 0; s < kGramStages; ++s) {
+            uint4* z = reinterpret_cast<uint4*>(smem + (size_t)s * stage_bytes + (size_t)nA_load * kBlk);
+            for (int i = threadIdx.x; i < (int)((nA - nA_load) * kBlk / 16); i += kGramThreads) z[i] = make_uint4(0, 0, 0, 0);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy zeros -> visible to the tensor core
+    }
     if (warp == 0 && lane == 0) { ptx::prefetch_tensormap(&a.tmQ[prob]); ptx::prefetch_tensormap(&a.tmK[prob]); }
     if (warp == 1) {
         if (lane == 0) {
@@ -343,10 +538,10 @@ gram_kernel(const __grid_constant__ GramArgs a) {
                 const int s = i % kGramStages;
                 const uint32_t ph = (uint32_t)(i / kGramStages) & 1u;
                 ptx::mbar_wait(&empty[s], ph ^ 1u);
-                ptx::mbar_expect_tx(&full[s], stage_bytes);
+                ptx::mbar_expect_tx(&full[s], (uint32_t)(nA_load + nB) * kBlk);
                 uint8_t* st = smem + (size_t)s * stage_bytes;
                 const int p0 = (c_begin + i) * 64;
-                for (int j = 0; j < nA; ++j) ptx::tma_load_3d(st + j * kBlk, &a.tmQ[prob], &full[s], j * 64, p0, b);
+                for (int j = 0; j < nA_load; ++j) ptx::tma_load_3d(st + j * kBlk, &a.tmQ[prob], &full[s], j * 64, p0, b);
                 for (int j = 0; j < nB; ++j) ptx::tma_load_3d(st + (nA + j) * kBlk, &a.tmK[prob], &full[s], j * 64, p0, b);
             }
         }

@@ -12,6 +12,21 @@
 
 namespace cidnet {
 
+#ifdef CIDNET_ACT_BF16
+#define CIDNET_FHFMA_SH "fma.rn.f32.bf16"
+#else
+#define CIDNET_FHFMA_SH "fma.rn.f32.f16"
+#endif
+// acc0/1 += lo/hi(a) * lo/hi(b): mixed-precision FMA (SASS FHFMA), 16-bit operands stay packed
+__device__ __forceinline__ void fhfma2(float& acc0, float& acc1, uint32_t a, uint32_t b) {
+    asm("{\n\t.reg .b16 al, ah, bl, bh;\n\t"
+        "mov.b32 {al, ah}, %2;\n\t"
+        "mov.b32 {bl, bh}, %3;\n\t"
+        CIDNET_FHFMA_SH " %0, al, bl, %0;\n\t"
+        CIDNET_FHFMA_SH " %1, ah, bh, %1;\n\t}"
+        : "+f"(acc0), "+f"(acc1) : "r"(a), "r"(b));
+}
+
 static constexpr int kTile = 16;          // 16x16 output pixels per CTA, 256 threads
 static constexpr int kHalo = kTile + 2;
 
@@ -126,15 +141,18 @@ head_kernel(const act_t* __restrict__ i_dec1, const act_t* __restrict__ hv_1, co
     extern __shared__ __align__(16) uint8_t head_smem[];
     act_t* s_i = reinterpret_cast<act_t*>(head_smem);
     act_t* s_hv = s_i + kHalo * kHalo * 40;
-    float* s_w = reinterpret_cast<float*>(s_hv + kHalo * kHalo * 40);     // [I | H | V]
+    act_t* s_w = s_hv + kHalo * kHalo * 40;                               // [I | H | V][9 taps][40 ch] 16-bit, zero padded
     const int b = blockIdx.z;
     const int y0 = blockIdx.y * kTile, x0 = blockIdx.x * kTile;
     const int tid = threadIdx.x;
     const long long hw = (long long)H * W;
     if (k_dev) pp.k = __ldg(k_dev);
 
-    for (int i = tid; i < 9 * 36; i += 256) s_w[i] = w_i[i];
-    for (int i = tid; i < 2 * 9 * 36; i += 256) s_w[9 * 36 + i] = w_hv[i];
+    for (int i = tid; i < 3 * 9 * 40; i += 256) {
+        const int o = i / 360, r = i - o * 360, t = r / 40, c = r - t * 40;
+        const float wv = c < 36 ? (o == 0 ? w_i[t * 36 + c] : w_hv[((o - 1) * 9 + t) * 36 + c]) : 0.f;
+        s_w[i] = f2act(wv);
+    }
     // stage both tiles with 16-byte vectors: 5 vectors per pixel per branch
     for (int i = tid; i < kHalo * kHalo * 5; i += 256) {
         const int p = i / 5, v = i - p * 5;
@@ -142,37 +160,38 @@ head_kernel(const act_t* __restrict__ i_dec1, const act_t* __restrict__ hv_1, co
         const int y = min(max(y0 + hy - 1, 0), H - 1);
         const int x = min(max(x0 + hx - 1, 0), W - 1);
         const long long g = (((long long)b * hw) + (long long)y * W + x) * pitch + v * 8;
-        reinterpret_cast<uint4*>(s_i)[i] = *reinterpret_cast<const uint4*>(i_dec1 + g);
-        reinterpret_cast<uint4*>(s_hv)[i] = *reinterpret_cast<const uint4*>(hv_1 + g);
+        uint4 vi = *reinterpret_cast<const uint4*>(i_dec1 + g);
+        uint4 vh = *reinterpret_cast<const uint4*>(hv_1 + g);
+        if (v == 4) { vi.z = vi.w = 0u; vh.z = vh.w = 0u; }     // channels 36..39 are pitch padding nobody writes
+        reinterpret_cast<uint4*>(s_i)[i] = vi;
+        reinterpret_cast<uint4*>(s_hv)[i] = vh;
     }
     __syncthreads();
 
     const int ty = tid / kTile, tx = tid - ty * kTile;
     const int y = y0 + ty, x = x0 + tx;
     if (y >= H || x >= W) return;
-    float oi = 0.f, oh = 0.f, ov = 0.f;
+    // 16-bit x 16-bit products accumulated in fp32 (FHFMA): operands stay packed, no conversions; the weights are
+    // rounded to the activation type like every tensor-core layer's.  Two partial sums per output (even / odd lanes
+    // of the packed pairs); channels 36..39 of data and weights are zero.
+    float oi0 = 0.f, oi1 = 0.f, oh0 = 0.f, oh1 = 0.f, ov0 = 0.f, ov1 = 0.f;
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
         const int p = (ty + t / 3) * kHalo + tx + t % 3;
-        const float* wi = s_w + t * 36;
-        const float* wh = s_w + 9 * 36 + t * 36;
-        const float* wv = s_w + 2 * 9 * 36 + t * 36;
+        const uint4* di = reinterpret_cast<const uint4*>(s_i + p * 40);
+        const uint4* dh = reinterpret_cast<const uint4*>(s_hv + p * 40);
+        const uint4* wi = reinterpret_cast<const uint4*>(s_w + t * 40);
+        const uint4* wh = reinterpret_cast<const uint4*>(s_w + 360 + t * 40);
+        const uint4* wv = reinterpret_cast<const uint4*>(s_w + 720 + t * 40);
 #pragma unroll
         for (int v = 0; v < 5; ++v) {
-            float fi[8], fh[8];
-            load8(s_i + p * 40 + v * 8, fi);
-            load8(s_hv + p * 40 + v * 8, fh);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int c = v * 8 + e;
-                if (c < 36) {
-                    oi = fmaf(fi[e], wi[c], oi);
-                    oh = fmaf(fh[e], wh[c], oh);
-                    ov = fmaf(fh[e], wv[c], ov);
-                }
-            }
+            const uint4 a = di[v], h = dh[v], x = wi[v], y = wh[v], z = wv[v];
+            fhfma2(oi0, oi1, a.x, x.x); fhfma2(oi0, oi1, a.y, x.y); fhfma2(oi0, oi1, a.z, x.z); fhfma2(oi0, oi1, a.w, x.w);
+            fhfma2(oh0, oh1, h.x, y.x); fhfma2(oh0, oh1, h.y, y.y); fhfma2(oh0, oh1, h.z, y.z); fhfma2(oh0, oh1, h.w, y.w);
+            fhfma2(ov0, ov1, h.x, z.x); fhfma2(ov0, ov1, h.y, z.y); fhfma2(ov0, ov1, h.z, z.z); fhfma2(ov0, ov1, h.w, z.w);
         }
     }
+    const float oi = oi0 + oi1, oh = oh0 + oh1, ov = ov0 + ov1;
     const long long pix = (long long)y * W + x;
     const float* hp = hvi + (long long)b * 3 * hw + pix;
     const float Hh = oh + hp[0], Vv = ov + hp[hw], Ii = oi + hp[2 * hw];   // cat([hv_0, i_dec0]) + hvi
@@ -192,7 +211,7 @@ int launch_head(const HeadArgs& a, cudaStream_t stream) {
     CIDNET_CHECK(a.pitch == 40, CIDNET_ERR_INVALID, "head: pitch must be 40");
     dim3 grid(ceil_div(a.W, kTile), ceil_div(a.H, kTile), a.B);
     PhvitParams pp{a.k_host, a.alpha_s, a.alpha, a.gated, a.gated2};
-    const size_t smem = 2 * kHalo * kHalo * 40 * sizeof(act_t) + 3 * 9 * 36 * sizeof(float);
+    const size_t smem = 2 * kHalo * kHalo * 40 * sizeof(act_t) + 3 * 9 * 40 * sizeof(act_t);
     static bool configured = false;
     if (!configured) {
         CIDNET_CUDA_OK(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
