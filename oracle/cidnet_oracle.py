@@ -24,6 +24,8 @@ Reference lines followed (relative to /root/reference):
   iel             net/LCA.py:60-67
   hv_lca / i_lca  net/LCA.py:78-81 / :90-93
   forward         net/CIDNet.py:71-122
+  spatial_attention / forward(mssa=True)
+                  net/CIDNet_MSSA.py:10-25 / :100-161 (the fork's MSSA variant)
 """
 from __future__ import annotations
 
@@ -215,16 +217,27 @@ def lca(x, y, sd, pfx, heads, residual_ffn: bool, taps: Optional[dict] = None):
     return x + g if residual_ffn else g
 
 
+def spatial_attention(x, w):
+    """SpatialAttention (net/CIDNet_MSSA.py:10-25): channel mean and max -> 7x7 conv (2 -> 1, zero
+    padding 3, no bias) -> sigmoid -> gate on every channel."""
+    avg = x.mean(dim=1, keepdim=True)
+    mx = x.max(dim=1, keepdim=True)[0]
+    y = F.conv2d(torch.cat([avg, mx], dim=1), w, padding=w.shape[-1] // 2)
+    return x * torch.sigmoid(y)
+
+
 # --------------------------------------------------------------------------- #
 # whole network
 # --------------------------------------------------------------------------- #
 def forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], gated=False, alpha_s=1.3,
             gated2=False, alpha=1.0, taps: Optional[dict] = None,
-            run_dead_block: bool = False) -> torch.Tensor:
+            run_dead_block: bool = False, mssa: bool = False) -> torch.Tensor:
     """net/CIDNet.py:71-122.  `taps`, when given, receives named intermediates
     (NCHW fp32) for per-kernel parity tests.  I_LCA5 (:105) is dead in the
     reference (its result is overwritten at :109) and is skipped unless
-    `run_dead_block` is set (used only for timing the reference's full work)."""
+    `run_dead_block` is set (used only for timing the reference's full work).
+    `mssa=True` follows net/CIDNet_MSSA.py:100-161 instead: a SpatialAttention gate after each of
+    the six up blocks, I_LCA5 live, and ID_block2 fed by I_LCA5's output (:143-144)."""
     h2, h3, h4 = HEADS[1], HEADS[2], HEADS[3]
     k = float(sd["trans.density_k"].reshape(-1)[0])
     hvi = hvit(x, k)
@@ -260,21 +273,27 @@ def forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], gated=False, alpha_s=1
     i_dec4 = tap("I_LCA4", lca(i_enc4, hv_4, sd, "I_LCA4", h4, True, taps))
     hv_4 = tap("HV_LCA4", lca(hv_4, i_enc4, sd, "HV_LCA4", h4, False, taps))
 
-    hv_3 = tap("hvd3", norm_upsample(hv_4, hv_jump2, sd, "HVD_block3"))
-    i_dec3 = tap("id3", norm_upsample(i_dec4, v_jump2, sd, "ID_block3"))
-    if run_dead_block:
+    def sa(name, t):
+        return spatial_attention(t, sd[name + ".conv1.weight"]) if mssa else t
+
+    hv_3 = tap("hvd3", sa("sa_hv3", norm_upsample(hv_4, hv_jump2, sd, "HVD_block3")))
+    i_dec3 = tap("id3", sa("sa_i3", norm_upsample(i_dec4, v_jump2, sd, "ID_block3")))
+    i_dec2 = i_dec3
+    if mssa:
+        i_dec2 = tap("I_LCA5", lca(i_dec3, hv_3, sd, "I_LCA5", h3, True, taps))   # live, CIDNet_MSSA.py:139
+    elif run_dead_block:
         lca(i_dec3, hv_3, sd, "I_LCA5", h3, True)                      # dead, :105
     hv_2 = tap("HV_LCA5", lca(hv_3, i_dec3, sd, "HV_LCA5", h3, False, taps))
 
-    hv_2 = tap("hvd2", norm_upsample(hv_2, hv_jump1, sd, "HVD_block2"))
-    i_dec2 = tap("id2", norm_upsample(i_dec3, v_jump1, sd, "ID_block2"))
+    hv_2 = tap("hvd2", sa("sa_hv2", norm_upsample(hv_2, hv_jump1, sd, "HVD_block2")))
+    i_dec2 = tap("id2", sa("sa_i2", norm_upsample(i_dec2, v_jump1, sd, "ID_block2")))
 
     i_dec1 = tap("I_LCA6", lca(i_dec2, hv_2, sd, "I_LCA6", h2, True, taps))
     hv_1 = tap("HV_LCA6", lca(hv_2, i_dec2, sd, "HV_LCA6", h2, False, taps))
 
-    i_dec1 = tap("id1", norm_upsample(i_dec1, i_jump0, sd, "ID_block1"))
+    i_dec1 = tap("id1", sa("sa_i1", norm_upsample(i_dec1, i_jump0, sd, "ID_block1")))
     i_dec0 = tap("i_dec0", block0(i_dec1, sd["ID_block0.1.weight"]))
-    hv_1 = tap("hvd1", norm_upsample(hv_1, hv_jump0, sd, "HVD_block1"))
+    hv_1 = tap("hvd1", sa("sa_hv1", norm_upsample(hv_1, hv_jump0, sd, "HVD_block1")))
     hv_0 = tap("hv_dec0", block0(hv_1, sd["HVD_block0.1.weight"]))
 
     out_hvi = tap("out_hvi", torch.cat([hv_0, i_dec0], dim=1) + hvi)
@@ -284,8 +303,9 @@ def forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], gated=False, alpha_s=1
 # --------------------------------------------------------------------------- #
 # state_dict surface and deterministic weights
 # --------------------------------------------------------------------------- #
-def state_dict_spec():
-    """Ordered {key: shape} for the 191 fp32 tensors of net.CIDNet.CIDNet."""
+def state_dict_spec(mssa: bool = False):
+    """Ordered {key: shape} for the 191 fp32 tensors of net.CIDNet.CIDNet (+ the six
+    `sa_*.conv1.weight [1,2,7,7]` of net.CIDNet_MSSA.CIDNet when `mssa`)."""
     c1, c2, c3, c4 = CHANNELS
     spec = {}
     spec["HVE_block0.1.weight"] = (c1, 3, 3, 3)
@@ -327,10 +347,13 @@ def state_dict_spec():
             lca_spec(f"{br}_LCA{n}", *lvl[n])
     spec["trans.density_k"] = (1,)
     assert len(spec) == 191
+    if mssa:
+        for name in ("sa_hv3", "sa_i3", "sa_hv2", "sa_i2", "sa_hv1", "sa_i1"):   # CIDNet_MSSA.py:93-98
+            spec[name + ".conv1.weight"] = (1, 2, 7, 7)
     return spec
 
 
-def make_state_dict(seed: int = 0, perturb: bool = True) -> Dict[str, torch.Tensor]:
+def make_state_dict(seed: int = 0, perturb: bool = True, mssa: bool = False) -> Dict[str, torch.Tensor]:
     """Deterministic synthetic weights that do not depend on torch's RNG (numpy
     PCG64, identical on every host).  Conv weights ~ U(-1/sqrt(fan_in), +) like
     PyTorch's default init.  With `perturb`, the parameters whose defaults are
@@ -339,7 +362,7 @@ def make_state_dict(seed: int = 0, perturb: bool = True) -> Dict[str, torch.Tens
     import numpy as np
     rng = np.random.default_rng(seed)
     sd = {}
-    for key, shape in state_dict_spec().items():
+    for key, shape in state_dict_spec(mssa).items():
         if key.endswith("norm.weight"):
             a = 1.0 + (rng.uniform(-0.3, 0.3, shape) if perturb else 0.0) * np.ones(shape)
         elif key.endswith("norm.bias"):
