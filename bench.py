@@ -55,15 +55,15 @@ def find_weights():
     return None
 
 
-def make_weights(tmpdir="/tmp"):
+def make_weights(tmpdir="/tmp", mssa=False):
     """state_dict for the bench: shipped LOL-Blur.pth if present, else seeded random-init saved and
     re-loaded through a real .pth file (same path a user takes: eval_SID_blur.py:22)."""
     import torch
-    w = find_weights()
+    w = None if mssa else find_weights()
     if w:
         return torch.load(w, map_location="cpu"), "LOL-Blur.pth"
     from oracle.cidnet_oracle import make_state_dict
-    sd = make_state_dict(0, perturb=False)
+    sd = make_state_dict(0, perturb=False, mssa=mssa)
     path = os.path.join(tmpdir, f"cidnet_bench_{os.getpid()}.pth")
     torch.save(sd, path)
     sd = torch.load(path, map_location="cpu")
@@ -174,21 +174,22 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     B, H, W, desc = WORKLOADS[args.workload if args.workload != "cfg3" else "cfg2"]
-    sd, wdesc = make_weights()
+    mssa = args.variant == "mssa"
+    sd, wdesc = make_weights(mssa=mssa)
     sd = {k: v.float() for k, v in sd.items()}
     sample_B, sample_H, sample_W = 1, H, W
     x = O.make_input("uniform", sample_B, sample_H, sample_W, seed=1234)
-    t0 = time.perf_counter(); O.forward(x, sd, run_dead_block=True); t1 = time.perf_counter() - t0
+    t0 = time.perf_counter(); O.forward(x, sd, run_dead_block=True, mssa=mssa); t1 = time.perf_counter() - t0
     budget = 150.0
     if (args.steps + args.warmup) * t1 > budget:      # bounded sample: a centre crop (multiple of 8)
         f = max(0.1, (budget / ((args.steps + args.warmup) * t1)) ** 0.5)
         sample_H, sample_W = max(64, int(H * f) // 8 * 8), max(64, int(W * f) // 8 * 8)
         x = O.make_input("uniform", 1, sample_H, sample_W, seed=1234)
     for _ in range(args.warmup):
-        O.forward(x, sd, run_dead_block=True)
+        O.forward(x, sd, run_dead_block=True, mssa=mssa)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.forward(x, sd, run_dead_block=True)
+        O.forward(x, sd, run_dead_block=True, mssa=mssa)
     dt = time.perf_counter() - t0
     mp = sample_H * sample_W / 1e6
     val = mp * args.steps / dt
@@ -196,13 +197,13 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "weights": wdesc},
+            "config": {"workload": f"{args.workload}: {desc}" + (" [MSSA variant, net/CIDNet_MSSA.py]" if mssa else ""), "weights": wdesc},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_sample(sd, H, W, seconds=12.0):
+def cpu_baseline_sample(sd, H, W, seconds=12.0, mssa=False):
     import torch
     from oracle import cidnet_oracle as O
     O.FAST_BILINEAR = True
@@ -212,10 +213,10 @@ def cpu_baseline_sample(sd, H, W, seconds=12.0):
     x = O.make_input("uniform", 1, h, w, seed=1234)
     sdf = {k: v.float() for k, v in sd.items()}
     with torch.no_grad():
-        O.forward(x, sdf, run_dead_block=True)
+        O.forward(x, sdf, run_dead_block=True, mssa=mssa)
         n, t0 = 0, time.perf_counter()
         while True:
-            O.forward(x, sdf, run_dead_block=True)
+            O.forward(x, sdf, run_dead_block=True, mssa=mssa)
             n += 1
             dt = time.perf_counter() - t0
             if dt > seconds or n >= 20:
@@ -227,7 +228,10 @@ def cpu_baseline_sample(sd, H, W, seconds=12.0):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from hvi_cidnet_b200.net.CIDNet import CIDNet
+    if args.variant == "mssa":
+        from hvi_cidnet_b200.net.CIDNet_MSSA import CIDNet
+    else:
+        from hvi_cidnet_b200.net.CIDNet import CIDNet
 
     torch.set_grad_enabled(False)
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -244,7 +248,7 @@ def run_ours(args):
     B, H, W, desc = WORKLOADS[args.workload]
     if args.workload == "cfg4":
         B = max(1, B // world)               # batch-sharded: fixed total, per-rank share
-    sd, wdesc = make_weights()
+    sd, wdesc = make_weights(mssa=args.variant == "mssa")
     model = CIDNet().to(dev).eval()
     model.load_state_dict(sd, strict=True)
     if args.workload == "cfg5" and world > 1:
@@ -360,12 +364,12 @@ def run_ours(args):
                 roof["traffic"] = tr["dram_bytes"]
                 roof["traffic_source"] = os.path.relpath(tpath, ROOT)
                 roof["algorithmic_bytes_per_launch"] = tr["algorithmic_bytes"]
-        cpu = cpu_baseline_sample(sd, H, W)
+        cpu = cpu_baseline_sample(sd, H, W, mssa=args.variant == "mssa")
         act = "fp16" if __import__("hvi_cidnet_b200._lib", fromlist=["lib"]).lib().cidnet_act_dtype() == 0 else "bf16"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": nwarm,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak" if args.workload != "cfg4" else "strong",
                 "vs_baseline": None, "dtype": act, "data": "synthetic",
-                "config": {"workload": f"{args.workload}: {desc}", "per_rank_batch": B, "H": H, "W": W, "weights": wdesc,
+                "config": {"workload": f"{args.workload}: {desc}" + (" [MSSA variant, net/CIDNet_MSSA.py]" if args.variant == "mssa" else ""), "per_rank_batch": B, "H": H, "W": W, "weights": wdesc,
                            "l2": f"inputs rotate over a ring of {ring} distinct images ({ring * img_bytes >> 20} MiB > L2); "
                                  "all intermediates are rewritten every step",
                            "accumulate": "fp32", "parallelism": f"dp{world} (independent images, no collective)"},
@@ -540,6 +544,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--variant", default="base", choices=["base", "mssa"],
+                    help="base = net/CIDNet.py (BASELINE.json's model); mssa = the fork's net/CIDNet_MSSA.py")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -43,6 +43,7 @@ SIGNATURES = {
     "cidnet_destroy": (C.c_int, [C.c_void_p]),
     "cidnet_set_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "cidnet_finalize_weights": (C.c_int, [C.c_void_p]),
+    "cidnet_set_variant": (C.c_int, [C.c_void_p, C.c_int]),
     "cidnet_workspace_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "cidnet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                  C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float, C.c_void_p]),

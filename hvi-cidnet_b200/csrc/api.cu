@@ -7,6 +7,7 @@
 #include "conv_gemm.cuh"
 #include "dwtc.cuh"
 #include "iel.cuh"
+#include "sa.cuh"
 #include "stem_head.cuh"
 #include "weights.cuh"
 
@@ -58,6 +59,8 @@ struct cidnet_ctx {
     UpWeights up[2][3];        // [branch][block3, block2, block1]  (index 0 = block3)
     StageWeights stage[6];
     PackedWeights eye[4];      // identity weights per level (residual adds inside the MMA)
+    int variant = CIDNET_VARIANT_BASE;   // CIDNET_VARIANT_MSSA: net/CIDNet_MSSA.py (spatial-attention gates, live I_LCA5)
+    float* sa_w[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // [branch][output level]: sa_{i,hv}{1,2,3}.conv1.weight
     std::vector<void*> owned;  // every cudaMalloc'ed pointer (freed in destroy)
     std::map<std::string, Tap> taps;
     int last_B = 0;
@@ -93,9 +96,8 @@ struct cidnet_ctx {
 namespace {
 
 // ---------------------------------------------------------------- weights ---
-const std::vector<std::string>& all_keys() {
-    static std::vector<std::string> keys;
-    if (!keys.empty()) return keys;
+std::vector<std::string> all_keys(int variant) {
+    std::vector<std::string> keys;
     auto lca = [&](const std::string& p) {
         for (const char* s : {".norm.weight", ".norm.bias", ".gdfn.project_in.weight", ".gdfn.dwconv.weight",
                               ".gdfn.dwconv1.weight", ".gdfn.dwconv2.weight", ".gdfn.project_out.weight",
@@ -122,6 +124,9 @@ const std::vector<std::string>& all_keys() {
     for (const char* br : {"HV", "I"})
         for (int n = 1; n <= 6; ++n) lca(std::string(br) + "_LCA" + std::to_string(n));
     keys.push_back("trans.density_k");
+    if (variant == CIDNET_VARIANT_MSSA)
+        for (const char* br : {"hv", "i"})
+            for (int n = 1; n <= 3; ++n) keys.push_back(std::string("sa_") + br + std::to_string(n) + ".conv1.weight");
     return keys;
 }
 
@@ -129,6 +134,7 @@ int64_t expected_numel(const std::string& key) {
     // shapes of SURVEY App. B, derived from the key
     auto lvl_of_lca = [](int n) { return n <= 3 ? n : 7 - n; };   // LCA1,6 -> 1; 2,5 -> 2; 3,4 -> 3
     if (key == "trans.density_k") return 1;
+    if (key.rfind("sa_", 0) == 0 && key.find(".conv1.weight") != std::string::npos) return 2 * 49;   // CIDNet_MSSA.py:17
     if (key.find("prelu.weight") != std::string::npos) return 1;
     if (key == "HVE_block0.1.weight") return 36 * 3 * 9;
     if (key == "IE_block0.1.weight") return 36 * 9;
@@ -225,7 +231,7 @@ int build_lca(cidnet_ctx* ctx, const std::string& pfx, int level, LcaWeights* L)
 
 int build_weights(cidnet_ctx* ctx) {
     auto& R = ctx->raw;
-    for (const std::string& k : all_keys())
+    for (const std::string& k : all_keys(ctx->variant))
         CIDNET_CHECK(R.count(k) && (int64_t)R[k].size() == expected_numel(k), CIDNET_ERR_STATE,
                      "finalize_weights: missing or mis-sized state_dict tensor '" + k + "'");
     int rc;
@@ -285,6 +291,12 @@ int build_weights(cidnet_ctx* ctx) {
             U.prelu = R[p + ".prelu.weight"][0];
         }
     }
+    if (ctx->variant == CIDNET_VARIANT_MSSA) {
+        const char* sa_br[2] = {"i", "hv"};
+        for (int br = 0; br < 2; ++br)
+            for (int n = 1; n <= 3; ++n)      // sa_x{n} gates the output of up block n, i.e. a tensor of level n-1
+                if ((rc = dev_f32(ctx, &ctx->sa_w[br][n - 1], R[std::string("sa_") + sa_br[br] + std::to_string(n) + ".conv1.weight"]))) return rc;
+    }
     for (int l = 1; l <= 3; ++l) {
         if ((rc = pack_identity(&ctx->eye[l], kCh[l]))) return rc;
         own(ctx, ctx->eye[l]);
@@ -293,7 +305,8 @@ int build_weights(cidnet_ctx* ctx) {
         const int level = n <= 3 ? n : 7 - n;
         StageWeights& S = ctx->stage[n - 1];
         const std::string pi = "I_LCA" + std::to_string(n), ph = "HV_LCA" + std::to_string(n);
-        S.lca[0].live = (n != 5);       // I_LCA5 is dead in the reference graph (CIDNet.py:105 vs :109)
+        // I_LCA5 is dead in the reference graph (CIDNet.py:105 vs :109) but live in the MSSA variant (CIDNet_MSSA.py:139,144)
+        S.lca[0].live = (n != 5) || ctx->variant == CIDNET_VARIANT_MSSA;
         S.lca[1].live = true;
         if (S.lca[0].live && (rc = build_lca(ctx, pi, level, &S.lca[0]))) return rc;
         if ((rc = build_lca(ctx, ph, level, &S.lca[1]))) return rc;
@@ -342,6 +355,7 @@ struct Plan {
     // per-level scratch for an LCA stage pair
     act_t *qkv[4][2], *qkvdw[4][2], *xp[4][2], *tin[4][2], *g[4][2], *mfold[4][2];
     float* stats; int64_t stats_bytes;
+    float2* sa_stats[2];                                   // MSSA: per-pixel (mean, max) of one up-block output per branch
     float *gram[6][2], *sq[6][2], *sk[6][2];
     int64_t bytes;
 };
@@ -353,6 +367,7 @@ void make_plan(Plan* P, void* ws, int B, int H, int W) {
     auto px = [&](int l) { return (int64_t)B * P->H[l] * P->W[l]; };
     P->hvi = bp.take<float>(px(0) * 3);
     P->out_hvi = bp.take<float>(px(0) * 3);
+    for (int s = 0; s < 2; ++s) P->sa_stats[s] = bp.take<float2>(px(0));
     P->i_enc0 = bp.take<act_t>(px(0) * 40); P->hv_0 = bp.take<act_t>(px(0) * 40);
     P->id1 = bp.take<act_t>(px(0) * 40);    P->hvd1 = bp.take<act_t>(px(0) * 40);
     for (int l = 1; l <= 3; ++l) {
@@ -518,6 +533,26 @@ struct Fwd {
         Bq.up = t; Bq.up_pitch = act_pitch(kCh[n - 1]); Bq.prelu = U.prelu;
         if (sh.on) { Bq.gH = sh.gH >> (n - 1); Bq.grow = sh.row0 >> (n - 1); }
         return gemm(Bq, "up" + std::to_string(n) + ".skip1x1_bilinear_prelu", br);
+    }
+
+    // MSSA variant: SpatialAttention gates on the I / HV outputs of an up-block pair, in place (level l tensors).
+    // The 7x7 conv over the (mean, max) map needs three valid halo rows (row-strip sharding).
+    int sa_pair(int l, act_t* xi, act_t* xhv) {
+        if (ctx->variant != CIDNET_VARIANT_MSSA) return CIDNET_OK;
+        const int C = kCh[l], Cp = act_pitch(C);
+        int rc;
+        if ((rc = ensure({{xi, l, Cp}, {xhv, l, Cp}}, 3))) return rc;
+        SaArgs a;
+        a.x[0] = xi; a.x[1] = xhv; a.w[0] = ctx->sa_w[0][l]; a.w[1] = ctx->sa_w[1][l];
+        a.stats[0] = P.sa_stats[0]; a.stats[1] = P.sa_stats[1];
+        a.B = P.B; a.H = P.H[l]; a.W = P.W[l]; a.C = C; a.pitch = Cp; a.nprob = 2;
+        const double px = 2.0 * P.B * P.H[l] * P.W[l];
+        mark("sa" + std::to_string(l + 1) + ".mean_max", px * (2.0 * C + 8), px * 2.0 * C);
+        if (live() && (rc = launch_sa_stats(a, st))) return rc;
+        mark("sa" + std::to_string(l + 1) + ".conv7x7_sigmoid_gate", px * (4.0 * C + 8), px * (2.0 * 98 + C));
+        if (live() && (rc = launch_sa_gate(a, st))) return rc;
+        if (split()) { setm(xi, mg(xi) - 3); setm(xhv, mg(xhv) - 3); }
+        return CIDNET_OK;
     }
 
     // one LCA stage: I_LCA(x_i, x_hv) and HV_LCA(x_hv, x_i)   (net/LCA.py:78-81, 90-93)
@@ -706,14 +741,19 @@ struct Fwd {
         if ((rc = up(1, 3, P.lca_hv[4], P.lca_hv[2], P.tup_hv[3], P.dec_hv[2]))) return rc;
         if ((rc = up(0, 3, P.lca_i[4], P.lca_i[2], P.tup_i[3], P.dec_i[2]))) return rc;
         join();
+        if ((rc = sa_pair(2, P.dec_i[2], P.dec_hv[2]))) return rc;
         tap("hvd3", P.dec_hv[2], 72, 2, 72); tap("id3", P.dec_i[2], 72, 2, 72);
-        // stage 5: I_LCA5 is dead, only HV_LCA5(hv_3, i_dec3)
-        if ((rc = lca_stage(5, P.dec_i[2], P.dec_hv[2], nullptr, P.lca_hv[5]))) return rc;
-        if ((rc = ensure({{P.lca_hv[5], 2, 72}, {P.dec_i[2], 2, 72}}, 2))) return rc;
+        // stage 5: I_LCA5 is dead in the base graph, only HV_LCA5(hv_3, i_dec3); the MSSA variant runs both and
+        // feeds ID_block2 with I_LCA5's output (CIDNet_MSSA.py:139-146)
+        const bool mssa = ctx->variant == CIDNET_VARIANT_MSSA;
+        act_t* i_dec2_in = mssa ? P.lca_i[5] : P.dec_i[2];
+        if ((rc = lca_stage(5, P.dec_i[2], P.dec_hv[2], mssa ? P.lca_i[5] : nullptr, P.lca_hv[5]))) return rc;
+        if ((rc = ensure({{P.lca_hv[5], 2, 72}, {i_dec2_in, 2, 72}}, 2))) return rc;
         fork();
         if ((rc = up(1, 2, P.lca_hv[5], P.lca_hv[1], P.tup_hv[2], P.dec_hv[1]))) return rc;
-        if ((rc = up(0, 2, P.dec_i[2], P.lca_i[1], P.tup_i[2], P.dec_i[1]))) return rc;   // takes i_dec3 (:109)
+        if ((rc = up(0, 2, i_dec2_in, P.lca_i[1], P.tup_i[2], P.dec_i[1]))) return rc;   // base graph: takes i_dec3 (:109)
         join();
+        if ((rc = sa_pair(1, P.dec_i[1], P.dec_hv[1]))) return rc;
         tap("hvd2", P.dec_hv[1], 36, 1, 40); tap("id2", P.dec_i[1], 36, 1, 40);
         if ((rc = lca_stage(6, P.dec_i[1], P.dec_hv[1], P.lca_i[6], P.lca_hv[6]))) return rc;
         if ((rc = ensure({{P.lca_i[6], 1, 40}, {P.lca_hv[6], 1, 40}}, 2))) return rc;
@@ -721,6 +761,7 @@ struct Fwd {
         if ((rc = up(0, 1, P.lca_i[6], P.i_enc0, P.tup_i[1], P.id1))) return rc;
         if ((rc = up(1, 1, P.lca_hv[6], P.hv_0, P.tup_hv[1], P.hvd1))) return rc;
         join();
+        if ((rc = sa_pair(0, P.id1, P.hvd1))) return rc;
         tap("id1", P.id1, 36, 0, 40); tap("hvd1", P.hvd1, 36, 0, 40);
         if ((rc = ensure({{P.id1, 0, 40}, {P.hvd1, 0, 40}}, 1))) return rc;
         HeadArgs ha{P.id1, P.hvd1, P.hvi, rgb_out, P.out_hvi, ctx->head_wi, ctx->head_whv,
@@ -776,6 +817,14 @@ extern "C" int cidnet_destroy(cidnet_ctx* ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
+    return CIDNET_OK;
+}
+
+extern "C" int cidnet_set_variant(cidnet_ctx* ctx, int variant) {
+    CIDNET_CHECK(ctx, CIDNET_ERR_INVALID, "set_variant: null ctx");
+    CIDNET_CHECK(variant == CIDNET_VARIANT_BASE || variant == CIDNET_VARIANT_MSSA, CIDNET_ERR_INVALID, "set_variant: unknown variant");
+    if (variant != ctx->variant) ctx->finalized = false;
+    ctx->variant = variant;
     return CIDNET_OK;
 }
 

@@ -86,6 +86,8 @@ def _block0(ci, co):
 
 
 class CIDNet(nn.Module, PyTorchModelHubMixin):
+    _variant = 0          # CIDNET_VARIANT_BASE; net/CIDNet_MSSA.py's mirror overrides it
+
     def __init__(self, channels=[36, 36, 72, 144], heads=[1, 2, 4, 8], norm=False):
         super(CIDNet, self).__init__()
         if list(channels) != _CHANNELS or list(heads) != _HEADS:
@@ -121,6 +123,7 @@ class CIDNet(nn.Module, PyTorchModelHubMixin):
             self._release()
             ctx = C.c_void_p()
             _lib.check(lib.cidnet_create(C.byref(ctx), device.index if device.index is not None else torch.cuda.current_device()))
+            _lib.check(lib.cidnet_set_variant(ctx, self._variant))
             self._ctx, self._ctx_device, self._synced = ctx, device, None
         sig = self._weights_signature()
         if self._synced != sig:

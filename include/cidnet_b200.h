@@ -64,6 +64,12 @@ CIDNET_API int cidnet_phvit(const float* hvi, float* rgb, int B, int H, int W, f
 CIDNET_API int cidnet_create(cidnet_ctx** ctx, int device);
 CIDNET_API int cidnet_destroy(cidnet_ctx* ctx);
 CIDNET_API int cidnet_set_weight(cidnet_ctx* ctx, const char* key, const float* host, int64_t numel);
+/* Model variant (before finalize_weights).  CIDNET_VARIANT_MSSA replaces the fork's
+ * net.CIDNet_MSSA.CIDNet (net/CIDNet_MSSA.py:28-161): six SpatialAttention gates (:10-25; keys
+ * sa_{hv,i}{1,2,3}.conv1.weight [1,2,7,7]) after the up blocks, I_LCA5 live, ID_block2 fed by I_LCA5. */
+#define CIDNET_VARIANT_BASE 0
+#define CIDNET_VARIANT_MSSA 1
+CIDNET_API int cidnet_set_variant(cidnet_ctx* ctx, int variant);
 CIDNET_API int cidnet_finalize_weights(cidnet_ctx* ctx);
 
 /* ---- forward --------------------------------------------------------------

@@ -100,6 +100,33 @@ def forward_cases():
     del taps_wanted
 
 
+def forward_mssa_cases():
+    """The fork's MSSA variant (net/CIDNet_MSSA.py): outputs + the tensors after each SpatialAttention gate."""
+    from net.CIDNet_MSSA import CIDNet as CIDNetMSSA
+    for seed, perturb, kind, (B, H, W) in [(3, True, "uniform", (2, 32, 48)), (4, False, "dark", (1, 40, 24))]:
+        sd = O.make_state_dict(seed, perturb, mssa=True)
+        model = CIDNetMSSA().eval()
+        model.load_state_dict(sd, strict=True)
+        x = O.make_input(kind, B, H, W, seed=100 + seed)
+        caps, hooks = {}, []
+        for name, tapname in [("sa_hv3", "hvd3"), ("sa_i3", "id3"), ("I_LCA5", "I_LCA5"), ("HV_LCA5", "HV_LCA5"),
+                              ("sa_hv2", "hvd2"), ("sa_i2", "id2"), ("sa_i1", "id1"), ("sa_hv1", "hvd1")]:
+            hooks.append(getattr(model, name).register_forward_hook(
+                lambda m, i, o, tapname=tapname: caps.__setitem__(tapname, o.detach().clone())))
+        y = model(x)
+        for h in hooks:
+            h.remove()
+        out = {"x": x.numpy(), "y": y.numpy(), "seed": np.int64(seed), "perturb": np.int64(perturb),
+               "weights_abs_sum": np.float64(checksum(sd))}
+        for k_, v in caps.items():
+            out["tap|" + k_] = v.numpy().astype(np.float32)
+        np.savez_compressed(os.path.join(OUT, f"forward_mssa_s{seed}.npz"), **out)
+        print("forward_mssa", seed, y.shape, float(y.mean()))
+    with open(os.path.join(OUT, "state_dict_keys_mssa.txt"), "w") as f:
+        for k_, v in CIDNetMSSA().state_dict().items():
+            f.write(f"{k_} {list(v.shape)}\n")
+
+
 def state_dict_keys():
     model = CIDNet()
     with open(os.path.join(OUT, "state_dict_keys.txt"), "w") as f:
@@ -111,4 +138,5 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     hvi_cases()
     forward_cases()
+    forward_mssa_cases()
     state_dict_keys()

@@ -45,3 +45,17 @@ def test_ops_refuse_cpu_tensors(built_lib):
         m.HVIT(torch.rand(1, 3, 8, 8))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.PHVIT(torch.rand(1, 3, 8, 8))
+
+
+def test_mssa_mirror_state_dict_surface():
+    """net/CIDNet_MSSA.py mirror: exactly the 197 keys / shapes of the reference's MSSA class (golden key list
+    dumped from /root/reference/net/CIDNet_MSSA.py by oracle/make_golden.py)."""
+    import os
+    from conftest import GOLDEN
+    from hvi_cidnet_b200.net.CIDNet_MSSA import CIDNet
+    lines = open(os.path.join(GOLDEN, "state_dict_keys_mssa.txt")).read().strip().splitlines()
+    ref = {l.split(" ", 1)[0]: eval(l.split(" ", 1)[1]) for l in lines}
+    sd = CIDNet().state_dict()
+    assert set(sd.keys()) == set(ref.keys()) and len(sd) == 197      # order is irrelevant for dict loading
+    for k, v in sd.items():
+        assert list(v.shape) == ref[k], k

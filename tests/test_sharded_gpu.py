@@ -19,7 +19,7 @@ from conftest import ROOT, max_err_robust
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, H, W, use_nccl, ret):
+def _worker(rank, world, port, H, W, use_nccl, ret, mssa=False):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dev = torch.device("cuda", rank if use_nccl else 0)
@@ -29,12 +29,15 @@ def _worker(rank, world, port, H, W, use_nccl, ret):
     else:
         dist.init_process_group("gloo", rank=rank, world_size=world)
     import hvi_cidnet_b200  # noqa: F401
-    from hvi_cidnet_b200.net.CIDNet import CIDNet
+    if mssa:
+        from hvi_cidnet_b200.net.CIDNet_MSSA import CIDNet
+    else:
+        from hvi_cidnet_b200.net.CIDNet import CIDNet
     from hvi_cidnet_b200.dist import RowShardedCIDNet
     from oracle import cidnet_oracle as O
     torch.set_grad_enabled(False)
     torch.set_num_threads(4)
-    sd = O.make_state_dict(5, True)
+    sd = O.make_state_dict(5, True, mssa=mssa)
     model = CIDNet().to(dev).eval()
     model.load_state_dict(sd, strict=True)
     x = O.make_input("uniform", 1, H, W, seed=33)
@@ -47,7 +50,7 @@ def _worker(rank, world, port, H, W, use_nccl, ret):
            "allreduce_calls": sum(1 for e in net.comm.log if e[0] == "allreduce"),
            "direct": bool(net.comm.direct)}
     if rank == 0:
-        ref = O.forward(x, sd)
+        ref = O.forward(x, sd, mssa=mssa)
         out["vs_oracle"] = max_err_robust(y.clamp(0, 1), ref.clamp(0, 1))
         out["psnr"] = float(O.psnr(y.clamp(0, 1), ref.clamp(0, 1)))
     ret[rank] = out
@@ -55,13 +58,15 @@ def _worker(rank, world, port, H, W, use_nccl, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,H,W", [(2, 128, 64), (3, 192, 40), (2, 400, 600)])
-def test_row_sharded_forward_matches_unsharded(world, H, W):
+@pytest.mark.parametrize("world,H,W,mssa", [(2, 128, 64, False), (3, 192, 40, False), (2, 400, 600, False),
+                                            (2, 128, 64, True), (3, 240, 40, True)])
+def test_row_sharded_forward_matches_unsharded(world, H, W, mssa):
+    """mssa=True: the MSSA variant -- its 7x7 spatial-attention gates need three valid halo rows per up block"""
     use_nccl = torch.cuda.device_count() >= world
-    port = 33000 + (os.getpid() % 2000) + world
+    port = 33000 + (os.getpid() % 2000) + world + 7 * int(mssa)
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, port, H, W, use_nccl, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, H, W, use_nccl, ret, mssa), nprocs=world, join=True)
     assert len(ret) == world
     for r in range(world):
         o = ret[r]
