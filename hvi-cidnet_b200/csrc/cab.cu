@@ -18,6 +18,7 @@
 #include "cab.cuh"
 #include "ptx_sm100.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -580,17 +581,30 @@ gram_kernel(const __grid_constant__ GramArgs a) {
         ptx::mbar_wait(done, 0);
         ptx::tc_fence_after();
         float* gdst = a.gram[prob] + (long long)b * a.heads * 324;
+        // Only the per-head 18x18 diagonal blocks of the C x C product are wanted.  The 32 q channels of a warp
+        // belong to at most 3 heads, so the warp reads just the k-column window of those heads (<= 5 x 16 columns
+        // instead of all N) and every thread adds its own 18 columns with 8-byte vector reductions (row bases are
+        // multiples of 18 floats = 72 B, pairs start on even columns).  ncu on the previous all-columns / scalar-RED
+        // epilogue: ~70 % of the kernel's stall samples (index arithmetic per element, RED drain at EXIT).
         for (int mt = 0; mt < mtiles; ++mt) {
+            const int ch_lo = mt * 128 + q4 * 32;                 // warp-uniform
+            if (ch_lo >= C) break;
+            const int ch_hi = min(ch_lo + 31, C - 1);
+            const int col_lo = ((ch_lo / 18) * 18) & ~15;
+            const int col_hi = min((ch_hi / 18) * 18 + 18, N);
             const int ch = mt * 128 + r;
+            const int head = ch / 18;
+            const int kc0 = head * 18;                            // this thread's first k column
+            float* rowp = gdst + (long long)ch * 18;              // (head * 18 + qi) * 18 == ch * 18
             const bool row_ok = ch < C;
-            const int head = ch / 18, qi = ch - head * 18;
-            for (int cc = 0; cc < N; cc += 16) {
+            for (int cc = col_lo; cc < col_hi; cc += 16) {
                 float v[16];
                 ptx::tmem_ld16(taddr + mt * N + cc, v);
+                const int rel = cc - kc0;                         // column of v[0] relative to the thread's block
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int kc = cc + j;
-                    if (row_ok && kc < C && kc / 18 == head) atomicAdd(gdst + (head * 18 + qi) * 18 + (kc - head * 18), v[j]);
+                for (int j = 0; j < 16; j += 2) {
+                    if (row_ok && (unsigned)(rel + j) < 18u)
+                        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" :: "l"(rowp + rel + j), "f"(v[j]), "f"(v[j + 1]) : "memory");
                 }
             }
         }
@@ -619,13 +633,19 @@ int launch_gram(const GramLaunch& L, cudaStream_t stream) {
         if ((rc = encode_map_generic(&a.tmK[p], L.k[p], 3, dims, str, box))) return rc;
         a.gram[p] = L.gram[p];
     }
-    int nsplit = (148 * 2) / (L.nprob * L.B);
+    const int nA = 2 * ceil_div(L.C, 128), nB = ceil_div(round_up(L.C, 16), 64);
+    const size_t smem = 1024 + (size_t)kGramStages * (nA + nB) * kBlk + 64;
+    // split-K over CTAs, sized for ONE wave: shared memory allows 3 / 2 / 1 CTAs per SM for C = 36 / 72 / 144 (and
+    // C = 144 needs all 512 TMEM columns).  A partial second wave doubled the kernel time at the coarse levels, and
+    // every extra CTA costs C x 18 more atomic adds.
+    int sms = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    const int per_sm = L.C >= 144 ? 1 : (int)std::min<size_t>(3, (227 * 1024) / smem);
+    int nsplit = (sms * per_sm) / (L.nprob * L.B);
     if (nsplit < 1) nsplit = 1;
     if (nsplit > a.nchunks) nsplit = a.nchunks;
     a.chunks_per_cta = ceil_div(a.nchunks, nsplit);
     nsplit = ceil_div(a.nchunks, a.chunks_per_cta);
-    const int nA = 2 * ceil_div(L.C, 128), nB = ceil_div(round_up(L.C, 16), 64);
-    const size_t smem = 1024 + (size_t)kGramStages * (nA + nB) * kBlk + 64;
     static bool configured = false;
     if (!configured) {
         CIDNET_CUDA_OK(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -685,7 +705,10 @@ cab_fold_kernel(const CabFoldArgs a) {
 
 int launch_cab_fold(const CabFoldArgs& a, cudaStream_t stream) {
     CIDNET_CHECK(a.C <= 144, CIDNET_ERR_INVALID, "fold: C too large");
-    dim3 grid(a.nprob, a.B, 16);
+    // row slices per (problem, image): <= 2 output elements per thread (the kernel is a chain of dependent L2
+    // latencies, not work: ncu 13 us at C = 144 with 16 slices of ~7 elements per thread)
+    const int slices = std::min(64, std::max(16, ceil_div(a.n_rows * a.kt, 512)));
+    dim3 grid(a.nprob, a.B, slices);
     cab_fold_kernel<<<grid, 256, 0, stream>>>(a);
     CIDNET_CUDA_OK(cudaGetLastError());
     return CIDNET_OK;

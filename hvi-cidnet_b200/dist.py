@@ -155,14 +155,26 @@ class RowShardedCIDNet:
 
     Each rank uploads / computes only its strip (+ halo); conv halos and the partial Gram sums
     travel over NCCL (NVLink) -- see include/cidnet_b200.h, "rows sharded over the GPUs of one node".
+
+    CUDA-graph replay (EXPERIMENTAL, opt-in: `graph=True` or CIDNET_SHARD_GRAPH=1): the ~90 kernel launches of the
+    strip AND the NCCL halo send/recvs and all-reduces the library's callbacks issue are captured into one CUDA
+    graph on the third call with the same (shape, flags) and replayed afterwards -- at 8 GPUs the eager schedule
+    spends more time in host-side launches (89 kernels + 15 NCCL calls driven from Python) than on the GPU.
+    Every rank captures / replays in the same call, so the collectives stay matched.  With replay the returned
+    tensor is a STATIC buffer that the next call overwrites.  Only taken with an NCCL group on CUDA buffers (the
+    gloo-staged transport of the single-GPU tests copies through the host and cannot be captured).
     """
 
-    def __init__(self, model, group=None, halo=16):
+    def __init__(self, model, group=None, halo=16, graph=None):
+        import os
         self.model, self.group, self.halo = model, group, int(halo)
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._ws = {}
         self.comm = None
+        self.use_graph = bool(graph) if graph is not None else os.environ.get("CIDNET_SHARD_GRAPH", "0") == "1"
+        self._graphs = {}                 # key -> dict(seen, g, x, out, sig)
+        self.replays = 0
 
     def _workspace(self, rows, W, device):
         key = (rows, W, str(device))
@@ -171,6 +183,7 @@ class RowShardedCIDNet:
             n = L.lib().cidnet_workspace_bytes(1, rows, W)
             ws = torch.empty(n + 1024, dtype=torch.uint8, device=device)
             self._ws = {key: (ws, StripComm(ws, self.group) if self.world > 1 else None)}
+            self._graphs = {}             # captured graphs point into the previous workspace
         return self._ws[key]
 
     def forward_strip(self, x_local, H_global):
@@ -185,27 +198,60 @@ class RowShardedCIDNet:
             raise RuntimeError(f"forward_strip expects a CUDA fp32 [1,3,{rows},W] local image, got {tuple(x_local.shape)} on {dev}")
         W = x_local.shape[3]
         x_local = x_local.contiguous()
-        out = torch.empty_like(x_local)
+        t = m.trans
         with torch.cuda.device(dev):
             ctx = m._ensure_ctx(dev)
             ws, comm = self._workspace(rows, W, dev)
             self.comm = comm
-            if comm is not None:
-                comm.log, comm.bytes_sent = [], 0            # per-forward record of the exchanges
-            off = (-ws.data_ptr()) % 1024
-            t = m.trans
-            kd = t.density_k.detach()
             t._note_hvit_called()
-            rc = L.lib().cidnet_forward_sharded(
-                ctx, x_local.data_ptr(), out.data_ptr(), W, _C.byref(sh), ws.data_ptr() + off, ws.numel() - off,
-                kd.data_ptr() if kd.dtype == torch.float32 else None,
-                int(bool(t.gated)), float(t.alpha_s), int(bool(t.gated2)), float(t.alpha),
-                comm.halo_cb if comm else L.HALO_FN(), comm.allreduce_cb if comm else L.ALLREDUCE_FN(), None,
-                L.stream_ptr(dev))
-            if comm is not None and comm.error is not None:
-                err, comm.error = comm.error, None
-                raise err
-            L.check(rc)
+            key = (rows, W, str(dev), bool(t.gated), float(t.alpha_s), bool(t.gated2), float(t.alpha), m._synced,
+                   t.density_k.data_ptr())
+            ent = self._graphs.setdefault(key, {"seen": 0, "g": None})
+            can_graph = self.use_graph and (comm is None or comm.direct)
+            if can_graph and ent["g"] is not None:
+                ent["x"].copy_(x_local, non_blocking=True)
+                ent["g"].replay()
+                self.replays += 1
+                return ent["out"], sh
+
+            def run(xin, xout):
+                if comm is not None:
+                    comm.log, comm.bytes_sent = [], 0            # per-forward record of the exchanges
+                off = (-ws.data_ptr()) % 1024
+                kd = t.density_k.detach()
+                rc = L.lib().cidnet_forward_sharded(
+                    ctx, xin.data_ptr(), xout.data_ptr(), W, _C.byref(sh), ws.data_ptr() + off, ws.numel() - off,
+                    kd.data_ptr() if kd.dtype == torch.float32 else None,
+                    int(bool(t.gated)), float(t.alpha_s), int(bool(t.gated2)), float(t.alpha),
+                    comm.halo_cb if comm else L.HALO_FN(), comm.allreduce_cb if comm else L.ALLREDUCE_FN(), None,
+                    L.stream_ptr(dev))
+                if comm is not None and comm.error is not None:
+                    err, comm.error = comm.error, None
+                    raise err
+                L.check(rc)
+
+            ent["seen"] += 1
+            if can_graph and ent["seen"] >= 3:
+                # two eager calls have set the kernels' attributes and opened NCCL's peer connections
+                sx, sout = x_local.clone(), torch.empty_like(x_local)
+                g = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                try:
+                    with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+                        run(sx, sout)
+                except Exception as e:      # keep working eagerly; every rank sees the same failure mode
+                    self.use_graph = False
+                    self.graph_error = repr(e)
+                    torch.cuda.synchronize(dev)
+                else:
+                    torch.cuda.current_stream(dev).wait_stream(side)
+                    ent.update(g=g, x=sx, out=sout)
+                    g.replay()
+                    self.replays += 1
+                    return sout, sh
+            out = torch.empty_like(x_local)
+            run(x_local, out)
         return out, sh
 
     def __call__(self, x, gather=True):

@@ -44,8 +44,11 @@ def _worker(rank, world, port, H, W, use_nccl, ret, mssa=False):
     net = RowShardedCIDNet(model, halo=16)
     y = net(x.pin_memory(), gather=True).cpu()           # full image on every rank
     y2 = net(x.to(dev), gather=True).cpu()               # second call: same workspace, device input
+    y3 = net(x.to(dev), gather=True).cpu()               # third / fourth call: CUDA-graph capture and replay of the
+    y4 = net(x.to(dev), gather=True).cpu()               # kernels + NCCL exchanges (NCCL transport only; eager otherwise)
     full = model(x.to(dev)).cpu()                        # unsharded CUDA forward on this rank's GPU
-    out = {"vs_full": max_err_robust(y, full), "repeat": max_err_robust(y, y2),
+    out = {"vs_full": max_err_robust(y, full), "repeat": max(max_err_robust(y, y2), max_err_robust(y, y3), max_err_robust(y, y4)),
+           "replays": net.replays, "graph_error": getattr(net, "graph_error", None),
            "halo_calls": sum(1 for e in net.comm.log if e[0] == "halo"),
            "allreduce_calls": sum(1 for e in net.comm.log if e[0] == "allreduce"),
            "direct": bool(net.comm.direct)}
@@ -74,6 +77,8 @@ def test_row_sharded_forward_matches_unsharded(world, H, W, mssa):
         assert o["repeat"] <= 5e-4, (r, o)
         assert o["allreduce_calls"] == 6 and o["halo_calls"] >= 6, (r, o)
         assert o["direct"] == use_nccl
+        # graph replay is opt-in (CIDNET_SHARD_GRAPH=1) and needs the NCCL transport
+        assert o["replays"] == (2 if (use_nccl and os.environ.get("CIDNET_SHARD_GRAPH") == "1") else 0), (r, o)
     assert ret[0]["vs_oracle"] <= 2e-3 and ret[0]["psnr"] >= 50.0, ret[0]
 
 
