@@ -454,6 +454,7 @@ def run_cfg5_sharded(args, model, sd, wdesc, dev, world, rank, peaks):
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "roofline": None, "cpu_baseline": None, "clocks": clocks}
         print(json.dumps(line), flush=True)
+    net.close()
     dist.destroy_process_group()
 
 

@@ -38,14 +38,14 @@ namespace cidnet {
 
 // ------------------------------------------------------------------ params ---
 struct ConvGemmArgs {
-    CUtensorMap tmA, tmA2, tmB, tmB2, tmOut;
+    CUtensorMap tmA, tmA2, tmB, tmB2, tmOut, tmUp;
     int taps, kchunks, kchunks2, cin, cin2;
     int Hv, Wv, TH, TW, tiles_x, tiles_y, num_tiles;
     int n_out, block_n, stages, per_image_w, b_resident, stg_bufs;
     int halo, halo_baseoff;          // 3x3: tile + halo loaded once per channel chunk, taps = row-shifted views
     int w_real;
     const float* bias; const float* wsum; float ln_eps;
-    const act_t* up; int up_H, up_W, up_pitch; long long up_img_stride; float up_ry, up_rx;
+    int up_H, up_W, up_chunks; float up_ry, up_rx;   // EPI_UP: low-res source (staged by TMA next to every A tile)
     float prelu; int use_prelu;
     float down_ry, down_rx; int in_H, in_W;
     // row-strip sharding: global row index of local output row 0 (DOWN: on the half-resolution grid,
@@ -59,6 +59,11 @@ static constexpr int kThreads = 64 + 128 * kEpiGroups;
 static constexpr uint32_t kSubTileBytes = 128 * 128;   // 128 rows x 64 elements x 2 B
 static constexpr uint32_t kStagingBytes = 128 * 128;   // one 64-channel output block of a tile
 static constexpr uint32_t kHaloTileBytes = 11 * 16 * 128;   // halo mode: 11 rows x 16 columns x 64 channels
+// EPI_UP: the low-res pixels an 8 x 16 output tile interpolates from (align_corners x2: <= 6 rows x 10 columns) are
+// one TMA box per 64 channels, staged behind the A tile of the same pipeline stage
+static constexpr int kUpBoxW = 10, kUpBoxH = 6;
+static constexpr uint32_t kUpBoxBytes = kUpBoxW * kUpBoxH * 128;   // what the TMA delivers (zero fill included)
+static constexpr uint32_t kUpTileBytes = 8192;                      // its slot (1024-byte aligned for the swizzle)
 
 __device__ __forceinline__ float prelu_f(float v, float slope) { return v >= 0.f ? v : v * slope; }
 
@@ -98,7 +103,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
     constexpr int kSub = (kMode == EPI_DOWN) ? 2 : 1;
-    const uint32_t a_stage = kSub * (a.halo ? kHaloTileBytes : kSubTileBytes);
+    const uint32_t a_stage = kSub * (a.halo ? kHaloTileBytes : kSubTileBytes) + (kMode == EPI_UP ? a.up_chunks * kUpTileBytes : 0u);
     const uint32_t b_chunk = (uint32_t)a.block_n * 128u;
     const int stages = a.stages;
     const int k1 = a.taps * a.kchunks;              // primary K chunks (weight chunks)
@@ -132,10 +137,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
         ptx::prefetch_tensormap(&a.tmB);
         ptx::prefetch_tensormap(&a.tmOut);
         if (a.kchunks2) { ptx::prefetch_tensormap(&a.tmA2); ptx::prefetch_tensormap(&a.tmB2); }
+        if (kMode == EPI_UP) ptx::prefetch_tensormap(&a.tmUp);
     }
     if (warp == 1) {
         if (lane == 0) {
-            const uint32_t empty_count = (kMode == EPI_LN) ? 5u : 1u;   // MMA commit (+ 4 epilogue warps for LN)
+            // MMA commit (+ the 4 epilogue warps of the tile's group for LN / UP, which read the stage themselves)
+            const uint32_t empty_count = (kMode == EPI_LN || kMode == EPI_UP) ? 5u : 1u;
             for (int s = 0; s < stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], empty_count); }
             ptx::mbar_init(bfull, 1);
             for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], 4); }
@@ -176,8 +183,16 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                     const int s = it % stages;
                     const uint32_t ph = (it / stages) & 1u;
                     ptx::mbar_wait(&empty[s], ph ^ 1u);
-                    ptx::mbar_expect_tx(&full[s], a_stage + (a.b_resident ? 0u : b_chunk));
+                    const bool up_here = (kMode == EPI_UP) && i == 0;      // the tile's low-res box rides with its first stage
+                    const uint32_t a_bytes = kSub * (a.halo ? kHaloTileBytes : kSubTileBytes);
+                    ptx::mbar_expect_tx(&full[s], a_bytes + (up_here ? a.up_chunks * kUpBoxBytes : 0u) + (a.b_resident ? 0u : b_chunk));
                     uint8_t* dstA = smA + (size_t)s * a_stage;
+                    if (up_here) {
+                        const int by0 = (int)(a.up_ry * (float)(y0 + a.up_row0)) - a.up_src_row0;
+                        const int bx0 = (int)(a.up_rx * (float)x0);
+                        for (int ch = 0; ch < a.up_chunks; ++ch)
+                            ptx::tma_load_4d(dstA + kSubTileBytes + ch * kUpTileBytes, &a.tmUp, &full[s], ch * 64, bx0, by0, img);
+                    }
                     if (a.halo) {
                         // i == channel chunk; one (DOWN: two, even / odd rows) halo box serves all 9 taps
                         if (kMode == EPI_DOWN) {
@@ -346,34 +361,30 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
             }
             it += kiters;
 
-            // EPI_UP: bilinear x2 taps of the low-res tensor (align_corners=True); pull them towards L1
-            // while the MMAs of this tile are still running
-            const act_t *t00 = nullptr, *t01 = nullptr, *t10 = nullptr, *t11 = nullptr;
+            // EPI_UP: bilinear x2 taps of the low-res tensor (align_corners=True), read from the box the producer
+            // staged with this tile's first pipeline stage (rows of 64 channels, SWIZZLE_128B)
+            const uint8_t* up_tile = nullptr;
+            uint32_t u00 = 0, u01 = 0, u10 = 0, u11 = 0;      // box row index (128-byte rows) of the four neighbours
             float uly = 0.f, ulx = 0.f;
-            if (kMode == EPI_UP && valid) {
-                const long long pix = (long long)y * a.Wv + x;
-                const int yr = (int)(pix / a.w_real), xr = (int)(pix - (long long)yr * a.w_real);
+            const uint32_t up_it = it - kiters;               // pipeline iteration of this tile's first stage
+            if (kMode == EPI_UP) {
+                const uint32_t s0 = up_it % stages;
+                ptx::mbar_wait(&full[s0], (up_it / stages) & 1u);
+                up_tile = smA + (size_t)s0 * a_stage + kSubTileBytes;
+                const int yr = y, xr = x;                                    // UP tiles are 8 x 16 rectangles of one image
                 const float sy = a.up_ry * (float)(yr + a.up_row0);          // GLOBAL source row
                 const int i0g = (int)sy; uly = sy - (float)i0g;
                 const int i1g = i0g + (i0g < a.up_Hg - 1 ? 1 : 0);
-                // local rows of the strip (clamped: rows outside it only feed halo rows that are invalid anyway)
-                const int i0 = min(max(i0g - a.up_src_row0, 0), a.up_H - 1);
-                const int i1 = min(max(i1g - a.up_src_row0, 0), a.up_H - 1);
                 const float sx = a.up_rx * (float)xr;
                 const int j0 = (int)sx; ulx = sx - (float)j0;
                 const int j1 = j0 + (j0 < a.up_W - 1 ? 1 : 0);
-                const act_t* tb = a.up + (long long)img * a.up_img_stride + n0;
-                t00 = tb + ((long long)i0 * a.up_W + j0) * a.up_pitch;
-                t01 = tb + ((long long)i0 * a.up_W + j1) * a.up_pitch;
-                t10 = tb + ((long long)i1 * a.up_W + j0) * a.up_pitch;
-                t11 = tb + ((long long)i1 * a.up_W + j1) * a.up_pitch;
-                const int bytes = min(a.block_n, a.n_out - n0) * 2;
-                for (int o = 0; o < bytes; o += 128) {
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(reinterpret_cast<const char*>(t00) + o));
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(reinterpret_cast<const char*>(t01) + o));
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(reinterpret_cast<const char*>(t10) + o));
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(reinterpret_cast<const char*>(t11) + o));
-                }
+                // box origin: the same arithmetic as the producer's.  Rows / columns clamp into the box: only pixels
+                // outside the image (never stored) or invalid halo rows of a row strip can fall outside it
+                const int by0 = (int)(a.up_ry * (float)(y0 + a.up_row0));
+                const int bx0 = (int)(a.up_rx * (float)x0);
+                const int r0 = min(max(i0g - by0, 0), kUpBoxH - 1), r1 = min(max(i1g - by0, 0), kUpBoxH - 1);
+                const int c0 = min(max(j0 - bx0, 0), kUpBoxW - 1), c1 = min(max(j1 - bx0, 0), kUpBoxW - 1);
+                u00 = r0 * kUpBoxW + c0; u01 = r0 * kUpBoxW + c1; u10 = r1 * kUpBoxW + c0; u11 = r1 * kUpBoxW + c1;
             }
             // EPI_DOWN geometry: y counts ROW PAIRS == output rows; even lanes own an output pixel
             float dly = 0.f, dlx = 0.f;
@@ -437,19 +448,21 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                             }
                         } else if (kMode == EPI_UP) {
                             const int nrem = a.n_out - (n0 + c);
-                            if (valid) {
+                            const uint8_t* ub = up_tile + cb * kUpTileBytes;
 #pragma unroll
-                                for (int h = 0; h < 4; ++h) {
-                                    if (nrem > 8 * h) {
-                                        float p00[8], p01[8], p10[8], p11[8];
-                                        load8(t00 + c + 8 * h, p00); load8(t01 + c + 8 * h, p01);
-                                        load8(t10 + c + 8 * h, p10); load8(t11 + c + 8 * h, p11);
+                            for (int h = 0; h < 4; ++h) {
+                                if (nrem > 8 * h) {                            // warp-uniform
+                                    const uint32_t ck = (uint32_t)(hh * 4 + h);   // 16-byte chunk of the 128-byte row
+                                    float p00[8], p01[8], p10[8], p11[8];
+                                    load8(reinterpret_cast<const act_t*>(ub + u00 * 128 + ((ck ^ (u00 & 7)) << 4)), p00);
+                                    load8(reinterpret_cast<const act_t*>(ub + u01 * 128 + ((ck ^ (u01 & 7)) << 4)), p01);
+                                    load8(reinterpret_cast<const act_t*>(ub + u10 * 128 + ((ck ^ (u10 & 7)) << 4)), p10);
+                                    load8(reinterpret_cast<const act_t*>(ub + u11 * 128 + ((ck ^ (u11 & 7)) << 4)), p11);
 #pragma unroll
-                                        for (int e = 0; e < 8; ++e) {
-                                            const float up = (1.f - uly) * ((1.f - ulx) * p00[e] + ulx * p01[e]) +
-                                                             uly * ((1.f - ulx) * p10[e] + ulx * p11[e]);
-                                            v[8 * h + e] = prelu_f(v[8 * h + e] + up, a.prelu);
-                                        }
+                                    for (int e = 0; e < 8; ++e) {
+                                        const float up = (1.f - uly) * ((1.f - ulx) * p00[e] + ulx * p01[e]) +
+                                                         uly * ((1.f - ulx) * p10[e] + ulx * p11[e]);
+                                        v[8 * h + e] = prelu_f(v[8 * h + e] + up, a.prelu);
                                     }
                                 }
                             }
@@ -479,7 +492,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
             // all TMEM reads of this buffer are done -> hand it back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
+            if (lane == 0) {
+                ptx::mbar_arrive(&tmem_empty[buf]);
+                if (kMode == EPI_UP)      // the low-res box has been read: co-release the tile's stages
+                    for (int i = 0; i < kiters; ++i) ptx::mbar_arrive(&empty[(up_it + i) % stages]);
+            }
         }
         if (issuer) ptx::tma_store_wait_all();
     }
@@ -631,7 +648,7 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
         const uint32_t obox[4] = {64, (uint32_t)(tw / 2), 8, 1};
         if ((rc = encode_map(&a.tmOut, L.out, 4, od, os, obox))) return rc;
     } else {
-        if (L.flat) { a.Hv = 1; a.Wv = (int)hw; a.TH = 1; a.TW = 128; }
+        if (L.flat && L.mode != EPI_UP) { a.Hv = 1; a.Wv = (int)hw; a.TH = 1; a.TW = 128; }   // UP tiles are always 8 x 16 rectangles
         else        { a.Hv = L.H; a.Wv = L.W; a.TH = 8; a.TW = tw; }
         const uint64_t dims[4] = {(uint64_t)wt.cin, (uint64_t)a.Wv, (uint64_t)a.Hv, (uint64_t)L.B};
         const uint64_t str[3] = {pb, pb * a.Wv, pb * hw};
@@ -658,8 +675,15 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
         }
         if (L.mode == EPI_UP) {
             CIDNET_CHECK(L.up != nullptr && L.H % 2 == 0 && L.W % 2 == 0, CIDNET_ERR_INVALID, "conv_gemm: UP needs t");
-            a.up = L.up; a.up_H = L.H / 2; a.up_W = L.W / 2; a.up_pitch = L.up_pitch;
-            a.up_img_stride = (hw / 4) * L.up_pitch;
+            CIDNET_CHECK(wt.n_blocks == 1 && L.up_pitch % 8 == 0 && !L.in2, CIDNET_ERR_INVALID, "conv_gemm: UP needs a single N block");
+            a.up_H = L.H / 2; a.up_W = L.W / 2; a.up_chunks = ceil_div(wt.n_out, 64);
+            {   // low-res tensor t [B][H/2][W/2][up_pitch]: one {64 ch, 10, 6} box per output tile and 64 channels
+                const uint64_t ub = (uint64_t)L.up_pitch * sizeof(act_t);
+                const uint64_t ud[4] = {(uint64_t)wt.n_out, (uint64_t)a.up_W, (uint64_t)a.up_H, (uint64_t)L.B};
+                const uint64_t us[3] = {ub, ub * a.up_W, ub * (uint64_t)a.up_W * a.up_H};
+                const uint32_t ubox[4] = {64, (uint32_t)kUpBoxW, (uint32_t)kUpBoxH, 1};
+                if ((rc = encode_map(&a.tmUp, L.up, 4, ud, us, ubox))) return rc;
+            }
             const int gH = L.gH ? L.gH : L.H;
             CIDNET_CHECK(gH % 2 == 0 && L.grow % 2 == 0 && L.grow + L.H <= gH, CIDNET_ERR_INVALID, "conv_gemm: bad row strip");
             a.up_ry = ac_scale(gH / 2, gH); a.up_rx = ac_scale(L.W / 2, L.W);
@@ -680,7 +704,8 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
     // shared-memory plan: [resident weights] [A ring] [streamed-weight ring] [2 staging] [barriers, bias]
     const int nbchunks = wt.taps * wt.kchunks + a.kchunks2;
     const int kiters = a.halo ? wt.kchunks : nbchunks;
-    const size_t a_stage = (size_t)ksub * (a.halo ? kHaloTileBytes : kSubTileBytes);
+    const size_t a_stage = (size_t)ksub * (a.halo ? kHaloTileBytes : kSubTileBytes) +
+                           (L.mode == EPI_UP ? (size_t)a.up_chunks * kUpTileBytes : 0);
     const size_t b_chunk = (size_t)wt.block_n * 128;
     const size_t budget = 226 * 1024;
     int min_stages = 2;
@@ -694,7 +719,9 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
     // per-tile cost (~3000-3900 cycles whatever N and K) is the epilogue's dependent-latency chain, not the
     // load pipeline -- so the ring stays at 2 tiles.  CIDNET_GEMM_DEPTH overrides (tiles).
     static const int depth = getenv("CIDNET_GEMM_DEPTH") ? atoi(getenv("CIDNET_GEMM_DEPTH")) : 2;
-    const int want = depth * kiters > min_stages ? depth * kiters : min_stages;
+    // UP: each epilogue group holds its tile's stages (the low-res box) until it is done -> one more tile of slack
+    const int tiles_in_ring = L.mode == EPI_UP ? depth + 2 : depth;
+    const int want = tiles_in_ring * kiters > min_stages ? tiles_in_ring * kiters : min_stages;
     int stages = 0;
     size_t fixed = 0;
     // preference: resident weights (2 staging buffers, then 1), else streamed weights (2, then 1)

@@ -176,6 +176,14 @@ class RowShardedCIDNet:
         self._graphs = {}                 # key -> dict(seen, g, x, out, sig)
         self.replays = 0
 
+    def close(self):
+        """Drop the captured CUDA graphs.  Call before `dist.destroy_process_group()`: tearing the NCCL
+        communicator down while instantiated graphs still hold its kernels blocks (measured: the 2-rank probe hung
+        in destroy_process_group until the graphs were released first)."""
+        if self._graphs:
+            torch.cuda.synchronize()
+        self._graphs = {}
+
     def _workspace(self, rows, W, device):
         key = (rows, W, str(device))
         if key not in self._ws:
@@ -238,7 +246,7 @@ class RowShardedCIDNet:
                 side = torch.cuda.Stream(device=dev)
                 side.wait_stream(torch.cuda.current_stream(dev))
                 try:
-                    with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+                    with torch.cuda.graph(g, stream=side, capture_error_mode="relaxed"):
                         run(sx, sout)
                 except Exception as e:      # keep working eagerly; every rank sees the same failure mode
                     self.use_graph = False

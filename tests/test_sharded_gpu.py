@@ -57,6 +57,7 @@ def _worker(rank, world, port, H, W, use_nccl, ret, mssa=False):
         out["vs_oracle"] = max_err_robust(y.clamp(0, 1), ref.clamp(0, 1))
         out["psnr"] = float(O.psnr(y.clamp(0, 1), ref.clamp(0, 1)))
     ret[rank] = out
+    net.close()                                          # captured graphs must go before the communicator
     dist.barrier()
     dist.destroy_process_group()
 
