@@ -166,10 +166,15 @@ __device__ __forceinline__ void hfma8(uint4& acc, const uint4& t, const uint4& w
     acc.z = hfma2u(t.z, w.z, acc.z); acc.w = hfma2u(t.w, w.w, acc.w);
 }
 
-template <bool kPrefetch, int kMinBlocks>
+// kWsmem: the 9 weight vectors are re-read from shared memory at every row (9 conflict-free LDS.128) instead of
+// living in 36 registers -> ~100 registers, 5 CTAs / SM WITH the one-row-ahead prefetch.  ncu on the register-weight
+// kernel (L1, cfg 2): issue slots 25 % busy, 21 % of the warp slots occupied, long_scoreboard 9.6 stall cycles per
+// issue -> bound by the latency of its own global loads, i.e. by how many rows are in flight per SM.
+template <bool kPrefetch, int kMinBlocks, bool kWsmem = false>
 __global__ void __launch_bounds__(kDwThreads, kMinBlocks)
 dw3x3_kernel(const Dw3Args a) {
     __shared__ float s_ssq[2 * 144];
+    __shared__ __align__(16) act_t s_w[kWsmem ? 9 * 432 : 8];
     const int prob = blockIdx.z % a.nprob, b = blockIdx.z / a.nprob;
     const int nv = a.nv;                                   // 16-byte vectors per pixel (all segments)
     const int idx = blockIdx.x * kDwThreads + threadIdx.x; // vector index along the row
@@ -184,18 +189,32 @@ dw3x3_kernel(const Dw3Args a) {
     const int y1 = min(y0 + kDwRows, a.H);
 
     for (int i = threadIdx.x; i < 2 * 144; i += kDwThreads) s_ssq[i] = 0.f;
+    if (kWsmem) {
+        const float* wp = a.w[prob];                                // [9][nv*8] tap major, fp32
+        for (int i = threadIdx.x; i < 9 * nv * 8; i += kDwThreads) s_w[i] = f2act(__ldg(wp + i));
+    }
     __syncthreads();
 
-    uint4 w[9];
-    {
+    uint4 wreg[kWsmem ? 1 : 9];
+    if (!kWsmem) {
         const float* wp = a.w[prob] + seg * a.seg_vecs * 8 + c0;   // [9][nv*8] tap major
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
-            act_t* h = reinterpret_cast<act_t*>(&w[t]);
+            act_t* h = reinterpret_cast<act_t*>(&wreg[t]);
 #pragma unroll
             for (int e = 0; e < 8; ++e) h[e] = f2act(active ? __ldg(wp + t * nv * 8 + e) : 0.f);
         }
     }
+    const uint4* wsm = reinterpret_cast<const uint4*>(s_w) + (active ? v : 0);     // tap t: wsm[t * nv]
+    // asm volatile: the loads must stay where they are used (hoisted out of the row loop they would occupy the
+    // 36 registers this variant exists to free)
+    const uint32_t wsm_addr = ptx::smem_u32(wsm);
+    auto W9 = [&](int t) -> uint4 {
+        if (!kWsmem) return wreg[kWsmem ? 0 : t];
+        uint4 r;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(wsm_addr + (uint32_t)(t * nv * 16)));
+        return r;
+    };
     float ssq[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) ssq[e] = 0.f;
@@ -216,13 +235,13 @@ dw3x3_kernel(const Dw3Args a) {
         auto step = [&](const uint4* r0, const uint4* r1, uint4* r2, int y) {
             if (kPrefetch) { r2[0] = pend[0]; r2[1] = pend[1]; r2[2] = pend[2]; issue(y + 2); }   // row y+1 arrives, y+2 leaves
             else           { issue(y + 1); r2[0] = pend[0]; r2[1] = pend[1]; r2[2] = pend[2]; }
-            uint4 pa = hmul8(r0[0], w[0]);
-            uint4 pb = hmul8(r2[0], w[6]);
-            hfma8(pa, r0[1], w[1]); hfma8(pb, r2[1], w[7]);
-            hfma8(pa, r0[2], w[2]); hfma8(pb, r2[2], w[8]);
-            hfma8(pa, r1[0], w[3]);
-            hfma8(pa, r1[1], w[4]);
-            hfma8(pa, r1[2], w[5]);
+            uint4 pa = hmul8(r0[0], W9(0));
+            uint4 pb = hmul8(r2[0], W9(6));
+            hfma8(pa, r0[1], W9(1)); hfma8(pb, r2[1], W9(7));
+            hfma8(pa, r0[2], W9(2)); hfma8(pb, r2[2], W9(8));
+            hfma8(pa, r1[0], W9(3));
+            hfma8(pa, r1[1], W9(4));
+            hfma8(pa, r1[2], W9(5));
             const uint4 raw = make_uint4(hadd2u(pa.x, pb.x), hadd2u(pa.y, pb.y), hadd2u(pa.z, pb.z), hadd2u(pa.w, pb.w));
             if (y >= a.stat_y0 && y < a.stat_y1) fhfma8(ssq, raw, raw);   // sum of squares of the STORED values
             *reinterpret_cast<uint4*>(dst + ((long long)y * a.W + x) * a.dst_pitch) = raw;
@@ -441,11 +460,15 @@ int launch_dw3(const Dw3Args& a_in, cudaStream_t stream) {
     CIDNET_CHECK(a.seg_vecs * 8 <= 144 && a.nv == 3 * a.seg_vecs, CIDNET_ERR_INVALID, "dw3: bad channel layout");
     dim3 grid(ceil_div(a.W * a.nv, kDwThreads), ceil_div(a.H, kDwRows), a.B * a.nprob);
 #ifndef CIDNET_ACT_BF16
-    // 0 (default): packed fp16, no prefetch, 4 CTAs / SM; 1: packed fp16, one-row prefetch, 3 CTAs / SM;
+    // 7 (default): packed fp16, weights re-read from smem, one-row prefetch, 4 CTAs / SM (3-8 % faster than 0 on B200);
+    // 0: weights in registers, no prefetch, 4 CTAs / SM; 1: weights in registers, one-row prefetch, 3 CTAs / SM; 5 / 6: 5 CTAs / SM (spills, slower);
     // 2: fp32-accumulate FHFMA kernel
-    static const int variant = getenv("CIDNET_DW_VARIANT") ? atoi(getenv("CIDNET_DW_VARIANT")) : 0;
+    static const int variant = getenv("CIDNET_DW_VARIANT") ? atoi(getenv("CIDNET_DW_VARIANT")) : 7;
     if (variant == 3 || variant == 4) return launch_dw3_v2(a, stream, variant == 3 ? 4 : 3);   // v2 (TMA ring), 4 / 3 CTAs per SM
-    if (variant == 0)      dw3x3_kernel<false, 4><<<grid, kDwThreads, 0, stream>>>(a);
+    if (variant == 5)      dw3x3_kernel<true, 5, true><<<grid, kDwThreads, 0, stream>>>(a);    // weights in smem, prefetch, 5 CTAs / SM
+    else if (variant == 6) dw3x3_kernel<false, 5, true><<<grid, kDwThreads, 0, stream>>>(a);   // weights in smem, no prefetch, 5 CTAs / SM
+    else if (variant == 7) dw3x3_kernel<true, 4, true><<<grid, kDwThreads, 0, stream>>>(a);    // weights in smem, prefetch, 4 CTAs / SM
+    else if (variant == 0) dw3x3_kernel<false, 4><<<grid, kDwThreads, 0, stream>>>(a);
     else if (variant == 1) dw3x3_kernel<true, 3><<<grid, kDwThreads, 0, stream>>>(a);
     else                   dw3x3_f32acc_kernel<<<grid, kDwThreads, 0, stream>>>(a);
 #else
