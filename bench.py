@@ -392,7 +392,7 @@ def run_cfg5_sharded(args, model, sd, wdesc, dev, world, rank, peaks):
     import torch.distributed as dist
     from hvi_cidnet_b200.dist import RowShardedCIDNet, strip_plan, strip_local_range
     B, H, W, desc = WORKLOADS["cfg5"]
-    net = RowShardedCIDNet(model, halo=16)
+    net = RowShardedCIDNet(model, halo=16, graph=True)       # kernels + NCCL exchanges replayed as one CUDA graph
     sh = strip_plan(H, world, rank, 16)
     a, b = strip_local_range(sh)
     g = torch.Generator().manual_seed(1234)
