@@ -55,6 +55,7 @@ struct cidnet_ctx {
     float k_host = 0.2f;
     float* k_dev = nullptr;
     float *stem_whv = nullptr, *stem_wi = nullptr, *head_wi = nullptr, *head_whv = nullptr;
+    const uint2 *stem_bfrag = nullptr, *head_bfrag = nullptr;
     DownWeights down[2][3];    // [branch 0=I,1=HV][block1..3]
     UpWeights up[2][3];        // [branch][block3, block2, block1]  (index 0 = block3)
     StageWeights stage[6];
@@ -256,6 +257,15 @@ int build_weights(cidnet_ctx* ctx) {
         if ((rc = dev_f32(ctx, &ctx->stem_wi, b))) return rc;
         if ((rc = dev_f32(ctx, &ctx->head_wi, c))) return rc;
         if ((rc = dev_f32(ctx, &ctx->head_whv, d))) return rc;
+        // per-lane B fragments of the stem / head tensor-core kernels (uint2 viewed as 2 floats for the upload helper)
+        std::vector<float> fs(3 * 5 * 32 * 2), fh(2 * 9 * 3 * 32 * 2);
+        pack_stem_bfrag(a.data(), b.data(), reinterpret_cast<uint2*>(fs.data()));
+        pack_head_bfrag(c.data(), d.data(), reinterpret_cast<uint2*>(fh.data()));
+        float *dfs = nullptr, *dfh = nullptr;
+        if ((rc = dev_f32(ctx, &dfs, fs))) return rc;
+        if ((rc = dev_f32(ctx, &dfh, fh))) return rc;
+        ctx->stem_bfrag = reinterpret_cast<const uint2*>(dfs);
+        ctx->head_bfrag = reinterpret_cast<const uint2*>(dfh);
     }
     const char* enc[2] = {"IE", "HVE"};
     const char* dec[2] = {"ID", "HVD"};
@@ -705,7 +715,7 @@ struct Fwd {
         int rc;
         if (live()) CIDNET_CUDA_OK(cudaMemsetAsync(P.stats, 0, (size_t)P.stats_bytes, st));
         StemArgs sa{rgb_in, P.hvi, P.i_enc0, P.hv_0, ctx->stem_whv, ctx->stem_wi, k_dev ? k_dev : ctx->k_dev,
-                    ctx->k_host, P.B, P.H[0], P.W[0], 40};
+                    ctx->k_host, P.B, P.H[0], P.W[0], 40, ctx->stem_bfrag};
         mark("L0.stem_hvit_block0", (double)P.B * P.H[0] * P.W[0] * 168.0, (double)P.B * P.H[0] * P.W[0] * 2.0 * 1296);
         if (live() && (rc = launch_stem(sa, st))) return rc;
         // the local input image carries the neighbours' rows: the replicate-padded 3x3 spoils the outermost one
@@ -765,7 +775,8 @@ struct Fwd {
         tap("id1", P.id1, 36, 0, 40); tap("hvd1", P.hvd1, 36, 0, 40);
         if ((rc = ensure({{P.id1, 0, 40}, {P.hvd1, 0, 40}}, 1))) return rc;
         HeadArgs ha{P.id1, P.hvd1, P.hvi, rgb_out, P.out_hvi, ctx->head_wi, ctx->head_whv,
-                    k_dev ? k_dev : ctx->k_dev, ctx->k_host, alpha_s, alpha, gated, gated2, P.B, P.H[0], P.W[0], 40};
+                    k_dev ? k_dev : ctx->k_dev, ctx->k_host, alpha_s, alpha, gated, gated2, P.B, P.H[0], P.W[0], 40,
+                    ctx->head_bfrag};
         mark("L0.head_block0_phvit", (double)P.B * P.H[0] * P.W[0] * 168.0, (double)P.B * P.H[0] * P.W[0] * 2.0 * 972);
         if (live() && (rc = launch_head(ha, st))) return rc;
         finish_marks();

@@ -10,6 +10,9 @@
 #include "stem_head.cuh"
 #include "hvi_math.cuh"
 
+#include <cstdlib>
+#include <cstring>
+
 namespace cidnet {
 
 #ifdef CIDNET_ACT_BF16
@@ -37,7 +40,7 @@ __global__ void __launch_bounds__(256)
 stem_kernel(const float* __restrict__ rgb, float* __restrict__ hvi, act_t* __restrict__ i_enc0,
             act_t* __restrict__ hv_0, const float* __restrict__ w_hv /*[27][36]*/,
             const float* __restrict__ w_i /*[9][36]*/, const float* __restrict__ k_dev, float k_host,
-            int H, int W, int pitch) {
+            int H, int W, int pitch, const uint2* __restrict__ /*bfrag: mma variant only*/) {
     __shared__ float s_hvi[3][kHalo * kHalo];
     __shared__ __align__(16) float s_whv[27 * 36];
     __shared__ __align__(16) float s_wi[9 * 36];
@@ -120,13 +123,215 @@ stem_kernel(const float* __restrict__ rgb, float* __restrict__ hvi, act_t* __res
     }
 }
 
-const void* stem_kernel_func() { return reinterpret_cast<const void*>(&stem_kernel); }
+
+// ---------------------------------------------------------------------------------------------
+// Warp-level tensor-core variants (default).  Both block0 stages are tiny GEMMs per pixel (stem: K = 27 / 9,
+// N = 36; head: K = 9 x 36, N = 1 / 2) that the fp32-FMA kernels above spend 1300-1700 instructions per pixel on
+// (ncu: issue-bound at 1.2-1.5 TB/s, 4-5x their HBM floor).  m16n8k16 `mma.sync` (16-bit operands, fp32 accumulate,
+// like every other conv of the path) needs ~30 (stem) / ~110 (head) MMAs per 32 pixels instead; operands come straight
+// from the halo tiles in shared memory (stem: gathered fp32 -> packed 16-bit A fragments; head: ldmatrix on the NHWC
+// tile) and the weights are pre-arranged as per-lane B fragments.  tcgen05 would need an im2col copy of the tile in
+// the UMMA layout plus TMEM round trips for N <= 36 -- the tensor pipe is idle either way, the instruction count is
+// what matters here.
+// ---------------------------------------------------------------------------------------------
+#ifdef CIDNET_ACT_BF16
+#define CIDNET_MMA_16816 "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32"
+#else
+#define CIDNET_MMA_16816 "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32"
+#endif
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile(CIDNET_MMA_16816 " {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
+#ifdef CIDNET_ACT_BF16
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+#else
+    __half2 h = __floats2half2_rn(lo, hi);
+#endif
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// stem K order: k 0..8 = taps of the I channel (c = 2), 9..17 = H (c = 0), 18..26 = V (c = 1), 27..31 = zero.
+// With the I taps first, IE_block0 (1 -> 36 on I) re-uses the A fragment of HVE_block0's first k-step.
+__device__ __forceinline__ int stem_k_to_ct(int k, int* c, int* t) {
+    if (k >= 27) return 0;
+    *c = k < 9 ? 2 : (k < 18 ? 0 : 1);
+    *t = k % 9;
+    return 1;
+}
+
+__global__ void __launch_bounds__(256)
+stem_mma_kernel(const float* __restrict__ rgb, float* __restrict__ hvi, act_t* __restrict__ i_enc0,
+                act_t* __restrict__ hv_0, const float* __restrict__ w_hv /*[27][36]*/,
+                const float* __restrict__ w_i /*[9][36]*/, const float* __restrict__ k_dev, float k_host,
+                int H, int W, int pitch, const uint2* __restrict__ bfrag /*[3][5][32], cidnet_pack_stem_bfrag*/) {
+    __shared__ float s_hvi[3 * kHalo * kHalo];
+    __shared__ __align__(16) uint2 s_bfrag[3][5][32];      // [HVE k-step 0, HVE k-step 1, IE][n8 tile][lane] = {b0, b1}
+    __shared__ __align__(16) act_t s_out[8][32 * 40];      // per warp: [pixel][40 channels]
+    const int b = blockIdx.z;
+    const int y0 = blockIdx.y * kTile, x0 = blockIdx.x * kTile;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    const float k = k_dev ? __ldg(k_dev) : k_host;
+    const long long hw = (long long)H * W;
+    const float* img = rgb + (long long)b * 3 * hw;
+
+    if (tid < 3 * 5 * 32 / 2)      // per-lane B fragments, packed once at weight-finalisation time
+        reinterpret_cast<uint4*>(&s_bfrag[0][0][0])[tid] = __ldg(reinterpret_cast<const uint4*>(bfrag) + tid);
+    for (int i = tid; i < kHalo * kHalo; i += 256) {
+        const int hy = i / kHalo, hx = i - hy * kHalo;
+        const int y = min(max(y0 + hy - 1, 0), H - 1);
+        const int x = min(max(x0 + hx - 1, 0), W - 1);
+        const long long o = (long long)y * W + x;
+        float hh, vv, ii;
+        hvit_px(img[o], img[o + hw], img[o + 2 * hw], k, hh, vv, ii);
+        s_hvi[i] = hh; s_hvi[kHalo * kHalo + i] = vv; s_hvi[2 * kHalo * kHalo + i] = ii;
+    }
+    __syncthreads();
+
+    const int ty = tid / kTile, tx = tid - ty * kTile;      // this thread's own pixel: warp w owns tile rows 2w, 2w + 1
+    const int y = y0 + ty, x = x0 + tx;
+    const bool inside = y < H && x < W;
+    const long long pix = (long long)y * W + x;
+    if (inside) {   // the HVI image itself (centre of the halo tile)
+        const int c = (ty + 1) * kHalo + tx + 1;
+        float* o = hvi + (long long)b * 3 * hw + pix;
+        o[0] = s_hvi[c]; o[hw] = s_hvi[kHalo * kHalo + c]; o[2 * hw] = s_hvi[2 * kHalo * kHalo + c];
+    }
+    // A fragments: a0 = (row g, k0, k0+1), a1 = (row g+8, ...), a2 = (row g, k0+8, k0+9), a3 = (row g+8, ...), k0 = 16 ks + 2 tig
+    int koff[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int kk = (j >> 2) * 16 + 2 * tig + (j & 1) + ((j >> 1) & 1) * 8;
+        int c = 0, t = 0;
+        koff[j] = stem_k_to_ct(kk, &c, &t) ? c * kHalo * kHalo + (t / 3) * kHalo + (t % 3) : -1;
+    }
+    uint32_t afrag[2][2][4];                                // [m tile][k-step][a0..a3]
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        const int base = (2 * warp + m) * kHalo + g;        // halo-tile offset of (tile row, column g), tap (0, 0)
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            float v[8];                                     // (k0, k0+1, k0+8, k0+9) x (row g, row g+8)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int off = koff[ks * 4 + e];
+                v[e] = off >= 0 ? s_hvi[off + base] : 0.f;
+                v[4 + e] = off >= 0 ? s_hvi[off + base + 8] : 0.f;
+            }
+            afrag[m][ks][0] = pack_act2(v[0], v[1]);
+            afrag[m][ks][1] = pack_act2(v[4], v[5]);
+            afrag[m][ks][2] = pack_act2(v[2], v[3]);
+            afrag[m][ks][3] = pack_act2(v[6], v[7]);
+        }
+    }
+    act_t* so = s_out[warp];
+#pragma unroll
+    for (int conv = 0; conv < 2; ++conv) {                  // 0: HVE_block0 (3 -> 36), 1: IE_block0 (1 -> 36)
+        float acc[2][5][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int n = 0; n < 5; ++n) { acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f; }
+#pragma unroll
+        for (int n = 0; n < 5; ++n) {
+            if (conv == 0) {
+                const uint2 b0 = s_bfrag[0][n][lane], b1 = s_bfrag[1][n][lane];
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    mma16816(acc[m][n], afrag[m][0], b0.x, b0.y);
+                    mma16816(acc[m][n], afrag[m][1], b1.x, b1.y);
+                }
+            } else {
+                const uint2 b2 = s_bfrag[2][n][lane];
+#pragma unroll
+                for (int m = 0; m < 2; ++m) mma16816(acc[m][n], afrag[m][0], b2.x, b2.y);
+            }
+        }
+        // C fragment: c0, c1 = (row g, channels 8n + 2 tig, +1), c2, c3 = (row g + 8, ...) -> per-warp staging, then
+        // every lane stores its own pixel's 40 channels with 16-byte vectors (channels 36..39 are exact zeros)
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int n = 0; n < 5; ++n) {
+                *reinterpret_cast<uint32_t*>(so + (m * 16 + g) * 40 + n * 8 + 2 * tig) = pack_act2(acc[m][n][0], acc[m][n][1]);
+                *reinterpret_cast<uint32_t*>(so + (m * 16 + g + 8) * 40 + n * 8 + 2 * tig) = pack_act2(acc[m][n][2], acc[m][n][3]);
+            }
+        __syncwarp();
+        if (inside) {
+            act_t* o = (conv == 0 ? hv_0 : i_enc0) + ((long long)b * hw + pix) * pitch;
+            const uint4* src = reinterpret_cast<const uint4*>(so + lane * 40);
+#pragma unroll
+            for (int v4 = 0; v4 < 5; ++v4) reinterpret_cast<uint4*>(o)[v4] = src[v4];
+        }
+    }
+}
+
+// Per-lane B fragments of the m16n8k16 MMAs, built on the host when the weights are finalised.
+//   b0 = (k = 2 tig, 2 tig + 1; n = g), b1 = (k + 8; n = g) with g = lane / 4, tig = lane % 4.
+static uint32_t host_pack2(float lo, float hi) {
+    const act_t a = f2act(lo), b = f2act(hi);
+    uint16_t ua, ub;
+    memcpy(&ua, &a, 2); memcpy(&ub, &b, 2);
+    return (uint32_t)ua | ((uint32_t)ub << 16);
+}
+void pack_stem_bfrag(const float* w_hv /*[27][36] (c*9+t major)*/, const float* w_i /*[9][36]*/, uint2* out /*[3][5][32]*/) {
+    for (int i = 0; i < 3 * 5 * 32; ++i) {
+        const int slot = i / 160, n = (i / 32) % 5, l = i & 31;
+        const int o = n * 8 + (l >> 2), tg = l & 3;
+        float wv[4];
+        for (int e = 0; e < 4; ++e) {
+            const int kk = (slot == 1 ? 16 : 0) + 2 * tg + (e & 1) + (e >> 1) * 8;
+            float v = 0.f;
+            if (o < 36 && kk < 27) {
+                const int c = kk < 9 ? 2 : (kk < 18 ? 0 : 1), t = kk % 9;      // stem K order: I taps, H taps, V taps
+                if (slot < 2) v = w_hv[(c * 9 + t) * 36 + o];
+                else if (c == 2) v = w_i[t * 36 + o];                          // IE_block0 sees only the I taps (k < 9)
+            }
+            wv[e] = v;
+        }
+        out[i] = make_uint2(host_pack2(wv[0], wv[1]), host_pack2(wv[2], wv[3]));
+    }
+}
+void pack_head_bfrag(const float* w_i /*[9][36]*/, const float* w_hv /*[2][9][36]*/, uint2* out /*[2][9][3][32]*/) {
+    for (int i = 0; i < 2 * 9 * 3 * 32; ++i) {
+        const int l = i & 31, ks = (i >> 5) % 3, t = (i / 96) % 9, br = i / 864;
+        const int n = l >> 2, tg = l & 3;        // output column n: branch 0 -> n == 0 (I), branch 1 -> n == 1, 2 (H, V)
+        float wv[4];
+        for (int e = 0; e < 4; ++e) {
+            const int c = ks * 16 + 2 * tg + (e & 1) + (e >> 1) * 8;
+            float v = 0.f;
+            if (c < 36) {
+                if (br == 0 && n == 0) v = w_i[t * 36 + c];
+                if (br == 1 && (n == 1 || n == 2)) v = w_hv[((n - 1) * 9 + t) * 36 + c];
+            }
+            wv[e] = v;
+        }
+        out[i] = make_uint2(host_pack2(wv[0], wv[1]), host_pack2(wv[2], wv[3]));
+    }
+}
+
+static bool use_mma_block0() {
+    static const bool on = getenv("CIDNET_BLOCK0_FMA") == nullptr;     // CIDNET_BLOCK0_FMA=1: the fp32-FMA kernels (A/B runs)
+    return on;
+}
+
+const void* stem_kernel_func() {
+    return use_mma_block0() ? reinterpret_cast<const void*>(&stem_mma_kernel) : reinterpret_cast<const void*>(&stem_kernel);
+}
 
 int launch_stem(const StemArgs& a, cudaStream_t stream) {
     CIDNET_CHECK(a.pitch == 40, CIDNET_ERR_INVALID, "stem: pitch must be 40");
     dim3 grid(ceil_div(a.W, kTile), ceil_div(a.H, kTile), a.B);
-    stem_kernel<<<grid, 256, 0, stream>>>(a.rgb, a.hvi, a.i_enc0, a.hv_0, a.w_hv, a.w_i, a.k_dev, a.k_host,
-                                          a.H, a.W, a.pitch);
+    if (use_mma_block0())
+        stem_mma_kernel<<<grid, 256, 0, stream>>>(a.rgb, a.hvi, a.i_enc0, a.hv_0, a.w_hv, a.w_i, a.k_dev, a.k_host,
+                                                  a.H, a.W, a.pitch, a.bfrag);
+    else
+        stem_kernel<<<grid, 256, 0, stream>>>(a.rgb, a.hvi, a.i_enc0, a.hv_0, a.w_hv, a.w_i, a.k_dev, a.k_host,
+                                              a.H, a.W, a.pitch, a.bfrag);
     CIDNET_CUDA_OK(cudaGetLastError());
     return CIDNET_OK;
 }
@@ -137,7 +342,7 @@ __global__ void __launch_bounds__(256)
 head_kernel(const act_t* __restrict__ i_dec1, const act_t* __restrict__ hv_1, const float* __restrict__ hvi,
             float* __restrict__ rgb, float* __restrict__ out_hvi_dbg, const float* __restrict__ w_i /*[9][36]*/,
             const float* __restrict__ w_hv /*[2][9][36]*/, const float* __restrict__ k_dev, PhvitParams pp,
-            int H, int W, int pitch) {
+            int H, int W, int pitch, const uint2* __restrict__ /*bfrag: mma variant only*/) {
     extern __shared__ __align__(16) uint8_t head_smem[];
     act_t* s_i = reinterpret_cast<act_t*>(head_smem);
     act_t* s_hv = s_i + kHalo * kHalo * 40;
@@ -205,20 +410,135 @@ head_kernel(const act_t* __restrict__ i_dec1, const act_t* __restrict__ hv_1, co
     o[0] = r; o[hw] = g; o[2 * hw] = bl;
 }
 
-const void* head_kernel_func() { return reinterpret_cast<const void*>(&head_kernel); }
+
+// head on warp-level tensor cores: per tap and 16-channel k-step one ldmatrix.x4 per 16-pixel row segment (A = the NHWC
+// halo tile itself: row = pixel, 80-byte pitch -> conflict-free) and one m16n8k16 MMA per branch; output columns
+// 0 = I (ID_block0, A = i_dec1 tile), 1, 2 = H, V (HVD_block0, A = hv_1 tile) of ONE accumulator tile.  Channels 36..39
+// of the tiles are zeroed when staged, channels 40..47 of the third k-step belong to the next pixel and meet zero weights.
+__global__ void __launch_bounds__(256, 3)
+head_mma_kernel(const act_t* __restrict__ i_dec1, const act_t* __restrict__ hv_1, const float* __restrict__ hvi,
+                float* __restrict__ rgb, float* __restrict__ out_hvi_dbg, const float* __restrict__ w_i /*[9][36]*/,
+                const float* __restrict__ w_hv /*[2][9][36]*/, const float* __restrict__ k_dev, PhvitParams pp,
+                int H, int W, int pitch, const uint2* __restrict__ bfrag /*[2][9][3][32], cidnet_pack_head_bfrag*/) {
+    extern __shared__ __align__(16) uint8_t head_smem[];
+    act_t* s_i = reinterpret_cast<act_t*>(head_smem);                        // [18*18 + 1 pad pixel][40]
+    act_t* s_hv = s_i + (kHalo * kHalo + 1) * 40;
+    uint2* s_bfrag = reinterpret_cast<uint2*>(s_hv + (kHalo * kHalo + 1) * 40);   // [2 branches][9 taps][3 k-steps][32 lanes]
+    float* s_res = reinterpret_cast<float*>(s_bfrag + 2 * 9 * 3 * 32);      // [8 warps][32 pixels][3] = (I, H, V)
+    const int b = blockIdx.z;
+    const int y0 = blockIdx.y * kTile, x0 = blockIdx.x * kTile;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    const long long hw = (long long)H * W;
+    if (k_dev) pp.k = __ldg(k_dev);
+
+    for (int i = tid; i < 2 * 9 * 3 * 32 / 2; i += 256)      // per-lane B fragments, packed once at weight-finalisation time
+        reinterpret_cast<uint4*>(s_bfrag)[i] = __ldg(reinterpret_cast<const uint4*>(bfrag) + i);
+    // stage both halo tiles: a tile row is 18 pixels x 5 16-byte vectors; threads 0..179 copy two rows per step with a
+    // fixed (pixel, vector) each -- no index arithmetic inside the loop
+    if (tid < 180) {
+        const int r = tid / 90, tv = tid - r * 90, px = tv / 5, v = tv - px * 5;
+        const int x = min(max(x0 + px - 1, 0), W - 1);
+        const long long col = (long long)x * pitch + v * 8;
+#pragma unroll 3
+        for (int hy = r; hy < kHalo; hy += 2) {
+            const int y = min(max(y0 + hy - 1, 0), H - 1);
+            const long long gi = ((long long)b * hw + (long long)y * W) * pitch + col;
+            uint4 vi = *reinterpret_cast<const uint4*>(i_dec1 + gi);
+            uint4 vh = *reinterpret_cast<const uint4*>(hv_1 + gi);
+            if (v == 4) { vi.z = vi.w = 0u; vh.z = vh.w = 0u; }     // channels 36..39 are pitch padding nobody writes
+            reinterpret_cast<uint4*>(s_i)[hy * 90 + tv] = vi;
+            reinterpret_cast<uint4*>(s_hv)[hy * 90 + tv] = vh;
+        }
+    } else if (tid < 185) {                                          // the zero pad pixel behind each tile
+        reinterpret_cast<uint4*>(s_i)[kHalo * 90 + tid - 180] = make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4*>(s_hv)[kHalo * 90 + tid - 180] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+
+    // ldmatrix lane address: matrices 0 / 1 = rows 0-7 / 8-15 at k 0-7, matrices 2 / 3 = the same rows at k 8-15
+    const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lk = (lane >> 4) * 8;
+    const uint32_t si_base = static_cast<uint32_t>(__cvta_generic_to_shared(s_i));
+    const uint32_t shv_base = static_cast<uint32_t>(__cvta_generic_to_shared(s_hv));
+    float acc[2][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f; }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+#pragma unroll
+        for (int ks = 0; ks < 3; ++ks) {
+            const uint2 bi = s_bfrag[(t * 3 + ks) * 32 + lane];
+            const uint2 bh = s_bfrag[((9 + t) * 3 + ks) * 32 + lane];
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const uint32_t off = (uint32_t)((((2 * warp + m + t / 3) * kHalo + lrow + t % 3) * 40 + ks * 16 + lk) * 2);
+                uint32_t a[4];
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(si_base + off));
+                mma16816(acc[m], a, bi.x, bi.y);
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(shv_base + off));
+                mma16816(acc[m], a, bh.x, bh.y);
+            }
+        }
+    }
+    // C fragment: c0, c1 = (row g, columns 2 tig, 2 tig + 1), c2, c3 = (row g + 8, ...): columns 0..2 live in tig 0 / 1
+    float* res = s_res + warp * 96;
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        if (tig == 0) {
+            res[(m * 16 + g) * 3 + 0] = acc[m][0]; res[(m * 16 + g) * 3 + 1] = acc[m][1];
+            res[(m * 16 + g + 8) * 3 + 0] = acc[m][2]; res[(m * 16 + g + 8) * 3 + 1] = acc[m][3];
+        } else if (tig == 1) {
+            res[(m * 16 + g) * 3 + 2] = acc[m][0];
+            res[(m * 16 + g + 8) * 3 + 2] = acc[m][2];
+        }
+    }
+    __syncwarp();
+    const int ty = tid / kTile, tx = tid - ty * kTile;      // == (2 warp + lane / 16, lane % 16): pixel `lane` of the warp
+    const int y = y0 + ty, x = x0 + tx;
+    if (y >= H || x >= W) return;
+    const float oi = res[lane * 3 + 0], oh = res[lane * 3 + 1], ov = res[lane * 3 + 2];
+    const long long pix = (long long)y * W + x;
+    const float* hp = hvi + (long long)b * 3 * hw + pix;
+    const float Hh = oh + hp[0], Vv = ov + hp[hw], Ii = oi + hp[2 * hw];   // cat([hv_0, i_dec0]) + hvi
+    if (out_hvi_dbg) {
+        float* d = out_hvi_dbg + (long long)b * 3 * hw + pix;
+        d[0] = Hh; d[hw] = Vv; d[2 * hw] = Ii;
+    }
+    float r, gg, bl;
+    phvit_px(Hh, Vv, Ii, pp, r, gg, bl);
+    float* o = rgb + (long long)b * 3 * hw + pix;
+    o[0] = r; o[hw] = gg; o[2 * hw] = bl;
+}
+
+const void* head_kernel_func() {
+    return use_mma_block0() ? reinterpret_cast<const void*>(&head_mma_kernel) : reinterpret_cast<const void*>(&head_kernel);
+}
 
 int launch_head(const HeadArgs& a, cudaStream_t stream) {
     CIDNET_CHECK(a.pitch == 40, CIDNET_ERR_INVALID, "head: pitch must be 40");
     dim3 grid(ceil_div(a.W, kTile), ceil_div(a.H, kTile), a.B);
     PhvitParams pp{a.k_host, a.alpha_s, a.alpha, a.gated, a.gated2};
-    const size_t smem = 2 * kHalo * kHalo * 40 * sizeof(act_t) + 3 * 9 * 40 * sizeof(act_t);
-    static bool configured = false;
-    if (!configured) {
-        CIDNET_CUDA_OK(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+    if (use_mma_block0()) {
+        const size_t smem = 2 * (kHalo * kHalo + 1) * 40 * sizeof(act_t) + 2 * 9 * 3 * 32 * sizeof(uint2) + 8 * 96 * sizeof(float);
+        static bool configured = false;
+        if (!configured) {
+            CIDNET_CUDA_OK(cudaFuncSetAttribute(head_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        head_mma_kernel<<<grid, 256, smem, stream>>>(a.i_dec1, a.hv_1, a.hvi, a.rgb, a.out_hvi_dbg, a.w_i, a.w_hv, a.k_dev, pp,
+                                                     a.H, a.W, a.pitch, a.bfrag);
+    } else {
+        const size_t smem = 2 * kHalo * kHalo * 40 * sizeof(act_t) + 3 * 9 * 40 * sizeof(act_t);
+        static bool configured = false;
+        if (!configured) {
+            CIDNET_CUDA_OK(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        head_kernel<<<grid, 256, smem, stream>>>(a.i_dec1, a.hv_1, a.hvi, a.rgb, a.out_hvi_dbg, a.w_i, a.w_hv, a.k_dev, pp,
+                                              a.H, a.W, a.pitch, a.bfrag);
     }
-    head_kernel<<<grid, 256, smem, stream>>>(a.i_dec1, a.hv_1, a.hvi, a.rgb, a.out_hvi_dbg, a.w_i, a.w_hv, a.k_dev, pp,
-                                          a.H, a.W, a.pitch);
     CIDNET_CUDA_OK(cudaGetLastError());
     return CIDNET_OK;
 }

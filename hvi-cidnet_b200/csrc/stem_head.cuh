@@ -10,6 +10,7 @@ struct StemArgs {
     const float* k_dev;  // optional: density_k read on the device (no host sync)
     float k_host;
     int B, H, W, pitch;
+    const uint2* bfrag;  // [3][5][32] per-lane MMA B fragments (pack_stem_bfrag)
 };
 int launch_stem(const StemArgs& a, cudaStream_t stream);
 
@@ -20,6 +21,7 @@ struct HeadArgs {
     const float* w_hv;   // [2][9][36]
     const float* k_dev; float k_host; float alpha_s; float alpha; int gated; int gated2;
     int B, H, W, pitch;
+    const uint2* bfrag;  // [2][9][3][32] per-lane MMA B fragments (pack_head_bfrag)
 };
 int launch_head(const HeadArgs& a, cudaStream_t stream);
 
@@ -27,7 +29,11 @@ int launch_head(const HeadArgs& a, cudaStream_t stream);
 // argument 3 of the head is the output image)
 const void* stem_kernel_func();
 const void* head_kernel_func();
-static constexpr int kStemNumArgs = 11, kStemArgIn = 0;
-static constexpr int kHeadNumArgs = 12, kHeadArgOut = 3;
+static constexpr int kStemNumArgs = 12, kStemArgIn = 0;
+static constexpr int kHeadNumArgs = 13, kHeadArgOut = 3;
+
+// host-side packing of the MMA B fragments (weights as uploaded by api.cu: tap-input major fp32)
+void pack_stem_bfrag(const float* w_hv, const float* w_i, uint2* out);
+void pack_head_bfrag(const float* w_i, const float* w_hv, uint2* out);
 
 }  // namespace cidnet
