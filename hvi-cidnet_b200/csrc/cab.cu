@@ -686,35 +686,63 @@ cab_fold_kernel(const CabFoldArgs a) {
     __shared__ float s_attn[144 * 18];
     const int prob = blockIdx.x, b = blockIdx.y;
     const int C = a.C, tid = threadIdx.x;
-    const float* G = a.gram[prob] + (long long)b * a.heads * 324;
-    const float* sq = a.sq[prob] + (long long)b * a.Cp;
-    const float* sk = a.sk[prob] + (long long)b * a.Cp;
+    const float* G = (prob ? a.gram[1] : a.gram[0]) + (long long)b * a.heads * 324;
+    const float* sq = (prob ? a.sq[1] : a.sq[0]) + (long long)b * a.Cp;
+    const float* sk = (prob ? a.sk[1] : a.sk[0]) + (long long)b * a.Cp;
+    const float* wo = prob ? a.wo[1] : a.wo[0];
+    // each CTA of the z dimension writes a slice of the rows (the softmax is recomputed by every slice: cheap)
+    const int rows_per = (a.n_rows + gridDim.z - 1) / gridDim.z;
+    const int i_begin = blockIdx.z * rows_per * a.kt;
+    const int i_end = min((int)(blockIdx.z + 1) * rows_per, a.n_rows) * a.kt;
+    // The kernel is a chain of dependent latencies (Gram loads -> softmax -> barrier -> W_o loads -> store), not work
+    // (ncu: ~9 us per CTA at every level).  So: the W_o segments of this thread's (<= 2) output elements are requested
+    // FIRST and arrive while the softmax runs, and the softmax uses the fast reciprocal / rsqrt / exp2 paths (the
+    // attention weights keep ~1e-6 relative accuracy; contract 2e-3 on the image).
+    float wv[2][18];
+    int wj[2], wh[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int i = i_begin + tid + u * 256;
+        const int o = i / a.kt, kin = i - o * a.kt;
+        const bool nz = i < i_end && o < C && kin < C;
+        wh[u] = nz ? kin / 18 : -1;
+        wj[u] = nz ? kin - wh[u] * 18 : 0;
+#pragma unroll
+        for (int c = 0; c < 18; ++c) wv[u][c] = nz ? __ldg(wo + o * C + wh[u] * 18 + c) : 0.f;
+    }
     if (tid < C) {
         const int head = tid / 18;
-        const float nq = fmaxf(sqrtf(sq[tid]), 1e-12f);
-        const float temp = a.temp[prob][head];
+        const float inv_nq = rsqrtf(fmaxf(__ldg(sq + tid), 1e-24f));      // 1 / max(sqrt(sum q^2), 1e-12)
+        const float temp = (prob ? a.temp[1] : a.temp[0])[head];
         float logit[18], mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 18; ++j) {
-            const float nk = fmaxf(sqrtf(sk[head * 18 + j]), 1e-12f);
-            logit[j] = (G[tid * 18 + j] / (nq * nk)) * temp;
+            const float inv_nk = rsqrtf(fmaxf(__ldg(sk + head * 18 + j), 1e-24f));
+            logit[j] = __ldcg(G + tid * 18 + j) * (inv_nq * inv_nk) * temp;
             mx = fmaxf(mx, logit[j]);
         }
         float sum = 0.f;
 #pragma unroll
-        for (int j = 0; j < 18; ++j) { logit[j] = expf(logit[j] - mx); sum += logit[j]; }
+        for (int j = 0; j < 18; ++j) { logit[j] = __expf(logit[j] - mx); sum += logit[j]; }
+        const float inv = __fdividef(1.0f, sum);
 #pragma unroll
-        for (int j = 0; j < 18; ++j) s_attn[tid * 18 + j] = logit[j] / sum;
+        for (int j = 0; j < 18; ++j) s_attn[tid * 18 + j] = logit[j] * inv;
     }
     __syncthreads();
     // M[o][kin] = sum_{c' in head(kin)} Wo[o][head*18 + c'] * attn[head*18 + c'][kin - head*18]
-    const float* wo = a.wo[prob];
-    act_t* m = a.m_out[prob] + (long long)b * a.n_rows * a.kt;
-    // each CTA of the z dimension writes a slice of the rows (the softmax above is recomputed: cheap)
-    const int rows_per = (a.n_rows + gridDim.z - 1) / gridDim.z;
-    const int i_begin = blockIdx.z * rows_per * a.kt;
-    const int i_end = min((int)(blockIdx.z + 1) * rows_per, a.n_rows) * a.kt;
-    for (int i = i_begin + tid; i < i_end; i += 256) {
+    act_t* m = (prob ? a.m_out[1] : a.m_out[0]) + (long long)b * a.n_rows * a.kt;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int i = i_begin + tid + u * 256;
+        if (i >= i_end) break;
+        float acc = 0.f;
+        if (wh[u] >= 0) {
+#pragma unroll
+            for (int c = 0; c < 18; ++c) acc = fmaf(wv[u][c], s_attn[(wh[u] * 18 + c) * 18 + wj[u]], acc);
+        }
+        m[i] = f2act(acc);
+    }
+    for (int i = i_begin + tid + 512; i < i_end; i += 256) {      // slices larger than 512 elements (not used by launch_cab_fold)
         const int o = i / a.kt, kin = i - o * a.kt;
         float acc = 0.f;
         if (o < C && kin < C) {
@@ -730,7 +758,8 @@ int launch_cab_fold(const CabFoldArgs& a, cudaStream_t stream) {
     CIDNET_CHECK(a.C <= 144, CIDNET_ERR_INVALID, "fold: C too large");
     // row slices per (problem, image): <= 2 output elements per thread (the kernel is a chain of dependent L2
     // latencies, not work: ncu 13 us at C = 144 with 16 slices of ~7 elements per thread)
-    const int slices = std::min(64, std::max(16, ceil_div(a.n_rows * a.kt, 512)));
+    // rows_per * kt <= 512 elements per slice where possible
+    const int slices = std::min(a.n_rows, std::max(16, ceil_div(a.n_rows, std::max(1, 512 / a.kt))));
     dim3 grid(a.nprob, a.B, slices);
     cab_fold_kernel<<<grid, 256, 0, stream>>>(a);
     CIDNET_CUDA_OK(cudaGetLastError());
