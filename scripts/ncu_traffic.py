@@ -8,7 +8,7 @@ launch list and (2) the per-launch DRAM traffic table bench.py's `roofline.traff
         [profiles/r01_launches_cfg2_final.csv]
 
 launches.csv holds 89 consecutive launches of back-to-back identical forwards (ncu's long CSV format: one row
-per metric); the window may start anywhere inside a forward, it is rotated so that `stem_kernel` comes first."""
+per metric); the window may start anywhere inside a forward, it is rotated so that the stem kernel comes first."""
 import csv, json, sys
 
 raw, marks, out, desc = sys.argv[1:5]
@@ -25,7 +25,7 @@ for r in data:
 seq = [launches[i] for i in sorted(launches)]
 mk = [l.split("\t") for l in open(marks).read().strip().splitlines()]
 assert len(seq) == len(mk), (len(seq), len(mk))
-first = next(i for i, e in enumerate(seq) if e["kernel"].startswith("stem_kernel"))
+first = next(i for i, e in enumerate(seq) if e["kernel"].startswith("stem_"))
 seq = seq[first:] + seq[:first]
 per = {}
 lines = ["launch,name,kernel,grid,block,ncu_time_us,event_time_us,dram_read_bytes,dram_write_bytes,algorithmic_bytes"]
