@@ -272,6 +272,116 @@ dw3x3_kernel(const Dw3Args a) {
 
 #ifndef CIDNET_ACT_BF16
 // ------------------------------------------------------------------------------------------------
+// dw3x3 with a per-thread cp.async ring (CIDNET_DW_VARIANT=8): the same thread <-> (column, 8 channels) mapping and
+// sliding window as dw3x3_kernel, but the three 16-byte loads of every input row (left, centre, right) are issued
+// kDepth rows ahead with cp.async (zero fill outside the image = the conv's padding) into the thread's own shared-
+// memory slots -- no registers held by loads in flight, no barriers (a thread only reads what it requested itself).
+// ------------------------------------------------------------------------------------------------
+template <int kDepth, int kMinBlocks>
+__global__ void __launch_bounds__(kDwThreads, kMinBlocks)
+dw3x3_cpasync_kernel(const Dw3Args a) {
+    extern __shared__ __align__(16) uint8_t dw_smem[];
+    uint4* ring = reinterpret_cast<uint4*>(dw_smem);                       // [kDepth][3][kDwThreads]
+    act_t* s_w = reinterpret_cast<act_t*>(ring + kDepth * 3 * kDwThreads);  // [9][nv * 8]
+    __shared__ float s_ssq[2 * 144];
+    const int prob = blockIdx.z % a.nprob, b = blockIdx.z / a.nprob;
+    const int nv = a.nv;
+    const int idx = blockIdx.x * kDwThreads + threadIdx.x;
+    const int x = idx / nv, v = idx - x * nv;
+    const bool active = x < a.W;
+    const int seg = active ? v / a.seg_vecs : 0;
+    const int c0 = (v - seg * a.seg_vecs) * 8;
+    const long long hw = (long long)a.H * a.W;
+    const act_t* src = a.src[prob][seg] + (long long)b * hw * a.src_pitch + c0;
+    act_t* dst = a.dst[prob] + (long long)b * hw * a.dst_pitch + seg * a.seg_vecs * 8 + c0;
+    const int y0 = blockIdx.y * kDwRows;
+    const int y1 = min(y0 + kDwRows, a.H);
+
+    for (int i = threadIdx.x; i < 2 * 144; i += kDwThreads) s_ssq[i] = 0.f;
+    {
+        const float* wp = a.w[prob];
+        for (int i = threadIdx.x; i < 9 * nv * 8; i += kDwThreads) s_w[i] = f2act(__ldg(wp + i));
+    }
+    __syncthreads();
+    const uint32_t wsm_addr = ptx::smem_u32(s_w) + (uint32_t)((active ? v : 0) * 16);
+    auto W9 = [&](int t) -> uint4 {
+        uint4 r;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(wsm_addr + (uint32_t)(t * nv * 16)));
+        return r;
+    };
+    float ssq[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ssq[e] = 0.f;
+
+    if (active) {
+        const bool has_l = x > 0, has_r = x + 1 < a.W;
+        const uint32_t slot0 = ptx::smem_u32(ring) + threadIdx.x * 16;
+        const int n_in = (y1 - y0) + 2;                      // input rows y0-1 .. y1
+        // request input row k (image row y0 - 1 + k) into ring slot k % kDepth; always commits one group
+        auto issue = [&](int k) {
+            if (k < n_in) {
+                const int y = y0 - 1 + k;
+                const bool row_ok = y >= 0 && y < a.H;
+                const act_t* p = src + ((long long)(row_ok ? y : 0) * a.W + x) * a.src_pitch;
+                const uint32_t d = slot0 + (uint32_t)((k % kDepth) * 3 * kDwThreads * 16);
+                const uint32_t nl = (row_ok && has_l) ? 16u : 0u, nc = row_ok ? 16u : 0u, nr = (row_ok && has_r) ? 16u : 0u;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(has_l ? p - a.src_pitch : p), "r"(nl) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d + kDwThreads * 16), "l"(p), "r"(nc) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d + 2 * kDwThreads * 16), "l"(has_r ? p + a.src_pitch : p), "r"(nr) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        // take input row k out of the ring (it has landed once at most kDepth - 1 younger groups are pending) and
+        // re-use its slot for row k + kDepth
+        auto fetch = [&](int k, uint4* r) {
+            asm volatile("cp.async.wait_group %0;" :: "n"(kDepth - 1) : "memory");
+            const uint32_t d = slot0 + (uint32_t)((k % kDepth) * 3 * kDwThreads * 16);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r[c].x), "=r"(r[c].y), "=r"(r[c].z), "=r"(r[c].w) : "r"(d + c * kDwThreads * 16));
+            issue(k + kDepth);
+        };
+        uint4 win0[3], win1[3], win2[3];
+        auto step = [&](const uint4* r0, const uint4* r1, uint4* r2, int y) {
+            fetch(y - y0 + 2, r2);                           // row y + 1
+            uint4 pa = hmul8(r0[0], W9(0));
+            uint4 pb = hmul8(r2[0], W9(6));
+            hfma8(pa, r0[1], W9(1)); hfma8(pb, r2[1], W9(7));
+            hfma8(pa, r0[2], W9(2)); hfma8(pb, r2[2], W9(8));
+            hfma8(pa, r1[0], W9(3));
+            hfma8(pa, r1[1], W9(4));
+            hfma8(pa, r1[2], W9(5));
+            const uint4 raw = make_uint4(hadd2u(pa.x, pb.x), hadd2u(pa.y, pb.y), hadd2u(pa.z, pb.z), hadd2u(pa.w, pb.w));
+            if (y >= a.stat_y0 && y < a.stat_y1) fhfma8(ssq, raw, raw);
+            *reinterpret_cast<uint4*>(dst + ((long long)y * a.W + x) * a.dst_pitch) = raw;
+        };
+#pragma unroll
+        for (int k = 0; k < kDepth; ++k) issue(k);
+        fetch(0, win0);
+        fetch(1, win1);
+        for (int y = y0; y < y1; y += 3) {
+            step(win0, win1, win2, y);
+            if (y + 1 < y1) step(win1, win2, win0, y + 1);
+            if (y + 2 < y1) step(win2, win0, win1, y + 2);
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (seg < 2) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(&s_ssq[seg * 144 + c0 + e], ssq[e]);
+        }
+    }
+    __syncthreads();
+    const int Cp = a.seg_vecs * 8;
+    for (int i = threadIdx.x; i < 2 * Cp; i += kDwThreads) {
+        const int sg = i / Cp, c = i - sg * Cp;
+        const float val = s_ssq[sg * 144 + c];
+        if (val != 0.f) atomicAdd((sg == 0 ? a.sq[prob] : a.sk[prob]) + (long long)b * Cp + c, val);
+    }
+}
+#endif
+
+#ifndef CIDNET_ACT_BF16
+// ------------------------------------------------------------------------------------------------
 // dw3x3 v2 (fp16 build, CIDNET_DW_VARIANT=3): the IEL gate's data path applied to the q|k|v depthwise conv.
 // A producer warp streams {16 channels, 34 columns, 4 rows} TMA boxes (SWIZZLE_32B, zero fill = the conv's
 // padding) of two 16-channel groups into a shared-memory ring; four compute warps (group x 8-channel vector,
@@ -460,11 +570,27 @@ int launch_dw3(const Dw3Args& a_in, cudaStream_t stream) {
     CIDNET_CHECK(a.seg_vecs * 8 <= 144 && a.nv == 3 * a.seg_vecs, CIDNET_ERR_INVALID, "dw3: bad channel layout");
     dim3 grid(ceil_div(a.W * a.nv, kDwThreads), ceil_div(a.H, kDwRows), a.B * a.nprob);
 #ifndef CIDNET_ACT_BF16
-    // 7 (default): packed fp16, weights re-read from smem, one-row prefetch, 4 CTAs / SM (3-8 % faster than 0 on B200);
+    // 8 (default): per-thread cp.async ring, 4 input rows in flight, weights re-read from smem, 5 CTAs / SM (L1 launch at cfg 2:
+    //    181 -> 147 us; 16x400x600: 712 -> 640 us); 9: the same with 6 rows in flight, 4 CTAs / SM;
+    // 7: register loads one row ahead, weights re-read from smem, 4 CTAs / SM;
     // 0: weights in registers, no prefetch, 4 CTAs / SM; 1: weights in registers, one-row prefetch, 3 CTAs / SM; 5 / 6: 5 CTAs / SM (spills, slower);
     // 2: fp32-accumulate FHFMA kernel
-    static const int variant = getenv("CIDNET_DW_VARIANT") ? atoi(getenv("CIDNET_DW_VARIANT")) : 7;
+    static const int variant = getenv("CIDNET_DW_VARIANT") ? atoi(getenv("CIDNET_DW_VARIANT")) : 8;
     if (variant == 3 || variant == 4) return launch_dw3_v2(a, stream, variant == 3 ? 4 : 3);   // v2 (TMA ring), 4 / 3 CTAs per SM
+    if (variant == 8 || variant == 9) {               // per-thread cp.async ring, 4 rows (8) / 6 rows (9) in flight
+        const int depth = variant == 8 ? 4 : 6;
+        const size_t smem = (size_t)depth * 3 * kDwThreads * 16 + (size_t)9 * a.nv * 8 * sizeof(act_t);
+        static bool configured = false;
+        if (!configured) {
+            CIDNET_CUDA_OK(cudaFuncSetAttribute(dw3x3_cpasync_kernel<4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            CIDNET_CUDA_OK(cudaFuncSetAttribute(dw3x3_cpasync_kernel<6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            configured = true;
+        }
+        if (variant == 8) dw3x3_cpasync_kernel<4, 5><<<grid, kDwThreads, smem, stream>>>(a);
+        else              dw3x3_cpasync_kernel<6, 4><<<grid, kDwThreads, smem, stream>>>(a);
+        CIDNET_CUDA_OK(cudaGetLastError());
+        return CIDNET_OK;
+    }
     if (variant == 5)      dw3x3_kernel<true, 5, true><<<grid, kDwThreads, 0, stream>>>(a);    // weights in smem, prefetch, 5 CTAs / SM
     else if (variant == 6) dw3x3_kernel<false, 5, true><<<grid, kDwThreads, 0, stream>>>(a);   // weights in smem, no prefetch, 5 CTAs / SM
     else if (variant == 7) dw3x3_kernel<true, 4, true><<<grid, kDwThreads, 0, stream>>>(a);    // weights in smem, prefetch, 4 CTAs / SM
