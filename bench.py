@@ -180,7 +180,7 @@ def run_reference(args):
     sample_B, sample_H, sample_W = 1, H, W
     x = O.make_input("uniform", sample_B, sample_H, sample_W, seed=1234)
     t0 = time.perf_counter(); O.forward(x, sd, run_dead_block=True, mssa=mssa); t1 = time.perf_counter() - t0
-    budget = 150.0
+    budget = 90.0
     if (args.steps + args.warmup) * t1 > budget:      # bounded sample: a centre crop (multiple of 8)
         f = max(0.1, (budget / ((args.steps + args.warmup) * t1)) ** 0.5)
         sample_H, sample_W = max(64, int(H * f) // 8 * 8), max(64, int(W * f) // 8 * 8)

@@ -596,7 +596,8 @@ static int launch_mode_g(const ConvGemmArgs& args, dim3 grid, size_t smem, cudaS
 }
 template <int kMode>
 static int launch_mode(const ConvGemmArgs& args, dim3 grid, size_t smem, cudaStream_t stream, int groups) {
-    return groups == 3 ? launch_mode_g<kMode, 3>(args, grid, smem, stream) : launch_mode_g<kMode, 2>(args, grid, smem, stream);
+    (void)groups;      // only the 2-group kernels are instantiated (see launch_conv_gemm for the 3-group experiment)
+    return launch_mode_g<kMode, 2>(args, grid, smem, stream);
 }
 
 int device_sm_count() { return num_sms(); }
@@ -614,7 +615,7 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
     CIDNET_CHECK(2 * ksub * wt.block_n <= 512, CIDNET_ERR_INVALID, "conv_gemm: accumulators exceed TMEM");
     // epilogue groups: always 2.  A third group for the 1x1 layers (3 accumulators fit the 512 TMEM columns; 448
     // threads, <= 146 registers) was measured on B200: no layer got faster at cfg 2 or 16x400x600, and the 400x600
-    // forward lost parity (2.9e-2) -- not root-caused, so the 3-group instantiation is compiled but never launched.
+    // forward lost parity (2.9e-2) -- not root-caused, so only the 2-group kernels are instantiated.
     const int kEpiGroups = 2;
 
     ConvGemmArgs a;
