@@ -440,20 +440,24 @@ head_mma_kernel(const act_t* __restrict__ i_dec1, const act_t* __restrict__ hv_1
         const int r = tid / 90, tv = tid - r * 90, px = tv / 5, v = tv - px * 5;
         const int x = min(max(x0 + px - 1, 0), W - 1);
         const long long col = (long long)x * pitch + v * 8;
-#pragma unroll 3
+        // cp.async: all 9 rows x 2 tensors of a thread are in flight at once, no registers in between; the last vector of
+        // a pixel copies 8 bytes and zero-fills the rest (channels 36..39 are pitch padding nobody writes)
+        const uint32_t nsrc = v == 4 ? 8u : 16u;
+        const uint32_t di = static_cast<uint32_t>(__cvta_generic_to_shared(s_i)) + (uint32_t)tv * 16u;
+        const uint32_t dh = static_cast<uint32_t>(__cvta_generic_to_shared(s_hv)) + (uint32_t)tv * 16u;
+#pragma unroll
         for (int hy = r; hy < kHalo; hy += 2) {
             const int y = min(max(y0 + hy - 1, 0), H - 1);
             const long long gi = ((long long)b * hw + (long long)y * W) * pitch + col;
-            uint4 vi = *reinterpret_cast<const uint4*>(i_dec1 + gi);
-            uint4 vh = *reinterpret_cast<const uint4*>(hv_1 + gi);
-            if (v == 4) { vi.z = vi.w = 0u; vh.z = vh.w = 0u; }     // channels 36..39 are pitch padding nobody writes
-            reinterpret_cast<uint4*>(s_i)[hy * 90 + tv] = vi;
-            reinterpret_cast<uint4*>(s_hv)[hy * 90 + tv] = vh;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(di + (uint32_t)hy * 1440u), "l"(i_dec1 + gi), "r"(nsrc) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dh + (uint32_t)hy * 1440u), "l"(hv_1 + gi), "r"(nsrc) : "memory");
         }
     } else if (tid < 185) {                                          // the zero pad pixel behind each tile
         reinterpret_cast<uint4*>(s_i)[kHalo * 90 + tid - 180] = make_uint4(0, 0, 0, 0);
         reinterpret_cast<uint4*>(s_hv)[kHalo * 90 + tid - 180] = make_uint4(0, 0, 0, 0);
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     // ldmatrix lane address: matrices 0 / 1 = rows 0-7 / 8-15 at k 0-7, matrices 2 / 3 = the same rows at k 8-15
