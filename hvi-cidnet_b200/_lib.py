@@ -55,6 +55,8 @@ SIGNATURES = {
                                          HALO_FN, ALLREDUCE_FN, C.c_void_p, C.c_void_p]),
     "cidnet_forward_sharded_dry": (C.c_int, [C.c_int, C.POINTER(Shard), C.c_void_p, C.c_int64, HALO_FN, ALLREDUCE_FN,
                                              C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "cidnet_forward_sharded_dry_variant": (C.c_int, [C.c_int, C.c_int, C.POINTER(Shard), C.c_void_p, C.c_int64, HALO_FN,
+                                                     ALLREDUCE_FN, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cidnet_pre_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "cidnet_post_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cidnet_read_tap": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int), C.c_void_p]),

@@ -1065,17 +1065,27 @@ extern "C" int cidnet_forward_sharded(cidnet_ctx* ctx, const float* rgb_local, f
 extern "C" int cidnet_forward_sharded_dry(int W, const cidnet_shard* sh, void* workspace, int64_t workspace_bytes,
                                           cidnet_halo_fn halo_fn, cidnet_allreduce_fn allreduce_fn, void* user,
                                           int* n_halo_calls, int* n_allreduce_calls) {
+    return cidnet_forward_sharded_dry_variant(CIDNET_VARIANT_BASE, W, sh, workspace, workspace_bytes, halo_fn, allreduce_fn, user,
+                                              n_halo_calls, n_allreduce_calls);
+}
+
+extern "C" int cidnet_forward_sharded_dry_variant(int variant, int W, const cidnet_shard* sh, void* workspace,
+                                                  int64_t workspace_bytes, cidnet_halo_fn halo_fn,
+                                                  cidnet_allreduce_fn allreduce_fn, void* user, int* n_halo_calls,
+                                                  int* n_allreduce_calls) {
+    CIDNET_CHECK(variant == CIDNET_VARIANT_BASE || variant == CIDNET_VARIANT_MSSA, CIDNET_ERR_INVALID, "forward_sharded_dry: unknown variant");
     int rc = check_shard(sh, W);
     if (rc) return rc;
     CIDNET_CHECK(sh->nranks == 1 || (halo_fn && allreduce_fn), CIDNET_ERR_INVALID, "forward_sharded_dry: callbacks required");
     CIDNET_CHECK(workspace && (reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, CIDNET_ERR_INVALID,
                  "forward_sharded_dry: workspace must be 1024-byte aligned");
     cidnet_ctx dummy;                      // weights are only dereferenced by the (skipped) launches
+    dummy.variant = variant;
     for (int n = 0; n < 6; ++n) {
         const int l = n < 3 ? n + 1 : 6 - n;
         for (int s = 0; s < 2; ++s) {
             LcaWeights& L = dummy.stage[n].lca[s];
-            L.live = !(n == 4 && s == 0);
+            L.live = !(n == 4 && s == 0) || variant == CIDNET_VARIANT_MSSA;
             L.C = kCh[l]; L.Cp = act_pitch(kCh[l]); L.heads = kHeads[l]; L.h = (int)(kCh[l] * 2.66); L.hp = round_up(L.h, 16);
             choose_blocking(L.C, &L.fold_tmpl.block_n, &L.fold_tmpl.n_blocks);
             L.fold_tmpl.n_rows = L.fold_tmpl.block_n * L.fold_tmpl.n_blocks;

@@ -147,6 +147,12 @@ CIDNET_API int cidnet_forward_sharded(cidnet_ctx* ctx, const float* rgb_local, f
 CIDNET_API int cidnet_forward_sharded_dry(int W, const cidnet_shard* sh, void* workspace, int64_t workspace_bytes,
                                           cidnet_halo_fn halo_fn, cidnet_allreduce_fn allreduce_fn, void* user,
                                           int* n_halo_calls, int* n_allreduce_calls);
+/* the same for a model variant (CIDNET_VARIANT_MSSA: one more halo refresh per up-block pair for the 7x7 gates,
+ * both problems of LCA stage 5) */
+CIDNET_API int cidnet_forward_sharded_dry_variant(int variant, int W, const cidnet_shard* sh, void* workspace,
+                                                  int64_t workspace_bytes, cidnet_halo_fn halo_fn,
+                                                  cidnet_allreduce_fn allreduce_fn, void* user, int* n_halo_calls,
+                                                  int* n_allreduce_calls);
 
 /* ---- 8-bit image I/O (the callers' pre / post-processing, one kernel each) ------------------
  * cidnet_pre_u8 : src dev u8 [B,h,w,3] (HWC, what PIL / a decoder yields) -> dst dev fp32 [B,3,H,W]:

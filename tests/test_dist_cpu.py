@@ -86,7 +86,7 @@ def _pattern(rank, nfloats):
     return (torch.arange(nfloats, dtype=torch.float32) % 997.0) + 1000.0 * (rank + 1)
 
 
-def _dry_worker(rank, world, port, H, W, ret):
+def _dry_worker(rank, world, port, H, W, ret, variant=0):
     import ctypes
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -104,8 +104,8 @@ def _dry_worker(rank, world, port, H, W, ret):
     ws.view(torch.float32).copy_(_pattern(rank, ws.numel() // 4))
     comm = StripComm(ws)
     nh, na = ctypes.c_int(), ctypes.c_int()
-    rc = L.cidnet_forward_sharded_dry(W, ctypes.byref(sh), ws.data_ptr(), ws.numel(), comm.halo_cb, comm.allreduce_cb,
-                                      None, ctypes.byref(nh), ctypes.byref(na))
+    rc = L.cidnet_forward_sharded_dry_variant(variant, W, ctypes.byref(sh), ws.data_ptr(), ws.numel(), comm.halo_cb,
+                                              comm.allreduce_cb, None, ctypes.byref(nh), ctypes.byref(na))
     assert rc == 0 and comm.error is None, (rc, comm.error, L.cidnet_last_error())
     logs = [None] * world
     dist.all_gather_object(logs, comm.log)
@@ -140,12 +140,13 @@ def _dry_worker(rank, world, port, H, W, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,H,W", [(2, 64, 16), (3, 64, 24)])
-def test_strip_schedule_dry_run_gloo(world, H, W):
-    port = 31000 + (os.getpid() % 2000) + world
+@pytest.mark.parametrize("world,H,W,variant", [(2, 64, 16, 0), (3, 64, 24, 0), (2, 64, 16, 1)])
+def test_strip_schedule_dry_run_gloo(world, H, W, variant):
+    """variant 1 = MSSA: its 7x7 spatial-attention gates add halo refreshes (three valid rows per up-block pair)"""
+    port = 31000 + (os.getpid() % 2000) + world + 5 * variant
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_dry_worker, args=(world, port, H, W, ret), nprocs=world, join=True)
+    mp.spawn(_dry_worker, args=(world, port, H, W, ret, variant), nprocs=world, join=True)
     assert len(ret) == world
     for r in range(world):
         bad, nh, na, nlog, sent = ret[r]
