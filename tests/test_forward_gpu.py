@@ -66,6 +66,21 @@ def test_against_oracle(model, kind, shape):
     _check(y, ref)
 
 
+def test_cfg2_full_size_against_oracle_and_batch_property(model):
+    """BASELINE.json configs[1] at its full size (1x3x640x1120): direct parity against the fp32 oracle, plus the
+    size-independent property that a batch of two copies gives two equal results equal to the single-image run."""
+    sd = O.make_state_dict(0, False)                 # the bench's weights (default init values)
+    model.load_state_dict(sd, strict=True)
+    x = O.make_input("uniform", 1, 640, 1120, seed=1234)
+    with torch.no_grad():
+        ref = O.forward(x, sd)
+        xd = x.cuda()
+        y = model(xd)
+        y2 = model(torch.cat([xd, xd]))
+    _check(y.cpu(), ref)
+    assert max_err_robust(y2[0:1], y2[1:2]) <= 5e-4 and max_err_robust(y2[0:1], y) <= 5e-4
+
+
 def test_default_init_state_dict_round_trip(model, tmp_path):
     """torch.save(state_dict) -> torch.load(map_location=cpu) -> strict load (eval_SID_blur.py:22)."""
     from hvi_cidnet_b200.net.CIDNet import CIDNet
