@@ -573,7 +573,7 @@ int launch_dw3(const Dw3Args& a_in, cudaStream_t stream) {
     // 8 (default): per-thread cp.async ring, 4 input rows in flight, weights re-read from smem, 5 CTAs / SM (L1 launch at cfg 2:
     //    181 -> 147 us; 16x400x600: 712 -> 640 us); 9: the same with 6 rows in flight, 4 CTAs / SM;
     // 7: register loads one row ahead, weights re-read from smem, 4 CTAs / SM;
-    // 0: weights in registers, no prefetch, 4 CTAs / SM; 1: weights in registers, one-row prefetch, 3 CTAs / SM; 5 / 6: 5 CTAs / SM (spills, slower);
+    // 0: weights in registers, no prefetch, 4 CTAs / SM; 1: weights in registers, one-row prefetch, 3 CTAs / SM;
     // 2: fp32-accumulate FHFMA kernel
     static const int variant = getenv("CIDNET_DW_VARIANT") ? atoi(getenv("CIDNET_DW_VARIANT")) : 8;
     if (variant == 3 || variant == 4) return launch_dw3_v2(a, stream, variant == 3 ? 4 : 3);   // v2 (TMA ring), 4 / 3 CTAs per SM
@@ -591,9 +591,8 @@ int launch_dw3(const Dw3Args& a_in, cudaStream_t stream) {
         CIDNET_CUDA_OK(cudaGetLastError());
         return CIDNET_OK;
     }
-    if (variant == 5)      dw3x3_kernel<true, 5, true><<<grid, kDwThreads, 0, stream>>>(a);    // weights in smem, prefetch, 5 CTAs / SM
-    else if (variant == 6) dw3x3_kernel<false, 5, true><<<grid, kDwThreads, 0, stream>>>(a);   // weights in smem, no prefetch, 5 CTAs / SM
-    else if (variant == 7) dw3x3_kernel<true, 4, true><<<grid, kDwThreads, 0, stream>>>(a);    // weights in smem, prefetch, 4 CTAs / SM
+    // (5 CTAs / SM with register loads needs spills and measured slower: profiles/r01_dw3x3_variants.txt, variants 5 / 6)
+    if (variant == 7)      dw3x3_kernel<true, 4, true><<<grid, kDwThreads, 0, stream>>>(a);    // weights in smem, prefetch, 4 CTAs / SM
     else if (variant == 0) dw3x3_kernel<false, 4><<<grid, kDwThreads, 0, stream>>>(a);
     else if (variant == 1) dw3x3_kernel<true, 3><<<grid, kDwThreads, 0, stream>>>(a);
     else                   dw3x3_f32acc_kernel<<<grid, kDwThreads, 0, stream>>>(a);
