@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcidnet_b200.so")
+# CIDNET_LIB selects another build of the same ABI (e.g. libcidnet_b200_bf16.so, `build.py --bf16`)
+LIB_PATH = os.environ.get("CIDNET_LIB") or os.path.join(_HERE, "libcidnet_b200.so")
 
 OK, ERR_INVALID, ERR_ARCH, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4
 

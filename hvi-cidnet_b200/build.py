@@ -19,6 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libcidnet_b200.so")
+LIB_BF16 = os.path.join(HERE, "libcidnet_b200_bf16.so")     # the -DCIDNET_ACT_BF16 build (select with CIDNET_LIB=<path>)
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -50,8 +51,8 @@ def headers_digest(extra):
     return h.hexdigest()
 
 
-def compile_one(src, extra, hdig, force, verbose):
-    obj = os.path.join(OBJ, src[:-3] + ".o")
+def compile_one(src, extra, hdig, force, verbose, objdir=OBJ):
+    obj = os.path.join(objdir, src[:-3] + ".o")
     stamp = obj + ".stamp"
     sdig = hashlib.sha1(open(os.path.join(CSRC, src), "rb").read()).hexdigest() + hdig
     if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == sdig:
@@ -65,19 +66,21 @@ def compile_one(src, extra, hdig, force, verbose):
 
 
 def build(force=False, bf16=False, verbose=False):
-    os.makedirs(OBJ, exist_ok=True)
+    objdir = OBJ + ("_bf16" if bf16 else "")
+    lib = LIB_BF16 if bf16 else LIB
+    os.makedirs(objdir, exist_ok=True)
     extra = ["-DCIDNET_ACT_BF16"] if bf16 else []
     hdig = headers_digest(extra)
     srcs = sources()
     rebuilt = False
     logs = {}
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        for src, log, did in ex.map(lambda s: compile_one(s, extra, hdig, force, verbose), srcs):
+        for src, log, did in ex.map(lambda s: compile_one(s, extra, hdig, force, verbose, objdir), srcs):
             rebuilt |= did
             logs[src] = log
-    if rebuilt or not os.path.exists(LIB):
-        objs = [os.path.join(OBJ, s[:-3] + ".o") for s in srcs]
-        cmd = [nvcc_path(), "-shared", "-o", LIB] + objs + ["-cudart", "static", "-Xlinker", "--no-undefined", "-ldl", "-lpthread", "-lrt"]
+    if rebuilt or not os.path.exists(lib):
+        objs = [os.path.join(objdir, s[:-3] + ".o") for s in srcs]
+        cmd = [nvcc_path(), "-shared", "-o", lib] + objs + ["-cudart", "static", "-Xlinker", "--no-undefined", "-ldl", "-lpthread", "-lrt"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
@@ -85,7 +88,7 @@ def build(force=False, bf16=False, verbose=False):
         for s, log in logs.items():
             if log:
                 print(f"==== {s}\n{log}")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

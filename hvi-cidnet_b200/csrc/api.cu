@@ -5,7 +5,6 @@
 // is kept as fp32 NCHW for the global residual (:119).
 #include "cab.cuh"
 #include "conv_gemm.cuh"
-#include "dwtc.cuh"
 #include "iel.cuh"
 #include "sa.cuh"
 #include "stem_head.cuh"
@@ -20,6 +19,15 @@ using namespace cidnet;
 
 namespace {
 
+// makes ctx->device current for the duration of an entry point (a process may drive several GPUs)
+struct DeviceGuard {
+    int prev = -1; bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
 const int kCh[4] = {36, 36, 72, 144};
 const int kHeads[4] = {1, 2, 4, 8};
 
@@ -27,7 +35,6 @@ struct LcaWeights {
     bool live = true;
     int C = 0, Cp = 0, heads = 0, h = 0, hp = 0;
     float* wqkv = nullptr;                               // depthwise weights [9][3*Cp]: q_dwconv | kv_dwconv (k) | (v)
-    DwtcWeights dw_q, dw_kv;                              // the same, as diagonal tensor-core tiles
     float* temp = nullptr;                               // [heads]
     float* wo = nullptr;                                 // [C][C]
     PackedWeights fold_tmpl;                             // geometry of the per-image folded weights
@@ -200,10 +207,6 @@ int build_lca(cidnet_ctx* ctx, const std::string& pfx, int level, LcaWeights* L)
         dw_tapmajor(R[pfx + ".ffn.kv_dwconv.weight"], 0, C, 3 * Cp, Cp, &wqkv);
         dw_tapmajor(R[pfx + ".ffn.kv_dwconv.weight"], C, C, 3 * Cp, 2 * Cp, &wqkv);
         if ((rc = dev_f32(ctx, &L->wqkv, wqkv))) return rc;
-        if ((rc = pack_dwtc_weights(&L->dw_q, wqkv.data(), 3 * Cp, 0, C))) return rc;
-        ctx->owned.push_back(L->dw_q.w);
-        if ((rc = pack_dwtc_weights(&L->dw_kv, wqkv.data(), 3 * Cp, Cp, Cp + C))) return rc;
-        ctx->owned.push_back(L->dw_kv.w);
     }
     if ((rc = dev_f32(ctx, &L->temp, R[pfx + ".ffn.temperature"]))) return rc;
     if ((rc = dev_f32(ctx, &L->wo, R[pfx + ".ffn.project_out.weight"]))) return rc;
@@ -363,10 +366,10 @@ struct Plan {
     act_t *dec_i[4], *dec_hv[4];                           // dec_x[l] = output of up block l+1 -> level l (l = 1, 2)
     act_t *tup_i[4], *tup_hv[4];                           // low-res pre-composed conv outputs at level l (l = 1..3)
     // per-level scratch for an LCA stage pair
-    act_t *qkv[4][2], *qkvdw[4][2], *xp[4][2], *tin[4][2], *g[4][2], *mfold[4][2];
-    float* stats; int64_t stats_bytes;
+    act_t *qkv[4][2], *qk[4][2], *vdw[4][2], *xp[4][2], *tin[4][2], *g[4][2], *mfold[4][2];
+    float* slab;                                           // split-K partials of the stage in flight (cab.cuh)
     float2* sa_stats[2];                                   // MSSA: per-pixel (mean, max) of one up-block output per branch
-    float *gram[6][2], *sq[6][2], *sk[6][2];
+    float* stat[6];                                        // per stage: reduced raw [Gram | sq | sk] per (problem, image)
     int64_t bytes;
 };
 
@@ -391,7 +394,8 @@ void make_plan(Plan* P, void* ws, int B, int H, int W) {
         const int64_t fold_elems = (int64_t)B * f.block_n * f.n_blocks * ceil_div(kCh[l], 64) * 64;
         for (int s = 0; s < 2; ++s) {
             P->qkv[l][s] = bp.take<act_t>(px(l) * 3 * Cp);
-            P->qkvdw[l][s] = bp.take<act_t>(px(l) * 3 * Cp);
+            P->qk[l][s] = bp.take<act_t>(px(l) * 2 * Cp);
+            P->vdw[l][s] = bp.take<act_t>(px(l) * Cp);
             P->xp[l][s] = bp.take<act_t>(px(l) * Cp);
             P->tin[l][s] = bp.take<act_t>(px(l) * 2 * hp);
             P->g[l][s] = bp.take<act_t>(px(l) * hp);
@@ -403,20 +407,12 @@ void make_plan(Plan* P, void* ws, int B, int H, int W) {
         P->lca_i[n] = bp.take<act_t>(px(l) * act_pitch(kCh[l]));
         P->lca_hv[n] = bp.take<act_t>(px(l) * act_pitch(kCh[l]));
     }
-    // attention statistics: one contiguous region, cleared by a single memset per forward
-    bp.off = (bp.off + 1023) & ~int64_t(1023);
-    const int64_t s0 = bp.off;
-    P->stats = bp.take<float>(0);
+    // attention statistics: the split-K slab (re-used by every stage) and the reduced vector of each stage
+    P->slab = bp.take<float>((int64_t)gram_max_slab_entries(2 * B) * (8 * 324 + 2 * 144));
     for (int n = 1; n <= 6; ++n) {
         const int l = n <= 3 ? n : 7 - n;
-        const int C = kCh[l], Cp = act_pitch(C), heads = kHeads[l];
-        for (int s = 0; s < 2; ++s) {
-            P->gram[n - 1][s] = bp.take<float>((int64_t)B * heads * 324);
-            P->sq[n - 1][s] = bp.take<float>((int64_t)B * Cp);
-            P->sk[n - 1][s] = bp.take<float>((int64_t)B * Cp);
-        }
+        P->stat[n - 1] = bp.take<float>((int64_t)2 * B * (kHeads[l] * 324 + 2 * act_pitch(kCh[l])));
     }
-    P->stats_bytes = bp.off - s0;
     P->bytes = bp.off + 1024;
 }
 
@@ -586,9 +582,11 @@ struct Fwd {
             if ((rc = gemm(L, "L" + std::to_string(l) + ".ln_qkv_1x1", s))) return rc;
         }
         join();
-        // 2. depthwise 3x3 of [q | k | v] (+ sum q^2, sum k^2), then the Gram on the tensor cores
+        // 2. depthwise 3x3 of [q | k | v], then the Gram (+ sum q^2, sum k^2) on the tensor cores
         int probs[2], np = 0;
         for (int s = 0; s < 2; ++s) if (S.lca[s].live) probs[np++] = s;
+        const int E = heads * 324 + 2 * Cp;                    // floats of one [Gram | sq | sk] vector
+        int nsplit = 1;
         {
             Dw3Args a; memset(&a, 0, sizeof a);
             GramLaunch gl; memset(&gl, 0, sizeof gl);
@@ -597,63 +595,44 @@ struct Fwd {
                 a.src[i][0] = P.qkv[l][s];                     // q of LCA s comes from its own tensor
                 a.src[i][1] = P.qkv[l][1 - s] + Cp;            // k, v from the sibling tensor
                 a.src[i][2] = P.qkv[l][1 - s] + 2 * Cp;
-                a.dst[i] = P.qkvdw[l][s];
+                a.dst_qk[i] = P.qk[l][s]; a.dst_v[i] = P.vdw[l][s];
                 a.w[i] = S.lca[s].wqkv;
-                a.sq[i] = P.sq[n - 1][s]; a.sk[i] = P.sk[n - 1][s];
-                gl.q[i] = P.qkvdw[l][s]; gl.k[i] = P.qkvdw[l][s] + Cp; gl.gram[i] = P.gram[n - 1][s];
+                gl.q[i] = P.qk[l][s]; gl.k[i] = P.qk[l][s] + Cp;
             }
-            a.src_pitch = 3 * Cp; a.dst_pitch = 3 * Cp; a.B = P.B; a.H = H; a.W = W;
+            a.src_pitch = 3 * Cp; a.B = P.B; a.H = H; a.W = W;
             a.nv = 3 * Cp / 8; a.seg_vecs = Cp / 8; a.nprob = np;
             // sharded: sum q^2, sum k^2 and the Gram run over the OWNED rows only (partial sums, all-reduced below)
             const int own0 = sh.on ? ht(l) : 0, own_n = sh.on ? own_rows(l) : H;
-            a.stat_y0 = own0; a.stat_y1 = own0 + own_n;
-            for (int i = 0; i < np; ++i) { gl.q[i] += (long long)own0 * W * 3 * Cp; gl.k[i] += (long long)own0 * W * 3 * Cp; }
+            for (int i = 0; i < np; ++i) { gl.q[i] += (long long)own0 * W * 2 * Cp; gl.k[i] += (long long)own0 * W * 2 * Cp; }
             mark("L" + std::to_string(l) + ".cab_dw3x3_qkv", (double)np * P.B * H * W * 12.0 * C, (double)np * P.B * H * W * 2.0 * 27 * C);
-            // default: FHFMA sliding-window kernel.  CIDNET_DW_TENSOR_CORES=1 selects the tcgen05 variant
-            // (dwtc.cu: correct, but per-tile latencies make it ~2x slower in its current form)
-            static const bool cuda_core_dw = getenv("CIDNET_DW_TENSOR_CORES") == nullptr;
-            if (!live()) {
-            } else if (cuda_core_dw || sh.on) {
-                if ((rc = launch_dw3(a, st))) return rc;
-            } else {
-                DwtcLaunch D;
-                D.B = P.B; D.H = H; D.W = W;
-                for (int i = 0; i < np; ++i) {
-                    const int s = probs[i];
-                    DwtcSeg& q = D.seg[D.nseg++];
-                    q.in = P.qkv[l][s]; q.in_pitch = 3 * Cp; q.out = P.qkvdw[l][s]; q.out_pitch = 3 * Cp;
-                    q.wt = &S.lca[s].dw_q; q.ssq = P.sq[n - 1][s]; q.ssq_pitch = Cp; q.ssq_channels = C;
-                    DwtcSeg& kv = D.seg[D.nseg++];
-                    kv.in = P.qkv[l][1 - s] + Cp; kv.in_pitch = 3 * Cp; kv.out = P.qkvdw[l][s] + Cp; kv.out_pitch = 3 * Cp;
-                    kv.wt = &S.lca[s].dw_kv; kv.ssq = P.sk[n - 1][s]; kv.ssq_pitch = Cp; kv.ssq_channels = C;
-                }
-                if ((rc = launch_dwtc(D, st))) return rc;
-            }
-            gl.pitch = 3 * Cp; gl.B = P.B; gl.H = own_n; gl.W = W; gl.C = C; gl.heads = heads; gl.nprob = np;
+            if (live() && (rc = launch_dw3(a, st))) return rc;
+            gl.pitch = 2 * Cp; gl.B = P.B; gl.H = own_n; gl.W = W; gl.C = C; gl.heads = heads; gl.nprob = np;
             gl.img_stride_px = (long long)H * W;
+            gl.slab = P.slab;
             mark("L" + std::to_string(l) + ".cab_gram_tc", (double)np * P.B * own_n * W * 4.0 * C, (double)np * P.B * own_n * W * 2.0 * C * C);
-            if (live() && (rc = launch_gram(gl, st))) return rc;
+            if (live() && (rc = launch_gram(gl, st, &nsplit))) return rc;
             if (split()) {
-                // one all-reduce (sum, fp32) of the raw partial [Gram | sum q^2 | sum k^2] of the live problems;
-                // normalisation, temperature and softmax then run identically on every rank
-                float* lo = P.gram[n - 1][probs[0]];
-                float* hi = P.sk[n - 1][probs[np - 1]] + (int64_t)P.B * Cp;
+                // this rank's partial [Gram | sum q^2 | sum k^2] of the live problems (fixed-order sum of its slab), then ONE
+                // all-reduce (sum, fp32) across the ranks; normalisation, temperature and softmax then run identically everywhere
+                ++launches;
+                if (live() && (rc = launch_cab_reduce(P.slab, P.stat[n - 1], nsplit, E, np * P.B, st))) return rc;
                 ++sh.allreduce_calls;
-                const int arc = sh.ar_fn(sh.user, lo, (int64_t)(hi - lo));
+                const int arc = sh.ar_fn(sh.user, P.stat[n - 1], (int64_t)np * P.B * E);
                 CIDNET_CHECK(arc == 0, CIDNET_ERR_STATE, "forward_sharded: all-reduce callback failed (" + std::to_string(arc) + ")");
             }
         }
-        // 3. normalise + temperature + softmax + fold into project_out
+        // 3. fixed-order sum of the split-K partials, normalise + temperature + softmax + fold into project_out
         {
             CabFoldArgs f; memset(&f, 0, sizeof f);
             for (int i = 0; i < np; ++i) {
                 const int s = probs[i];
-                f.gram[i] = P.gram[n - 1][s]; f.sq[i] = P.sq[n - 1][s]; f.sk[i] = P.sk[n - 1][s];
                 f.temp[i] = S.lca[s].temp; f.wo[i] = S.lca[s].wo; f.m_out[i] = P.mfold[l][s];
             }
+            if (split()) { f.slab = P.stat[n - 1]; f.nsplit = 1; f.raw_out = nullptr; }
+            else         { f.slab = P.slab; f.nsplit = nsplit; f.raw_out = P.stat[n - 1]; }
             const PackedWeights& t = S.lca[probs[0]].fold_tmpl;
             f.B = P.B; f.C = C; f.Cp = Cp; f.heads = heads; f.nprob = np; f.n_rows = t.n_rows; f.kt = t.ktot();
-            mark("L" + std::to_string(l) + ".cab_softmax_fold", (double)np * P.B * (C * C * 6.0), (double)np * P.B * 36.0 * C * C);
+            mark("L" + std::to_string(l) + ".cab_softmax_fold", (double)np * P.B * (C * C * 6.0 + 4.0 * nsplit * E), (double)np * P.B * 36.0 * C * C);
             if (live() && (rc = launch_cab_fold(f, st))) return rc;
         }
         const bool both = np == 2;        // stage 5 has a single live problem: it keeps all the SMs
@@ -664,7 +643,7 @@ struct Fwd {
             // 4. x' = x + (W_o * blockdiag(attn_b)) v      (per-image 1x1)
             PackedWeights fw = Lw.fold_tmpl; fw.w = P.mfold[l][s]; fw.n_img = P.B > 1 ? P.B : 1;
             ConvGemmLaunch A;
-            A.mode = EPI_STORE; A.in = P.qkvdw[l][s] + 2 * Cp; A.B = P.B; A.H = H; A.W = W; A.in_pitch = 3 * Cp; A.flat = true;
+            A.mode = EPI_STORE; A.in = P.vdw[l][s]; A.B = P.B; A.H = H; A.W = W; A.in_pitch = Cp; A.flat = true;
             A.wt = &fw; A.out = P.xp[l][s]; A.out_pitch = Cp; A.in2 = x[s]; A.in2_pitch = Cp; A.wt2 = &ctx->eye[l];
             if (P.B == 1) fw.n_img = 1;
             if ((rc = gemm(A, "L" + std::to_string(l) + ".cab_attnv_proj_res", s, both))) return rc;
@@ -713,7 +692,6 @@ struct Fwd {
 
     int run(const float* rgb_in, float* rgb_out, const float* k_dev, int gated, float alpha_s, int gated2, float alpha) {
         int rc;
-        if (live()) CIDNET_CUDA_OK(cudaMemsetAsync(P.stats, 0, (size_t)P.stats_bytes, st));
         StemArgs sa{rgb_in, P.hvi, P.i_enc0, P.hv_0, ctx->stem_whv, ctx->stem_wi, k_dev ? k_dev : ctx->k_dev,
                     ctx->k_host, P.B, P.H[0], P.W[0], 40, ctx->stem_bfrag};
         mark("L0.stem_hvit_block0", (double)P.B * P.H[0] * P.W[0] * 168.0, (double)P.B * P.H[0] * P.W[0] * 2.0 * 1296);
@@ -880,6 +858,7 @@ extern "C" int cidnet_forward(cidnet_ctx* ctx, const float* rgb_in, float* rgb_o
                  "forward: H and W must be multiples of 8 (got " + std::to_string(H) + "x" + std::to_string(W) +
                      "); the reference fails in torch.cat for such inputs, callers pad first");
     if (B == 0) return CIDNET_OK;
+    DeviceGuard guard(ctx->device);
     CIDNET_CHECK(rgb_in && rgb_out && workspace, CIDNET_ERR_INVALID, "forward: null pointer");
     CIDNET_CHECK((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, CIDNET_ERR_INVALID, "forward: workspace must be 1024-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1046,6 +1025,7 @@ extern "C" int cidnet_forward_sharded(cidnet_ctx* ctx, const float* rgb_local, f
     CIDNET_CHECK(sh->nranks == 1 || (halo_fn && allreduce_fn), CIDNET_ERR_INVALID, "forward_sharded: callbacks required");
     CIDNET_CHECK(rgb_local && rgb_out_local && workspace, CIDNET_ERR_INVALID, "forward_sharded: null pointer");
     CIDNET_CHECK((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, CIDNET_ERR_INVALID, "forward_sharded: workspace must be 1024-byte aligned");
+    DeviceGuard guard(ctx->device);
     Fwd f;
     f.ctx = ctx; f.st = (cudaStream_t)stream;
     shard_state(sh, &f.sh);

@@ -29,6 +29,13 @@ __host__ __device__ __forceinline__ act_t f2act(float v) { return __float2half_r
 void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: raise it once per (current
+// device, kernel) pair (a process may hold contexts on several GPUs; a process-wide `static bool` would leave the
+// second device at the 48 KB default).  Returns CIDNET_OK or an error code.
+int ensure_dynamic_smem(const void* kernel, int bytes);
+// SM count of the CURRENT device (cached per device ordinal)
+int device_sm_count();
+
 #define CIDNET_CUDA_OK(expr)                                                              \
     do {                                                                                  \
         cudaError_t _e = (expr);                                                          \

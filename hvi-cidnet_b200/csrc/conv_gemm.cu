@@ -42,7 +42,7 @@ struct ConvGemmArgs {
     int taps, kchunks, kchunks2, cin, cin2;
     int Hv, Wv, TH, TW, tiles_x, tiles_y, num_tiles;
     int n_out, block_n, stages, per_image_w, b_resident, stg_bufs;
-    int halo, halo_baseoff;          // 3x3: tile + halo loaded once per channel chunk, taps = row-shifted views
+    int halo;                        // 3x3: tile + halo loaded once per channel chunk, taps = row-shifted views
     int w_real;
     const float* bias; const float* wsum; float ln_eps;
     int up_H, up_W, up_chunks; float up_ry, up_rx;   // EPI_UP: low-res source (staged by TMA next to every A tile)
@@ -254,8 +254,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                     // descriptors, the accumulate flag is an immediate and only `k < ksteps` stays a uniform branch.
                     int ksteps = (a.cin - i * 64 + 15) >> 4;
                     if (ksteps > 4) ksteps = 4;
-                    const uint64_t dA0 = ptx::umma_smem_desc_sw128_rowshift(ptx::smem_u32(smA + (size_t)s * a_stage),
-                                                                            0u);
+                    const uint64_t dA0 = ptx::umma_smem_desc_sw128(ptx::smem_u32(smA + (size_t)s * a_stage));
                     uint64_t descB = ptx::umma_smem_desc_sw128(ptx::smem_u32(smBres + (size_t)i * b_chunk));
                     const uint64_t b_tap = (uint64_t)(((uint32_t)a.kchunks * b_chunk) >> 4);   // next tap's weights
                     const uint32_t d0 = d_tmem, d1 = d_tmem + (uint32_t)a.block_n;
@@ -571,25 +570,10 @@ static inline float ac_scale(int n_in, int n_out) {
     return n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.f;
 }
 
-static int num_sms() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
-}
-
 template <int kMode, int kEpiGroups>
 static int launch_mode_g(const ConvGemmArgs& args, dim3 grid, size_t smem, cudaStream_t stream) {
-    static bool configured = false;   // per instantiation; the attribute is sticky per function
-    if (!configured) {
-        CIDNET_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<kMode, kEpiGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            227 * 1024));
-        configured = true;
-    }
+    int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(conv_gemm_kernel<kMode, kEpiGroups>), 227 * 1024);
+    if (rc) return rc;
     conv_gemm_kernel<kMode, kEpiGroups><<<grid, 64 + 128 * kEpiGroups, smem, stream>>>(args);
     CIDNET_CUDA_OK(cudaGetLastError());
     return CIDNET_OK;
@@ -599,8 +583,6 @@ static int launch_mode(const ConvGemmArgs& args, dim3 grid, size_t smem, cudaStr
     (void)groups;      // only the 2-group kernels are instantiated (see launch_conv_gemm for the 3-group experiment)
     return launch_mode_g<kMode, 2>(args, grid, smem, stream);
 }
-
-int device_sm_count() { return num_sms(); }
 
 int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
     const PackedWeights& wt = *L.wt;
@@ -631,14 +613,12 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
     // 3x3 halo mode: possible when all 9 taps' weights stay resident next to >= 2 halo stages
     {
         static const bool no_halo = getenv("CIDNET_NO_HALO") != nullptr;
-        // measured on B200: the SWIZZLE_128B XOR is applied to ABSOLUTE shared-memory address bits, so a
+        // (measured on B200: the SWIZZLE_128B XOR is applied to ABSOLUTE shared-memory address bits, so a
         // descriptor that starts on an arbitrary 128-byte row of a 1024-byte aligned TMA tile reads the
-        // right data with base_offset = 0 (setting (addr >> 7) & 7 there gives wrong results)
-        static const bool no_baseoff = getenv("CIDNET_HALO_BASEOFF") == nullptr;
+        // right data with base_offset = 0; setting (addr >> 7) & 7 there gives wrong results)
         const size_t fixed1 = 1024 + (size_t)kEpiGroups * kStagingBytes + 512 + 2 * round_up(wt.block_n, 32) * sizeof(float);
         const size_t need = fixed1 + (size_t)9 * wt.kchunks * wt.block_n * 128 + (size_t)2 * ksub * kHaloTileBytes;
         a.halo = (wt.taps == 9 && !L.in2 && !a.per_image_w && !no_halo && need <= 226 * 1024) ? 1 : 0;
-        a.halo_baseoff = no_baseoff ? 0 : 1;
     }
     const int tw = a.halo ? 14 : 16;                            // halo mode: 16-wide smem rows, 14 valid columns
     const uint64_t pb = (uint64_t)L.in_pitch * sizeof(act_t);   // bytes per pixel row
@@ -757,7 +737,7 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
     a.stages = stages;
     const size_t smem = fixed + (a.b_resident ? bres : 0) + (size_t)stages * (a_stage + (a.b_resident ? 0 : b_chunk));
 
-    int gx = (L.max_ctas > 0 ? L.max_ctas : num_sms()) / wt.n_blocks;
+    int gx = (L.max_ctas > 0 ? L.max_ctas : device_sm_count()) / wt.n_blocks;
     if (gx < 1) gx = 1;
     if (gx > a.num_tiles) gx = a.num_tiles;
     dim3 grid((unsigned)gx, (unsigned)wt.n_blocks, 1);

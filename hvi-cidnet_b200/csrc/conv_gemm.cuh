@@ -72,7 +72,6 @@ struct ConvGemmLaunch {
 };
 
 int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream);
-int device_sm_count();
 
 // layout helpers (tests / taps only)
 int launch_nchw_to_nhwc(const float* src, act_t* dst, int B, int C, int H, int W, int pitch, cudaStream_t s);

@@ -4,14 +4,9 @@
 //   d  = dwconv(t)            (3x3 depthwise on [x1 | x2], zero pad)
 //   x1 = tanh(dwconv1(d1)) + d1 ;  x2 = tanh(dwconv2(d2)) + d2 ;  g = x1 * x2
 //
-// A warp = 32 image columns (lane = column) x 8 hidden channels of ONE half, walking down a strip
-// of rows; a CTA = 4 warps = {x1, x2} x 2 channel vectors.  Per row each thread issues ONE 16-byte
-// global load (its own column of t); the left/right neighbours of t and of d come from warp
-// shuffles (the two edge lanes fetch their outer neighbour themselves), so there is no shared
-// memory staging and no block-wide barrier.  The first depthwise runs on FHFMA (fp16 x fp16 + fp32,
-// `fma.rn.f32.f16`: no conversion instructions); d, the second depthwise, tanh and the product are
-// fp32.  d is ZERO outside the image (= the zero padding dwconv1/dwconv2 see).  The x2 warp hands
-// its tanh(..)+d to the x1 warp through 1 KB of shared memory and a 64-thread named barrier.
+// (fp16 build: iel_gate_v6_kernel, packed HFMA2; bf16 build: iel_gate_v4_kernel, fp32 accumulation.  Both are fed by a
+// TMA ring of t; the register-shuffle v3, the smem-weight v5 and the cp.async-producer experiments of round 1 were
+// measured slower (profiles/r01_summary.md) and are gone.)
 #include "iel.cuh"
 #include "ptx_sm100.cuh"
 
@@ -22,7 +17,6 @@ namespace cidnet {
 
 static constexpr int kCols = 32;       // columns per warp (outputs: lanes 1..30)
 static constexpr int kRows = 32;       // output rows per CTA
-static constexpr int kThreadsIel = 128;
 
 #ifdef CIDNET_ACT_BF16
 #define CIDNET_FHFMA "fma.rn.f32.bf16"
@@ -62,143 +56,6 @@ __device__ __forceinline__ uint4 shfl_down4(const uint4& v) {
 struct TRow { uint4 l, c, r; };          // raw 16-bit t values: left / centre / right column
 struct DRow { uint4 l, c, r; float cf[8]; };   // d: 16-bit packed left / centre / right (dwconv1/2 operands) + fp32 centre (residual)
 
-__global__ void __launch_bounds__(kThreadsIel, 4)
-iel_gate_v3_kernel(const IelGateArgs a) {
-    __shared__ __align__(16) act_t s_w0[9 * 2 * 16];      // dwconv    [tap][half][16]  16-bit
-    __shared__ __align__(16) act_t s_w12[9 * 2 * 16];     // dwconv1/2 [tap][half][16]  16-bit
-    __shared__ float4 s_x[2 * 2 * 2 * kCols];             // [vec][row parity][plane][lane]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int half = warp >> 1, vec = warp & 1;
-    const int hp = a.hp, ngroups = hp / 16;
-    const int prob = blockIdx.z % a.nprob, b = blockIdx.z / a.nprob;
-    const int cg = blockIdx.x % ngroups, strip = blockIdx.x / ngroups;
-    const int c0 = cg * 16;
-    const int x = strip * (kCols - 2) - 1 + lane;         // image column of this lane
-    const int y0 = blockIdx.y * kRows;
-    const int y1 = min(y0 + kRows, a.H);
-    const int pitch_t = 2 * hp;
-    const long long hw = (long long)a.H * a.W;
-
-    for (int i = tid; i < 9 * 2 * 16; i += kThreadsIel) {
-        const int c = i & 15, hf = (i >> 4) & 1, tap = i >> 5;
-        s_w0[i] = f2act(a.w0[prob][tap * 2 * hp + hf * hp + c0 + c]);
-        s_w12[i] = f2act((hf == 0 ? a.w1[prob] : a.w2[prob])[tap * hp + c0 + c]);
-    }
-    __syncthreads();
-
-    const bool col_in = x >= 0 && x < a.W;
-    const bool left_in = x - 1 >= 0 && x - 1 < a.W, right_in = x + 1 >= 0 && x + 1 < a.W;
-    const act_t* tsrc = a.t[prob] + (long long)b * hw * pitch_t + half * hp + c0 + vec * 8;
-    act_t* gdst = a.g[prob] + (long long)b * hw * hp + c0 + vec * 8;
-    const bool writer = half == 0 && lane >= 1 && lane <= kCols - 2 && col_in;
-    const uint4 zero4 = make_uint4(0, 0, 0, 0);
-
-    // global loads run ONE ROW AHEAD of their use: `pend_*` holds row r+2 while iteration r computes
-    uint4 pend_c = zero4, pend_e = zero4;      // own column; outer neighbour (edge lanes 0 / 31 only)
-    auto issue_load = [&](int y) {
-        pend_c = zero4; pend_e = zero4;
-        const bool row_in = y >= 0 && y < a.H;
-        const act_t* p = tsrc + ((long long)y * a.W + x) * pitch_t;
-        if (row_in && col_in) pend_c = *reinterpret_cast<const uint4*>(p);
-        if (lane == 0 && row_in && left_in) pend_e = *reinterpret_cast<const uint4*>(p - pitch_t);
-        if (lane == 31 && row_in && right_in) pend_e = *reinterpret_cast<const uint4*>(p + pitch_t);
-    };
-    auto take_trow = [&](TRow& t) {
-        t.c = pend_c;
-        t.l = shfl_up4(t.c);
-        t.r = shfl_down4(t.c);
-        if (lane == 0) t.l = pend_e;
-        if (lane == 31) t.r = pend_e;
-    };
-    auto dw0_row = [&](const TRow& t, int tap0, float* acc) {
-        const uint4* w = reinterpret_cast<const uint4*>(s_w0) + (half * 2 + vec);   // + tap * 4 uint4
-        fhfma8(acc, t.l, w[(tap0 + 0) * 4]);
-        fhfma8(acc, t.c, w[(tap0 + 1) * 4]);
-        fhfma8(acc, t.r, w[(tap0 + 2) * 4]);
-    };
-    auto dw12_row = [&](const DRow& d, int tap0, float* o) {
-        const uint4* w = reinterpret_cast<const uint4*>(s_w12) + (half * 2 + vec);   // + tap * 4 uint4
-        fhfma8(o, d.l, w[(tap0 + 0) * 4]);
-        fhfma8(o, d.c, w[(tap0 + 1) * 4]);
-        fhfma8(o, d.r, w[(tap0 + 2) * 4]);
-    };
-    auto pack8h = [](const float* f) -> uint4 {
-        uint4 raw;
-        act_t* o = reinterpret_cast<act_t*>(&raw);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = f2act(f[e]);
-        return raw;
-    };
-
-    // one iteration: d(r) from t rows (r-1, r, r+1) = (t0, t1, t2); then output row r-1 from d rows
-    // (r-2, r-1, r) = (d0, d1, d2).  t2 and d2 are (re)filled here; the roles rotate in the caller.
-    auto iter = [&](int r, const TRow& t0, const TRow& t1, TRow& t2, const DRow& d0, const DRow& d1, DRow& d2) {
-        take_trow(t2);             // row r+1 (its load was issued one iteration ago)
-        issue_load(r + 2);         // in flight while this iteration computes
-#pragma unroll
-        for (int e = 0; e < 8; ++e) d2.cf[e] = 0.f;
-        if (r >= 0 && r < a.H && col_in) {
-            dw0_row(t0, 0, d2.cf);
-            dw0_row(t1, 3, d2.cf);
-            dw0_row(t2, 6, d2.cf);
-        }
-        d2.c = pack8h(d2.cf);              // 16-bit copy: operand of dwconv1/2 (and what the neighbours see)
-        d2.l = shfl_up4(d2.c);
-        d2.r = shfl_down4(d2.c);
-        const int yo = r - 1;
-        float xs[8];
-        {
-            float o[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = 0.f;
-            dw12_row(d0, 0, o);
-            dw12_row(d1, 3, o);
-            dw12_row(d2, 6, o);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) xs[e] = tanh_approx(o[e]) + d1.cf[e];
-        }
-        // x2 warp -> shared -> x1 warp of the same channel vector (64-thread named barrier)
-        float4* slot = s_x + ((vec * 2 + (yo & 1)) * 2) * kCols + lane;
-        if (half == 1) {
-            slot[0] = make_float4(xs[0], xs[1], xs[2], xs[3]);
-            slot[kCols] = make_float4(xs[4], xs[5], xs[6], xs[7]);
-        }
-        asm volatile("bar.sync %0, 64;" :: "r"(1 + vec) : "memory");
-        if (writer && yo >= y0) {
-            const float4 pa = slot[0], pb = slot[kCols];
-            uint4 raw;
-            act_t* ov = reinterpret_cast<act_t*>(&raw);
-            ov[0] = f2act(xs[0] * pa.x); ov[1] = f2act(xs[1] * pa.y); ov[2] = f2act(xs[2] * pa.z); ov[3] = f2act(xs[3] * pa.w);
-            ov[4] = f2act(xs[4] * pb.x); ov[5] = f2act(xs[5] * pb.y); ov[6] = f2act(xs[6] * pb.z); ov[7] = f2act(xs[7] * pb.w);
-            *reinterpret_cast<uint4*>(gdst + ((long long)yo * a.W + x) * hp) = raw;
-        }
-    };
-
-    TRow tA, tB, tC;
-    DRow dA, dB, dC;
-    dA.l = dA.c = dA.r = zero4; dB.l = dB.c = dB.r = zero4;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { dA.cf[e] = 0.f; dB.cf[e] = 0.f; }
-    issue_load(y0 - 2); take_trow(tA);
-    issue_load(y0 - 1); take_trow(tB);
-    issue_load(y0);
-    // d rows r = y0-1 .. y1; register roles rotate with period 3 (no register moves)
-    for (int r = y0 - 1; r <= y1; r += 3) {
-        iter(r, tA, tB, tC, dA, dB, dC);
-        if (r + 1 <= y1) iter(r + 1, tB, tC, tA, dB, dC, dA);
-        if (r + 2 <= y1) iter(r + 2, tC, tA, tB, dC, dA, dB);
-    }
-}
-
-static int launch_iel_gate_v3(const IelGateArgs& a, cudaStream_t stream) {
-    CIDNET_CHECK(a.hp % 16 == 0, CIDNET_ERR_INVALID, "iel: hp % 16");
-    const int strips = ceil_div(a.W, kCols - 2);
-    dim3 grid(strips * (a.hp / 16), ceil_div(a.H, kRows), a.B * a.nprob);
-    iel_gate_v3_kernel<<<grid, kThreadsIel, 0, stream>>>(a);
-    CIDNET_CUDA_OK(cudaGetLastError());
-    return CIDNET_OK;
-}
-
 // ================================================================================================
 // v4: TMA-fed.  A producer warp streams row blocks of t -- {16 channels, 34 columns (1-column halo),
 // 4 rows} per half, zero-filled outside the image -- into a SWIZZLE_32B shared-memory ring; the four
@@ -218,6 +75,7 @@ struct IelV4Args {
     IelGateArgs g;
 };
 
+#ifdef CIDNET_ACT_BF16
 __global__ void __launch_bounds__(kV4Threads, 2)
 iel_gate_v4_kernel(const __grid_constant__ IelV4Args A) {
     const IelGateArgs& a = A.g;
@@ -369,7 +227,7 @@ iel_gate_v4_kernel(const __grid_constant__ IelV4Args A) {
     }
 }
 
-#ifndef CIDNET_ACT_BF16
+#else
 // ================================================================================================
 // v5 (fp16 build): the v4 data path (TMA-fed SWIZZLE_32B ring, lane = column, LDS neighbours) with the
 // whole chain in PACKED fp16: HFMA2 does two multiply-adds per issue slot (the v4 kernel is
@@ -412,18 +270,25 @@ __device__ __forceinline__ uint4 hadd8(const uint4& a, const uint4& b) {
 
 static constexpr int kV5Stages = 4;
 
-template <int kMinBlocks>
-__global__ void __launch_bounds__(kV4Threads, kMinBlocks)
-iel_gate_v5_kernel(const __grid_constant__ IelV4Args A) {
+// ================================================================================================
+// v6 (fp16 build): v5's data path, but the 18 weight vectors (dwconv + dwconv1/2, 8 channels) live in
+// REGISTERS -- ncu on v5 showed the shared-memory data pipe as the top unit (66 %: two wavefronts per
+// warp-uniform LDS.128, 36 of the 52 wavefronts per warp-row were weight re-loads).  To pay for the
+// 72 weight registers the two 3x3 stages are evaluated in SCATTER form: an arriving row updates the
+// three output rows it touches (three running partial sums) instead of three input rows being kept, so
+// only the arriving (l, c, r) vectors are live.  Same arithmetic, same fp16 rounding points as v5 up to
+// the summation order (row-major chains).
+// ================================================================================================
+__global__ void __launch_bounds__(kV4Threads, 3)
+iel_gate_v6_kernel(const __grid_constant__ IelV4Args A) {
     const IelGateArgs& a = A.g;
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
     uint8_t* ring = smem;                                                  // kV5Stages x kV4StageBytes
-    act_t* s_w0 = reinterpret_cast<act_t*>(ring + kV5Stages * kV4StageBytes);   // [9][2][16]
-    act_t* s_w12 = s_w0 + 9 * 2 * 16;
-    uint4* s_x = reinterpret_cast<uint4*>(s_w12 + 9 * 2 * 16);            // [vec][parity][lane] packed x2
-    uint64_t* full = reinterpret_cast<uint64_t*>(s_x + 2 * 2 * kCols);
+    uint4* s_x = reinterpret_cast<uint4*>(ring + kV5Stages * kV4StageBytes);   // [vec][slot 0..3][lane] packed x2
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_x + 2 * 4 * kCols);
     uint64_t* empty = full + kV5Stages;
+    act_t* s_w12 = reinterpret_cast<act_t*>(empty + kV5Stages);               // [9][2][16] dwconv1/2 weights
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int hp = a.hp, ngroups = hp / 16;
@@ -438,7 +303,6 @@ iel_gate_v5_kernel(const __grid_constant__ IelV4Args A) {
 
     for (int i = tid; i < 9 * 2 * 16; i += kV4Threads) {
         const int c = i & 15, hf = (i >> 4) & 1, tap = i >> 5;
-        s_w0[i] = f2act(a.w0[prob][tap * 2 * hp + hf * hp + c0 + c]);
         s_w12[i] = f2act((hf == 0 ? a.w1[prob] : a.w2[prob])[tap * hp + c0 + c]);
     }
     if (tid == 0) {
@@ -470,204 +334,21 @@ iel_gate_v5_kernel(const __grid_constant__ IelV4Args A) {
     const bool writer = half == 0 && lane >= 1 && lane <= kCols - 2 && col_in;
     const uint4 zero4 = make_uint4(0, 0, 0, 0);
 
-    auto swz = [](uint32_t o) { return o ^ (((o >> 7) & 1u) << 4); };
-    const uint32_t off_l = swz((uint32_t)lane * 32u + (uint32_t)vec * 16u);
-    const uint32_t off_c = swz((uint32_t)(lane + 1) * 32u + (uint32_t)vec * 16u);
-    const uint32_t off_r = swz((uint32_t)(lane + 2) * 32u + (uint32_t)vec * 16u);
-    auto lds_trow = [&](int j, TRow& t) {
-        const int k = j / kRB, rr = j - k * kRB;
-        const int s = k % kV5Stages;
-        if (rr == 0) ptx::mbar_wait(&full[s], (k / kV5Stages) & 1u);
-        const uint8_t* base = ring + (size_t)s * kV4StageBytes + half * kHalfBoxBytes + rr * (kBoxCols * 32);
-        t.l = *reinterpret_cast<const uint4*>(base + off_l);
-        t.c = *reinterpret_cast<const uint4*>(base + off_c);
-        t.r = *reinterpret_cast<const uint4*>(base + off_r);
-        if (rr == kRB - 1 || j == nrows - 1) {
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&empty[s]);
-        }
-    };
-    const uint4* w0 = reinterpret_cast<const uint4*>(s_w0) + (half * 2 + vec);      // + tap * 4
-    const uint4* w12 = reinterpret_cast<const uint4*>(s_w12) + (half * 2 + vec);
-    // 3x3 over three (l, c, r) rows: two independent chains (rows 0-1, row 2), one final add
-    auto conv9 = [&](const uint4* w, const TRow& r0, const TRow& r1, const TRow& r2) -> uint4 {
-        uint4 pa = hmul8(r0.l, w[0 * 4]);
-        uint4 pb = hmul8(r2.l, w[6 * 4]);
-        hfma8(pa, r0.c, w[1 * 4]); hfma8(pb, r2.c, w[7 * 4]);
-        hfma8(pa, r0.r, w[2 * 4]); hfma8(pb, r2.r, w[8 * 4]);
-        hfma8(pa, r1.l, w[3 * 4]);
-        hfma8(pa, r1.c, w[4 * 4]);
-        hfma8(pa, r1.r, w[5 * 4]);
-        return hadd8(pa, pb);
-    };
-    auto iter = [&](int r, const TRow& t0, const TRow& t1, TRow& t2, const TRow& d0, const TRow& d1, TRow& d2) {
-        lds_trow(r + 1 - (y0 - 2), t2);
-        d2.c = zero4;
-        if (r >= 0 && r < a.H && col_in) d2.c = conv9(w0, t0, t1, t2);      // d is zero outside the image
-        d2.l = shfl_up4(d2.c);
-        d2.r = shfl_down4(d2.c);
-        const int yo = r - 1;
-        const uint4 o = conv9(w12, d0, d1, d2);
-        const uint4 xs = make_uint4(hadd2u(htanh2u(o.x), d1.c.x), hadd2u(htanh2u(o.y), d1.c.y),
-                                    hadd2u(htanh2u(o.z), d1.c.z), hadd2u(htanh2u(o.w), d1.c.w));
-        uint4* slot = s_x + (vec * 2 + (yo & 1)) * kCols + lane;
-        if (half == 1) *slot = xs;
-        asm volatile("bar.sync %0, 64;" :: "r"(1 + vec) : "memory");
-        if (writer && yo >= y0)
-            *reinterpret_cast<uint4*>(gdst + ((long long)yo * a.W + x) * hp) = hmul8(xs, *slot);
-    };
-    TRow tA, tB, tC, dA, dB, dC;
-    dA.l = dA.c = dA.r = zero4; dB.l = dB.c = dB.r = zero4;
-    lds_trow(0, tA);
-    lds_trow(1, tB);
-    for (int r = y0 - 1; r <= y1; r += 3) {
-        iter(r, tA, tB, tC, dA, dB, dC);
-        if (r + 1 <= y1) iter(r + 1, tB, tC, tA, dB, dC, dA);
-        if (r + 2 <= y1) iter(r + 2, tC, tA, tB, dC, dA, dB);
-    }
-}
-
-// ================================================================================================
-// v6 (fp16 build): v5's data path, but the 18 weight vectors (dwconv + dwconv1/2, 8 channels) live in
-// REGISTERS -- ncu on v5 showed the shared-memory data pipe as the top unit (66 %: two wavefronts per
-// warp-uniform LDS.128, 36 of the 52 wavefronts per warp-row were weight re-loads).  To pay for the
-// 72 weight registers the two 3x3 stages are evaluated in SCATTER form: an arriving row updates the
-// three output rows it touches (three running partial sums) instead of three input rows being kept, so
-// only the arriving (l, c, r) vectors are live.  Same arithmetic, same fp16 rounding points as v5 up to
-// the summation order (row-major chains).
-// ================================================================================================
-// kCpAsync (experiment, CIDNET_IEL_V6=4): the producer warp fills the ring with 16-byte cp.async copies (all 32
-// lanes, zero fill outside the image, completion through cp.async.mbarrier.arrive) instead of TMA boxes, same
-// shared-memory layout (the 32-byte swizzle applied by hand).  Written to test whether the 32-byte box rows
-// (320 TMA requests per 4-row block) limit the kernel: they do not -- measured 15 % SLOWER than the TMA producer
-// (cfg4 L1: 4.24 vs 3.67 ms), so TMA stays the default.
-template <int kMinBlocks, bool kW12Smem, bool kCpAsync>
-__global__ void __launch_bounds__(kV4Threads, kMinBlocks)
-iel_gate_v6_kernel(const __grid_constant__ IelV4Args A) {
-    const IelGateArgs& a = A.g;
-    extern __shared__ __align__(1024) uint8_t smem[];
-    if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
-    uint8_t* ring = smem;                                                  // kV5Stages x kV4StageBytes
-    uint4* s_x = reinterpret_cast<uint4*>(ring + kV5Stages * kV4StageBytes);   // [vec][slot 0..3][lane] packed x2
-    uint64_t* full = reinterpret_cast<uint64_t*>(s_x + 2 * 4 * kCols);
-    uint64_t* empty = full + kV5Stages;
-    act_t* s_w12 = reinterpret_cast<act_t*>(empty + kV5Stages);               // kW12Smem: [9][2][16] dwconv1/2 weights
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int hp = a.hp, ngroups = hp / 16;
-    const int prob = blockIdx.z % a.nprob, b = blockIdx.z / a.nprob;
-    const int cg = blockIdx.x % ngroups, strip = blockIdx.x / ngroups;
-    const int c0 = cg * 16;
-    const int X0 = strip * (kCols - 2) - 1;               // image column of lane 0
-    const int y0 = blockIdx.y * kRows;
-    const int y1 = min(y0 + kRows, a.H);
-    const int nrows = (y1 - y0) + 4;                      // t rows y0-2 .. y1+1
-    const int nblocks = (nrows + kRB - 1) / kRB;
-
-    if (kW12Smem) {
-        for (int i = tid; i < 9 * 2 * 16; i += kV4Threads) {
-            const int c = i & 15, hf = (i >> 4) & 1, tap = i >> 5;
-            s_w12[i] = f2act((hf == 0 ? a.w1[prob] : a.w2[prob])[tap * hp + c0 + c]);
-        }
-    }
-    if (tid == 0) {
-        for (int s = 0; s < kV5Stages; ++s) { ptx::mbar_init(&full[s], kCpAsync ? 32 : 1); ptx::mbar_init(&empty[s], 4); }
-        ptx::fence_barrier_init();
-        if (!kCpAsync) ptx::prefetch_tensormap(&A.tmT[prob]);
-    }
-    __syncthreads();
-
-    if (warp == 4) {
-        if (kCpAsync) {
-            // chunk q = 0..79 of a box row: column c = q >> 1, 16-byte half h = q & 1; lanes take q = lane + 32 m
-            const long long hwp = (long long)a.H * a.W;
-            const act_t* tbase = a.t[prob] + (long long)b * hwp * (2 * hp) + c0;
-            for (int k = 0; k < nblocks; ++k) {
-                const int s = k % kV5Stages;
-                ptx::mbar_wait(&empty[s], ((k / kV5Stages) & 1u) ^ 1u);
-                const uint32_t dst0 = ptx::smem_u32(ring + (size_t)s * kV4StageBytes);
-                const int yb = y0 - 2 + k * kRB;
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-#pragma unroll
-                    for (int rr = 0; rr < kRB; ++rr) {
-                        const int y = yb + rr;
-                        const bool row_in = y >= 0 && y < a.H;
-                        const act_t* rowp = tbase + (long long)(row_in ? y : 0) * a.W * (2 * hp) + hf * hp;
-#pragma unroll
-                        for (int m = 0; m < 3; ++m) {
-                            const int q = lane + 32 * m;
-                            if (q < 2 * kBoxCols) {
-                                const int c = q >> 1, h = q & 1;
-                                const int x = X0 - 1 + c;
-                                const bool in = row_in && x >= 0 && x < a.W;
-                                const act_t* src = rowp + (long long)(in ? x : 0) * (2 * hp) + h * 8;
-                                uint32_t o = (uint32_t)(rr * (kBoxCols * 32) + c * 32 + h * 16);
-                                o ^= ((o >> 7) & 1u) << 4;                       // SWIZZLE_32B
-                                const uint32_t dst = dst0 + hf * kHalfBoxBytes + o;
-                                const uint32_t nbytes = in ? 16u : 0u;           // 0 -> the 16 bytes are zero filled
-                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
-                                             :: "r"(dst), "l"(src), "r"(nbytes) : "memory");
-                            }
-                        }
-                    }
-                }
-                // this lane's copies of the stage -> one of the 32 arrivals the full barrier expects
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];"
-                             :: "r"(ptx::smem_u32(&full[s])) : "memory");
-            }
-            asm volatile("cp.async.wait_all;" ::: "memory");
-            return;
-        }
-        if (lane == 0) {
-            for (int k = 0; k < nblocks; ++k) {
-                const int s = k % kV5Stages;
-                ptx::mbar_wait(&empty[s], ((k / kV5Stages) & 1u) ^ 1u);
-                ptx::mbar_expect_tx(&full[s], 2 * kHalfBoxBytes);
-                uint8_t* dst = ring + (size_t)s * kV4StageBytes;
-                const int yb = y0 - 2 + k * kRB;
-                ptx::tma_load_4d(dst, &A.tmT[prob], &full[s], c0, X0 - 1, yb, b);
-                ptx::tma_load_4d(dst + kHalfBoxBytes, &A.tmT[prob], &full[s], hp + c0, X0 - 1, yb, b);
-            }
-        }
-        return;
-    }
-    const int half = warp >> 1, vec = warp & 1;
-    const int x = X0 + lane;
-    const bool col_in = x >= 0 && x < a.W;
-    const long long hw = (long long)a.H * a.W;
-    act_t* gdst = a.g[prob] + (long long)b * hw * hp + c0 + vec * 8;
-    const bool writer = half == 0 && lane >= 1 && lane <= kCols - 2 && col_in;
-    const uint4 zero4 = make_uint4(0, 0, 0, 0);
-
-    // the weight vectors of this thread's 8 channels, packed fp16, in registers for the whole strip
-    // (kW12Smem: only dwconv's; dwconv1/2's are re-read from shared memory -> 36 registers less, 3 CTAs / SM)
-    uint4 w0[9], w12[kW12Smem ? 1 : 9];
-    const uint4* w12p = kW12Smem ? reinterpret_cast<const uint4*>(s_w12) + (half * 2 + vec) : w12;
-    constexpr int kW12Stride = kW12Smem ? 4 : 1;
+    // dwconv's 9 weight vectors of this thread's 8 channels: packed fp16, in registers for the whole strip;
+    // dwconv1/2's are re-read from shared memory (36 registers less -> 128 registers, 3 CTAs / SM)
+    uint4 w0[9];
+    const uint4* w12p = reinterpret_cast<const uint4*>(s_w12) + (half * 2 + vec);
     {
         const float* p0 = a.w0[prob] + half * hp + c0 + vec * 8;                     // [tap][2*hp]
-        const float* p1 = (half == 0 ? a.w1[prob] : a.w2[prob]) + c0 + vec * 8;      // [tap][hp]
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
             const float4 a0 = __ldg(reinterpret_cast<const float4*>(p0 + t * 2 * hp));
             const float4 a1 = __ldg(reinterpret_cast<const float4*>(p0 + t * 2 * hp) + 1);
-            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-            if (!kW12Smem) {
-                b0 = __ldg(reinterpret_cast<const float4*>(p1 + t * hp));
-                b1 = __ldg(reinterpret_cast<const float4*>(p1 + t * hp) + 1);
-            }
             __half2 h;
             h = __floats2half2_rn(a0.x, a0.y); w0[t].x = *reinterpret_cast<uint32_t*>(&h);
             h = __floats2half2_rn(a0.z, a0.w); w0[t].y = *reinterpret_cast<uint32_t*>(&h);
             h = __floats2half2_rn(a1.x, a1.y); w0[t].z = *reinterpret_cast<uint32_t*>(&h);
             h = __floats2half2_rn(a1.z, a1.w); w0[t].w = *reinterpret_cast<uint32_t*>(&h);
-            if (!kW12Smem) {
-                h = __floats2half2_rn(b0.x, b0.y); w12[t].x = *reinterpret_cast<uint32_t*>(&h);
-                h = __floats2half2_rn(b0.z, b0.w); w12[t].y = *reinterpret_cast<uint32_t*>(&h);
-                h = __floats2half2_rn(b1.x, b1.y); w12[t].z = *reinterpret_cast<uint32_t*>(&h);
-                h = __floats2half2_rn(b1.z, b1.w); w12[t].w = *reinterpret_cast<uint32_t*>(&h);
-            }
         }
     }
 
@@ -707,7 +388,7 @@ iel_gate_v6_kernel(const __grid_constant__ IelV4Args A) {
         D.c = (rd >= 0 && rd < a.H && col_in) ? pf : zero4;           // d is zero outside the image
         D.l = shfl_up4(D.c);
         D.r = shfl_down4(D.c);
-        scatter(w12p, kW12Stride, D, qn, qm, qf);
+        scatter(w12p, 4, D, qn, qm, qf);
         const int yo = rd - 1;                                         // the output row finished now
         const uint4 xs = make_uint4(hadd2u(htanh2u(qf.x), dprev.x), hadd2u(htanh2u(qf.y), dprev.y),
                                     hadd2u(htanh2u(qf.z), dprev.z), hadd2u(htanh2u(qf.w), dprev.w));
@@ -726,14 +407,12 @@ iel_gate_v6_kernel(const __grid_constant__ IelV4Args A) {
         if (j + 2 < nrows) iter(j + 2, pB, pC, pA, qB, qC, qA, dprev);
     }
 }
-#endif  // !CIDNET_ACT_BF16
+#endif  // CIDNET_ACT_BF16
 
 int encode_map_generic_swz(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                            const uint32_t* box, int swizzle_bytes);   // conv_gemm.cu
 
 int launch_iel_gate(const IelGateArgs& a, cudaStream_t stream) {
-    static const bool use_v3 = getenv("CIDNET_IEL_V3") != nullptr;
-    if (use_v3) return launch_iel_gate_v3(a, stream);
     CIDNET_CHECK(a.hp % 16 == 0, CIDNET_ERR_INVALID, "iel: hp % 16");
     IelV4Args A;
     memset(&A, 0, sizeof A);
@@ -749,51 +428,18 @@ int launch_iel_gate(const IelGateArgs& a, cudaStream_t stream) {
     }
     const int strips = ceil_div(a.W, kCols - 2);
     dim3 grid(strips * (a.hp / 16), ceil_div(a.H, kRows), a.B * a.nprob);
+    int rc;
 #ifndef CIDNET_ACT_BF16
-    static const bool use_v4 = getenv("CIDNET_IEL_V4") != nullptr;      // fp32-accumulate variant (FHFMA)
-    static const int v6 = getenv("CIDNET_IEL_V6") ? atoi(getenv("CIDNET_IEL_V6")) : 3;   // 3 (default): dwconv weights in registers, 3 CTAs / SM; 2: all weights in registers, 2 CTAs / SM; 0 = v5
-    if (!use_v4 && v6) {
-        const size_t smem6 = 1024 + (size_t)kV5Stages * kV4StageBytes + 2 * 4 * kCols * sizeof(uint4) +
-                             2 * kV5Stages * sizeof(uint64_t) + 9 * 2 * 16 * sizeof(act_t) + 64;
-        static bool configured6 = false;
-        if (!configured6) {
-            CIDNET_CUDA_OK(cudaFuncSetAttribute(iel_gate_v6_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
-            CIDNET_CUDA_OK(cudaFuncSetAttribute(iel_gate_v6_kernel<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
-            CIDNET_CUDA_OK(cudaFuncSetAttribute(iel_gate_v6_kernel<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
-            configured6 = true;
-        }
-        // 2: all 18 weight vectors in registers, 2 CTAs / SM;  3: dwconv1/2 weights from shared memory, 3 CTAs / SM;
-        // 4: as 3 with the cp.async producer instead of TMA
-        if (v6 == 2)      iel_gate_v6_kernel<2, false, false><<<grid, kV4Threads, smem6, stream>>>(A);
-        else if (v6 == 3) iel_gate_v6_kernel<3, true, false><<<grid, kV4Threads, smem6, stream>>>(A);
-        else              iel_gate_v6_kernel<3, true, true><<<grid, kV4Threads, smem6, stream>>>(A);
-        CIDNET_CUDA_OK(cudaGetLastError());
-        return CIDNET_OK;
-    }
-    if (!use_v4) {
-        const size_t smem5 = 1024 + (size_t)kV5Stages * kV4StageBytes + 2 * 9 * 2 * 16 * sizeof(act_t) +
-                             2 * 2 * kCols * sizeof(uint4) + 2 * kV5Stages * sizeof(uint64_t) + 64;
-        static bool configured5 = false;
-        if (!configured5) {
-            CIDNET_CUDA_OK(cudaFuncSetAttribute(iel_gate_v5_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
-            CIDNET_CUDA_OK(cudaFuncSetAttribute(iel_gate_v5_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
-            configured5 = true;
-        }
-        static const bool three = getenv("CIDNET_IEL_3CTA") != nullptr;    // 3 CTAs / SM, no register spills
-        if (three) iel_gate_v5_kernel<3><<<grid, kV4Threads, smem5, stream>>>(A);
-        else       iel_gate_v5_kernel<4><<<grid, kV4Threads, smem5, stream>>>(A);
-        CIDNET_CUDA_OK(cudaGetLastError());
-        return CIDNET_OK;
-    }
-#endif
+    const size_t smem6 = 1024 + (size_t)kV5Stages * kV4StageBytes + 2 * 4 * kCols * sizeof(uint4) +
+                         2 * kV5Stages * sizeof(uint64_t) + 9 * 2 * 16 * sizeof(act_t) + 64;
+    if ((rc = ensure_dynamic_smem(reinterpret_cast<const void*>(iel_gate_v6_kernel), (int)smem6))) return rc;
+    iel_gate_v6_kernel<<<grid, kV4Threads, smem6, stream>>>(A);
+#else
     const size_t smem = 1024 + (size_t)kV4Stages * kV4StageBytes + 2 * 9 * 2 * 16 * sizeof(act_t) +
                         2 * 2 * 2 * kCols * sizeof(float4) + 2 * kV4Stages * sizeof(uint64_t) + 64;
-    static bool configured = false;
-    if (!configured) {
-        CIDNET_CUDA_OK(cudaFuncSetAttribute(iel_gate_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    if ((rc = ensure_dynamic_smem(reinterpret_cast<const void*>(iel_gate_v4_kernel), (int)smem))) return rc;
     iel_gate_v4_kernel<<<grid, kV4Threads, smem, stream>>>(A);
+#endif
     CIDNET_CUDA_OK(cudaGetLastError());
     return CIDNET_OK;
 }

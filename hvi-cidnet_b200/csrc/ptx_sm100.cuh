@@ -195,15 +195,9 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                          // layout = SWIZZLE_128B [61,64)
     return d;
 }
-// Same layout, but the tile may start on ANY 128-byte row of a 1024-byte aligned buffer (row-shifted
-// views of a halo tile for the 3x3 taps).  Measured on B200: the swizzle XOR uses absolute smem
-// address bits, so such a view needs NO base offset (use_base_offset = 0); the field [49,52) is only
-// kept switchable for experiments.
-__device__ __forceinline__ uint64_t umma_smem_desc_sw128_rowshift(uint32_t smem_addr, uint32_t use_base_offset) {
-    uint64_t d = umma_smem_desc_sw128(smem_addr);
-    if (use_base_offset) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
-    return d;
-}
+// The same descriptor also serves a tile that starts on ANY 128-byte row of a 1024-byte aligned buffer (row-shifted
+// views of a halo tile for the 3x3 taps): measured on B200, the swizzle XOR uses absolute smem address bits, so such
+// a view needs no base offset (field [49,52) stays 0).
 // instruction descriptor for kind::f16: fp32 accumulate, A/B K-major, M=128
 __host__ __device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t fmt /*0 fp16, 1 bf16*/, uint32_t n) {
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
