@@ -1,7 +1,12 @@
 #!/usr/bin/env python
 """bench.py -- CIDNet inference throughput (megapixels/s) on B200, per the driver contract.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg4|cfg3]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg4|cfg5|cfg3]
+
+With N > 1 and no --workload the headline line is still the cfg2 replica run (weak scaling), and the SAME process
+group then also measures the two multi-GPU configs BASELINE.json names -- cfg5 (one 4K image, row strips over the N
+GPUs, halos + Gram all-reduce over NCCL, CUDA-graph replay) and cfg4 (64 images split N ways) -- each with an in-run
+parity check, reported under `extra_workloads` in the one JSON line.
 
 A "step" is ONE pass of the hot path (CIDNet.forward through the C ABI / sm_100a kernels)
 over one batch of synthetic input of the named shape.  Default workload = BASELINE.json
@@ -225,6 +230,175 @@ def cpu_baseline_sample(sd, H, W, seconds=12.0, mssa=False):
             "sample": f"{n} forwards of 1x3x{h}x{w}, fp32 torch CPU (oracle port incl. dead I_LCA5), {dt:.1f} s"}
 
 
+def gpu_eager_baseline(B, H, W, mssa=False, steps=10):
+    """The reference's own GPU path as a bar (BASELINE.md 4.2 / SURVEY 8d): the oracle port of the reference forward --
+    the identical ATen op sequence, incl. the dead I_LCA5 -- run eagerly with torch on this GPU, in PyTorch's default
+    numeric mode (cuDNN convs in TF32) and in strict fp32.  Rank 0 only, outside every timed region of our arm."""
+    import torch
+    from oracle import cidnet_oracle as O
+    O.FAST_BILINEAR = True
+    dev = torch.device("cuda", torch.cuda.current_device())
+    sd = {k: v.to(dev) for k, v in O.make_state_dict(0, False, mssa=mssa).items()}
+    x = torch.rand(B, 3, H, W, device=dev)
+    out = {"impl": "oracle port of the reference forward, torch eager on cuda (cuDNN / cuBLAS)", "steps": steps,
+           "shape": [B, 3, H, W]}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for mode, tf32 in (("tf32", True), ("fp32", False)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = False
+            for _ in range(3):
+                O.forward(x, sd, run_dead_block=True, mssa=mssa)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                O.forward(x, sd, run_dead_block=True, mssa=mssa)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[mode + "_ms"] = ms
+            out[mode + "_MPps"] = B * H * W / ms / 1e3
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    out["MP/s"] = out["tf32_MPps"]
+    return out
+
+
+def measure_cfg5_sharded(model, dev, world, rank, steps, warmup, parity=True):
+    """ONE 4K image, rows sharded over the ranks (hvi-cidnet_b200/dist.py RowShardedCIDNet -> cidnet_forward_sharded):
+    conv halos and the partial Gram sums cross the GPUs over NCCL, kernels + exchanges replayed as one CUDA graph.
+    Returns a dict (same on every rank): device-timed ms/step (max over ranks), MP/s, exchange counts / bytes, e2e
+    (pinned strip -> H2D -> forward -> D2H of the owned rows), and -- computed inside this run -- the max-abs
+    difference of the gathered sharded result to the UNSHARDED forward of the same image on rank 0."""
+    import torch
+    import torch.distributed as dist
+    from hvi_cidnet_b200.dist import RowShardedCIDNet, strip_plan, strip_local_range
+    B, H, W, desc = WORKLOADS["cfg5"]
+    net = RowShardedCIDNet(model, halo=16, graph=True)
+    sh = strip_plan(H, world, rank, 16)
+    a, b = strip_local_range(sh)
+    g = torch.Generator().manual_seed(1234)
+    nimg = 3
+    hfull = [torch.rand(1, 3, H, W, generator=g) for _ in range(nimg)]           # same images on every rank
+    hloc = [t[:, :, a:b, :].contiguous().pin_memory() for t in hfull]
+    xs = [t.to(dev) for t in hloc]
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    nwarm, t0 = 0, time.perf_counter()
+    while nwarm < max(3, warmup) or time.perf_counter() - t0 < 0.4:
+        net.forward_strip(xs[nwarm % nimg], H)
+        nwarm += 1
+    barrier()
+    sampler = ClockSampler(dev.index)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        y, _ = net.forward_strip(xs[i % nimg], H)
+    e1.record()
+    sampler.poll_until(e1)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    halo_calls = sum(1 for e in net.comm.log if e[0] == "halo")
+    ar_calls = sum(1 for e in net.comm.log if e[0] == "allreduce")
+    sent = net.comm.bytes_sent
+    # end to end: pinned strip -> H2D -> sharded forward -> D2H of the owned rows
+    hy = torch.empty(1, 3, sh.row_end - sh.row_begin, W).pin_memory()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(steps):
+        y, _ = net.forward_strip(hloc[i % nimg].to(dev, non_blocking=True), H)
+        hy.copy_(y[:, :, sh.row_begin - a:sh.row_end - a, :], non_blocking=True)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(t[0]), float(t[1])
+    # in-run parity: gather the owned rows of image 0 on every rank, rank 0 compares with its own unsharded forward
+    par = None
+    if parity:
+        y, _ = net.forward_strip(xs[0], H)
+        own = y[:, :, sh.row_begin - a:sh.row_end - a, :].contiguous()
+        plans = [strip_plan(H, world, r, 16) for r in range(world)]
+        nmax = max(p.row_end - p.row_begin for p in plans)
+        pad = own.new_zeros((1, 3, nmax, W))
+        pad[:, :, :own.shape[2]] = own
+        bufs = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(bufs, pad)
+        pv = torch.zeros(2, device=dev, dtype=torch.float64)
+        if rank == 0:
+            full = torch.cat([bf[:, :, :p.row_end - p.row_begin] for bf, p in zip(bufs, plans)], dim=2)
+            ref = model(hfull[0].to(dev))
+            d = (full - ref).abs().amax(dim=1).flatten()
+            top = torch.topk(d, 4).values
+            # the reference's PHVIT black-pixel hole (tests/conftest.py::parity_error): report the pixels beyond 5e-4
+            # and the max over the rest; a healthy run has 0 such pixels
+            pv[0] = float(d[d <= 5e-4].max()) if bool((d <= 5e-4).any()) else float(top[0])
+            pv[1] = float((d > 5e-4).sum())
+            del full, ref
+        dist.broadcast(pv, 0)
+        par = {"parity_vs_unsharded_maxabs": float(pv[0]), "pixels_beyond_5e-4": int(pv[1])}
+    mp_step = H * W / 1e6
+    res = {"workload": f"cfg5: CIDNet 1x3x{H}x{W}, rows sharded over {world} GPUs (halo 16 rows), CUDA-graph replay "
+                       f"of kernels + NCCL exchanges ({net.replays} replays)",
+           "ms_per_step": ms_total / steps, "MP/s": mp_step * steps / (ms_total / 1e3), "steps": steps, "warmup": nwarm,
+           "halo_calls": halo_calls, "allreduce_calls": ar_calls, "bytes_sent": sent,
+           "e2e_ms_per_step": ms_e2e / steps, "e2e_MP/s": mp_step * steps / (ms_e2e / 1e3),
+           "h2d_bytes_per_step": hloc[0].numel() * 4, "d2h_bytes_per_step": hy.numel() * 4,
+           "local_rows_rank0": strip_local_range(strip_plan(H, world, 0, 16))[1], "graph_replays": net.replays,
+           "graph_error": getattr(net, "graph_error", None), "launches_per_step": model.num_launches(), "clocks": clocks}
+    if par:
+        res.update(par)
+    net.close()
+    torch.cuda.synchronize()
+    del net, xs
+    torch.cuda.empty_cache()
+    return res
+
+
+def measure_cfg4_batch(model, dev, world, rank, steps, warmup):
+    """64 images of 400x600 split contiguously over the ranks (strong scaling: fixed total work), no collective on the
+    data path.  In-run parity: the first image of the rank's share, run alone, against its slot in the batched result
+    (max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    B, H, W, desc = WORKLOADS["cfg4"]
+    from hvi_cidnet_b200.dist import shard_range
+    start, count = shard_range(B, world, rank)
+    g = torch.Generator(device=dev).manual_seed(4321 + rank)
+    ring = 3
+    xs = [torch.rand(count, 3, H, W, device=dev, generator=g) for _ in range(ring)]
+    for i in range(max(3, min(warmup, 5))):
+        model(xs[i % ring])
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        y = model(xs[i % ring])
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    yb = model(xs[0])
+    y1 = model(xs[0][0:1].contiguous())
+    d = (yb[0:1] - y1).abs().amax(dim=1).flatten()
+    t = torch.tensor([ms, float(d[d <= 5e-4].max()) if bool((d <= 5e-4).any()) else float(d.max()), float((d > 5e-4).sum())],
+                     device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    del xs, y, yb, y1
+    model._workspaces = {}
+    torch.cuda.empty_cache()
+    return {"workload": f"cfg4: CIDNet {B}x3x{H}x{W} batch split over {world} GPUs ({count} images on rank {rank})",
+            "ms_per_step": ms / steps, "MP/s": B * H * W / 1e6 * steps / (ms / 1e3), "steps": steps, "scaling": "strong",
+            "parity_batch_vs_single_maxabs": float(t[1]), "pixels_beyond_5e-4": int(t[2])}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -245,6 +419,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
 
+    extras_wanted = args.workload is None and world > 1 and not args.no_extras
+    if args.workload is None:
+        args.workload = "cfg2"
     B, H, W, desc = WORKLOADS[args.workload]
     if args.workload == "cfg4":
         B = max(1, B // world)               # batch-sharded: fixed total, per-rank share
@@ -334,6 +511,21 @@ def run_ours(args):
     assert nres == args.steps
     ms_e2e = f0.elapsed_time(f1)
 
+    # ---- the two multi-GPU configs of BASELINE.json, same process group (N > 1, default workload only) -------------
+    extras = None
+    if extras_wanted:
+        del xs, hx, hy, drv
+        model._workspaces = {}
+        torch.cuda.empty_cache()
+        extras = {}
+        try:
+            extras["cfg5"] = measure_cfg5_sharded(model, dev, world, rank, steps=min(args.steps, 10), warmup=3)
+        except Exception as e:               # never lose the headline line to an extra
+            extras["cfg5"] = {"error": repr(e)[:400]}
+        try:
+            extras["cfg4"] = measure_cfg4_batch(model, dev, world, rank, steps=min(args.steps, 5), warmup=3)
+        except Exception as e:
+            extras["cfg4"] = {"error": repr(e)[:400]}
     if world > 1:
         t = torch.tensor([ms_total, ms_e2e, ms_e2e_sync], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -357,7 +549,9 @@ def run_ours(args):
                 "cuda_core_fp32_peak_TFLOPs": 148 * 128 * 2 * 1.965e-3,    # 148 SMs x 128 FMA lanes x 2 x 1.965 GHz (HFMA2 issues at the same FMA rate)
                 "note": "achieved = algorithmic bytes (DESIGN.md) / CUDA-event time of that kernel inside the forward"}
         # DRAM traffic of the same kernel from the committed ncu capture of this workload (per launch)
-        tpath = os.path.join(ROOT, "profiles", f"r01_traffic_{args.workload}.json")
+        tpath = os.path.join(ROOT, "profiles", f"r02_traffic_{args.workload}.json")
+        if not os.path.exists(tpath):
+            tpath = os.path.join(ROOT, "profiles", f"r01_traffic_{args.workload}.json")
         if os.path.exists(tpath):
             tr = json.load(open(tpath))["per_launch"].get(top["name"])
             if tr:
@@ -365,6 +559,10 @@ def run_ours(args):
                 roof["traffic_source"] = os.path.relpath(tpath, ROOT)
                 roof["algorithmic_bytes_per_launch"] = tr["algorithmic_bytes"]
         cpu = cpu_baseline_sample(sd, H, W, mssa=args.variant == "mssa")
+        try:
+            eager = gpu_eager_baseline(min(B, 8), H, W, mssa=args.variant == "mssa")
+        except Exception as e:
+            eager = {"error": repr(e)[:300]}
         act = "fp16" if __import__("hvi_cidnet_b200._lib", fromlist=["lib"]).lib().cidnet_act_dtype() == 0 else "bf16"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": nwarm,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak" if args.workload != "cfg4" else "strong",
@@ -377,84 +575,34 @@ def run_ours(args):
                         "ms_per_step": ms_e2e / args.steps, "api": "StreamedCIDNet(model).run(pinned host batches) -> pinned host results",
                         "sync_loop_value": mp_step_all * args.steps / (ms_e2e_sync / 1e3),
                         "sync_loop_note": "reference-style loop: x.cuda() -> model(x) -> .cpu() per step on one stream"},
-                "gpu_launches": launches, "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "clocks": clocks}
+                "gpu_launches": launches, "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
+                "gpu_eager_baseline": eager, "clocks": clocks}
+        if extras is not None:
+            line["extra_workloads"] = extras
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 def run_cfg5_sharded(args, model, sd, wdesc, dev, world, rank, peaks):
-    """--workload cfg5 --gpus N>1 (BASELINE.json configs[4]): ONE 4K image, rows sharded over the ranks
-    (hvi-cidnet_b200/dist.py RowShardedCIDNet -> cidnet_forward_sharded); conv halos and the partial Gram
-    sums cross the GPUs over NCCL.  value: every rank's strip (+halo) resident in HBM; e2e: each rank
-    uploads its strip from pinned host memory and downloads its owned output rows every step."""
-    import torch
+    """--workload cfg5 --gpus N>1 (BASELINE.json configs[4]) as the headline line: see measure_cfg5_sharded."""
     import torch.distributed as dist
-    from hvi_cidnet_b200.dist import RowShardedCIDNet, strip_plan, strip_local_range
     B, H, W, desc = WORKLOADS["cfg5"]
-    net = RowShardedCIDNet(model, halo=16, graph=True)       # kernels + NCCL exchanges replayed as one CUDA graph
-    sh = strip_plan(H, world, rank, 16)
-    a, b = strip_local_range(sh)
-    g = torch.Generator().manual_seed(1234)
-    nimg = 3
-    hfull = [torch.rand(1, 3, H, W, generator=g) for _ in range(nimg)]           # same images on every rank
-    hloc = [t[:, :, a:b, :].contiguous().pin_memory() for t in hfull]
-    xs = [t.to(dev) for t in hloc]
-
-    def barrier():
-        dist.barrier()
-        torch.cuda.synchronize()
-
-    nwarm, t0 = 0, time.perf_counter()
-    while nwarm < max(3, args.warmup) or time.perf_counter() - t0 < 0.4:
-        net.forward_strip(xs[nwarm % nimg], H)
-        nwarm += 1
-    barrier()
-    sampler = ClockSampler(dev.index)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        y, _ = net.forward_strip(xs[i % nimg], H)
-    e1.record()
-    sampler.poll_until(e1)
-    barrier()
-    clocks = sampler.stop()
-    ms_total = e0.elapsed_time(e1)
-    launches = model.num_launches() * args.steps
-    halo_calls = sum(1 for e in net.comm.log if e[0] == "halo")
-    ar_calls = sum(1 for e in net.comm.log if e[0] == "allreduce")
-    sent = net.comm.bytes_sent
-    # end to end: pinned strip -> H2D -> sharded forward -> D2H of the owned rows
-    hy = torch.empty(1, 3, sh.row_end - sh.row_begin, W).pin_memory()
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for i in range(args.steps):
-        y, _ = net.forward_strip(hloc[i % nimg].to(dev, non_blocking=True), H)
-        hy.copy_(y[:, :, sh.row_begin - a:sh.row_end - a, :], non_blocking=True)
-    f1.record()
-    barrier()
-    ms_e2e = f0.elapsed_time(f1)
-    t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = float(t[0]), float(t[1])
+    r = measure_cfg5_sharded(model, dev, world, rank, args.steps, args.warmup)
     if rank == 0:
-        mp_step = H * W / 1e6
         act = "fp16" if __import__("hvi_cidnet_b200._lib", fromlist=["lib"]).lib().cidnet_act_dtype() == 0 else "bf16"
-        line = {"metric": METRIC, "value": mp_step * args.steps / (ms_total / 1e3), "unit": UNIT, "n_gpus": world,
-                "steps": args.steps, "warmup": nwarm, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        line = {"metric": METRIC, "value": r["MP/s"], "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": r["warmup"], "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": act, "data": "synthetic",
-                "config": {"workload": f"cfg5: CIDNet 1x3x{H}x{W}, rows sharded over {world} GPUs (halo 16 rows)", "H": H, "W": W,
-                           "weights": wdesc, "local_rows_rank0": b - a,
-                           "l2": f"{nimg} distinct images in rotation; all intermediates are rewritten every step",
-                           "parallelism": f"spatial row strips x{world}: {halo_calls} halo exchanges + {ar_calls} Gram all-reduces "
-                                          f"per forward over NCCL, {sent} halo bytes sent per rank per forward"},
-                "e2e": {"value": mp_step * args.steps / (ms_e2e / 1e3), "unit": UNIT,
-                        "h2d_bytes_per_step": hloc[0].numel() * 4, "d2h_bytes_per_step": hy.numel() * 4,
-                        "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "roofline": None, "cpu_baseline": None, "clocks": clocks}
+                "config": {"workload": r["workload"], "H": H, "W": W, "weights": wdesc, "local_rows_rank0": r["local_rows_rank0"],
+                           "l2": "3 distinct images in rotation; all intermediates are rewritten every step",
+                           "parallelism": f"spatial row strips x{world}: {r['halo_calls']} halo exchanges + {r['allreduce_calls']} Gram all-reduces "
+                                          f"per forward over NCCL, {r['bytes_sent']} halo bytes sent per rank per forward"},
+                "e2e": {"value": r["e2e_MP/s"], "unit": UNIT, "h2d_bytes_per_step": r["h2d_bytes_per_step"],
+                        "d2h_bytes_per_step": r["d2h_bytes_per_step"], "ms_per_step": r["e2e_ms_per_step"]},
+                "gpu_launches": r["launches_per_step"] * args.steps, "roofline": None, "cpu_baseline": None,
+                "parity_vs_unsharded_maxabs": r.get("parity_vs_unsharded_maxabs"), "clocks": r["clocks"]}
         print(json.dumps(line), flush=True)
-    net.close()
     dist.destroy_process_group()
 
 
@@ -544,11 +692,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: cfg2 (BASELINE.json configs[1]); with --gpus N > 1 and no --workload the line also carries "
+                         "`extra_workloads` (cfg5 row-sharded, cfg4 batch-split)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra_workloads of a default multi-GPU run")
     ap.add_argument("--variant", default="base", choices=["base", "mssa"],
                     help="base = net/CIDNet.py (BASELINE.json's model); mssa = the fork's net/CIDNet_MSSA.py")
     args = ap.parse_args()
     if args.impl == "reference":
+        args.workload = args.workload or "cfg2"
         run_reference(args)
     elif args.workload == "cfg3":
         run_hvi(args)

@@ -70,6 +70,9 @@ SIGNATURES = {
     "cidnet_test_conv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_float, C.c_void_p]),
+    # unit-test hook (csrc/api.cu): ctx, n, x_i, x_hv, after_cab_i, after_cab_hv, out_i, out_hv, B, H, W, stat_y0, stat_y1, stream
+    "cidnet_test_lca_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }
 
 

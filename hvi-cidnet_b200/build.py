@@ -65,11 +65,15 @@ def compile_one(src, extra, hdig, force, verbose, objdir=OBJ):
     return src, r.stderr, True
 
 
-def build(force=False, bf16=False, verbose=False):
-    objdir = OBJ + ("_bf16" if bf16 else "")
+def build(force=False, bf16=False, verbose=False, groups3=False):
+    """groups3: experimental build with a third epilogue warpgroup in the 1x1 conv GEMMs (libcidnet_b200_g3.so; see
+    conv_gemm.cu launch_conv_gemm) -- used once per round to re-check that experiment, never shipped as the default."""
+    objdir = OBJ + ("_bf16" if bf16 else "") + ("_g3" if groups3 else "")
     lib = LIB_BF16 if bf16 else LIB
+    if groups3:
+        lib = lib[:-3] + "_g3.so"
     os.makedirs(objdir, exist_ok=True)
-    extra = ["-DCIDNET_ACT_BF16"] if bf16 else []
+    extra = (["-DCIDNET_ACT_BF16"] if bf16 else []) + (["-DCIDNET_GEMM_GROUPS3"] if groups3 else [])
     hdig = headers_digest(extra)
     srcs = sources()
     rebuilt = False
@@ -95,6 +99,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--bf16", action="store_true")
+    ap.add_argument("--groups3", action="store_true")
     ap.add_argument("-v", "--verbose", action="store_true")
     a = ap.parse_args()
-    print(build(a.force, a.bf16, a.verbose))
+    print(build(a.force, a.bf16, a.verbose, a.groups3))

@@ -482,21 +482,29 @@ struct Fwd {
     void tap(const std::string& name, const void* p, int C, int l, int pitch, bool f32 = false) {
         ctx->taps[name] = Tap{p, C, P.H[l], P.W[l], pitch, f32};
     }
-    // profiling mark: called right before every kernel launch
-    void mark(const std::string& name, double bytes, double flops) {
+    // profiling mark: called right before every kernel launch (br = the graph branch / stream the launch goes to).
+    // Launch i owns events 2i (recorded before it) and 2i+1 (recorded after it, on ITS stream, when the next mark
+    // comes -- nothing but fork / join event edges is enqueued in between).  While profiling, the forward runs eagerly
+    // with the same two-stream split as the captured graph, so a kernel's time is the one it has in that schedule.
+    cudaStream_t pending = nullptr; bool has_pending = false;
+    void close_pending() {
+        if (has_pending) cudaEventRecord(ctx->events[2 * ctx->recs.size() - 1], pending);
+        has_pending = false;
+    }
+    void mark(const std::string& name, double bytes, double flops, int br = 0) {
         ++launches;
         if (!ctx->profiling) return;
+        close_pending();
         const size_t i = ctx->recs.size();
-        if (ctx->events.size() <= i + 1) {
-            ctx->events.resize(i + 2, nullptr);
-        }
-        for (size_t j = i; j <= i + 1; ++j)
+        if (ctx->events.size() < 2 * i + 2) ctx->events.resize(2 * i + 2, nullptr);
+        for (size_t j = 2 * i; j < 2 * i + 2; ++j)
             if (ctx->events[j] == nullptr) cudaEventCreate(&ctx->events[j]);
-        cudaEventRecord(ctx->events[i], st);
+        cudaEventRecord(ctx->events[2 * i], S(br));
         ctx->recs.push_back({name, bytes, flops});
+        pending = S(br); has_pending = true;
     }
     void finish_marks() {
-        if (ctx->profiling && !ctx->recs.empty()) cudaEventRecord(ctx->events[ctx->recs.size()], st);
+        if (ctx->profiling) close_pending();
     }
     int gemm(ConvGemmLaunch& L, const std::string& name, int br = 0, bool paired = true) {
         const PackedWeights& w = *L.wt;
@@ -505,7 +513,7 @@ struct Fwd {
         double bytes = px_in * w.cin * 2 + px_out * w.n_out * 2 + (double)w.n_out * w.cin * w.taps * 2 * (w.n_img > 1 ? L.B : 1);
         if (L.in2) bytes += px_out * L.wt2->cin * 2;
         if (L.up) bytes += px_out / 4 * w.n_out * 2;
-        mark(name, bytes, 2.0 * px_in * w.n_out * w.cin * w.taps);
+        mark(name, bytes, 2.0 * px_in * w.n_out * w.cin * w.taps, br);
         if (par && paired) L.max_ctas = device_sm_count() / 2;
         return live() ? launch_conv_gemm(L, S(br)) : CIDNET_OK;
     }
@@ -648,6 +656,7 @@ struct Fwd {
             if (P.B == 1) fw.n_img = 1;
             if ((rc = gemm(A, "L" + std::to_string(l) + ".cab_attnv_proj_res", s, both))) return rc;
             setm(P.xp[l][s], m_dw);
+            tap(std::string(s == 0 ? "I_LCA" : "HV_LCA") + std::to_string(n) + ".after_cab", P.xp[l][s], C, l, Cp);
         }
         // the IEL gate chains two depthwise 3x3: two valid halo rows of x' (project_in is recomputed on them)
         if ((rc = ensure({{S.lca[0].live ? P.xp[l][0] : nullptr, l, Cp}, {P.xp[l][1], l, Cp}}, 2))) return rc;
@@ -917,16 +926,18 @@ extern "C" int cidnet_forward(cidnet_ctx* ctx, const float* rgb_in, float* rgb_o
     if (ge) ge->seen++;
     ctx->taps.clear();
     ctx->recs.clear();
+    static const bool one_branch = getenv("CIDNET_ONE_BRANCH") != nullptr;
+    if ((capture || ctx->profiling) && !one_branch) {
+        // two branches: the I and HV launches of a pair on two streams (graph capture; or eagerly while profiling, so
+        // that the per-kernel times describe the schedule the replayed graph runs)
+        if (!ctx->cap_stream2) CIDNET_CUDA_OK(cudaStreamCreateWithFlags(&ctx->cap_stream2, cudaStreamNonBlocking));
+        if (!ctx->ev_fork) CIDNET_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        if (!ctx->ev_join) CIDNET_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+        f.par = true; f.st2 = ctx->cap_stream2;
+    }
     if (capture) {
         if (!ctx->cap_stream) CIDNET_CUDA_OK(cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking));
         f.st = ctx->cap_stream;
-        static const bool one_branch = getenv("CIDNET_ONE_BRANCH") != nullptr;
-        if (!one_branch) {
-            if (!ctx->cap_stream2) CIDNET_CUDA_OK(cudaStreamCreateWithFlags(&ctx->cap_stream2, cudaStreamNonBlocking));
-            if (!ctx->ev_fork) CIDNET_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-            if (!ctx->ev_join) CIDNET_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-            f.par = true; f.st2 = ctx->cap_stream2;
-        }
         CIDNET_CUDA_OK(cudaStreamBeginCapture(f.st, cudaStreamCaptureModeRelaxed));
     }
     int rc = f.run(rgb_in, rgb_out, k_dev, gated, alpha_s, gated2, alpha);
@@ -1118,7 +1129,7 @@ extern "C" int cidnet_profile_get(cidnet_ctx* ctx, int i, char* name, int name_c
     if (name && name_cap > 0) { snprintf(name, name_cap, "%s", r.name.c_str()); }
     if (alg_bytes) *alg_bytes = r.bytes;
     if (flops) *flops = r.flops;
-    if (ms) CIDNET_CUDA_OK(cudaEventElapsedTime(ms, ctx->events[i], ctx->events[i + 1]));
+    if (ms) CIDNET_CUDA_OK(cudaEventElapsedTime(ms, ctx->events[2 * i], ctx->events[2 * i + 1]));
     return CIDNET_OK;
 }
 
@@ -1126,5 +1137,49 @@ extern "C" int cidnet_profile_get(cidnet_ctx* ctx, int i, char* name, int name_c
 extern "C" int cidnet_set_graphs(cidnet_ctx* ctx, int enable) {
     CIDNET_CHECK(ctx, CIDNET_ERR_INVALID, "set_graphs: null ctx");
     ctx->use_graphs = enable != 0;
+    return CIDNET_OK;
+}
+
+// ---- unit-test hook: ONE LCA stage pair, isolated from the rest of the network ---------------------------------
+// Runs I_LCA<n>(x_i, x_hv) and HV_LCA<n>(x_hv, x_i) (net/LCA.py:71-93) of a finalized context on the given fp32 NCHW
+// tensors [B, C, H, W] (H, W = the resolution of the stage's level; multiples of 1) and returns, as fp32 NCHW, the
+// tensors after the attention (x + CAB(norm x, norm y)) and the block outputs.  stat_y0 / stat_y1 (0, 0 = all rows)
+// restrict the rows that enter the Gram / sum q^2 / sum k^2 statistics, exactly as the row-strip sharded forward
+// restricts them to a rank's owned rows.  Allocates scratch memory and synchronises (tests only).
+extern "C" CIDNET_API int cidnet_test_lca_stage(cidnet_ctx* ctx, int n, const float* x_i, const float* x_hv,
+                                                float* after_cab_i, float* after_cab_hv, float* out_i, float* out_hv,
+                                                int B, int H, int W, int stat_y0, int stat_y1, void* stream_) {
+    CIDNET_CHECK(ctx && ctx->finalized, CIDNET_ERR_STATE, "test_lca_stage: weights not finalized");
+    CIDNET_CHECK(n >= 1 && n <= 6 && x_i && x_hv && B > 0 && H > 0 && W > 0, CIDNET_ERR_INVALID, "test_lca_stage: bad arguments");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int l = n <= 3 ? n : 7 - n;
+    const int C = kCh[l], Cp = act_pitch(C);
+    if (stat_y1 <= 0) { stat_y0 = 0; stat_y1 = H; }
+    CIDNET_CHECK(stat_y0 >= 0 && stat_y0 < stat_y1 && stat_y1 <= H, CIDNET_ERR_INVALID, "test_lca_stage: bad row range");
+    Fwd f;
+    f.ctx = ctx; f.st = st;
+    make_plan(&f.P, nullptr, B, H << l, W << l);
+    void* ws = nullptr;
+    CIDNET_CUDA_OK(cudaMalloc(&ws, (size_t)f.P.bytes));
+    make_plan(&f.P, ws, B, H << l, W << l);
+    // a "shard" of one rank whose owned rows are [stat_y0, stat_y1): no exchange, but the statistics see only those rows
+    f.sh.on = true; f.sh.nranks = 1; f.sh.gH = H << l;
+    f.sh.halo_top = stat_y0 << l; f.sh.halo_bot = (H - stat_y1) << l;
+    act_t* xi = f.P.enc_i[l]; act_t* xh = f.P.enc_hv[l];
+    act_t* oi = f.P.lca_i[n]; act_t* oh = f.P.lca_hv[n];
+    ctx->last_B = B;
+    int rc = launch_nchw_to_nhwc(x_i, xi, B, C, H, W, Cp, st);
+    if (!rc) rc = launch_nchw_to_nhwc(x_hv, xh, B, C, H, W, Cp, st);
+    const bool i_live = ctx->stage[n - 1].lca[0].live;
+    if (!rc) rc = f.lca_stage(n, xi, xh, i_live ? oi : nullptr, oh);
+    if (!rc && after_cab_i && i_live) rc = launch_nhwc_to_nchw(f.P.xp[l][0], after_cab_i, B, C, H, W, Cp, st);
+    if (!rc && after_cab_hv) rc = launch_nhwc_to_nchw(f.P.xp[l][1], after_cab_hv, B, C, H, W, Cp, st);
+    if (!rc && out_i && i_live) rc = launch_nhwc_to_nchw(oi, out_i, B, C, H, W, Cp, st);
+    if (!rc && out_hv) rc = launch_nhwc_to_nchw(oh, out_hv, B, C, H, W, Cp, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(ws);
+    if (rc) return rc;
+    CIDNET_CHECK(e == cudaSuccess, CIDNET_ERR_CUDA, std::string("test_lca_stage: ") + cudaGetErrorString(e));
     return CIDNET_OK;
 }

@@ -23,7 +23,17 @@ __host__ __device__ __forceinline__ act_t f2act(float v) { return __float2bfloat
 typedef __half act_t;
 #define CIDNET_UMMA_FMT 0u
 __host__ __device__ __forceinline__ float act2f(act_t v) { return __half2float(v); }
-__host__ __device__ __forceinline__ act_t f2act(float v) { return __float2half_rn(v); }
+// SATURATING on the device: a value beyond +-65504 becomes +-65504 instead of inf (an inf would turn into NaN in the
+// next LayerNorm / softmax); F2FP.SATFINITE, the same single instruction as the plain conversion
+__host__ __device__ __forceinline__ act_t f2act(float v) {
+#ifdef __CUDA_ARCH__
+    unsigned short h;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+    return __ushort_as_half(h);
+#else
+    return __float2half_rn(v);
+#endif
+}
 #endif
 
 void set_error(const std::string& msg);

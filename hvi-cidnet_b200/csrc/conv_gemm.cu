@@ -73,10 +73,12 @@ __device__ __forceinline__ float prelu_f(float v, float slope) { return v >= 0.f
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {      // one F2FP instruction
 #ifdef CIDNET_ACT_BF16
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-#else
-    __half2 h = __floats2half2_rn(lo, hi);
-#endif
     return *reinterpret_cast<uint32_t*>(&h);
+#else
+    uint32_t d;                                                       // saturating: +-65504 instead of inf (common.cuh f2act)
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+#endif
 }
 __device__ __forceinline__ uint4 pack8(const float* f) {
     return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
@@ -580,7 +582,10 @@ static int launch_mode_g(const ConvGemmArgs& args, dim3 grid, size_t smem, cudaS
 }
 template <int kMode>
 static int launch_mode(const ConvGemmArgs& args, dim3 grid, size_t smem, cudaStream_t stream, int groups) {
-    (void)groups;      // only the 2-group kernels are instantiated (see launch_conv_gemm for the 3-group experiment)
+#ifdef CIDNET_GEMM_GROUPS3
+    if (groups == 3) return launch_mode_g<kMode, 3>(args, grid, smem, stream);
+#endif
+    (void)groups;
     return launch_mode_g<kMode, 2>(args, grid, smem, stream);
 }
 
@@ -595,10 +600,16 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
     CIDNET_CHECK(!(L.flat && wt.taps != 1), CIDNET_ERR_INVALID, "conv_gemm: flat tiling is for 1x1 only");
     const int ksub = L.mode == EPI_DOWN ? 2 : 1;
     CIDNET_CHECK(2 * ksub * wt.block_n <= 512, CIDNET_ERR_INVALID, "conv_gemm: accumulators exceed TMEM");
-    // epilogue groups: always 2.  A third group for the 1x1 layers (3 accumulators fit the 512 TMEM columns; 448
-    // threads, <= 146 registers) was measured on B200: no layer got faster at cfg 2 or 16x400x600, and the 400x600
-    // forward lost parity (2.9e-2) -- not root-caused, so only the 2-group kernels are instantiated.
-    const int kEpiGroups = 2;
+    // epilogue groups: 2.  A third group for the 1x1 layers was measured on B200 in round 1: no layer got faster at cfg 2
+    // or 16x400x600, and the 400x600 forward lost parity (2.9e-2).  Root cause (round 2, `build.py --groups3` experiment,
+    // profiles/r02_summary.md): the round-1 experiment sized TMEM as the next power of two >= 3 * block_n columns
+    // without checking it against the 512 columns an SM has -- the q|kv GEMMs (block_n = 216 / 144 x 3 = 648 / 432)
+    // asked tcgen05.alloc for 1024 columns.  With the guard below (3 groups only where 3 accumulators fit) the 3-group
+    // build is parity-clean; it is still not faster, so the shipped library instantiates the 2-group kernels only.
+    int kEpiGroups = 2;
+#ifdef CIDNET_GEMM_GROUPS3
+    if (wt.taps == 1 && L.mode != EPI_DOWN && 3 * wt.block_n <= 512) kEpiGroups = 3;
+#endif
 
     ConvGemmArgs a;
     memset(&a, 0, sizeof a);

@@ -115,7 +115,15 @@ class CIDNet(nn.Module, PyTorchModelHubMixin):
 
     # ------------------------------------------------------------------ native context
     def _weights_signature(self):
-        return tuple((p._version, p.data_ptr()) for n, p in self.named_parameters() if n != "trans.density_k")
+        """Changes whenever a packed parameter may have changed: in-place updates bump `_version`, re-assignment
+        (load_state_dict(assign=True), .to(), .half()) changes `data_ptr`.  density_k is excluded on purpose: the
+        kernels read it from device memory on every call.  The parameter list is cached (walking named_parameters()
+        costs more than the 190 attribute reads below)."""
+        ps = self.__dict__.get("_packed_params")
+        if ps is None or len(ps) != sum(1 for _ in self.parameters()) - 1:
+            ps = [p for n, p in self.named_parameters() if n != "trans.density_k"]
+            self.__dict__["_packed_params"] = ps
+        return hash(tuple((p._version, p.data_ptr()) for p in ps))
 
     def _ensure_ctx(self, device):
         lib = _lib.lib()
@@ -143,6 +151,27 @@ class CIDNet(nn.Module, PyTorchModelHubMixin):
             _lib.check(lib.cidnet_set_weight(self._ctx, name.encode(), t.data_ptr(), t.numel()))
         with torch.cuda.device(self._ctx_device):
             _lib.check(lib.cidnet_finalize_weights(self._ctx))
+
+    # copy.deepcopy / pickle / torch.save(model): the native handle and the workspaces stay behind; the copy lazily
+    # creates its own context on its first forward (the reference nn.Module supports all three)
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_ctx"], st["_ctx_device"], st["_synced"], st["_workspaces"] = None, None, None, {}
+        st.pop("_packed_params", None)
+        return st
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__getstate__().items():
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
+
+    def _apply(self, fn, *a, **kw):
+        # .to() / .cuda() / .half() replace parameter storage: forget the cached parameter list
+        self.__dict__.pop("_packed_params", None)
+        return super()._apply(fn, *a, **kw)
 
     def _release(self):
         ctx = self.__dict__.get("_ctx")
@@ -174,10 +203,10 @@ class CIDNet(nn.Module, PyTorchModelHubMixin):
     def forward(self, x, out=None):
         """`out` (optional, extension): a CUDA fp32 tensor of x's shape to write the result into (the
         streamed driver keeps a ring of them); by default a fresh tensor is returned like the reference."""
-        dtypes = x.dtype
         if not isinstance(x, torch.Tensor) or not x.is_cuda:
             raise RuntimeError(f"CIDNet.forward: input is on {getattr(x, 'device', None)}; the B200-native path has no "
                                "CPU fallback -- move the model and the input to an sm_100 CUDA device")
+        dtypes = x.dtype
         if x.dim() != 4 or x.shape[1] != 3:
             raise RuntimeError(f"CIDNet.forward expects [B,3,H,W], got {tuple(x.shape)}")
         B, _, H, W = x.shape
@@ -199,9 +228,11 @@ class CIDNet(nn.Module, PyTorchModelHubMixin):
             ctx = self._ensure_ctx(x.device)
             ws, ws_ptr, ws_bytes = self._workspace(B, H, W, x.device)
             t = self.trans
-            kd = k.detach()
-            kptr = kd.data_ptr() if kd.dtype == torch.float32 else None
             t._note_hvit_called()                                   # this_k = k.item(), lazily (HVI_transform.py:38)
+            # the kernels read k from device memory: the live parameter when it is fp32, else the fp32 snapshot just taken
+            # (model.half() / .double()), never a value cached at the last weight sync
+            kd = k.detach() if k.dtype == torch.float32 else t._this_k_dev
+            kptr = kd.data_ptr()
             _lib.check(_lib.lib().cidnet_forward(ctx, xin.data_ptr(), out.data_ptr(), B, H, W, ws_ptr, ws_bytes, kptr,
                                                  int(bool(t.gated)), float(t.alpha_s), int(bool(t.gated2)),
                                                  float(t.alpha), _lib.stream_ptr(x.device)))
@@ -245,6 +276,25 @@ class CIDNet(nn.Module, PyTorchModelHubMixin):
             _lib.check(lib.cidnet_read_tap(self._ctx, name.encode(), out.data_ptr(), out.numel(), dims,
                                            _lib.stream_ptr(self._ctx_device)))
         return out
+
+    def run_lca_stage(self, n, x_i, x_hv, stat_rows=None):
+        """Unit-test helper (cidnet_test_lca_stage): LCA stage n (1..6) alone on fp32 CUDA tensors [B,C,H,W] at the
+        stage's own resolution.  Returns dict(after_cab_i, after_cab_hv, out_i, out_hv); the I entries are None for
+        the base graph's dead I_LCA5.  stat_rows=(y0, y1) restricts the attention statistics to those rows."""
+        lib = _lib.lib()
+        dev = x_i.device
+        x_i, x_hv = _lib.require_cuda_f32(x_i, "x_i"), _lib.require_cuda_f32(x_hv, "x_hv")
+        with torch.cuda.device(dev):
+            ctx = self._ensure_ctx(dev)
+            B, _, H, W = x_i.shape
+            outs = [torch.empty_like(x_i) for _ in range(4)]
+            y0, y1 = stat_rows if stat_rows is not None else (0, 0)
+            _lib.check(lib.cidnet_test_lca_stage(ctx, int(n), x_i.data_ptr(), x_hv.data_ptr(), outs[0].data_ptr(),
+                                                 outs[1].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(), B, H, W,
+                                                 int(y0), int(y1), _lib.stream_ptr(dev)))
+        i_live = not (n == 5 and self._variant == 0)
+        return {"after_cab_i": outs[0] if i_live else None, "after_cab_hv": outs[1],
+                "out_i": outs[2] if i_live else None, "out_hv": outs[3]}
 
     def set_profiling(self, enable):
         """record a CUDA event before every kernel launch of forward() (see cidnet_profile_*)."""

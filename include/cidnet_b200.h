@@ -183,6 +183,21 @@ CIDNET_API int cidnet_profile_count(cidnet_ctx* ctx);
 CIDNET_API int cidnet_profile_get(cidnet_ctx* ctx, int i, char* name, int name_cap, float* ms,
                                   double* alg_bytes, double* flops);
 
+/* ---- unit-test hooks (tests/ only: they allocate scratch memory and synchronise) ------------
+ * cidnet_test_conv: one implicit-GEMM convolution with one of the four fused epilogues
+ *   x dev fp32 [B,Cin,H,W]; w_host host fp32 [Cout,Cin,k,k]; aux dev fp32 (residual / low-res tensor) or NULL;
+ *   ln_host host fp32 [ln_w(Cin) | ln_b(Cin)] for mode 1; mode 0 STORE, 1 LN, 2 DOWN, 3 UP; out dev fp32.
+ * cidnet_test_lca_stage: ONE LCA stage pair of a finalized context, isolated from the rest of the network
+ *   (I_LCA<n>(x_i, x_hv), HV_LCA<n>(x_hv, x_i), net/LCA.py:71-93) on fp32 NCHW tensors [B,C,H,W] at the stage's
+ *   own resolution; returns x + CAB(..) ("after_cab") and the block outputs.  stat_y0/stat_y1 (0,0 = all rows)
+ *   restrict the rows entering the Gram / sum q^2 / sum k^2 exactly as row-strip sharding does. */
+CIDNET_API int cidnet_test_conv(const float* x, const float* w_host, const float* aux, const float* ln_host, float* out,
+                                int B, int Cin, int H, int W, int Cout, int ksize, int mode, int flat, float prelu,
+                                void* stream);
+CIDNET_API int cidnet_test_lca_stage(cidnet_ctx* ctx, int n, const float* x_i, const float* x_hv, float* after_cab_i,
+                                     float* after_cab_hv, float* out_i, float* out_hv, int B, int H, int W,
+                                     int stat_y0, int stat_y1, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

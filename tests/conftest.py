@@ -29,21 +29,49 @@ def pytest_collection_modifyitems(config, items):
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
-def max_err_robust(y, ref, max_outlier_px=3):
-    """max |y - ref| over all pixels except at most `max_outlier_px` of them.
+def hue_wrap_candidates(out_hvi, k, band=1e-3):
+    """Pixels of the ORACLE's output_hvi (net/CIDNet.py:119) that sit on the one discontinuity of the reference's PHVIT
+    (net/HVI_transform.py:63-107): the hue angle atan2(V', H') is ~0, so `h % 1` can come out as exactly 1.0, `hi == 6`
+    matches none of the six sextant masks and the pixel is BLACK.  A difference of the order of the forward's own
+    error (1e-4) moves a pixel on or off that set.  Returns a bool mask [B, H, W]: H' > 0 and |V'| <= band."""
+    import math
+    import torch
+    eps = 1e-8
+    Hc, Vc, Ic = out_hvi[:, 0].clamp(-1, 1), out_hvi[:, 1].clamp(-1, 1), out_hvi[:, 2].clamp(0, 1)
+    cs = ((Ic * 0.5 * math.pi).sin() + eps).pow(k)
+    Hn, Vn = (Hc / (cs + eps)).clamp(-1, 1), (Vc / (cs + eps)).clamp(-1, 1)
+    return (Hn > 0) & (Vn.abs() <= band)
 
-    The reference's PHVIT (net/HVI_transform.py:63-107) is discontinuous on a measure-zero set: a hue that
-    lands exactly on the wrap (h*6 == 6 after the `% 1`) matches none of the six sextant masks and the pixel
-    comes out BLACK.  A last-bit difference upstream (e.g. the order of the Gram's fp32 atomics, which is run
-    dependent) can move a pixel on or off that set, changing it by ~1.0 while every other pixel agrees to 1e-4.
-    Observed about once per hundred 400x600 forwards.  Such pixels are excluded (and counted) here."""
+
+def parity_error(y, ref, tol, out_hvi=None, k=None, max_outliers=3):
+    """max |y - ref| over the pixels, after EXCUSING (not silently dropping) the reference's black-pixel hole:
+    a pixel whose error exceeds `tol` is excused only if (a) it is exactly black (all channels 0) in y or in ref,
+    (b) there are at most `max_outliers` of them, and (c) -- when the oracle's `out_hvi` and `k` are given -- the
+    oracle itself puts that pixel on the hue wrap (hue_wrap_candidates).  Anything else fails the assertion.
+    Returns (max error over the remaining pixels, number of excused pixels, bool mask [B,H,W] of the pixels kept)."""
     import torch
     d = (y - ref).abs()
-    if d.dim() == 4:
-        d = d.amax(dim=1)                       # per pixel, over channels
-    flat = d.flatten()
-    k = min(max_outlier_px, flat.numel() - 1)
-    if k <= 0:
-        return float(flat.max())
-    top = torch.topk(flat, k + 1).values
-    return float(top[-1])
+    per_px = d.amax(dim=1) if d.dim() == 4 else d
+    bad = (per_px > tol).nonzero()
+    n_bad = int(bad.shape[0])
+    assert n_bad <= max_outliers, f"{n_bad} pixels differ by more than {tol} (max {float(per_px.max()):.3e})"
+    if n_bad == 0:
+        return float(per_px.max()), 0, torch.ones_like(per_px, dtype=torch.bool)
+    cand = hue_wrap_candidates(out_hvi, k) if out_hvi is not None else None
+    keep = torch.ones_like(per_px, dtype=torch.bool)
+    for idx in bad.tolist():
+        b, yy, xx = idx
+        black = bool((y[b, :, yy, xx] == 0).all()) or bool((ref[b, :, yy, xx] == 0).all())
+        assert black, f"pixel {idx}: error {float(per_px[b, yy, xx]):.3e} and not the black-pixel hole (y={y[b, :, yy, xx].tolist()}, ref={ref[b, :, yy, xx].tolist()})"
+        if cand is not None:
+            assert bool(cand[b, yy, xx]), f"pixel {idx}: black in one output but the oracle's hue is not on the wrap"
+        keep[b, yy, xx] = False
+    return float(per_px[keep].max()), n_bad, keep
+
+
+def psnr_kept(y, ref, keep):
+    """PSNR over the kept pixels only (see parity_error)."""
+    import torch
+    m = keep[:, None].expand_as(y)
+    mse = float(((y - ref)[m] ** 2).mean())
+    return float("inf") if mse == 0 else 10.0 * __import__("math").log10(1.0 / mse)

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import cidnet_oracle as O
-from conftest import GOLDEN, max_err_robust
+from conftest import GOLDEN, parity_error, psnr_kept
 
 pytestmark = pytest.mark.gpu
 MAXABS, PSNR = 2e-3, 50.0
@@ -21,11 +21,15 @@ def model():
     return CIDNet().cuda().eval()
 
 
-def _check(y, ref):
+def _check(y, ref, x, sd, **kw):
+    """2e-3 / 50 dB on the clamped output; a pixel may exceed it only on the reference's black-pixel hole, verified
+    against the oracle's own output_hvi at that pixel (conftest.parity_error)."""
+    taps = {}
+    O.forward(x, sd, taps=taps, **kw)
     y, ref = y.clamp(0, 1), ref.clamp(0, 1)
-    err = max_err_robust(y, ref)             # all but <= 3 pixels (PHVIT's black-pixel discontinuity, see conftest)
-    ps = O.psnr(y, ref)
-    assert err <= MAXABS and ps >= PSNR, f"max-abs {err:.3e}, PSNR {ps:.1f} dB"
+    err, excused, keep = parity_error(y, ref, MAXABS, taps["out_hvi"], float(sd["trans.density_k"].reshape(-1)[0]))
+    ps = psnr_kept(y, ref, keep)
+    assert err <= MAXABS and ps >= PSNR, f"max-abs {err:.3e}, PSNR {ps:.1f} dB, {excused} excused"
     return err, ps
 
 
@@ -38,7 +42,11 @@ def test_golden_reference_outputs(model, seed):
     x = torch.from_numpy(g["x"]).cuda()
     with torch.no_grad():
         y = model(x).cpu()
-    _check(y, torch.from_numpy(g["y"]))
+    _check(y, torch.from_numpy(g["y"]), torch.from_numpy(g["x"]), sd)
+    # output_hvi (before PHVIT, no discontinuity): no pixel is excused
+    taps = {}
+    O.forward(torch.from_numpy(g["x"]), sd, taps=taps)
+    assert float((model.read_tap("out_hvi").cpu() - taps["out_hvi"]).abs().max()) <= MAXABS
     # per-stage taps against the reference's own sub-module outputs
     for key in g.files:
         if key.startswith("tap|"):
@@ -49,7 +57,7 @@ def test_golden_reference_outputs(model, seed):
     model.trans.gated, model.trans.gated2, model.trans.alpha_s, model.trans.alpha = True, True, 1.3, 0.9
     with torch.no_grad():
         yg = model(x).cpu()
-    _check(yg, torch.from_numpy(g["y_gated"]))
+    _check(yg, torch.from_numpy(g["y_gated"]), torch.from_numpy(g["x"]), sd, gated=True, alpha_s=1.3, gated2=True, alpha=0.9)
     model.trans.gated = model.trans.gated2 = False
     model.trans.alpha = 1.0
 
@@ -63,7 +71,7 @@ def test_against_oracle(model, kind, shape):
     with torch.no_grad():
         ref = O.forward(x, sd)
         y = model(x.cuda()).cpu()
-    _check(y, ref)
+    _check(y, ref, x, sd)
 
 
 def test_cfg2_full_size_against_oracle_and_batch_property(model):
@@ -77,8 +85,8 @@ def test_cfg2_full_size_against_oracle_and_batch_property(model):
         xd = x.cuda()
         y = model(xd)
         y2 = model(torch.cat([xd, xd]))
-    _check(y.cpu(), ref)
-    assert max_err_robust(y2[0:1], y2[1:2]) <= 5e-4 and max_err_robust(y2[0:1], y) <= 5e-4
+    _check(y.cpu(), ref, x, sd)
+    assert torch.equal(y2[0:1], y2[1:2]) and torch.equal(y2[0:1], y)       # bit-exact: no atomics, fixed summation orders
 
 
 def test_default_init_state_dict_round_trip(model, tmp_path):
@@ -94,7 +102,7 @@ def test_default_init_state_dict_round_trip(model, tmp_path):
     with torch.no_grad():
         y = model(x.cuda()).cpu()
         ref = O.forward(x, {k: v.float() for k, v in sd.items()})
-    _check(y, ref)
+    _check(y, ref, x, {k: v.float() for k, v in sd.items()})
     assert abs(model.trans.this_k - 0.2) < 1e-6        # set by forward's HVIT (HVI_transform.py:38)
 
 
@@ -114,9 +122,12 @@ def test_batch_independence(model):
     with torch.no_grad():
         yb = model(x)
         ys = torch.cat([model(x[i:i + 1]) for i in range(3)])
-    # fp32 atomics accumulate the Gram partial sums in a run-dependent order; downstream fp16 roundings amplify
-    # the last-bit differences to ~1.5e-4 on the output (measured over 300 replays: scripts/stress_repeat.py)
-    assert max_err_robust(yb, ys) <= 5e-4
+        again = model(x)
+    # the split-K Gram partials are summed in a fixed order (no atomics): bit-equal run to run; a batch and its images
+    # run alone use different split-K partitions of the same pixels -> equal up to fp32 summation order only
+    assert torch.equal(yb, again)
+    err, _, _ = parity_error(yb, ys, 5e-4)
+    assert err <= 5e-4
 
 
 def test_streamed_driver_matches_plain_forward(model):
@@ -129,8 +140,8 @@ def test_streamed_driver_matches_plain_forward(model):
         want = [model(x.cuda()).cpu() for x in xs]
         got = [y.clone() for y in StreamedCIDNet(model, depth=3).run(iter(xs))]
     assert len(got) == len(want)
-    for g, w in zip(got, want):        # not bit-equal: the Gram's fp32 atomics are order dependent run to run
-        assert max_err_robust(g, w) <= 5e-4
+    for g, w in zip(got, want):        # same kernels, same shapes, fixed summation orders: bit-equal
+        assert torch.equal(g, w)
     with pytest.raises(RuntimeError):
         model(xs[0].cuda(), out=torch.empty(1, 3, 8, 8, device="cuda"))
 
@@ -169,3 +180,48 @@ def test_u8_pre_post_and_enhance(model, h, w, gamma):
     assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 0.1
     with pytest.raises(RuntimeError):
         model.enhance_u8(img)                                     # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("scale_in,scale_dw", [(4.0, 1.0), (16.0, 1.0), (8.0, 8.0)])
+def test_dynamic_range_of_the_fp16_hidden_tensors(model, scale_in, scale_dw):
+    """Activations are stored as fp16 (max 65504) and the IEL gate chain computes in fp16.  Scaling every IEL's
+    project_in (x scale_in) and dwconv (x scale_dw) weights multiplies the hidden tensors t / d by up to 64 and the
+    gated product x1 * x2 by up to 4096 relative to default-init statistics: the forward must stay finite and inside
+    the contract.  (The documented limit is |x1 * x2| < 65504; the bf16 build has fp32 range.)"""
+    sd = O.make_state_dict(5, True)
+    for k in list(sd):
+        if k.endswith(".gdfn.project_in.weight"):
+            sd[k] = sd[k] * scale_in
+        if k.endswith(".gdfn.dwconv.weight"):
+            sd[k] = sd[k] * scale_dw
+        if k.endswith(".gdfn.project_out.weight"):           # keep the block's output O(1) so the rest of the net is unchanged
+            sd[k] = sd[k] / (scale_in * scale_dw) ** 2
+    model.load_state_dict(sd, strict=True)
+    x = O.make_input("uniform", 1, 128, 160, seed=77)
+    with torch.no_grad():
+        taps = {}
+        ref = O.forward(x, sd, taps=taps)
+        y = model(x.cuda())
+    assert torch.isfinite(y).all()
+    for name in ("I_LCA1", "HV_LCA1", "I_LCA3", "HV_LCA4", "HV_LCA6", "id1", "hvd1"):
+        assert torch.isfinite(model.read_tap(name)).all(), name
+    _check(y.cpu(), ref, x, sd)
+
+
+def test_two_contexts_in_one_process(model):
+    """two models (two native contexts) alive in one process, interleaved calls; with >= 2 GPUs the second one lives
+    on cuda:1 (kernel attributes such as the dynamic shared-memory limit are per device)."""
+    from hvi_cidnet_b200.net.CIDNet import CIDNet
+    sd = O.make_state_dict(5, True)
+    model.load_state_dict(sd, strict=True)
+    dev2 = torch.device("cuda", 1 if torch.cuda.device_count() > 1 else 0)
+    other = CIDNet().to(dev2).eval()
+    other.load_state_dict(O.make_state_dict(6, True), strict=True)
+    x = O.make_input("uniform", 1, 64, 96, seed=8)
+    with torch.no_grad():
+        a1 = model(x.cuda())
+        b1 = other(x.to(dev2))
+        a2 = model(x.cuda())
+        b2 = other(x.to(dev2))
+    assert torch.equal(a1, a2) and torch.equal(b1, b2) and not torch.equal(a1.cpu(), b1.cpu())
+    _check(b1.cpu(), O.forward(x, O.make_state_dict(6, True)), x, O.make_state_dict(6, True))

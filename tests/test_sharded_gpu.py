@@ -5,7 +5,8 @@ The ranks are real processes.  With >= world GPUs every rank takes its own GPU a
 Gram sums travel over NCCL (NVLink); on a single-GPU box the ranks share cuda:0 and the very same
 callbacks are staged through gloo -- the schedule, the kernels and the row arithmetic under test
 are identical.  Tolerances: owned rows equal the unsharded forward up to the summation order of the
-Gram (fp32 atomics), amplified by the fp16 roundings downstream -> 5e-4 (typical 1.5e-4); against the oracle the usual 2e-3 / 50 dB contract."""
+Gram (each rank sums its own rows, then the ranks are summed), amplified by the fp16 roundings downstream -> 5e-4 (typical
+1.5e-4); repeated sharded forwards are bit-equal; against the oracle the usual 2e-3 / 50 dB contract."""
 import os
 import sys
 
@@ -14,7 +15,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from conftest import ROOT, max_err_robust
+from conftest import ROOT, parity_error, psnr_kept
 
 pytestmark = pytest.mark.gpu
 
@@ -47,15 +48,19 @@ def _worker(rank, world, port, H, W, use_nccl, ret, mssa=False):
     y3 = net(x.to(dev), gather=True).cpu()               # third / fourth call: CUDA-graph capture and replay of the
     y4 = net(x.to(dev), gather=True).cpu()               # kernels + NCCL exchanges (NCCL transport only; eager otherwise)
     full = model(x.to(dev)).cpu()                        # unsharded CUDA forward on this rank's GPU
-    out = {"vs_full": max_err_robust(y, full), "repeat": max(max_err_robust(y, y2), max_err_robust(y, y3), max_err_robust(y, y4)),
+    # sharded vs unsharded: different split of the same fp32 sums -> small differences; a pixel beyond 5e-4 must be the
+    # reference's black-pixel hole (conftest.parity_error).  Repeats of the SAME sharded forward are bit-equal (no atomics).
+    out = {"vs_full": parity_error(y, full, 5e-4)[0], "repeat_equal": bool(torch.equal(y, y2) and torch.equal(y, y3) and torch.equal(y, y4)),
            "replays": net.replays, "graph_error": getattr(net, "graph_error", None),
            "halo_calls": sum(1 for e in net.comm.log if e[0] == "halo"),
            "allreduce_calls": sum(1 for e in net.comm.log if e[0] == "allreduce"),
            "direct": bool(net.comm.direct)}
     if rank == 0:
-        ref = O.forward(x, sd, mssa=mssa)
-        out["vs_oracle"] = max_err_robust(y.clamp(0, 1), ref.clamp(0, 1))
-        out["psnr"] = float(O.psnr(y.clamp(0, 1), ref.clamp(0, 1)))
+        taps = {}
+        ref = O.forward(x, sd, mssa=mssa, taps=taps)
+        err, _, keep = parity_error(y.clamp(0, 1), ref.clamp(0, 1), 2e-3, taps["out_hvi"], float(sd["trans.density_k"].reshape(-1)[0]))
+        out["vs_oracle"] = err
+        out["psnr"] = psnr_kept(y.clamp(0, 1), ref.clamp(0, 1), keep)
     ret[rank] = out
     net.close()                                          # captured graphs must go before the communicator
     dist.barrier()
@@ -75,7 +80,7 @@ def test_row_sharded_forward_matches_unsharded(world, H, W, mssa):
     for r in range(world):
         o = ret[r]
         assert o["vs_full"] <= 5e-4, (r, o)
-        assert o["repeat"] <= 5e-4, (r, o)
+        assert o["repeat_equal"], (r, o)
         assert o["allreduce_calls"] == 6 and o["halo_calls"] >= 6, (r, o)
         assert o["direct"] == use_nccl
         # graph replay is opt-in (CIDNET_SHARD_GRAPH=1) and needs the NCCL transport
@@ -95,4 +100,4 @@ def test_sharded_entry_with_one_rank_is_the_plain_forward():
     x = O.make_input("uniform", 1, 64, 96, seed=4).cuda()
     y = RowShardedCIDNet(model)(x)
     full = model(x)
-    assert max_err_robust(y, full) <= 5e-4
+    assert torch.equal(y, full)
