@@ -71,6 +71,8 @@ dw3x3_f32acc_kernel(const Dw3Args a) {
     const int nv = a.nv;                                   // 16-byte vectors per pixel (all segments)
     const int idx = blockIdx.x * kDwThreads + threadIdx.x; // vector index along the row
     const int x = idx / nv, v = idx - x * nv;
+    ptx::pdl_wait();
+    ptx::pdl_trigger();
     if (x >= a.W) return;
     const int seg = v / a.seg_vecs;                        // 0 = q, 1 = k, 2 = v
     const int c0 = (v - seg * a.seg_vecs) * 8;             // channel within the segment
@@ -98,9 +100,9 @@ dw3x3_f32acc_kernel(const Dw3Args a) {
         r[0] = r[1] = r[2] = zero4;
         if (y < 0 || y >= a.H) return;
         const act_t* p = src + ((long long)y * a.W + x) * a.src_pitch;
-        r[1] = *reinterpret_cast<const uint4*>(p);
-        if (has_l) r[0] = *reinterpret_cast<const uint4*>(p - a.src_pitch);
-        if (has_r) r[2] = *reinterpret_cast<const uint4*>(p + a.src_pitch);
+        r[1] = __ldcg(reinterpret_cast<const uint4*>(p));
+        if (has_l) r[0] = __ldcg(reinterpret_cast<const uint4*>(p - a.src_pitch));
+        if (has_r) r[2] = __ldcg(reinterpret_cast<const uint4*>(p + a.src_pitch));
     };
     auto step = [&](const uint4* r0, const uint4* r1, uint4* r2, int y) {
         load_row(y + 1, r2);
@@ -184,6 +186,8 @@ dw3x3_cpasync_kernel(const Dw3Args a) {
         for (int i = threadIdx.x; i < 9 * nv * 8; i += kDwThreads) s_w[i] = f2act(__ldg(wp + i));
     }
     __syncthreads();
+    ptx::pdl_wait();          // the weights above are constants; everything below reads the previous kernel's output
+    ptx::pdl_trigger();
     if (!active) return;
     const uint32_t wsm_addr = ptx::smem_u32(s_w) + (uint32_t)(v * 16);
     // asm volatile: the loads must stay where they are used (hoisted out of the row loop they would occupy the
@@ -253,9 +257,10 @@ int launch_dw3(const Dw3Args& a, cudaStream_t stream) {
     const size_t smem = (size_t)4 * 3 * kDwThreads * 16 + (size_t)9 * a.nv * 8 * sizeof(act_t);
     int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(dw3x3_cpasync_kernel<4, 5>), 64 * 1024);
     if (rc) return rc;
-    dw3x3_cpasync_kernel<4, 5><<<grid, kDwThreads, smem, stream>>>(a);
+    if ((rc = launch_k(dw3x3_cpasync_kernel<4, 5>, grid, dim3(kDwThreads), smem, stream, a))) return rc;
 #else
-    dw3x3_f32acc_kernel<<<grid, kDwThreads, 0, stream>>>(a);
+    int rc = launch_k(dw3x3_f32acc_kernel, grid, dim3(kDwThreads), 0, stream, a);
+    if (rc) return rc;
 #endif
     CIDNET_CUDA_OK(cudaGetLastError());
     return CIDNET_OK;
@@ -338,6 +343,8 @@ gram_kernel(const __grid_constant__ GramArgs a) {
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
+    ptx::pdl_wait();
+    ptx::pdl_trigger();
     const uint32_t tmem_base = *tmem_slot;
     float* slab = a.slab + (((long long)prob * a.B + b) * a.nsplit + blockIdx.x) * (long long)(a.heads * 324 + 2 * a.Cp);
 
@@ -514,7 +521,7 @@ int launch_gram(const GramLaunch& L, cudaStream_t stream, int* nsplit_out) {
     int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gram_kernel), 200 * 1024);
     if (rc) return rc;
     dim3 grid(nsplit, L.nprob, L.B);
-    gram_kernel<<<grid, kGramThreads, smem, stream>>>(a);
+    if ((rc = launch_k(gram_kernel, grid, dim3(kGramThreads), smem, stream, a))) return rc;
     CIDNET_CUDA_OK(cudaGetLastError());
     return CIDNET_OK;
 }
@@ -525,12 +532,19 @@ int launch_gram(const GramLaunch& L, cudaStream_t stream, int* nsplit_out) {
 __device__ __forceinline__ float4 ordered_sum4(const float* p, long long stride, int n) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int s = 0;
-    for (; s + 8 <= n; s += 8) {
-        float4 v[8];
+    for (; s + 16 <= n; s += 16) {          // 16 L2 round trips in flight per thread: the loop is latency-, not bandwidth-bound
+        float4 v[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldcg(reinterpret_cast<const float4*>(p + (long long)(s + u) * stride));
+        for (int u = 0; u < 16; ++u) v[u] = __ldcg(reinterpret_cast<const float4*>(p + (long long)(s + u) * stride));
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+        for (int u = 0; u < 16; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
+    for (; s + 4 <= n; s += 4) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldcg(reinterpret_cast<const float4*>(p + (long long)(s + u) * stride));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
     }
     for (; s < n; ++s) {
         const float4 v = __ldcg(reinterpret_cast<const float4*>(p + (long long)s * stride));
@@ -541,12 +555,19 @@ __device__ __forceinline__ float4 ordered_sum4(const float* p, long long stride,
 __device__ __forceinline__ float ordered_sum1(const float* p, long long stride, int n) {
     float acc = 0.f;
     int s = 0;
-    for (; s + 8 <= n; s += 8) {
-        float v[8];
+    for (; s + 16 <= n; s += 16) {
+        float v[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = __ldcg(p + (long long)(s + u) * stride);
+        for (int u = 0; u < 16; ++u) v[u] = __ldcg(p + (long long)(s + u) * stride);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc += v[u];
+        for (int u = 0; u < 16; ++u) acc += v[u];
+    }
+    for (; s + 4 <= n; s += 4) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldcg(p + (long long)(s + u) * stride);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc += v[u];
     }
     for (; s < n; ++s) acc += __ldcg(p + (long long)s * stride);
     return acc;
@@ -555,7 +576,9 @@ __device__ __forceinline__ float ordered_sum1(const float* p, long long stride, 
 static constexpr int kFoldThreads = 512;
 static constexpr int kFoldGroups = 4;          // split groups summed independently, then combined in group order
 
-// grid (nprob * heads, B).  One CTA = one head of one image of one problem.
+// grid (nprob * heads, B, kFoldSlices).  One CTA = a slice of the output rows of one head of one image of one problem;
+// every slice repeats the (cheap, L2-resident) reduction and softmax of its head -- the kernel is a chain of dependent
+// latencies, so more CTAs with less serial work each is what shortens it.
 __global__ void __launch_bounds__(kFoldThreads)
 cab_fold_kernel(const CabFoldArgs a) {
     __shared__ __align__(16) float s_part[kFoldGroups][368];   // per split group: [324 Gram | 18 sq | 18 sk] (+ pad)
@@ -565,7 +588,9 @@ cab_fold_kernel(const CabFoldArgs a) {
     const long long E = (long long)a.heads * 324 + 2 * a.Cp;
     const float* slab = a.slab + ((long long)prob * a.B + b) * a.nsplit * E;
     const float* wo = prob ? a.wo[1] : a.wo[0];
-    const int n_el = a.n_rows * 18;                              // M elements of this head: [n_rows][18 columns]
+    const int rows_per = (a.n_rows + gridDim.z - 1) / gridDim.z;
+    const int o_begin = blockIdx.z * rows_per, o_end = min(o_begin + rows_per, a.n_rows);
+    const int n_el = max(o_end - o_begin, 0) * 18;               // M elements of this CTA: [rows of the slice][18 columns]
     // The kernel is a chain of dependent latencies (slab loads -> softmax -> W_o -> store), not work.  So: the W_o
     // segments of this thread's first output elements are requested FIRST and arrive while the reduction runs.
     constexpr int kPre = 2;
@@ -573,11 +598,13 @@ cab_fold_kernel(const CabFoldArgs a) {
 #pragma unroll
     for (int u = 0; u < kPre; ++u) {
         const int i = tid + u * kFoldThreads;
-        const int o = i / 18;
+        const int o = o_begin + i / 18;
         const bool nz = i < n_el && o < C;
 #pragma unroll
         for (int c = 0; c < 18; ++c) wv[u][c] = nz ? __ldg(wo + o * C + head * 18 + c) : 0.f;
     }
+    ptx::pdl_wait();          // W_o (requested above) is a constant; the slab is the Gram kernel's output
+    ptx::pdl_trigger();
     // ---- fixed-order reduction of this head's [18x18 | sq | sk] over the split-K slab entries
     {
         const int grp = tid >> 7, t = tid & 127;                // 4 groups of 128 threads
@@ -594,7 +621,7 @@ cab_fold_kernel(const CabFoldArgs a) {
     __syncthreads();
     if (tid < 360) s_part[0][tid] = ((s_part[0][tid] + s_part[1][tid]) + s_part[2][tid]) + s_part[3][tid];
     __syncthreads();
-    if (a.raw_out) {          // tests / taps: the reduced raw statistics of this head
+    if (a.raw_out && blockIdx.z == 0) {          // tests / taps: the reduced raw statistics of this head
         float* ro = a.raw_out + ((long long)prob * a.B + b) * E;
         if (tid < 324) ro[head * 324 + tid] = s_part[0][tid];
         else if (tid < 360) { const int i = tid - 324, which = i / 18; ro[a.heads * 324 + which * a.Cp + head * 18 + (i - which * 18)] = s_part[0][tid]; }
@@ -623,14 +650,14 @@ cab_fold_kernel(const CabFoldArgs a) {
     for (int u = 0; u < kPre; ++u) {
         const int i = tid + u * kFoldThreads;
         if (i >= n_el) break;
-        const int o = i / 18, j = i - o * 18;
+        const int o = o_begin + i / 18, j = i % 18;
         float acc = 0.f;
 #pragma unroll
         for (int c = 0; c < 18; ++c) acc = fmaf(wv[u][c], s_attn[c * 18 + j], acc);
         m[(long long)o * a.kt + j] = f2act(acc);
     }
     for (int i = tid + kPre * kFoldThreads; i < n_el; i += kFoldThreads) {
-        const int o = i / 18, j = i - o * 18;
+        const int o = o_begin + i / 18, j = i % 18;
         float acc = 0.f;
         if (o < C) {
 #pragma unroll
@@ -642,8 +669,8 @@ cab_fold_kernel(const CabFoldArgs a) {
     if (head == a.heads - 1) {
         const int padw = a.kt - C;
         act_t* mp = (prob ? a.m_out[1] : a.m_out[0]) + (long long)b * a.n_rows * a.kt + C;
-        for (int i = tid; i < a.n_rows * padw; i += kFoldThreads) {
-            const int o = i / padw, j = i - o * padw;
+        for (int i = tid; i < max(o_end - o_begin, 0) * padw; i += kFoldThreads) {
+            const int o = o_begin + i / padw, j = i % padw;
             mp[(long long)o * a.kt + j] = f2act(0.f);
         }
     }
@@ -652,8 +679,11 @@ cab_fold_kernel(const CabFoldArgs a) {
 int launch_cab_fold(const CabFoldArgs& a, cudaStream_t stream) {
     CIDNET_CHECK(a.C <= 144 && a.C == a.heads * 18, CIDNET_ERR_INVALID, "fold: C must be heads * 18 <= 144");
     CIDNET_CHECK(a.slab != nullptr && a.nsplit >= 1, CIDNET_ERR_INVALID, "fold: null slab");
-    dim3 grid(a.nprob * a.heads, a.B);
-    cab_fold_kernel<<<grid, kFoldThreads, 0, stream>>>(a);
+    // row slices: <= ~2 output elements per thread (48 / 80 / 144 rows x 18 columns per head)
+    const int slices = std::max(1, std::min(8, ceil_div(a.n_rows * 18, 2 * kFoldThreads)));
+    dim3 grid(a.nprob * a.heads, a.B, slices);
+    int rc = launch_k(cab_fold_kernel, grid, dim3(kFoldThreads), 0, stream, a);
+    if (rc) return rc;
     CIDNET_CUDA_OK(cudaGetLastError());
     return CIDNET_OK;
 }
@@ -663,6 +693,8 @@ int launch_cab_fold(const CabFoldArgs& a, cudaStream_t stream) {
 __global__ void __launch_bounds__(256)
 cab_reduce_kernel(const float* __restrict__ slab, float* __restrict__ out, int nsplit, int E4) {
     const long long E = 4ll * E4;
+    ptx::pdl_wait();
+    ptx::pdl_trigger();
     const float* src = slab + (long long)blockIdx.y * nsplit * E;
     for (int i = blockIdx.x * 256 + threadIdx.x; i < E4; i += gridDim.x * 256) {
         const float4 v = ordered_sum4(src + 4 * i, E, nsplit);
@@ -673,7 +705,8 @@ cab_reduce_kernel(const float* __restrict__ slab, float* __restrict__ out, int n
 int launch_cab_reduce(const float* slab, float* out, int nsplit, int E, int nvec, cudaStream_t stream) {
     CIDNET_CHECK(E % 4 == 0, CIDNET_ERR_INVALID, "reduce: E % 4");
     dim3 grid(ceil_div(E / 4, 256), nvec);
-    cab_reduce_kernel<<<grid, 256, 0, stream>>>(slab, out, nsplit, E / 4);
+    int rc = launch_k(cab_reduce_kernel, grid, dim3(256), 0, stream, slab, out, nsplit, E / 4);
+    if (rc) return rc;
     CIDNET_CUDA_OK(cudaGetLastError());
     return CIDNET_OK;
 }

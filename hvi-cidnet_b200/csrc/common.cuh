@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <utility>
 
 #include "../../include/cidnet_b200.h"
 
@@ -59,6 +60,24 @@ int device_sm_count();
     do {                                                                                  \
         if (!(cond)) return ::cidnet::fail((code), (msg));                                \
     } while (0)
+
+// Kernel launch with (optionally) programmatic stream serialization: see ptx_sm100.cuh pdl_wait / pdl_trigger.  Only
+// kernels that execute pdl_wait() before touching non-constant global memory may be launched through this helper.
+bool pdl_enabled();            // CIDNET_PDL=0 turns the attribute off (A/B runs)
+template <typename... KArgs, typename... Args>
+inline int launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    if (pdl_enabled()) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+    }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+    if (e != cudaSuccess) return fail(CIDNET_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+    return CIDNET_OK;
+}
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }

@@ -123,7 +123,15 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
     uint64_t* bfull = empty + stages;
     uint64_t* tmem_full = bfull + 1;                       // [kEpiGroups]
     uint64_t* tmem_empty = tmem_full + kEpiGroups;         // [kEpiGroups]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + kEpiGroups);
+    // a_ready[buf]: "every pipeline stage of the tile that accumulates into TMEM buffer `buf` has landed".  The LN / UP
+    // epilogues read the A tile / the low-res box straight from the ring; they wait HERE, never on the ring's `full`
+    // barriers.  A parity wait on full[s] is only sound when the PREVIOUS phase of that stage is known to be complete:
+    // true for the MMA warp (it consumes the ring in order), not for an epilogue group that skips the other groups' tiles
+    // -- with fewer tiles in the ring than groups (or an smem-limited ring) the wait could succeed on the old phase and
+    // the LayerNorm statistics were read from the previous tile's data (the round-1 "3 epilogue groups lose parity"
+    // failure, profiles/r02_summary.md).  The MMA warp arrives once per tile, so a group sees consecutive phases.
+    uint64_t* a_ready = tmem_empty + kEpiGroups;           // [kEpiGroups]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + kEpiGroups + (kEpiGroups & 1));   // (+ pad: s_bias stays 16-byte aligned)
     float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);
     const int bn32 = (a.block_n + 31) & ~31;
     float* s_wsum = s_bias + bn32;
@@ -150,7 +158,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
             const uint32_t empty_count = (kMode == EPI_LN || kMode == EPI_UP) ? 5u : 1u;
             for (int s = 0; s < stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], empty_count); }
             ptx::mbar_init(bfull, 1);
-            for (int i = 0; i < kEpiGroups; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], 4); }
+            for (int i = 0; i < kEpiGroups; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], 4); ptx::mbar_init(&a_ready[i], 1); }
             ptx::fence_barrier_init();
         }
         __syncwarp();
@@ -168,16 +176,21 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // resident weights are CONSTANTS of the model (per-image folded weights are never resident): requested before the
+    // programmatic-dependency wait, they land while the previous kernel of the stream is still finishing
+    if (warp == 0 && lane == 0 && a.b_resident) {
+        ptx::mbar_expect_tx(bfull, (uint32_t)nbchunks * b_chunk);
+        for (int i = 0; i < nbchunks; ++i) {
+            if (i < k1) ptx::tma_load_3d(smBres + (size_t)i * b_chunk, &a.tmB, bfull, i * 64, n0, 0);
+            else        ptx::tma_load_3d(smBres + (size_t)i * b_chunk, &a.tmB2, bfull, (i - k1) * 64, n0, 0);
+        }
+    }
+    ptx::pdl_wait();
+    ptx::pdl_trigger();
+
     if (warp == 0) {
         // ------------------------------------------------------- TMA producer
         if (lane == 0) {
-            if (a.b_resident) {
-                ptx::mbar_expect_tx(bfull, (uint32_t)nbchunks * b_chunk);
-                for (int i = 0; i < nbchunks; ++i) {
-                    if (i < k1) ptx::tma_load_3d(smBres + (size_t)i * b_chunk, &a.tmB, bfull, i * 64, n0, 0);
-                    else        ptx::tma_load_3d(smBres + (size_t)i * b_chunk, &a.tmB2, bfull, (i - k1) * 64, n0, 0);
-                }
-            }
             uint32_t it = 0;
             for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
                 const int img = t / tiles_per_img;
@@ -249,6 +262,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                 const uint32_t ph = (it / stages) & 1u;
                 ptx::mbar_wait(&full[s], ph);
                 ptx::tc_fence_after();
+                if ((kMode == EPI_LN || kMode == EPI_UP) && i == kiters - 1 && lane == 0) ptx::mbar_arrive(&a_ready[buf]);
                 if (a.halo) {
                     // One (elected) lane issues every tcgen05.mma, the whole warp runs the loop convergently; ncu showed the tensor pipe busy only ~55 % of the time
                     // behind this loop (~150 cycles of uniform-datapath descriptor arithmetic per MMA), so the
@@ -339,8 +353,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
             if (kMode == EPI_LN) {
                 // per-pixel LayerNorm statistics from the A tile (all K chunks of this tile are resident:
                 // the host guarantees stages >= kchunks + 1); then co-release the stages
-                for (int kc = 0; kc < a.kchunks; ++kc)
-                    ptx::mbar_wait(&full[(it + kc) % stages], ((it + kc) / stages) & 1u);
+                ptx::mbar_wait(&a_ready[j % kEpiGroups], (j / kEpiGroups) & 1u);
                 // one pass: sum and sum of squares with FHFMA (x*1 and x*x, exact 16-bit products, fp32
                 // accumulation; channels >= Cin are TMA zero fill and contribute nothing)
                 float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
@@ -373,7 +386,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
             const uint32_t up_it = it - kiters;               // pipeline iteration of this tile's first stage
             if (kMode == EPI_UP) {
                 const uint32_t s0 = up_it % stages;
-                ptx::mbar_wait(&full[s0], (up_it / stages) & 1u);
+                ptx::mbar_wait(&a_ready[j % kEpiGroups], (j / kEpiGroups) & 1u);
                 up_tile = smA + (size_t)s0 * a_stage + kSubTileBytes;
                 const int yr = y, xr = x;                                    // UP tiles are 8 x 16 rectangles of one image
                 const float sy = a.up_ry * (float)(yr + a.up_row0);          // GLOBAL source row
@@ -576,9 +589,7 @@ template <int kMode, int kEpiGroups>
 static int launch_mode_g(const ConvGemmArgs& args, dim3 grid, size_t smem, cudaStream_t stream) {
     int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(conv_gemm_kernel<kMode, kEpiGroups>), 227 * 1024);
     if (rc) return rc;
-    conv_gemm_kernel<kMode, kEpiGroups><<<grid, 64 + 128 * kEpiGroups, smem, stream>>>(args);
-    CIDNET_CUDA_OK(cudaGetLastError());
-    return CIDNET_OK;
+    return launch_k(conv_gemm_kernel<kMode, kEpiGroups>, grid, dim3(64 + 128 * kEpiGroups), smem, stream, args);
 }
 template <int kMode>
 static int launch_mode(const ConvGemmArgs& args, dim3 grid, size_t smem, cudaStream_t stream, int groups) {
@@ -601,11 +612,13 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
     const int ksub = L.mode == EPI_DOWN ? 2 : 1;
     CIDNET_CHECK(2 * ksub * wt.block_n <= 512, CIDNET_ERR_INVALID, "conv_gemm: accumulators exceed TMEM");
     // epilogue groups: 2.  A third group for the 1x1 layers was measured on B200 in round 1: no layer got faster at cfg 2
-    // or 16x400x600, and the 400x600 forward lost parity (2.9e-2).  Root cause (round 2, `build.py --groups3` experiment,
-    // profiles/r02_summary.md): the round-1 experiment sized TMEM as the next power of two >= 3 * block_n columns
-    // without checking it against the 512 columns an SM has -- the q|kv GEMMs (block_n = 216 / 144 x 3 = 648 / 432)
-    // asked tcgen05.alloc for 1024 columns.  With the guard below (3 groups only where 3 accumulators fit) the 3-group
-    // build is parity-clean; it is still not faster, so the shipped library instantiates the 2-group kernels only.
+    // or 16x400x600, and the 400x600 forward lost parity (2.9e-2).  Root cause, found in round 2 with the
+    // `build.py --groups3` experiment (profiles/r02_summary.md): (1) TMEM was sized as the next power of two >= 3 * block_n
+    // columns without checking the 512 an SM has (guard below); (2) the LN / UP epilogues waited on the ring's `full`
+    // barriers by parity although an epilogue group does not see every phase of a stage -- with 2 tiles in the ring and
+    // 3 groups the wait could succeed on the previous phase (see `a_ready` in the kernel).  The same hole was latent in
+    // the shipped 2-group kernels whenever shared memory limited the ring to fewer than 2 tiles; the a_ready barrier closes
+    // it for every configuration.  3 groups are still not faster, so the library instantiates the 2-group kernels only.
     int kEpiGroups = 2;
 #ifdef CIDNET_GEMM_GROUPS3
     if (wt.taps == 1 && L.mode != EPI_DOWN && 3 * wt.block_n <= 512) kEpiGroups = 3;

@@ -1,6 +1,7 @@
 // Thread-local error string behind cidnet_last_error().
 #include "common.cuh"
 
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -25,6 +26,11 @@ int ensure_dynamic_smem(const void* kernel, int bytes) {
     CIDNET_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     have = bytes;
     return CIDNET_OK;
+}
+
+bool pdl_enabled() {
+    static const bool on = [] { const char* v = getenv("CIDNET_PDL"); return !(v && v[0] == '0'); }();
+    return on;
 }
 
 int device_sm_count() {

@@ -110,6 +110,8 @@ iel_gate_v4_kernel(const __grid_constant__ IelV4Args A) {
         ptx::prefetch_tensormap(&A.tmT[prob]);
     }
     __syncthreads();
+    ptx::pdl_wait();          // weights (above) are constants; t is the previous kernel's output
+    ptx::pdl_trigger();
 
     if (warp == 4) {
         // ------------------------------------------------------------ TMA producer
@@ -311,9 +313,11 @@ iel_gate_v6_kernel(const __grid_constant__ IelV4Args A) {
         ptx::prefetch_tensormap(&A.tmT[prob]);
     }
     __syncthreads();
+    ptx::pdl_trigger();
 
     if (warp == 4) {
         if (lane == 0) {
+            ptx::pdl_wait();          // t is the previous kernel's output (the weights are constants)
             for (int k = 0; k < nblocks; ++k) {
                 const int s = k % kV5Stages;
                 ptx::mbar_wait(&empty[s], ((k / kV5Stages) & 1u) ^ 1u);
@@ -433,12 +437,12 @@ int launch_iel_gate(const IelGateArgs& a, cudaStream_t stream) {
     const size_t smem6 = 1024 + (size_t)kV5Stages * kV4StageBytes + 2 * 4 * kCols * sizeof(uint4) +
                          2 * kV5Stages * sizeof(uint64_t) + 9 * 2 * 16 * sizeof(act_t) + 64;
     if ((rc = ensure_dynamic_smem(reinterpret_cast<const void*>(iel_gate_v6_kernel), (int)smem6))) return rc;
-    iel_gate_v6_kernel<<<grid, kV4Threads, smem6, stream>>>(A);
+    if ((rc = launch_k(iel_gate_v6_kernel, grid, dim3(kV4Threads), smem6, stream, A))) return rc;
 #else
     const size_t smem = 1024 + (size_t)kV4Stages * kV4StageBytes + 2 * 9 * 2 * 16 * sizeof(act_t) +
                         2 * 2 * 2 * kCols * sizeof(float4) + 2 * kV4Stages * sizeof(uint64_t) + 64;
     if ((rc = ensure_dynamic_smem(reinterpret_cast<const void*>(iel_gate_v4_kernel), (int)smem))) return rc;
-    iel_gate_v4_kernel<<<grid, kV4Threads, smem, stream>>>(A);
+    if ((rc = launch_k(iel_gate_v4_kernel, grid, dim3(kV4Threads), smem, stream, A))) return rc;
 #endif
     CIDNET_CUDA_OK(cudaGetLastError());
     return CIDNET_OK;

@@ -203,6 +203,17 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t fmt /*0 fp1
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// ------------------------------------------------ programmatic dependent launch ---
+// Every kernel of the forward is launched with cudaLaunchAttributeProgrammaticStreamSerialization (common.cuh launch_k):
+// its CTAs may become resident -- and run their prologue: barrier init, TMEM allocation, descriptor prefetch, loads of
+// CONSTANT weights -- while the previous kernel of the stream is still draining.  pdl_wait() blocks until that kernel
+// has completed and its writes are visible; it is executed by ALL threads before the first access to anything another
+// kernel of the forward produces or still reads, so data-wise the forward behaves exactly like serial launches.
+// pdl_trigger() lets the NEXT kernel's CTAs start their own prologue as soon as every CTA of this one has issued it.
+// Both are no-ops when the kernel was launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(

@@ -4,6 +4,7 @@
 //   sa_stats_kernel  reads x once (2*pitch B/px), writes 8 B/px
 //   sa_gate_kernel   reads the 7x7 neighbourhood of the statistics from a shared-memory tile, reads x, writes x
 #include "sa.cuh"
+#include "ptx_sm100.cuh"
 
 namespace cidnet {
 
@@ -22,8 +23,10 @@ sa_stats_kernel(SaStatsParams p) {
     const int npx = (int)min((long long)kStatPx, p.npx - px0);
     const int nvec = npx * p.nv;
     const uint4* src = reinterpret_cast<const uint4*>(x) + px0 * p.nv;     // pitch = 8 * nv: pixels are contiguous
+    ptx::pdl_wait();
+    ptx::pdl_trigger();
     for (int i = threadIdx.x; i < nvec; i += 256) {
-        const uint4 raw = __ldg(src + i);
+        const uint4 raw = __ldcg(src + i);
         const act_t* a = reinterpret_cast<const act_t*>(&raw);
         const int c0 = (i % p.nv) * 8;
         float s = 0.f, m = -INFINITY;
@@ -57,10 +60,12 @@ sa_gate_kernel(SaGateParams p) {
     const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
     const float2* __restrict__ st = (prob ? p.stats[1] : p.stats[0]) + (long long)b * p.H * p.W;
     if (threadIdx.x < 98) wsm[threadIdx.x] = (prob ? p.w[1] : p.w[0])[threadIdx.x];
+    ptx::pdl_wait();
+    ptx::pdl_trigger();
     for (int i = threadIdx.x; i < (kTH + 6) * (kTW + 6); i += 256) {
         const int ty = i / (kTW + 6), tx = i % (kTW + 6);
         const int y = y0 + ty - 3, x = x0 + tx - 3;
-        tile[i] = (y >= 0 && y < p.H && x >= 0 && x < p.W) ? st[(long long)y * p.W + x] : make_float2(0.f, 0.f);
+        tile[i] = (y >= 0 && y < p.H && x >= 0 && x < p.W) ? __ldcg(st + (long long)y * p.W + x) : make_float2(0.f, 0.f);
     }
     __syncthreads();
     {
@@ -84,7 +89,7 @@ sa_gate_kernel(SaGateParams p) {
         const int y = y0 + ty, x = x0 + tx;
         if (y >= p.H || x >= p.W) continue;
         uint4* ptr = reinterpret_cast<uint4*>(xb) + ((long long)y * p.W + x0) * p.nv + r;
-        uint4 raw = *ptr;
+        uint4 raw = __ldcg(ptr);
         act_t* a = reinterpret_cast<act_t*>(&raw);
         const float g = gate[ty * kTW + tx];
 #pragma unroll
@@ -109,9 +114,7 @@ int launch_sa_stats(const SaArgs& a, cudaStream_t stream) {
     for (int i = 0; i < 2; ++i) { p.x[i] = a.x[i]; p.stats[i] = a.stats[i]; }
     p.npx = (long long)a.B * a.H * a.W; p.C = a.C; p.nv = a.pitch / 8;
     dim3 grid((unsigned)((p.npx + kStatPx - 1) / kStatPx), a.nprob);
-    sa_stats_kernel<<<grid, 256, 0, stream>>>(p);
-    CIDNET_CUDA_OK(cudaGetLastError());
-    return CIDNET_OK;
+    return launch_k(sa_stats_kernel, grid, dim3(256), 0, stream, p);
 }
 
 int launch_sa_gate(const SaArgs& a, cudaStream_t stream) {
@@ -122,9 +125,7 @@ int launch_sa_gate(const SaArgs& a, cudaStream_t stream) {
     p.B = a.B; p.H = a.H; p.W = a.W; p.nv = a.pitch / 8;
     CIDNET_CHECK((long long)a.B * a.nprob <= 65535, CIDNET_ERR_INVALID, "spatial attention: batch too large for one launch");
     dim3 grid(ceil_div(a.W, kTW), ceil_div(a.H, kTH), a.B * a.nprob);
-    sa_gate_kernel<<<grid, 256, 0, stream>>>(p);
-    CIDNET_CUDA_OK(cudaGetLastError());
-    return CIDNET_OK;
+    return launch_k(sa_gate_kernel, grid, dim3(256), 0, stream, p);
 }
 
 }  // namespace cidnet

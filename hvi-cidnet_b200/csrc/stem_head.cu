@@ -8,6 +8,7 @@
 //        = net/CIDNet.py:115,117,119,120.
 // Replicate padding == clamping the source coordinate, done while staging the tile.
 #include "stem_head.cuh"
+#include "ptx_sm100.cuh"
 #include "hvi_math.cuh"
 
 #include <cstdlib>
@@ -81,19 +82,21 @@ stem_mma_kernel(const float* __restrict__ rgb, float* __restrict__ hvi, act_t* _
     const int y0 = blockIdx.y * kTile, x0 = blockIdx.x * kTile;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, tig = lane & 3;
-    const float k = k_dev ? __ldg(k_dev) : k_host;
     const long long hw = (long long)H * W;
     const float* img = rgb + (long long)b * 3 * hw;
 
     if (tid < 3 * 5 * 32 / 2)      // per-lane B fragments, packed once at weight-finalisation time
         reinterpret_cast<uint4*>(&s_bfrag[0][0][0])[tid] = __ldg(reinterpret_cast<const uint4*>(bfrag) + tid);
+    ptx::pdl_wait();               // constants above; the image, k and the outputs belong to the stream's earlier work
+    ptx::pdl_trigger();
+    const float k = k_dev ? __ldcg(k_dev) : k_host;
     for (int i = tid; i < kHalo * kHalo; i += 256) {
         const int hy = i / kHalo, hx = i - hy * kHalo;
         const int y = min(max(y0 + hy - 1, 0), H - 1);
         const int x = min(max(x0 + hx - 1, 0), W - 1);
         const long long o = (long long)y * W + x;
         float hh, vv, ii;
-        hvit_px(img[o], img[o + hw], img[o + 2 * hw], k, hh, vv, ii);
+        hvit_px(__ldcg(img + o), __ldcg(img + o + hw), __ldcg(img + o + 2 * hw), k, hh, vv, ii);   // L2 loads: see ptx::pdl_wait
         s_hvi[i] = hh; s_hvi[kHalo * kHalo + i] = vv; s_hvi[2 * kHalo * kHalo + i] = ii;
     }
     __syncthreads();
@@ -226,10 +229,8 @@ const void* stem_kernel_func() { return reinterpret_cast<const void*>(&stem_mma_
 int launch_stem(const StemArgs& a, cudaStream_t stream) {
     CIDNET_CHECK(a.pitch == 40, CIDNET_ERR_INVALID, "stem: pitch must be 40");
     dim3 grid(ceil_div(a.W, kTile), ceil_div(a.H, kTile), a.B);
-    stem_mma_kernel<<<grid, 256, 0, stream>>>(a.rgb, a.hvi, a.i_enc0, a.hv_0, a.w_hv, a.w_i, a.k_dev, a.k_host,
-                                              a.H, a.W, a.pitch, a.bfrag);
-    CIDNET_CUDA_OK(cudaGetLastError());
-    return CIDNET_OK;
+    return launch_k(stem_mma_kernel, grid, dim3(256), 0, stream, a.rgb, a.hvi, a.i_enc0, a.hv_0, a.w_hv, a.w_i, a.k_dev,
+                    a.k_host, a.H, a.W, a.pitch, a.bfrag);
 }
 
 // ------------------------------------------------------------------ head ----
@@ -252,10 +253,12 @@ head_mma_kernel(const act_t* __restrict__ i_dec1, const act_t* __restrict__ hv_1
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, tig = lane & 3;
     const long long hw = (long long)H * W;
-    if (k_dev) pp.k = __ldg(k_dev);
 
     for (int i = tid; i < 2 * 9 * 3 * 32 / 2; i += 256)      // per-lane B fragments, packed once at weight-finalisation time
         reinterpret_cast<uint4*>(s_bfrag)[i] = __ldg(reinterpret_cast<const uint4*>(bfrag) + i);
+    ptx::pdl_wait();               // constants above; the activations and k belong to the stream's earlier work
+    ptx::pdl_trigger();
+    if (k_dev) pp.k = __ldcg(k_dev);
     // stage both halo tiles: a tile row is 18 pixels x 5 16-byte vectors; threads 0..179 copy two rows per step with a
     // fixed (pixel, vector) each -- no index arithmetic inside the loop
     if (tid < 180) {
@@ -327,7 +330,7 @@ head_mma_kernel(const act_t* __restrict__ i_dec1, const act_t* __restrict__ hv_1
     const float oi = res[lane * 3 + 0], oh = res[lane * 3 + 1], ov = res[lane * 3 + 2];
     const long long pix = (long long)y * W + x;
     const float* hp = hvi + (long long)b * 3 * hw + pix;
-    const float Hh = oh + hp[0], Vv = ov + hp[hw], Ii = oi + hp[2 * hw];   // cat([hv_0, i_dec0]) + hvi
+    const float Hh = oh + __ldcg(hp), Vv = ov + __ldcg(hp + hw), Ii = oi + __ldcg(hp + 2 * hw);   // cat([hv_0, i_dec0]) + hvi
     if (out_hvi_dbg) {
         float* d = out_hvi_dbg + (long long)b * 3 * hw + pix;
         d[0] = Hh; d[hw] = Vv; d[2 * hw] = Ii;
@@ -347,10 +350,8 @@ int launch_head(const HeadArgs& a, cudaStream_t stream) {
     const size_t smem = 2 * (kHalo * kHalo + 1) * 40 * sizeof(act_t) + 2 * 9 * 3 * 32 * sizeof(uint2) + 8 * 96 * sizeof(float);
     int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(head_mma_kernel), (int)smem);
     if (rc) return rc;
-    head_mma_kernel<<<grid, 256, smem, stream>>>(a.i_dec1, a.hv_1, a.hvi, a.rgb, a.out_hvi_dbg, a.w_i, a.w_hv, a.k_dev, pp,
-                                                 a.H, a.W, a.pitch, a.bfrag);
-    CIDNET_CUDA_OK(cudaGetLastError());
-    return CIDNET_OK;
+    return launch_k(head_mma_kernel, grid, dim3(256), smem, stream, a.i_dec1, a.hv_1, a.hvi, a.rgb, a.out_hvi_dbg, a.w_i,
+                    a.w_hv, a.k_dev, pp, a.H, a.W, a.pitch, a.bfrag);
 }
 
 }  // namespace cidnet

@@ -225,3 +225,21 @@ def test_two_contexts_in_one_process(model):
         b2 = other(x.to(dev2))
     assert torch.equal(a1, a2) and torch.equal(b1, b2) and not torch.equal(a1.cpu(), b1.cpu())
     _check(b1.cpu(), O.forward(x, O.make_state_dict(6, True)), x, O.make_state_dict(6, True))
+
+
+def test_repeated_forwards_are_bit_equal(model):
+    """Determinism stress (also the detector for launch-ordering holes: every kernel is launched with programmatic
+    stream serialization and may start before its predecessor has drained): 60 CUDA-graph replays alternating between
+    two inputs, plus eager launches in between, must reproduce the first results bit for bit."""
+    sd = O.make_state_dict(3, True)
+    model.load_state_dict(sd, strict=True)
+    xa = O.make_input("uniform", 1, 400, 600, seed=1).cuda()
+    xb = O.make_input("dark", 1, 400, 600, seed=2).cuda()
+    with torch.no_grad():
+        ya, yb = model(xa).clone(), model(xb).clone()
+        for i in range(60):
+            x, want = (xa, ya) if i % 2 == 0 else (xb, yb)
+            assert torch.equal(model(x), want), f"replay {i} differs"
+        # a different shape in between (new graph entry, eager first call), then back
+        model(O.make_input("uniform", 2, 64, 96, seed=3).cuda())
+        assert torch.equal(model(xa), ya) and torch.equal(model(xb), yb)
