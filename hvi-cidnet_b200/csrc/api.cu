@@ -652,7 +652,7 @@ struct Fwd {
             PackedWeights fw = Lw.fold_tmpl; fw.w = P.mfold[l][s]; fw.n_img = P.B > 1 ? P.B : 1;
             ConvGemmLaunch A;
             A.mode = EPI_STORE; A.in = P.vdw[l][s]; A.B = P.B; A.H = H; A.W = W; A.in_pitch = Cp; A.flat = true;
-            A.wt = &fw; A.out = P.xp[l][s]; A.out_pitch = Cp; A.in2 = x[s]; A.in2_pitch = Cp; A.wt2 = &ctx->eye[l];
+            A.wt = &fw; A.dynamic_weights = true; A.out = P.xp[l][s]; A.out_pitch = Cp; A.in2 = x[s]; A.in2_pitch = Cp; A.wt2 = &ctx->eye[l];
             if (P.B == 1) fw.n_img = 1;
             if ((rc = gemm(A, "L" + std::to_string(l) + ".cab_attnv_proj_res", s, both))) return rc;
             setm(P.xp[l][s], m_dw);

@@ -428,9 +428,11 @@ gram_kernel(const __grid_constant__ GramArgs a) {
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&empty[s]);
         }
-        // all MMAs have retired (and every TMA load was consumed before that): the pipeline stages are free
+        // all MMAs have retired (and every TMA load was consumed before that), and -- the barrier -- all four statistics
+        // warps have finished READING the last chunk: only then may stage 0 be re-used as s_ss
         ptx::mbar_wait(done, 0);
         ptx::tc_fence_after();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         // per-warp partials -> shared memory; the four are summed in a fixed order below
 #pragma unroll
         for (int j = 0; j < 3; ++j) {

@@ -42,6 +42,7 @@ struct ConvGemmArgs {
     int taps, kchunks, kchunks2, cin, cin2;
     int Hv, Wv, TH, TW, tiles_x, tiles_y, num_tiles;
     int n_out, block_n, stages, per_image_w, b_resident, stg_bufs;
+    int w_early;                     // resident weights are model constants: request them before the programmatic-dependency wait
     int halo;                        // 3x3: tile + halo loaded once per channel chunk, taps = row-shifted views
     int w_real;
     const float* bias; const float* wsum; float ln_eps;
@@ -176,17 +177,20 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // resident weights are CONSTANTS of the model (per-image folded weights are never resident): requested before the
-    // programmatic-dependency wait, they land while the previous kernel of the stream is still finishing
-    if (warp == 0 && lane == 0 && a.b_resident) {
+    // resident weights that are CONSTANTS of the model are requested before the programmatic-dependency wait: they land
+    // while the previous kernel of the stream is still finishing.  The attention's folded weights (written by
+    // cab_fold_kernel a moment ago; resident when the batch is 1) must wait like every activation.
+    auto load_resident_weights = [&]() {
         ptx::mbar_expect_tx(bfull, (uint32_t)nbchunks * b_chunk);
         for (int i = 0; i < nbchunks; ++i) {
             if (i < k1) ptx::tma_load_3d(smBres + (size_t)i * b_chunk, &a.tmB, bfull, i * 64, n0, 0);
             else        ptx::tma_load_3d(smBres + (size_t)i * b_chunk, &a.tmB2, bfull, (i - k1) * 64, n0, 0);
         }
-    }
+    };
+    if (warp == 0 && lane == 0 && a.b_resident && a.w_early) load_resident_weights();
     ptx::pdl_wait();
     ptx::pdl_trigger();
+    if (warp == 0 && lane == 0 && a.b_resident && !a.w_early) load_resident_weights();
 
     if (warp == 0) {
         // ------------------------------------------------------- TMA producer
@@ -631,6 +635,7 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
     a.bias = wt.bias; a.wsum = wt.wsum; a.ln_eps = L.ln_eps;
     a.prelu = L.prelu; a.use_prelu = L.use_prelu ? 1 : 0;
     a.w_real = L.W;
+    a.w_early = L.dynamic_weights ? 0 : 1;
     const long long hw = (long long)L.H * L.W;
     int rc;
 

@@ -46,6 +46,7 @@ struct ConvGemmLaunch {
     int B = 0, H = 0, W = 0, in_pitch = 0;
     bool flat = false;            // 1x1 only: tile over the flattened H*W axis (128 consecutive pixels)
     const PackedWeights* wt = nullptr;
+    bool dynamic_weights = false; // wt->w is written by an earlier kernel of the same forward (the CAB fold), not a model constant
     // output
     act_t* out = nullptr;
     int out_pitch = 0;

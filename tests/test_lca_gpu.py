@@ -87,3 +87,19 @@ def test_lca_stage_is_bit_reproducible(model):
         again = model.run_lca_stage(1, x_i, x_hv)
         for k in first:
             assert torch.equal(first[k], again[k]), k
+
+
+@pytest.mark.parametrize("H,W", [(320, 560), (104, 64), (200, 300)])
+def test_lca_stage_full_size_split_k_partitions(model, H, W):
+    """L1 at BASELINE configs[1] size (320x560 = 2800 pixel chunks -> 13 chunks per Gram CTA, the case where the last
+    chunk lives in pipeline stage 0) and two sizes with a ragged last chunk: the split-K partition must not matter."""
+    sd = O.make_state_dict(11, True)
+    g = torch.Generator().manual_seed(H)
+    x_i = _act_round(torch.randn(1, 36, H, W, generator=g) * 0.7 + 0.1)
+    x_hv = _act_round(torch.randn(1, 36, H, W, generator=g) * 0.5)
+    got = model.run_lca_stage(1, x_i.cuda(), x_hv.cuda())
+    for pfx, xa, xb, res, key in (("I_LCA1", x_i, x_hv, True, "i"), ("HV_LCA1", x_hv, x_i, False, "hv")):
+        ref_a, ref_o = _lca_ref(xa, xb, sd, pfx, 2, res, (0, H))
+        for name, ref, tol in ((f"after_cab_{key}", ref_a, 4e-3), (f"out_{key}", ref_o, 8e-3)):
+            rel = float((got[name].cpu() - ref).abs().max() / ref.abs().max())
+            assert rel <= tol, (name, rel)
