@@ -529,113 +529,142 @@ int launch_gram(const GramLaunch& L, cudaStream_t stream, int* nsplit_out) {
 }
 
 // ------------------------------------------------- slab reduction + fold ----
-// Sum `n` consecutive float4 / float loads spaced `stride` floats apart, in index order (unrolled by 8 so that
-// eight loads are in flight; the additions stay strictly sequential -> the result depends on nothing but the data).
+// Sum `n` float4 / float values spaced `stride` floats apart, in index order.  The loads of a batch are issued back to
+// back BEFORE the first addition (volatile asm keeps them ahead of the `pin` statements every addition depends on): left
+// to itself the compiler interleaved each L2 load with the additions of the previous one -- three loads in flight, one L2
+// round trip per three slab entries, 23 us for the L1 fold (SASS / ncu, profiles/r02_summary.md).  The additions stay
+// strictly sequential -> the result depends on nothing but the data.
+__device__ __forceinline__ float4 ldcg4_issue(const float* p) {
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void pin4(float4& a, float4& b, float4& c, float4& d) {
+    asm volatile("" : "+f"(a.x), "+f"(a.y), "+f"(a.z), "+f"(a.w), "+f"(b.x), "+f"(b.y), "+f"(b.z), "+f"(b.w),
+                      "+f"(c.x), "+f"(c.y), "+f"(c.z), "+f"(c.w), "+f"(d.x), "+f"(d.y), "+f"(d.z), "+f"(d.w));
+}
 __device__ __forceinline__ float4 ordered_sum4(const float* p, long long stride, int n) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int s = 0;
-    for (; s + 16 <= n; s += 16) {          // 16 L2 round trips in flight per thread: the loop is latency-, not bandwidth-bound
+    for (; s + 16 <= n; s += 16) {
         float4 v[16];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) v[u] = __ldcg(reinterpret_cast<const float4*>(p + (long long)(s + u) * stride));
+        for (int u = 0; u < 16; ++u) v[u] = ldcg4_issue(p + (long long)(s + u) * stride);
+#pragma unroll
+        for (int u = 0; u < 16; u += 4) pin4(v[u], v[u + 1], v[u + 2], v[u + 3]);
 #pragma unroll
         for (int u = 0; u < 16; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
     }
-    for (; s + 4 <= n; s += 4) {
-        float4 v[4];
+    if (s < n) {                              // ragged tail: still one batch, missing entries contribute +0
+        float4 v[16];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = __ldcg(reinterpret_cast<const float4*>(p + (long long)(s + u) * stride));
+        for (int u = 0; u < 16; ++u) v[u] = (s + u < n) ? ldcg4_issue(p + (long long)(s + u) * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
-    }
-    for (; s < n; ++s) {
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(p + (long long)s * stride));
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        for (int u = 0; u < 16; u += 4) pin4(v[u], v[u + 1], v[u + 2], v[u + 3]);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) if (s + u < n) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
     }
     return acc;
 }
 __device__ __forceinline__ float ordered_sum1(const float* p, long long stride, int n) {
     float acc = 0.f;
-    int s = 0;
-    for (; s + 16 <= n; s += 16) {
-        float v[16];
+    for (int s = 0; s < n; s += 16) {
+        float4 v[4];                          // 16 scalars of a batch, packed so that pin4 covers them
+        float* f = reinterpret_cast<float*>(v);
 #pragma unroll
-        for (int u = 0; u < 16; ++u) v[u] = __ldcg(p + (long long)(s + u) * stride);
+        for (int u = 0; u < 16; ++u) {
+            f[u] = 0.f;
+            if (s + u < n) asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(f[u]) : "l"(p + (long long)(s + u) * stride));
+        }
+        pin4(v[0], v[1], v[2], v[3]);
 #pragma unroll
-        for (int u = 0; u < 16; ++u) acc += v[u];
+        for (int u = 0; u < 16; ++u) if (s + u < n) acc += f[u];
     }
-    for (; s + 4 <= n; s += 4) {
-        float v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = __ldcg(p + (long long)(s + u) * stride);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) acc += v[u];
-    }
-    for (; s < n; ++s) acc += __ldcg(p + (long long)s * stride);
     return acc;
 }
 
 static constexpr int kFoldThreads = 512;
-static constexpr int kFoldGroups = 4;          // split groups summed independently, then combined in group order
+static constexpr int kFoldLanes = 4;           // split lanes per CTA (128 threads each): one 16-deep batch of loads per lane
+static constexpr int kFoldCluster = 4;         // CTAs per (problem, head, image): thread-block cluster along grid.z
 
-// grid (nprob * heads, B, kFoldSlices).  One CTA = a slice of the output rows of one head of one image of one problem;
-// every slice repeats the (cheap, L2-resident) reduction and softmax of its head -- the kernel is a chain of dependent
-// latencies, so more CTAs with less serial work each is what shortens it.
-__global__ void __launch_bounds__(kFoldThreads)
+// grid (nprob * heads, B, kFoldCluster), cluster (1, 1, kFoldCluster).  The kernel is a chain of dependent latencies (slab
+// loads -> softmax -> W_o -> store), not work; ncu on the first one-CTA-per-head version: 40 cycles of warp latency per
+// issued instruction, ~1000 dependent instructions per warp, 23 us.  So the chain is cut four ways twice:
+//   * the CTAs of a cluster each reduce a QUARTER of the split-K slab entries of their head, with four 128-thread lanes
+//     taking an eighth of that each -- nsplit <= 256 is one batch of <= 16 independent float4 loads per thread;
+//   * the four per-CTA partials are exchanged through distributed shared memory (one cluster barrier) and summed by
+//     every CTA in CTA-rank order; each CTA then runs the (tiny) softmax and folds its own quarter of the output rows.
+// All summation orders are fixed (split order inside a lane, lane order, CTA-rank order): bit-reproducible.
+__global__ void __launch_bounds__(kFoldThreads, 1)
 cab_fold_kernel(const CabFoldArgs a) {
-    __shared__ __align__(16) float s_part[kFoldGroups][368];   // per split group: [324 Gram | 18 sq | 18 sk] (+ pad)
+    __shared__ __align__(16) float s_lane[kFoldLanes][368];    // per lane: [324 Gram | 18 sq | 18 sk] (+ pad)
+    __shared__ __align__(16) float s_cta[368];                 // this CTA's partial (read by the whole cluster)
+    __shared__ float s_tot[368];
     __shared__ float s_attn[18 * 18];
+    __shared__ float s_wo[36 * 18];                            // W_o[o][head * 18 + c] of this CTA's output rows
     const int prob = blockIdx.x / a.heads, head = blockIdx.x - prob * a.heads, b = blockIdx.y;
+    const int rank = blockIdx.z;                               // == %cluster_ctarank: the cluster spans grid.z
     const int C = a.C, tid = threadIdx.x;
     const long long E = (long long)a.heads * 324 + 2 * a.Cp;
     const float* slab = a.slab + ((long long)prob * a.B + b) * a.nsplit * E;
     const float* wo = prob ? a.wo[1] : a.wo[0];
-    const int rows_per = (a.n_rows + gridDim.z - 1) / gridDim.z;
-    const int o_begin = blockIdx.z * rows_per, o_end = min(o_begin + rows_per, a.n_rows);
-    const int n_el = max(o_end - o_begin, 0) * 18;               // M elements of this CTA: [rows of the slice][18 columns]
-    // The kernel is a chain of dependent latencies (slab loads -> softmax -> W_o -> store), not work.  So: the W_o
-    // segments of this thread's first output elements are requested FIRST and arrive while the reduction runs.
-    constexpr int kPre = 2;
-    float wv[kPre][18];
-#pragma unroll
-    for (int u = 0; u < kPre; ++u) {
-        const int i = tid + u * kFoldThreads;
+    const int rows_per = (a.n_rows + kFoldCluster - 1) / kFoldCluster;         // <= 36
+    const int o_begin = rank * rows_per, o_end = min(o_begin + rows_per, a.n_rows);
+    const int n_el = max(o_end - o_begin, 0) * 18;             // M elements of this CTA: [rows of the slice][18 columns]
+    // W_o is a model constant: staged before the programmatic-dependency wait (it arrives while the Gram kernel drains)
+    for (int i = tid; i < n_el; i += kFoldThreads) {
         const int o = o_begin + i / 18;
-        const bool nz = i < n_el && o < C;
-#pragma unroll
-        for (int c = 0; c < 18; ++c) wv[u][c] = nz ? __ldg(wo + o * C + head * 18 + c) : 0.f;
+        s_wo[i] = o < C ? __ldg(wo + o * C + head * 18 + i % 18) : 0.f;
     }
-    ptx::pdl_wait();          // W_o (requested above) is a constant; the slab is the Gram kernel's output
+    ptx::pdl_wait();
     ptx::pdl_trigger();
-    // ---- fixed-order reduction of this head's [18x18 | sq | sk] over the split-K slab entries
+    // ---- this CTA's quarter of the slab entries, four lanes
     {
-        const int grp = tid >> 7, t = tid & 127;                // 4 groups of 128 threads
-        const int s0 = (a.nsplit * grp) / kFoldGroups, s1 = (a.nsplit * (grp + 1)) / kFoldGroups;
+        const int lane4 = tid >> 7, t = tid & 127;
+        const int c0 = (a.nsplit * rank) / kFoldCluster, c1 = (a.nsplit * (rank + 1)) / kFoldCluster;
+        const int n = c1 - c0;
+        const int s0 = c0 + (n * lane4) / kFoldLanes, s1 = c0 + (n * (lane4 + 1)) / kFoldLanes;
         const float* base = slab + (long long)s0 * E;
         if (t < 81) {
             const float4 v = ordered_sum4(base + head * 324 + 4 * t, E, s1 - s0);
-            *reinterpret_cast<float4*>(&s_part[grp][4 * t]) = v;
+            *reinterpret_cast<float4*>(&s_lane[lane4][4 * t]) = v;
         } else if (t < 81 + 36) {
             const int i = t - 81, which = i / 18, c = i - which * 18;
-            s_part[grp][324 + i] = ordered_sum1(base + a.heads * 324 + which * a.Cp + head * 18 + c, E, s1 - s0);
+            s_lane[lane4][324 + i] = ordered_sum1(base + a.heads * 324 + which * a.Cp + head * 18 + c, E, s1 - s0);
         }
     }
     __syncthreads();
-    if (tid < 360) s_part[0][tid] = ((s_part[0][tid] + s_part[1][tid]) + s_part[2][tid]) + s_part[3][tid];
-    __syncthreads();
-    if (a.raw_out && blockIdx.z == 0) {          // tests / taps: the reduced raw statistics of this head
-        float* ro = a.raw_out + ((long long)prob * a.B + b) * E;
-        if (tid < 324) ro[head * 324 + tid] = s_part[0][tid];
-        else if (tid < 360) { const int i = tid - 324, which = i / 18; ro[a.heads * 324 + which * a.Cp + head * 18 + (i - which * 18)] = s_part[0][tid]; }
+    if (tid < 360) s_cta[tid] = ((s_lane[0][tid] + s_lane[1][tid]) + s_lane[2][tid]) + s_lane[3][tid];
+    // ---- exchange the per-CTA partials through distributed shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (tid < 360) {
+        const uint32_t local = ptx::smem_u32(&s_cta[tid]);
+        float tot = 0.f;
+#pragma unroll
+        for (int r = 0; r < kFoldCluster; ++r) {
+            uint32_t remote; float v;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+            asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+            tot += v;
+        }
+        s_tot[tid] = tot;
+        if (a.raw_out && rank == 0) {          // tests / sharding: the reduced raw statistics of this head
+            float* ro = a.raw_out + ((long long)prob * a.B + b) * E;
+            if (tid < 324) ro[head * 324 + tid] = tot;
+            else { const int i = tid - 324, which = i / 18; ro[a.heads * 324 + which * a.Cp + head * 18 + (i - which * 18)] = tot; }
+        }
     }
+    // nobody may exit (and release its shared memory) before every CTA of the cluster has read it
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    __syncthreads();
     if (tid < 18) {
-        const float inv_nq = rsqrtf(fmaxf(s_part[0][324 + tid], 1e-24f));      // 1 / max(sqrt(sum q^2), 1e-12)
+        const float inv_nq = rsqrtf(fmaxf(s_tot[324 + tid], 1e-24f));      // 1 / max(sqrt(sum q^2), 1e-12)
         const float temp = __ldg((prob ? a.temp[1] : a.temp[0]) + head);
         float logit[18], mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 18; ++j) {
-            const float inv_nk = rsqrtf(fmaxf(s_part[0][342 + j], 1e-24f));
-            logit[j] = s_part[0][tid * 18 + j] * (inv_nq * inv_nk) * temp;
+            const float inv_nk = rsqrtf(fmaxf(s_tot[342 + j], 1e-24f));
+            logit[j] = s_tot[tid * 18 + j] * (inv_nq * inv_nk) * temp;
             mx = fmaxf(mx, logit[j]);
         }
         float sum = 0.f;
@@ -648,26 +677,14 @@ cab_fold_kernel(const CabFoldArgs a) {
     __syncthreads();
     // M[o][head*18 + j] = sum_c Wo[o][head*18 + c] * attn[c][j]; rows o >= C (N padding) are zero
     act_t* m = (prob ? a.m_out[1] : a.m_out[0]) + (long long)b * a.n_rows * a.kt + head * 18;
-#pragma unroll
-    for (int u = 0; u < kPre; ++u) {
-        const int i = tid + u * kFoldThreads;
-        if (i >= n_el) break;
-        const int o = o_begin + i / 18, j = i % 18;
+    for (int i = tid; i < n_el; i += kFoldThreads) {
+        const int r = i / 18, j = i - r * 18;
         float acc = 0.f;
 #pragma unroll
-        for (int c = 0; c < 18; ++c) acc = fmaf(wv[u][c], s_attn[c * 18 + j], acc);
-        m[(long long)o * a.kt + j] = f2act(acc);
+        for (int c = 0; c < 18; ++c) acc = fmaf(s_wo[r * 18 + c], s_attn[c * 18 + j], acc);
+        m[(long long)(o_begin + r) * a.kt + j] = f2act(acc);
     }
-    for (int i = tid + kPre * kFoldThreads; i < n_el; i += kFoldThreads) {
-        const int o = o_begin + i / 18, j = i % 18;
-        float acc = 0.f;
-        if (o < C) {
-#pragma unroll
-            for (int c = 0; c < 18; ++c) acc = fmaf(__ldg(wo + o * C + head * 18 + c), s_attn[c * 18 + j], acc);
-        }
-        m[(long long)o * a.kt + j] = f2act(acc);
-    }
-    // the K padding columns [C, kt) of every row: written (as zeros) by the last head's CTA
+    // the K padding columns [C, kt) of every row: written (as zeros) by the last head's CTAs
     if (head == a.heads - 1) {
         const int padw = a.kt - C;
         act_t* mp = (prob ? a.m_out[1] : a.m_out[0]) + (long long)b * a.n_rows * a.kt + C;
@@ -676,23 +693,20 @@ cab_fold_kernel(const CabFoldArgs a) {
             mp[(long long)o * a.kt + j] = f2act(0.f);
         }
     }
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 int launch_cab_fold(const CabFoldArgs& a, cudaStream_t stream) {
     CIDNET_CHECK(a.C <= 144 && a.C == a.heads * 18, CIDNET_ERR_INVALID, "fold: C must be heads * 18 <= 144");
     CIDNET_CHECK(a.slab != nullptr && a.nsplit >= 1, CIDNET_ERR_INVALID, "fold: null slab");
-    // row slices: <= ~2 output elements per thread (48 / 80 / 144 rows x 18 columns per head)
-    const int slices = std::max(1, std::min(8, ceil_div(a.n_rows * 18, 2 * kFoldThreads)));
-    dim3 grid(a.nprob * a.heads, a.B, slices);
-    int rc = launch_k(cab_fold_kernel, grid, dim3(kFoldThreads), 0, stream, a);
-    if (rc) return rc;
-    CIDNET_CUDA_OK(cudaGetLastError());
-    return CIDNET_OK;
+    CIDNET_CHECK(ceil_div(a.n_rows, kFoldCluster) <= 36, CIDNET_ERR_INVALID, "fold: too many output rows per CTA");
+    dim3 grid(a.nprob * a.heads, a.B, kFoldCluster);
+    return launch_k_cluster(cab_fold_kernel, grid, dim3(kFoldThreads), 0, stream, dim3(1, 1, kFoldCluster), a);
 }
 
 // Row-strip sharding: slab -> this rank's raw partial [Gram | sum q^2 | sum k^2] per (problem, image), laid out
 // exactly like ONE slab entry, so that after the host's all-reduce the fold runs on it with nsplit = 1.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 1)
 cab_reduce_kernel(const float* __restrict__ slab, float* __restrict__ out, int nsplit, int E4) {
     const long long E = 4ll * E4;
     ptx::pdl_wait();

@@ -64,19 +64,32 @@ int device_sm_count();
 // Kernel launch with (optionally) programmatic stream serialization: see ptx_sm100.cuh pdl_wait / pdl_trigger.  Only
 // kernels that execute pdl_wait() before touching non-constant global memory may be launched through this helper.
 bool pdl_enabled();            // CIDNET_PDL=0 turns the attribute off (A/B runs)
+// `cluster`: thread-block cluster dimensions (grid must be divisible by them); {1,1,1} = no cluster attribute.
 template <typename... KArgs, typename... Args>
-inline int launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+inline int launch_k_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, dim3 cluster,
+                            Args&&... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
+    unsigned n = 0;
     if (pdl_enabled()) {
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
     }
+    if (cluster.x * cluster.y * cluster.z > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster.x; attr[n].val.clusterDim.y = cluster.y; attr[n].val.clusterDim.z = cluster.z;
+        ++n;
+    }
+    cfg.attrs = attr; cfg.numAttrs = n;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
     if (e != cudaSuccess) return fail(CIDNET_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
     return CIDNET_OK;
+}
+template <typename... KArgs, typename... Args>
+inline int launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    return launch_k_cluster(kernel, grid, block, smem, stream, dim3(1, 1, 1), std::forward<Args>(args)...);
 }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
