@@ -275,7 +275,7 @@ def measure_cfg5_sharded(model, dev, world, rank, steps, warmup, parity=True):
     import torch.distributed as dist
     from hvi_cidnet_b200.dist import RowShardedCIDNet, strip_plan, strip_local_range
     B, H, W, desc = WORKLOADS["cfg5"]
-    net = RowShardedCIDNet(model, halo=16, graph=True)
+    net = RowShardedCIDNet(model, halo=16, graph=True, transport=os.environ.get("CIDNET_SHARD_TRANSPORT"))   # default: peer memory
     sh = strip_plan(H, world, rank, 16)
     a, b = strip_local_range(sh)
     g = torch.Generator().manual_seed(1234)
@@ -303,9 +303,23 @@ def measure_cfg5_sharded(model, dev, world, rank, steps, warmup, parity=True):
     barrier()
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
-    halo_calls = sum(1 for e in net.comm.log if e[0] == "halo")
-    ar_calls = sum(1 for e in net.comm.log if e[0] == "allreduce")
-    sent = net.comm.bytes_sent
+    if net.transport == "peer":
+        # the schedule is the library's (the same as the callback transport's): count it with the host-only dry run
+        import ctypes as C
+        from hvi_cidnet_b200 import _lib
+        L = _lib.lib()
+        nb = L.cidnet_workspace_bytes(1, b - a, W)
+        nh, na = C.c_int(), C.c_int()
+        dummy = (C.c_char * 2048)()
+        noop_h = _lib.HALO_FN(lambda u, r, n: 0)
+        noop_a = _lib.ALLREDUCE_FN(lambda u, p, c: 0)
+        base = (C.addressof(dummy) + 1023) & ~1023
+        L.cidnet_forward_sharded_dry(W, C.byref(sh), C.c_void_p(base), C.c_int64(1 << 62), noop_h, noop_a, None, C.byref(nh), C.byref(na))
+        halo_calls, ar_calls, sent = nh.value, na.value, None
+    else:
+        halo_calls = sum(1 for e in net.comm.log if e[0] == "halo")
+        ar_calls = sum(1 for e in net.comm.log if e[0] == "allreduce")
+        sent = net.comm.bytes_sent
     # end to end: pinned strip -> H2D -> sharded forward -> D2H of the owned rows
     hy = torch.empty(1, 3, sh.row_end - sh.row_begin, W).pin_memory()
     barrier()
@@ -320,6 +334,7 @@ def measure_cfg5_sharded(model, dev, world, rank, steps, warmup, parity=True):
     t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e = float(t[0]), float(t[1])
+    launches_per_step = model.num_launches()
     # in-run parity: gather the owned rows of image 0 on every rank, rank 0 compares with its own unsharded forward
     par = None
     if parity:
@@ -345,14 +360,17 @@ def measure_cfg5_sharded(model, dev, world, rank, steps, warmup, parity=True):
         dist.broadcast(pv, 0)
         par = {"parity_vs_unsharded_maxabs": float(pv[0]), "pixels_beyond_5e-4": int(pv[1])}
     mp_step = H * W / 1e6
-    res = {"workload": f"cfg5: CIDNet 1x3x{H}x{W}, rows sharded over {world} GPUs (halo 16 rows), CUDA-graph replay "
-                       f"of kernels + NCCL exchanges ({net.replays} replays)",
+    how = ("peer-memory transport: halo rows / attention statistics read from the neighbours' HBM over NVLink by the library's "
+           "own kernels, one CUDA graph per strip" if net.transport == "peer" else
+           f"NCCL send/recv + all-reduce from host callbacks, CUDA-graph replay of kernels + NCCL exchanges ({net.replays} replays)")
+    res = {"workload": f"cfg5: CIDNet 1x3x{H}x{W}, rows sharded over {world} GPUs (halo 16 rows), {how}",
+           "transport": net.transport, "peer_error": net.peer_error() if net.transport == "peer" else None,
            "ms_per_step": ms_total / steps, "MP/s": mp_step * steps / (ms_total / 1e3), "steps": steps, "warmup": nwarm,
            "halo_calls": halo_calls, "allreduce_calls": ar_calls, "bytes_sent": sent,
            "e2e_ms_per_step": ms_e2e / steps, "e2e_MP/s": mp_step * steps / (ms_e2e / 1e3),
            "h2d_bytes_per_step": hloc[0].numel() * 4, "d2h_bytes_per_step": hy.numel() * 4,
            "local_rows_rank0": strip_local_range(strip_plan(H, world, 0, 16))[1], "graph_replays": net.replays,
-           "graph_error": getattr(net, "graph_error", None), "launches_per_step": model.num_launches(), "clocks": clocks}
+           "graph_error": getattr(net, "graph_error", None), "launches_per_step": launches_per_step, "clocks": clocks}
     if par:
         res.update(par)
     net.close()

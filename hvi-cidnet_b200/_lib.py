@@ -58,6 +58,14 @@ SIGNATURES = {
                                              C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cidnet_forward_sharded_dry_variant": (C.c_int, [C.c_int, C.c_int, C.POINTER(Shard), C.c_void_p, C.c_int64, HALO_FN,
                                                      ALLREDUCE_FN, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "cidnet_peer_workspace_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "cidnet_peer_alloc": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
+    "cidnet_peer_open": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "cidnet_peer_close": (C.c_int, [C.c_void_p]),
+    "cidnet_peer_free": (C.c_int, [C.c_void_p]),
+    "cidnet_peer_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "cidnet_forward_sharded_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Shard), C.POINTER(C.c_void_p),
+                                              C.c_int64, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float, C.c_void_p]),
     "cidnet_pre_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "cidnet_post_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cidnet_read_tap": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int), C.c_void_p]),

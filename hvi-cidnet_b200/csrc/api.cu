@@ -6,6 +6,7 @@
 #include "cab.cuh"
 #include "conv_gemm.cuh"
 #include "iel.cuh"
+#include "peer.cuh"
 #include "sa.cuh"
 #include "stem_head.cuh"
 #include "weights.cuh"
@@ -80,6 +81,7 @@ struct cidnet_ctx {
     struct GraphEntry {
         int B = 0, H = 0, W = 0, gated = 0, gated2 = 0; float alpha_s = 0, alpha = 0;
         const void* ws = nullptr; const float* k_dev = nullptr;
+        uint64_t extra = 0;                   // sharded forwards: signature of the shard geometry and the peer mappings
         int seen = 0;                         // eager runs with this key before capturing
         cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
         cudaGraphNode_t stem_node = nullptr, head_node = nullptr;
@@ -370,6 +372,7 @@ struct Plan {
     float* slab;                                           // split-K partials of the stage in flight (cab.cuh)
     float2* sa_stats[2];                                   // MSSA: per-pixel (mean, max) of one up-block output per branch
     float* stat[6];                                        // per stage: reduced raw [Gram | sq | sk] per (problem, image)
+    float* statsum;                                        // peer transport: the cross-rank sum of the stage in flight
     int64_t bytes;
 };
 
@@ -413,7 +416,23 @@ void make_plan(Plan* P, void* ws, int B, int H, int W) {
         const int l = n <= 3 ? n : 7 - n;
         P->stat[n - 1] = bp.take<float>((int64_t)2 * B * (kHeads[l] * 324 + 2 * act_pitch(kCh[l])));
     }
+    P->statsum = bp.take<float>((int64_t)2 * B * (8 * 324 + 2 * 144));
     P->bytes = bp.off + 1024;
+}
+
+// every NHWC activation of a plan in a fixed order: index i of one rank's list is the same tensor as index i of another's
+std::vector<const void*> plan_tensors(const Plan& P) {
+    std::vector<const void*> v = {P.i_enc0, P.hv_0, P.id1, P.hvd1};
+    for (int l = 1; l <= 3; ++l) {
+        v.push_back(P.enc_i[l]); v.push_back(P.enc_hv[l]); v.push_back(P.tup_i[l]); v.push_back(P.tup_hv[l]);
+        if (l <= 2) { v.push_back(P.dec_i[l]); v.push_back(P.dec_hv[l]); }
+        for (int s = 0; s < 2; ++s) {
+            v.push_back(P.qkv[l][s]); v.push_back(P.qk[l][s]); v.push_back(P.vdw[l][s]); v.push_back(P.xp[l][s]);
+            v.push_back(P.tin[l][s]); v.push_back(P.g[l][s]);
+        }
+    }
+    for (int n = 1; n <= 6; ++n) { v.push_back(P.lca_i[n]); v.push_back(P.lca_hv[n]); }
+    return v;
 }
 
 // ---------------------------------------------------------------- forward ---
@@ -428,6 +447,12 @@ struct ShardState {
     cidnet_halo_fn halo_fn = nullptr; cidnet_allreduce_fn ar_fn = nullptr; void* user = nullptr;
     std::map<const void*, int> margin;
     int halo_calls = 0, allreduce_calls = 0;
+    // peer-memory transport (cidnet_forward_sharded_peer): every rank's workspace is mapped into this process
+    bool peer = false;
+    uint8_t* ws_all[kPeerMaxRanks] = {};       // [r]: this process's mapping of rank r's workspace (header first, plan after it)
+    std::vector<Plan> plans;                   // every rank's plan (addresses inside ws_all[r])
+    std::vector<cidnet_shard> shards;          // every rank's shard geometry
+    int64_t halo_bytes = 0;
 };
 struct HaloT { const void* p; int level; int pitch; };
 static const int kNoLimit = 1 << 28;
@@ -466,7 +491,7 @@ struct Fwd {
             cidnet_halo_req r;
             r.base = const_cast<void*>(t.p);
             r.row_bytes = (int64_t)P.W[t.level] * t.pitch * (int64_t)sizeof(act_t);
-            r.rows = P.H[t.level]; r.halo_top = ht(t.level); r.halo_bot = hb(t.level);
+            r.rows = P.H[t.level]; r.halo_top = ht(t.level); r.halo_bot = hb(t.level); r.reserved = t.level;
             reqs.push_back(r);
             const int full = (sh.halo_top > 0 ? sh.halo_top : sh.halo_bot) >> t.level;
             CIDNET_CHECK(full >= need, CIDNET_ERR_INVALID, "forward_sharded: halo too small for this stage");
@@ -474,9 +499,60 @@ struct Fwd {
         }
         if (reqs.empty()) return CIDNET_OK;
         ++sh.halo_calls;
+        if (sh.peer) return peer_halo(reqs);
         const int rc = sh.halo_fn(sh.user, reqs.data(), (int)reqs.size());
         CIDNET_CHECK(rc == 0, CIDNET_ERR_STATE, "forward_sharded: halo exchange callback failed (" + std::to_string(rc) + ")");
         return CIDNET_OK;
+    }
+
+    // ---- peer-memory transport -------------------------------------------------------------------------------------
+    void peer_sync(PeerSync* ps, bool all_ranks) {
+        ps->me = reinterpret_cast<PeerHdr*>(sh.ws_all[sh.rank]);
+        ps->rank = sh.rank; ps->npartners = 0;
+        for (int r = 0; r < sh.nranks; ++r) {
+            if (r == sh.rank || (!all_ranks && r != sh.rank - 1 && r != sh.rank + 1)) continue;
+            ps->partner[ps->npartners] = reinterpret_cast<PeerHdr*>(sh.ws_all[r]);
+            ps->partner_rank[ps->npartners++] = r;
+        }
+    }
+    // pull the neighbours' boundary rows of the requested tensors into this rank's halo rows (one kernel)
+    int peer_halo(const std::vector<cidnet_halo_req>& reqs) {
+        PeerHaloArgs a; memset(&a, 0, sizeof a);
+        peer_sync(&a.sync, false);
+        const std::vector<const void*> mine = plan_tensors(P);
+        for (const cidnet_halo_req& q : reqs) {
+            size_t idx = 0;
+            while (idx < mine.size() && mine[idx] != q.base) ++idx;
+            CIDNET_CHECK(idx < mine.size(), CIDNET_ERR_STATE, "forward_sharded_peer: halo request for an unknown tensor");
+            uint8_t* base = reinterpret_cast<uint8_t*>(q.base);
+            for (int dir = 0; dir < 2; ++dir) {               // 0: rows from rank - 1 (top halo), 1: from rank + 1 (bottom halo)
+                const int h = dir == 0 ? q.halo_top : q.halo_bot;
+                if (h == 0) continue;
+                const int nb = dir == 0 ? sh.rank - 1 : sh.rank + 1;
+                const cidnet_shard& ns = sh.shards[nb];
+                // the neighbour's local image at this tensor's level: [its top halo | its owned rows | its bottom halo]
+                const int lvl_shift = q.reserved;             // the tensor's level (set by ensure())
+                const int n_top = ((nb > 0 ? ns.halo : 0) >> lvl_shift), n_own = (ns.row_end - ns.row_begin) >> lvl_shift;
+                const int src_row = dir == 0 ? n_top + n_own - h : n_top;
+                const int dst_row = dir == 0 ? 0 : q.rows - h;
+                const uint8_t* nbase = reinterpret_cast<const uint8_t*>(plan_tensors(sh.plans[nb])[idx]);
+                CIDNET_CHECK(a.njobs < kPeerMaxJobs, CIDNET_ERR_STATE, "forward_sharded_peer: too many halo jobs");
+                a.job[a.njobs++] = PeerCopyJob{base + (int64_t)dst_row * q.row_bytes, nbase + (int64_t)src_row * q.row_bytes,
+                                               (long long)h * q.row_bytes};
+                sh.halo_bytes += (int64_t)h * q.row_bytes;
+            }
+        }
+        ++launches;
+        return live() ? launch_peer_halo(a, st) : CIDNET_OK;
+    }
+    // sum the ranks' partial statistics vectors (rank order) into P.statsum
+    int peer_allreduce(int stage, int count) {
+        PeerReduceArgs a; memset(&a, 0, sizeof a);
+        peer_sync(&a.sync, true);
+        for (int r = 0; r < sh.nranks; ++r) a.src[r] = sh.plans[r].stat[stage];
+        a.dst = P.statsum; a.count = count; a.nranks = sh.nranks;
+        ++launches;
+        return live() ? launch_peer_allreduce(a, st) : CIDNET_OK;
     }
 
     void tap(const std::string& name, const void* p, int C, int l, int pitch, bool f32 = false) {
@@ -625,8 +701,12 @@ struct Fwd {
                 ++launches;
                 if (live() && (rc = launch_cab_reduce(P.slab, P.stat[n - 1], nsplit, E, np * P.B, st))) return rc;
                 ++sh.allreduce_calls;
-                const int arc = sh.ar_fn(sh.user, P.stat[n - 1], (int64_t)np * P.B * E);
-                CIDNET_CHECK(arc == 0, CIDNET_ERR_STATE, "forward_sharded: all-reduce callback failed (" + std::to_string(arc) + ")");
+                if (sh.peer) {
+                    if ((rc = peer_allreduce(n - 1, np * P.B * E))) return rc;
+                } else {
+                    const int arc = sh.ar_fn(sh.user, P.stat[n - 1], (int64_t)np * P.B * E);
+                    CIDNET_CHECK(arc == 0, CIDNET_ERR_STATE, "forward_sharded: all-reduce callback failed (" + std::to_string(arc) + ")");
+                }
             }
         }
         // 3. fixed-order sum of the split-K partials, normalise + temperature + softmax + fold into project_out
@@ -636,7 +716,7 @@ struct Fwd {
                 const int s = probs[i];
                 f.temp[i] = S.lca[s].temp; f.wo[i] = S.lca[s].wo; f.m_out[i] = P.mfold[l][s];
             }
-            if (split()) { f.slab = P.stat[n - 1]; f.nsplit = 1; f.raw_out = nullptr; }
+            if (split()) { f.slab = sh.peer ? P.statsum : P.stat[n - 1]; f.nsplit = 1; f.raw_out = nullptr; }
             else         { f.slab = P.slab; f.nsplit = nsplit; f.raw_out = P.stat[n - 1]; }
             const PackedWeights& t = S.lca[probs[0]].fold_tmpl;
             f.B = P.B; f.C = C; f.Cp = Cp; f.heads = heads; f.nprob = np; f.n_rows = t.n_rows; f.kt = t.ktot();
@@ -658,8 +738,11 @@ struct Fwd {
             setm(P.xp[l][s], m_dw);
             tap(std::string(s == 0 ? "I_LCA" : "HV_LCA") + std::to_string(n) + ".after_cab", P.xp[l][s], C, l, Cp);
         }
-        // the IEL gate chains two depthwise 3x3: two valid halo rows of x' (project_in is recomputed on them)
+        // the IEL gate chains two depthwise 3x3: two valid halo rows of x' (project_in is recomputed on them).  The exchange
+        // is issued on the main stream: both branches must have produced their x' first
+        if (split()) join();
         if ((rc = ensure({{S.lca[0].live ? P.xp[l][0] : nullptr, l, Cp}, {P.xp[l][1], l, Cp}}, 2))) return rc;
+        if (split()) fork();
         for (int i = 0; i < np; ++i) {
             const int s = probs[i];
             LcaWeights& Lw = S.lca[s];
@@ -857,35 +940,21 @@ extern "C" int64_t cidnet_workspace_bytes(int B, int H, int W) {
     return P.bytes;
 }
 
-extern "C" int cidnet_forward(cidnet_ctx* ctx, const float* rgb_in, float* rgb_out, int B, int H, int W,
-                              void* workspace, int64_t workspace_bytes, const float* k_dev,
-                              int gated, float alpha_s, int gated2, float alpha, void* stream) {
-    CIDNET_CHECK(ctx, CIDNET_ERR_INVALID, "forward: null ctx");
-    CIDNET_CHECK(ctx->finalized, CIDNET_ERR_STATE, "forward: weights not finalized (call cidnet_finalize_weights)");
-    CIDNET_CHECK(B >= 0 && H > 0 && W > 0, CIDNET_ERR_INVALID, "forward: bad shape");
-    CIDNET_CHECK(H % 8 == 0 && W % 8 == 0, CIDNET_ERR_INVALID,
-                 "forward: H and W must be multiples of 8 (got " + std::to_string(H) + "x" + std::to_string(W) +
-                     "); the reference fails in torch.cat for such inputs, callers pad first");
-    if (B == 0) return CIDNET_OK;
-    DeviceGuard guard(ctx->device);
-    CIDNET_CHECK(rgb_in && rgb_out && workspace, CIDNET_ERR_INVALID, "forward: null pointer");
-    CIDNET_CHECK((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, CIDNET_ERR_INVALID, "forward: workspace must be 1024-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
-    Fwd f;
-    f.ctx = ctx; f.st = st;
-    make_plan(&f.P, workspace, B, H, W);
-    CIDNET_CHECK(workspace_bytes >= f.P.bytes, CIDNET_ERR_STATE,
-                 "forward: workspace too small: need " + std::to_string(f.P.bytes) + " bytes");
-    ctx->last_B = B;
-
-    // ---- CUDA-graph path (skipped while profiling, inside somebody else's capture, or when disabled)
+// One forward of an already planned executor `f` (unsharded, or a row strip with the peer-memory transport): replayed as a
+// CUDA graph when possible -- one entry per (shape, workspace, flags, extra); the input / output image pointers are patched
+// into the stem / head kernel nodes when they change.  Skipped while profiling, inside somebody else's capture, or when
+// graphs are disabled: then the launches go out eagerly.
+static int run_forward_cached(cidnet_ctx* ctx, Fwd& f, uint64_t extra, const float* rgb_in, float* rgb_out, const float* k_dev,
+                              int gated, float alpha_s, int gated2, float alpha, cudaStream_t st) {
+    const int B = f.P.B, H = f.P.H[0], W = f.P.W[0];
+    const void* workspace = f.P.hvi;                       // first tensor of the plan: identifies the workspace
     cidnet_ctx::GraphEntry* ge = nullptr;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (ctx->use_graphs && !ctx->profiling && cudaStreamIsCapturing(st, &cap) == cudaSuccess &&
         cap == cudaStreamCaptureStatusNone) {
         for (auto* g : ctx->graphs)
             if (g->B == B && g->H == H && g->W == W && g->ws == workspace && g->k_dev == k_dev && g->gated == gated &&
-                g->gated2 == gated2 && g->alpha_s == alpha_s && g->alpha == alpha) { ge = g; break; }
+                g->gated2 == gated2 && g->alpha_s == alpha_s && g->alpha == alpha && g->extra == extra) { ge = g; break; }
         if (!ge) {
             if (ctx->graphs.size() >= 8) {                    // evict the least recently used entry
                 size_t lru = 0;
@@ -898,7 +967,7 @@ extern "C" int cidnet_forward(cidnet_ctx* ctx, const float* rgb_in, float* rgb_o
             }
             ge = new cidnet_ctx::GraphEntry();
             ge->B = B; ge->H = H; ge->W = W; ge->ws = workspace; ge->k_dev = k_dev; ge->gated = gated; ge->gated2 = gated2;
-            ge->alpha_s = alpha_s; ge->alpha = alpha;
+            ge->alpha_s = alpha_s; ge->alpha = alpha; ge->extra = extra;
             ctx->graphs.push_back(ge);
         }
         ge->last_use = ++ctx->use_clock;
@@ -940,6 +1009,7 @@ extern "C" int cidnet_forward(cidnet_ctx* ctx, const float* rgb_in, float* rgb_o
         f.st = ctx->cap_stream;
         CIDNET_CUDA_OK(cudaStreamBeginCapture(f.st, cudaStreamCaptureModeRelaxed));
     }
+    const std::map<const void*, int> margin0 = f.sh.margin;
     int rc = f.run(rgb_in, rgb_out, k_dev, gated, alpha_s, gated2, alpha);
     ctx->launches = f.launches;
     if (capture) {
@@ -973,6 +1043,7 @@ extern "C" int cidnet_forward(cidnet_ctx* ctx, const float* rgb_in, float* rgb_o
             cudaGraphDestroy(graph);
             ge->seen = -1000000;
             f.par = false;
+            f.sh.margin = margin0; f.sh.halo_calls = f.sh.allreduce_calls = 0; f.launches = 0;
             return f.run(rgb_in, rgb_out, k_dev, gated, alpha_s, gated2, alpha);
         }
         ge->graph = graph; ge->exec = exec;
@@ -982,6 +1053,29 @@ extern "C" int cidnet_forward(cidnet_ctx* ctx, const float* rgb_in, float* rgb_o
         return CIDNET_OK;
     }
     return rc;
+}
+
+extern "C" int cidnet_forward(cidnet_ctx* ctx, const float* rgb_in, float* rgb_out, int B, int H, int W,
+                              void* workspace, int64_t workspace_bytes, const float* k_dev,
+                              int gated, float alpha_s, int gated2, float alpha, void* stream) {
+    CIDNET_CHECK(ctx, CIDNET_ERR_INVALID, "forward: null ctx");
+    CIDNET_CHECK(ctx->finalized, CIDNET_ERR_STATE, "forward: weights not finalized (call cidnet_finalize_weights)");
+    CIDNET_CHECK(B >= 0 && H > 0 && W > 0, CIDNET_ERR_INVALID, "forward: bad shape");
+    CIDNET_CHECK(H % 8 == 0 && W % 8 == 0, CIDNET_ERR_INVALID,
+                 "forward: H and W must be multiples of 8 (got " + std::to_string(H) + "x" + std::to_string(W) +
+                     "); the reference fails in torch.cat for such inputs, callers pad first");
+    if (B == 0) return CIDNET_OK;
+    DeviceGuard guard(ctx->device);
+    CIDNET_CHECK(rgb_in && rgb_out && workspace, CIDNET_ERR_INVALID, "forward: null pointer");
+    CIDNET_CHECK((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, CIDNET_ERR_INVALID, "forward: workspace must be 1024-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    Fwd f;
+    f.ctx = ctx; f.st = st;
+    make_plan(&f.P, workspace, B, H, W);
+    CIDNET_CHECK(workspace_bytes >= f.P.bytes, CIDNET_ERR_STATE,
+                 "forward: workspace too small: need " + std::to_string(f.P.bytes) + " bytes");
+    ctx->last_B = B;
+    return run_forward_cached(ctx, f, 0, rgb_in, rgb_out, k_dev, gated, alpha_s, gated2, alpha, st);
 }
 
 // ---- row-strip sharded forward (single image over the GPUs of one node) -------------------
@@ -1050,6 +1144,56 @@ extern "C" int cidnet_forward_sharded(cidnet_ctx* ctx, const float* rgb_local, f
     ctx->recs.clear();
     rc = f.run(rgb_local, rgb_out_local, k_dev, gated, alpha_s, gated2, alpha);
     ctx->launches = f.launches;
+    return rc;
+}
+
+// ---- the same with the peer-memory transport: no host callbacks, the exchanges are kernels of this library --------
+extern "C" int64_t cidnet_peer_workspace_bytes(int H_global, int W, int nranks, int halo) {
+    // one size for every rank (the largest strip) + the synchronisation header
+    int64_t mx = 0;
+    for (int r = 0; r < nranks; ++r) {
+        cidnet_shard s;
+        if (cidnet_shard_plan(H_global, nranks, r, halo, &s)) return 0;
+        Plan P;
+        make_plan(&P, nullptr, 1, cidnet_shard_local_rows(&s), W);
+        mx = std::max(mx, P.bytes);
+    }
+    return mx + kPeerHdrBytes;
+}
+
+extern "C" int cidnet_forward_sharded_peer(cidnet_ctx* ctx, const float* rgb_local, float* rgb_out_local, int W,
+                                           const cidnet_shard* sh, void* const* ws_all, int64_t ws_bytes,
+                                           const float* k_dev, int gated, float alpha_s, int gated2, float alpha,
+                                           void* stream) {
+    CIDNET_CHECK(ctx, CIDNET_ERR_INVALID, "forward_sharded_peer: null ctx");
+    CIDNET_CHECK(ctx->finalized, CIDNET_ERR_STATE, "forward_sharded_peer: weights not finalized (call cidnet_finalize_weights)");
+    int rc = check_shard(sh, W);
+    if (rc) return rc;
+    CIDNET_CHECK(sh->nranks <= kPeerMaxRanks && ws_all && rgb_local && rgb_out_local, CIDNET_ERR_INVALID,
+                 "forward_sharded_peer: bad arguments (at most 8 ranks)");
+    CIDNET_CHECK(ws_bytes >= cidnet_peer_workspace_bytes(sh->H_global, W, sh->nranks, sh->halo), CIDNET_ERR_STATE,
+                 "forward_sharded_peer: workspace too small (cidnet_peer_workspace_bytes)");
+    DeviceGuard guard(ctx->device);
+    Fwd f;
+    f.ctx = ctx; f.st = (cudaStream_t)stream;
+    shard_state(sh, &f.sh);
+    f.sh.peer = sh->nranks > 1;
+    uint64_t sig = 1469598103934665603ull;                     // FNV-1a over the shard geometry and the mappings
+    auto mix = [&](uint64_t v) { sig = (sig ^ v) * 1099511628211ull; };
+    mix((uint64_t)sh->rank); mix((uint64_t)sh->nranks); mix((uint64_t)sh->H_global); mix((uint64_t)sh->row_begin);
+    mix((uint64_t)sh->row_end); mix((uint64_t)sh->halo);
+    f.sh.plans.resize(sh->nranks); f.sh.shards.resize(sh->nranks);
+    for (int r = 0; r < sh->nranks; ++r) {
+        CIDNET_CHECK(ws_all[r] && (reinterpret_cast<uintptr_t>(ws_all[r]) & 1023) == 0, CIDNET_ERR_INVALID,
+                     "forward_sharded_peer: every rank's workspace mapping must be non-null and 1024-byte aligned");
+        f.sh.ws_all[r] = reinterpret_cast<uint8_t*>(ws_all[r]);
+        if ((rc = cidnet_shard_plan(sh->H_global, sh->nranks, r, sh->halo, &f.sh.shards[r]))) return rc;
+        make_plan(&f.sh.plans[r], f.sh.ws_all[r] + kPeerHdrBytes, 1, cidnet_shard_local_rows(&f.sh.shards[r]), W);
+        mix(reinterpret_cast<uint64_t>(ws_all[r]));
+    }
+    f.P = f.sh.plans[sh->rank];
+    ctx->last_B = 1;
+    rc = run_forward_cached(ctx, f, sig | 1ull, rgb_local, rgb_out_local, k_dev, gated, alpha_s, gated2, alpha, (cudaStream_t)stream);
     return rc;
 }
 

@@ -165,7 +165,13 @@ class RowShardedCIDNet:
     gloo-staged transport of the single-GPU tests copies through the host and cannot be captured).
     """
 
-    def __init__(self, model, group=None, halo=16, graph=None):
+    def __init__(self, model, group=None, halo=16, graph=None, transport=None):
+        """transport: "peer" -- the strips' workspaces are CUDA-IPC mapped into every rank and the halo rows / partial
+        attention statistics are read straight from the neighbours' memory by kernels of the library (no NCCL on the data
+        path, the strip forward is one CUDA graph inside the library; needs one GPU per rank on one node);
+        "callbacks" -- torch.distributed send/recv + all_reduce issued from the library's host callbacks (NCCL, or gloo
+        staged through the host); None -- "peer" when every rank has its own GPU and the group is NCCL, else "callbacks"
+        (CIDNET_SHARD_TRANSPORT overrides)."""
         import os
         self.model, self.group, self.halo = model, group, int(halo)
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -175,14 +181,91 @@ class RowShardedCIDNet:
         self.use_graph = bool(graph) if graph is not None else os.environ.get("CIDNET_SHARD_GRAPH", "0") == "1"
         self._graphs = {}                 # key -> dict(seen, g, x, out, sig)
         self.replays = 0
+        transport = transport or os.environ.get("CIDNET_SHARD_TRANSPORT")
+        if transport is None:
+            own_gpu = (torch.cuda.is_available() and self.world > 1 and self.world <= torch.cuda.device_count()
+                       and dist.is_initialized() and dist.get_backend(group) == "nccl")
+            transport = "peer" if own_gpu else "callbacks"
+        if transport not in ("peer", "callbacks"):
+            raise ValueError(f"unknown transport {transport!r}")
+        self.transport = transport if self.world > 1 else "callbacks"
+        self._peer = {}                   # (H, W, device) -> dict(own, ptrs, arr, nbytes)
+        self.peer_forwards = 0
 
     def close(self):
-        """Drop the captured CUDA graphs.  Call before `dist.destroy_process_group()`: tearing the NCCL
-        communicator down while instantiated graphs still hold its kernels blocks (measured: the 2-rank probe hung
-        in destroy_process_group until the graphs were released first)."""
-        if self._graphs:
+        """Drop the captured CUDA graphs and the peer mappings.  Call before `dist.destroy_process_group()`: tearing the
+        NCCL communicator down while instantiated graphs still hold its kernels blocks (measured: the 2-rank probe hung
+        in destroy_process_group until the graphs were released first); the peer workspaces are unmapped by every rank
+        before their owners free them (barrier)."""
+        if self._graphs or self._peer:
             torch.cuda.synchronize()
         self._graphs = {}
+        if self._peer:
+            L = _clib()
+            for ent in self._peer.values():
+                for r, p in enumerate(ent["ptrs"]):
+                    if r != self.rank and p:
+                        L.lib().cidnet_peer_close(_C.c_void_p(p))
+            if dist.is_initialized():
+                dist.barrier(group=self.group)
+            for ent in self._peer.values():
+                L.lib().cidnet_peer_free(_C.c_void_p(ent["own"]))
+            self._peer = {}
+
+    # ------------------------------------------------------------------ peer-memory transport
+    def _peer_setup(self, H_global, W, dev):
+        """allocate this rank's strip workspace, exchange the CUDA IPC handles, map every other rank's workspace"""
+        key = (int(H_global), int(W), str(dev))
+        ent = self._peer.get(key)
+        if ent is not None:
+            return ent
+        L = _clib()
+        lib = L.lib()
+        nbytes = int(lib.cidnet_peer_workspace_bytes(int(H_global), int(W), self.world, self.halo))
+        if nbytes <= 0:
+            raise RuntimeError("cidnet_peer_workspace_bytes failed: " + lib.cidnet_last_error().decode())
+        own = _C.c_void_p()
+        handle = _C.create_string_buffer(64)
+        L.check(lib.cidnet_peer_alloc(dev.index, nbytes, _C.byref(own), handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=self.group)
+        ptrs = []
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs.append(own.value)
+            else:
+                p = _C.c_void_p()
+                L.check(lib.cidnet_peer_open(dev.index, handles[r], _C.byref(p)))
+                ptrs.append(p.value)
+        dist.barrier(group=self.group)                      # everybody has mapped everybody before the first exchange
+        ent = {"own": own.value, "ptrs": ptrs, "arr": (_C.c_void_p * self.world)(*ptrs), "nbytes": nbytes}
+        self._peer = {key: ent}
+        return ent
+
+    def peer_error(self):
+        """1 if a handshake of the peer transport timed out (a partner never arrived), else 0"""
+        L = _clib()
+        err = _C.c_int(0)
+        for ent in self._peer.values():
+            L.check(L.lib().cidnet_peer_error(_C.c_void_p(ent["own"]), _C.byref(err)))
+        return int(err.value)
+
+    def _forward_strip_peer(self, x_local, H_global, sh, rows):
+        L = _clib()
+        m, t = self.model, self.model.trans
+        dev = x_local.device
+        W = x_local.shape[3]
+        with torch.cuda.device(dev):
+            ctx = m._ensure_ctx(dev)
+            ent = self._peer_setup(H_global, W, dev)
+            t._note_hvit_called()
+            kd = t.density_k.detach() if t.density_k.dtype == torch.float32 else t._this_k_dev
+            out = torch.empty_like(x_local)
+            L.check(L.lib().cidnet_forward_sharded_peer(
+                ctx, x_local.data_ptr(), out.data_ptr(), W, _C.byref(sh), ent["arr"], ent["nbytes"], kd.data_ptr(),
+                int(bool(t.gated)), float(t.alpha_s), int(bool(t.gated2)), float(t.alpha), L.stream_ptr(dev)))
+            self.peer_forwards += 1
+        return out, sh
 
     def _workspace(self, rows, W, device):
         key = (rows, W, str(device))
@@ -207,6 +290,8 @@ class RowShardedCIDNet:
         W = x_local.shape[3]
         x_local = x_local.contiguous()
         t = m.trans
+        if self.transport == "peer" and self.world > 1:
+            return self._forward_strip_peer(x_local, H_global, sh, rows)
         with torch.cuda.device(dev):
             ctx = m._ensure_ctx(dev)
             ws, comm = self._workspace(rows, W, dev)

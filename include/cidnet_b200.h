@@ -141,6 +141,24 @@ CIDNET_API int cidnet_forward_sharded(cidnet_ctx* ctx, const float* rgb_local, f
                                       const float* k_dev, int gated, float alpha_s, int gated2, float alpha,
                                       cidnet_halo_fn halo_fn, cidnet_allreduce_fn allreduce_fn, void* user,
                                       void* stream);
+/* ---- the same forward with the PEER-MEMORY transport (no host callbacks, no NCCL on the data path) -------------
+ * Every rank allocates its workspace with cidnet_peer_alloc (one cudaMalloc'ed block of cidnet_peer_workspace_bytes,
+ * zero-initialised; the first 4 KB are a synchronisation header) and hands the 64-byte CUDA IPC handle to the other
+ * ranks of the node, which map it with cidnet_peer_open.  ws_all[r] is THIS process's pointer to rank r's workspace
+ * (ws_all[rank] = the own allocation).  The halo rows and the partial attention statistics are then read straight from
+ * the neighbours' memory over NVLink by two kernels of this library (csrc/peer.cu: flag handshake, rank-ordered sums),
+ * and the whole strip forward replays as ONE CUDA graph.  Every rank must call this the same number of times with the
+ * same geometry (the exchange counters advance in lockstep).  cidnet_peer_error reports a timed-out handshake. */
+CIDNET_API int64_t cidnet_peer_workspace_bytes(int H_global, int W, int nranks, int halo);
+CIDNET_API int cidnet_peer_alloc(int device, int64_t bytes, void** dev_ptr, void* handle64);
+CIDNET_API int cidnet_peer_open(int device, const void* handle64, void** dev_ptr);
+CIDNET_API int cidnet_peer_close(void* dev_ptr);
+CIDNET_API int cidnet_peer_free(void* dev_ptr);
+CIDNET_API int cidnet_peer_error(const void* own_ws, int* error_out);
+CIDNET_API int cidnet_forward_sharded_peer(cidnet_ctx* ctx, const float* rgb_local, float* rgb_out_local, int W,
+                                           const cidnet_shard* sh, void* const* ws_all, int64_t ws_bytes,
+                                           const float* k_dev, int gated, float alpha_s, int gated2, float alpha,
+                                           void* stream);
 /* host-only dry run of the same schedule (no device, no kernels): calls the callbacks exactly as
  * cidnet_forward_sharded would, with `workspace` any host buffer of the same size -- used by the
  * CPU (gloo) tests of the exchange logic.  Needs no weights. */

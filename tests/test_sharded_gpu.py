@@ -20,7 +20,7 @@ from conftest import ROOT, parity_error, psnr_kept
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, H, W, use_nccl, ret, mssa=False):
+def _worker(rank, world, port, H, W, use_nccl, ret, mssa=False, transport=None):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dev = torch.device("cuda", rank if use_nccl else 0)
@@ -42,7 +42,7 @@ def _worker(rank, world, port, H, W, use_nccl, ret, mssa=False):
     model = CIDNet().to(dev).eval()
     model.load_state_dict(sd, strict=True)
     x = O.make_input("uniform", 1, H, W, seed=33)
-    net = RowShardedCIDNet(model, halo=16)
+    net = RowShardedCIDNet(model, halo=16, transport=transport)
     y = net(x.pin_memory(), gather=True).cpu()           # full image on every rank
     y2 = net(x.to(dev), gather=True).cpu()               # second call: same workspace, device input
     y3 = net(x.to(dev), gather=True).cpu()               # third / fourth call: CUDA-graph capture and replay of the
@@ -51,10 +51,12 @@ def _worker(rank, world, port, H, W, use_nccl, ret, mssa=False):
     # sharded vs unsharded: different split of the same fp32 sums -> small differences; a pixel beyond 5e-4 must be the
     # reference's black-pixel hole (conftest.parity_error).  Repeats of the SAME sharded forward are bit-equal (no atomics).
     out = {"vs_full": parity_error(y, full, 5e-4)[0], "repeat_equal": bool(torch.equal(y, y2) and torch.equal(y, y3) and torch.equal(y, y4)),
-           "replays": net.replays, "graph_error": getattr(net, "graph_error", None),
-           "halo_calls": sum(1 for e in net.comm.log if e[0] == "halo"),
-           "allreduce_calls": sum(1 for e in net.comm.log if e[0] == "allreduce"),
-           "direct": bool(net.comm.direct)}
+           "replays": net.replays, "graph_error": getattr(net, "graph_error", None), "transport": net.transport}
+    if net.transport == "peer":
+        out.update(peer_forwards=net.peer_forwards, peer_error=net.peer_error())
+    else:
+        out.update(halo_calls=sum(1 for e in net.comm.log if e[0] == "halo"),
+                   allreduce_calls=sum(1 for e in net.comm.log if e[0] == "allreduce"), direct=bool(net.comm.direct))
     if rank == 0:
         taps = {}
         ref = O.forward(x, sd, mssa=mssa, taps=taps)
@@ -67,24 +69,36 @@ def _worker(rank, world, port, H, W, use_nccl, ret, mssa=False):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("transport", ["callbacks", "peer"])
 @pytest.mark.parametrize("world,H,W,mssa", [(2, 128, 64, False), (3, 192, 40, False), (2, 400, 600, False),
-                                            (2, 128, 64, True), (3, 240, 40, True)])
-def test_row_sharded_forward_matches_unsharded(world, H, W, mssa):
-    """mssa=True: the MSSA variant -- its 7x7 spatial-attention gates need three valid halo rows per up block"""
+                                            (2, 128, 64, True), (3, 240, 40, True), (2, 2160, 3840, False)])
+def test_row_sharded_forward_matches_unsharded(world, H, W, mssa, transport):
+    """mssa=True: the MSSA variant -- its 7x7 spatial-attention gates need three valid halo rows per up block.
+    transport "peer" (CUDA-IPC mapped workspaces, halo / statistics kernels reading the neighbours' memory over NVLink,
+    one CUDA graph) needs one GPU per rank: ranks that share a GPU must not spin on one another's flags.  The 4K case
+    (BASELINE.json configs[4] at full size) runs where every rank has its own GPU."""
     use_nccl = torch.cuda.device_count() >= world
-    port = 33000 + (os.getpid() % 2000) + world + 7 * int(mssa)
+    if transport == "peer" and not use_nccl:
+        pytest.skip("peer-memory transport needs one GPU per rank")
+    if H >= 2160 and not use_nccl:
+        pytest.skip("the 4K strip case needs one GPU per rank")
+    port = 33000 + (os.getpid() % 2000) + world + 7 * int(mssa) + 13 * (transport == "peer") + (H // 100)
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, port, H, W, use_nccl, ret, mssa), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, H, W, use_nccl, ret, mssa, transport), nprocs=world, join=True)
     assert len(ret) == world
     for r in range(world):
         o = ret[r]
         assert o["vs_full"] <= 5e-4, (r, o)
         assert o["repeat_equal"], (r, o)
-        assert o["allreduce_calls"] == 6 and o["halo_calls"] >= 6, (r, o)
-        assert o["direct"] == use_nccl
-        # graph replay is opt-in (CIDNET_SHARD_GRAPH=1) and needs the NCCL transport
-        assert o["replays"] == (2 if (use_nccl and os.environ.get("CIDNET_SHARD_GRAPH") == "1") else 0), (r, o)
+        assert o["transport"] == transport
+        if transport == "peer":
+            assert o["peer_forwards"] == 4 and o["peer_error"] == 0, (r, o)
+        else:
+            assert o["allreduce_calls"] == 6 and o["halo_calls"] >= 6, (r, o)
+            assert o["direct"] == use_nccl
+            # graph replay of the callback transport is opt-in (CIDNET_SHARD_GRAPH=1) and needs NCCL
+            assert o["replays"] == (2 if (use_nccl and os.environ.get("CIDNET_SHARD_GRAPH") == "1") else 0), (r, o)
     assert ret[0]["vs_oracle"] <= 2e-3 and ret[0]["psnr"] >= 50.0, ret[0]
 
 
