@@ -528,6 +528,20 @@ def run_ours(args):
     barrier()
     assert nres == args.steps
     ms_e2e = f0.elapsed_time(f1)
+    # the 8-bit path: uint8 HWC in pinned host memory -> H2D -> forward with the conversions fused into its first / last
+    # kernel -> D2H of the uint8 result (6 B/px over PCIe instead of 24)
+    h8 = [torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8).pin_memory() for _ in range(min(ring, 4))]
+    for _ in drv.run_u8(h8[i % len(h8)] for i in range(3)):
+        pass
+    barrier()
+    f0.record()
+    nres = 0
+    for res in drv.run_u8(h8[i % len(h8)] for i in range(args.steps)):
+        nres += 1
+    f1.record()
+    barrier()
+    ms_e2e_u8 = f0.elapsed_time(f1)
+    del h8
 
     # ---- the two multi-GPU configs of BASELINE.json, same process group (N > 1, default workload only) -------------
     extras = None
@@ -545,9 +559,9 @@ def run_ours(args):
         except Exception as e:
             extras["cfg4"] = {"error": repr(e)[:400]}
     if world > 1:
-        t = torch.tensor([ms_total, ms_e2e, ms_e2e_sync], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_total, ms_e2e, ms_e2e_sync, ms_e2e_u8], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_e2e, ms_e2e_sync = float(t[0]), float(t[1]), float(t[2])
+        ms_total, ms_e2e, ms_e2e_sync, ms_e2e_u8 = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     mp_step_all = B * H * W * world / 1e6
     value = mp_step_all * args.steps / (ms_total / 1e3)
     e2e_value = mp_step_all * args.steps / (ms_e2e / 1e3)
@@ -592,7 +606,10 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": img_bytes, "d2h_bytes_per_step": img_bytes,
                         "ms_per_step": ms_e2e / args.steps, "api": "StreamedCIDNet(model).run(pinned host batches) -> pinned host results",
                         "sync_loop_value": mp_step_all * args.steps / (ms_e2e_sync / 1e3),
-                        "sync_loop_note": "reference-style loop: x.cuda() -> model(x) -> .cpu() per step on one stream"},
+                        "sync_loop_note": "reference-style loop: x.cuda() -> model(x) -> .cpu() per step on one stream",
+                        "u8_value": mp_step_all * args.steps / (ms_e2e_u8 / 1e3), "u8_bytes_per_step_each_way": B * H * W * 3,
+                        "u8_api": "StreamedCIDNet(model).run_u8(pinned uint8 HWC batches): ToTensor / pad / gamma / clamp / crop / "
+                                  "quantise fused into the stem and head kernels (cidnet_forward_u8)"},
                 "gpu_launches": launches, "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
                 "gpu_eager_baseline": eager, "clocks": clocks}
         if extras is not None:

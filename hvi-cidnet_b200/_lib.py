@@ -66,6 +66,8 @@ SIGNATURES = {
     "cidnet_peer_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "cidnet_forward_sharded_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Shard), C.POINTER(C.c_void_p),
                                               C.c_int64, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float, C.c_void_p]),
+    "cidnet_forward_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int64,
+                                    C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float, C.c_void_p]),
     "cidnet_pre_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "cidnet_post_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cidnet_read_tap": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int), C.c_void_p]),

@@ -87,7 +87,7 @@ struct cidnet_ctx {
         cudaGraphNode_t stem_node = nullptr, head_node = nullptr;
         cudaKernelNodeParams stem_p{}, head_p{};
         void* stem_args[16]; void* head_args[16];
-        const float* cur_in = nullptr; float* cur_out = nullptr;
+        const void* cur_in = nullptr; void* cur_out = nullptr;
         std::map<std::string, Tap> taps; int launches = 0;
         uint64_t last_use = 0;
     };
@@ -621,6 +621,9 @@ struct Fwd {
         Bq.mode = EPI_UP; Bq.in = skip; Bq.B = P.B; Bq.H = P.H[n - 1]; Bq.W = P.W[n - 1]; Bq.in_pitch = act_pitch(kCh[n - 1]);
         Bq.flat = true; Bq.wt = &U.w1; Bq.out = out; Bq.out_pitch = act_pitch(kCh[n - 1]);
         Bq.up = t; Bq.up_pitch = act_pitch(kCh[n - 1]); Bq.prelu = U.prelu;
+        // MSSA variant: the SpatialAttention gate that follows needs the channel mean / max of this output -- the epilogue
+        // thread holds its pixel's whole channel vector, so the statistics cost no extra pass over the tensor
+        if (ctx->variant == CIDNET_VARIANT_MSSA) Bq.sa_stats = P.sa_stats[br];
         if (sh.on) { Bq.gH = sh.gH >> (n - 1); Bq.grow = sh.row0 >> (n - 1); }
         return gemm(Bq, "up" + std::to_string(n) + ".skip1x1_bilinear_prelu", br);
     }
@@ -637,8 +640,7 @@ struct Fwd {
         a.stats[0] = P.sa_stats[0]; a.stats[1] = P.sa_stats[1];
         a.B = P.B; a.H = P.H[l]; a.W = P.W[l]; a.C = C; a.pitch = Cp; a.nprob = 2;
         const double px = 2.0 * P.B * P.H[l] * P.W[l];
-        mark("sa" + std::to_string(l + 1) + ".mean_max", px * (2.0 * C + 8), px * 2.0 * C);
-        if (live() && (rc = launch_sa_stats(a, st))) return rc;
+        // (mean, max) per pixel were written by the up block's epilogue (ConvGemmLaunch::sa_stats)
         mark("sa" + std::to_string(l + 1) + ".conv7x7_sigmoid_gate", px * (4.0 * C + 8), px * (2.0 * 98 + C));
         if (live() && (rc = launch_sa_gate(a, st))) return rc;
         if (split()) { setm(xi, mg(xi) - 3); setm(xhv, mg(xhv) - 3); }
@@ -782,11 +784,15 @@ struct Fwd {
         return CIDNET_OK;
     }
 
-    int run(const float* rgb_in, float* rgb_out, const float* k_dev, int gated, float alpha_s, int gated2, float alpha) {
+    // 8-bit I/O fused into the stem's load and the head's store (cidnet_forward_u8): rgb_in / rgb_out are then uint8 HWC
+    struct { bool on = false; int h = 0, w = 0; float gamma = 1.f; } u8;
+
+    int run(const void* rgb_in, void* rgb_out, const float* k_dev, int gated, float alpha_s, int gated2, float alpha) {
         int rc;
         StemArgs sa{rgb_in, P.hvi, P.i_enc0, P.hv_0, ctx->stem_whv, ctx->stem_wi, k_dev ? k_dev : ctx->k_dev,
                     ctx->k_host, P.B, P.H[0], P.W[0], 40, ctx->stem_bfrag};
-        mark("L0.stem_hvit_block0", (double)P.B * P.H[0] * P.W[0] * 168.0, (double)P.B * P.H[0] * P.W[0] * 2.0 * 1296);
+        if (u8.on) { sa.in_u8 = 1; sa.h_src = u8.h; sa.w_src = u8.w; sa.gamma = u8.gamma; }
+        mark("L0.stem_hvit_block0", (double)P.B * P.H[0] * P.W[0] * (u8.on ? 159.0 : 168.0), (double)P.B * P.H[0] * P.W[0] * 2.0 * 1296);
         if (live() && (rc = launch_stem(sa, st))) return rc;
         // the local input image carries the neighbours' rows: the replicate-padded 3x3 spoils the outermost one
         setm(P.i_enc0, (sh.halo_top > 0 ? sh.halo_top : sh.halo_bot) - 1);
@@ -847,7 +853,8 @@ struct Fwd {
         HeadArgs ha{P.id1, P.hvd1, P.hvi, rgb_out, P.out_hvi, ctx->head_wi, ctx->head_whv,
                     k_dev ? k_dev : ctx->k_dev, ctx->k_host, alpha_s, alpha, gated, gated2, P.B, P.H[0], P.W[0], 40,
                     ctx->head_bfrag};
-        mark("L0.head_block0_phvit", (double)P.B * P.H[0] * P.W[0] * 168.0, (double)P.B * P.H[0] * P.W[0] * 2.0 * 972);
+        if (u8.on) { ha.out_u8 = 1; ha.h_dst = u8.h; ha.w_dst = u8.w; }
+        mark("L0.head_block0_phvit", (double)P.B * P.H[0] * P.W[0] * (u8.on ? 159.0 : 168.0), (double)P.B * P.H[0] * P.W[0] * 2.0 * 972);
         if (live() && (rc = launch_head(ha, st))) return rc;
         finish_marks();
         tap("out_hvi", P.out_hvi, 3, 0, 0, true);
@@ -944,7 +951,7 @@ extern "C" int64_t cidnet_workspace_bytes(int B, int H, int W) {
 // CUDA graph when possible -- one entry per (shape, workspace, flags, extra); the input / output image pointers are patched
 // into the stem / head kernel nodes when they change.  Skipped while profiling, inside somebody else's capture, or when
 // graphs are disabled: then the launches go out eagerly.
-static int run_forward_cached(cidnet_ctx* ctx, Fwd& f, uint64_t extra, const float* rgb_in, float* rgb_out, const float* k_dev,
+static int run_forward_cached(cidnet_ctx* ctx, Fwd& f, uint64_t extra, const void* rgb_in, void* rgb_out, const float* k_dev,
                               int gated, float alpha_s, int gated2, float alpha, cudaStream_t st) {
     const int B = f.P.B, H = f.P.H[0], W = f.P.W[0];
     const void* workspace = f.P.hvi;                       // first tensor of the plan: identifies the workspace
@@ -1076,6 +1083,32 @@ extern "C" int cidnet_forward(cidnet_ctx* ctx, const float* rgb_in, float* rgb_o
                  "forward: workspace too small: need " + std::to_string(f.P.bytes) + " bytes");
     ctx->last_B = B;
     return run_forward_cached(ctx, f, 0, rgb_in, rgb_out, k_dev, gated, alpha_s, gated2, alpha, st);
+}
+
+// ---- 8-bit in, 8-bit out: the callers' pre / post-processing fused into the stem's load and the head's store ------------
+extern "C" int cidnet_forward_u8(cidnet_ctx* ctx, const uint8_t* in_hwc, uint8_t* out_hwc, int B, int h, int w, float gamma,
+                                 void* workspace, int64_t workspace_bytes, const float* k_dev, int gated, float alpha_s,
+                                 int gated2, float alpha, void* stream) {
+    CIDNET_CHECK(ctx, CIDNET_ERR_INVALID, "forward_u8: null ctx");
+    CIDNET_CHECK(ctx->finalized, CIDNET_ERR_STATE, "forward_u8: weights not finalized (call cidnet_finalize_weights)");
+    CIDNET_CHECK(B >= 0 && h > 0 && w > 0, CIDNET_ERR_INVALID, "forward_u8: bad shape");
+    if (B == 0) return CIDNET_OK;
+    // the callers pad to the next multiple of 8 only when needed (data/eval_sets.py:22-27)
+    const int H = (h % 8) ? (h / 8 + 1) * 8 : h, W = (w % 8) ? (w / 8 + 1) * 8 : w;
+    CIDNET_CHECK(H - h < h && W - w < w, CIDNET_ERR_INVALID, "forward_u8: reflect padding must be smaller than the image");
+    DeviceGuard guard(ctx->device);
+    CIDNET_CHECK(in_hwc && out_hwc && workspace, CIDNET_ERR_INVALID, "forward_u8: null pointer");
+    CIDNET_CHECK((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, CIDNET_ERR_INVALID, "forward_u8: workspace must be 1024-byte aligned");
+    Fwd f;
+    f.ctx = ctx; f.st = (cudaStream_t)stream;
+    make_plan(&f.P, workspace, B, H, W);
+    CIDNET_CHECK(workspace_bytes >= f.P.bytes, CIDNET_ERR_STATE,
+                 "forward_u8: workspace too small: need " + std::to_string(f.P.bytes) + " bytes (cidnet_workspace_bytes of the padded shape)");
+    f.u8.on = true; f.u8.h = h; f.u8.w = w; f.u8.gamma = gamma;
+    uint32_t gbits; memcpy(&gbits, &gamma, 4);
+    const uint64_t extra = (((uint64_t)h << 40) ^ ((uint64_t)w << 20) ^ gbits) * 0x9E3779B97F4A7C15ull | 2ull;
+    ctx->last_B = B;
+    return run_forward_cached(ctx, f, extra, in_hwc, out_hwc, k_dev, gated, alpha_s, gated2, alpha, (cudaStream_t)stream);
 }
 
 // ---- row-strip sharded forward (single image over the GPUs of one node) -------------------

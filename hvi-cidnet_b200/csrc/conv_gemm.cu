@@ -42,6 +42,7 @@ struct ConvGemmArgs {
     int taps, kchunks, kchunks2, cin, cin2;
     int Hv, Wv, TH, TW, tiles_x, tiles_y, num_tiles;
     int n_out, block_n, stages, per_image_w, b_resident, stg_bufs;
+    float2* sa_stats;                // EPI_UP, MSSA variant: per-pixel (mean, max) over the output channels (SpatialAttention input)
     int w_early;                     // resident weights are model constants: request them before the programmatic-dependency wait
     int halo;                        // 3x3: tile + halo loaded once per channel chunk, taps = row-shifted views
     int w_real;
@@ -109,7 +110,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
     constexpr int kSub = (kMode == EPI_DOWN) ? 2 : 1;
-    const uint32_t a_stage = kSub * (a.halo ? kHaloTileBytes : kSubTileBytes) + (kMode == EPI_UP ? a.up_chunks * kUpTileBytes : 0u);
+    constexpr bool kUp = (kMode == EPI_UP || kMode == EPI_UP_SA);      // EPI_UP_SA: EPI_UP + per-pixel channel (mean, max)
+    constexpr bool kSa = (kMode == EPI_UP_SA);
+    const uint32_t a_stage = kSub * (a.halo ? kHaloTileBytes : kSubTileBytes) + (kUp ? a.up_chunks * kUpTileBytes : 0u);
     const uint32_t b_chunk = (uint32_t)a.block_n * 128u;
     const int stages = a.stages;
     const int k1 = a.taps * a.kchunks;              // primary K chunks (weight chunks)
@@ -151,12 +154,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
         ptx::prefetch_tensormap(&a.tmB);
         ptx::prefetch_tensormap(&a.tmOut);
         if (a.kchunks2) { ptx::prefetch_tensormap(&a.tmA2); ptx::prefetch_tensormap(&a.tmB2); }
-        if (kMode == EPI_UP) ptx::prefetch_tensormap(&a.tmUp);
+        if (kUp) ptx::prefetch_tensormap(&a.tmUp);
     }
     if (warp == 1) {
         if (lane == 0) {
             // MMA commit (+ the 4 epilogue warps of the tile's group for LN / UP, which read the stage themselves)
-            const uint32_t empty_count = (kMode == EPI_LN || kMode == EPI_UP) ? 5u : 1u;
+            const uint32_t empty_count = (kMode == EPI_LN || kUp) ? 5u : 1u;
             for (int s = 0; s < stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], empty_count); }
             ptx::mbar_init(bfull, 1);
             for (int i = 0; i < kEpiGroups; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], 4); ptx::mbar_init(&a_ready[i], 1); }
@@ -205,7 +208,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                     const int s = it % stages;
                     const uint32_t ph = (it / stages) & 1u;
                     ptx::mbar_wait(&empty[s], ph ^ 1u);
-                    const bool up_here = (kMode == EPI_UP) && i == 0;      // the tile's low-res box rides with its first stage
+                    const bool up_here = (kUp) && i == 0;      // the tile's low-res box rides with its first stage
                     const uint32_t a_bytes = kSub * (a.halo ? kHaloTileBytes : kSubTileBytes);
                     ptx::mbar_expect_tx(&full[s], a_bytes + (up_here ? a.up_chunks * kUpBoxBytes : 0u) + (a.b_resident ? 0u : b_chunk));
                     uint8_t* dstA = smA + (size_t)s * a_stage;
@@ -266,7 +269,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                 const uint32_t ph = (it / stages) & 1u;
                 ptx::mbar_wait(&full[s], ph);
                 ptx::tc_fence_after();
-                if ((kMode == EPI_LN || kMode == EPI_UP) && i == kiters - 1 && lane == 0) ptx::mbar_arrive(&a_ready[buf]);
+                if ((kMode == EPI_LN || kUp) && i == kiters - 1 && lane == 0) ptx::mbar_arrive(&a_ready[buf]);
                 if (a.halo) {
                     // One (elected) lane issues every tcgen05.mma, the whole warp runs the loop convergently; ncu showed the tensor pipe busy only ~55 % of the time
                     // behind this loop (~150 cycles of uniform-datapath descriptor arithmetic per MMA), so the
@@ -388,7 +391,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
             uint32_t u00 = 0, u01 = 0, u10 = 0, u11 = 0;      // box row index (128-byte rows) of the four neighbours
             float uly = 0.f, ulx = 0.f;
             const uint32_t up_it = it - kiters;               // pipeline iteration of this tile's first stage
-            if (kMode == EPI_UP) {
+            if (kUp) {
                 const uint32_t s0 = up_it % stages;
                 ptx::mbar_wait(&a_ready[j % kEpiGroups], (j / kEpiGroups) & 1u);
                 up_tile = smA + (size_t)s0 * a_stage + kSubTileBytes;
@@ -427,6 +430,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + buf * acc_cols + ((uint32_t)(q * 32) << 16);
 
+            float sa_sum = 0.f, sa_max = -INFINITY;               // EPI_UP + sa_stats: channel statistics of this thread's pixel
             for (int cb = 0; cb < nblk64; ++cb, sb ^= sb_toggle) {
                 uint8_t* stg = stg_base + sb * kStagingBytes;
                 // the TMA store that used this staging buffer two blocks ago must have read it
@@ -467,7 +471,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
 #pragma unroll
                                 for (int e = 0; e < 32; ++e) v[e] = prelu_f(v[e], a.prelu);
                             }
-                        } else if (kMode == EPI_UP) {
+                        } else if (kUp) {
                             const int nrem = a.n_out - (n0 + c);
                             const uint8_t* ub = up_tile + cb * kUpTileBytes;
 #pragma unroll
@@ -484,6 +488,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                                         const float up = (1.f - uly) * ((1.f - ulx) * p00[e] + ulx * p01[e]) +
                                                          uly * ((1.f - ulx) * p10[e] + ulx * p11[e]);
                                         v[8 * h + e] = prelu_f(v[8 * h + e] + up, a.prelu);
+                                        if (kSa && 8 * h + e < nrem) {
+                                            const float r16 = act2f(f2act(v[8 * h + e]));      // the value as it is stored
+                                            sa_sum += r16; sa_max = fmaxf(sa_max, r16);
+                                        }
                                     }
                                 }
                             }
@@ -510,12 +518,14 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                     ptx::tma_store_commit();
                 }
             }
+            if (kSa && valid)
+                a.sa_stats[((long long)img * a.Hv + y) * a.Wv + x] = make_float2(sa_sum / (float)a.n_out, sa_max);
             // all TMEM reads of this buffer are done -> hand it back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) {
                 ptx::mbar_arrive(&tmem_empty[buf]);
-                if (kMode == EPI_UP)      // the low-res box has been read: co-release the tile's stages
+                if (kUp)      // the low-res box has been read: co-release the tile's stages
                     for (int i = 0; i < kiters; ++i) ptx::mbar_arrive(&empty[(up_it + i) % stages]);
             }
         }
@@ -636,6 +646,8 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
     a.prelu = L.prelu; a.use_prelu = L.use_prelu ? 1 : 0;
     a.w_real = L.W;
     a.w_early = L.dynamic_weights ? 0 : 1;
+    a.sa_stats = L.mode == EPI_UP ? L.sa_stats : nullptr;
+    const EpiMode kmode = (L.mode == EPI_UP && L.sa_stats) ? EPI_UP_SA : L.mode;
     const long long hw = (long long)L.H * L.W;
     int rc;
 
@@ -770,11 +782,12 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
     if (gx < 1) gx = 1;
     if (gx > a.num_tiles) gx = a.num_tiles;
     dim3 grid((unsigned)gx, (unsigned)wt.n_blocks, 1);
-    switch (L.mode) {
+    switch (kmode) {
         case EPI_STORE: return launch_mode<EPI_STORE>(a, grid, smem, stream, kEpiGroups);
         case EPI_LN:    return launch_mode<EPI_LN>(a, grid, smem, stream, kEpiGroups);
         case EPI_DOWN:  return launch_mode<EPI_DOWN>(a, grid, smem, stream, kEpiGroups);
         case EPI_UP:    return launch_mode<EPI_UP>(a, grid, smem, stream, kEpiGroups);
+        case EPI_UP_SA: return launch_mode<EPI_UP_SA>(a, grid, smem, stream, kEpiGroups);
     }
     return fail(CIDNET_ERR_INVALID, "conv_gemm: bad mode");
 }

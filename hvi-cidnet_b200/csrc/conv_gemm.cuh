@@ -9,6 +9,8 @@ enum EpiMode {
     EPI_LN    = 1,  // out = rstd[p] * (acc - mean[p] * wsum[n]) + bias[n]   (LayerNorm folded into the 1x1)
     EPI_DOWN  = 2,  // out = PReLU(bilinear_x0.5(acc))                        (NormDownsample)
     EPI_UP    = 3,  // out = PReLU(acc + bilinear_x2(t)[p, n])                (NormUpsample tail)
+    EPI_UP_SA = 4,  // EPI_UP that also writes the per-pixel channel (mean, max) of its output (chosen by the launcher when
+                    // ConvGemmLaunch::sa_stats is set; MSSA variant)
 };
 
 // Weights of one GEMM, packed on the device as act_t [n_img][n_rows][taps*kchunks*64]
@@ -62,6 +64,7 @@ struct ConvGemmLaunch {
     // EPI_UP: low-resolution tensor t [B, H/2, W/2, up_pitch] to be upsampled x2 and added
     const act_t* up = nullptr;
     int up_pitch = 0;
+    float2* sa_stats = nullptr;   // EPI_UP (MSSA variant): also write the per-pixel channel (mean, max) of the output, [B][H][W]
     // Row-strip sharding of ONE image (cidnet_forward_sharded): this launch covers local rows
     // [0, H) = global rows [grow, grow + H) of an image with gH rows on this launch's INPUT pixel
     // grid (gH == 0: not sharded).  Only the align_corners bilinear weights of EPI_DOWN / EPI_UP

@@ -1,7 +1,8 @@
 // SpatialAttention gates of the fork's MSSA variant (/root/reference/net/CIDNet_MSSA.py:10-25, used at :132-153):
 //   avg = mean_C(x); mx = max_C(x); y = conv7x7(cat[avg, mx]) (zero padding 3, no bias); x * sigmoid(y)
-// Both kernels are HBM-bound elementwise passes over an NHWC 16-bit tensor:
-//   sa_stats_kernel  reads x once (2*pitch B/px), writes 8 B/px
+// The per-pixel channel statistics (mean, max) are produced by the up block's GEMM epilogue (conv_gemm.cu, EPI_UP with
+// ConvGemmLaunch::sa_stats: each epilogue thread holds its pixel's whole channel vector); what is left is ONE
+// HBM-bound elementwise kernel per up-block pair:
 //   sa_gate_kernel   reads the 7x7 neighbourhood of the statistics from a shared-memory tile, reads x, writes x
 #include "sa.cuh"
 #include "ptx_sm100.cuh"
@@ -10,42 +11,7 @@ namespace cidnet {
 
 namespace {
 
-constexpr int kStatPx = 128;        // pixels per CTA of the statistics kernel
 constexpr int kMaxVec = 18;         // 144 channels / 8
-
-struct SaStatsParams { const act_t* x[2]; float2* stats[2]; long long npx; int C, nv; };
-
-__global__ void __launch_bounds__(256)
-sa_stats_kernel(SaStatsParams p) {
-    __shared__ float2 part[kStatPx * kMaxVec];
-    const act_t* __restrict__ x = blockIdx.y ? p.x[1] : p.x[0];
-    const long long px0 = (long long)blockIdx.x * kStatPx;
-    const int npx = (int)min((long long)kStatPx, p.npx - px0);
-    const int nvec = npx * p.nv;
-    const uint4* src = reinterpret_cast<const uint4*>(x) + px0 * p.nv;     // pitch = 8 * nv: pixels are contiguous
-    ptx::pdl_wait();
-    ptx::pdl_trigger();
-    for (int i = threadIdx.x; i < nvec; i += 256) {
-        const uint4 raw = __ldcg(src + i);
-        const act_t* a = reinterpret_cast<const act_t*>(&raw);
-        const int c0 = (i % p.nv) * 8;
-        float s = 0.f, m = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (c0 + j < p.C) { const float v = act2f(a[j]); s += v; m = fmaxf(m, v); }
-        }
-        part[i] = make_float2(s, m);
-    }
-    __syncthreads();
-    if (threadIdx.x < npx) {
-        float s = 0.f, m = -INFINITY;
-        for (int v = 0; v < p.nv; ++v) {
-            const float2 q = part[threadIdx.x * p.nv + v];
-            s += q.x; m = fmaxf(m, q.y);
-        }
-        (blockIdx.y ? p.stats[1] : p.stats[0])[px0 + threadIdx.x] = make_float2(s / (float)p.C, m);
-    }
-}
 
 constexpr int kTW = 32, kTH = 8;    // pixel tile of the gate kernel
 
@@ -106,16 +72,6 @@ int check(const SaArgs& a) {
 }
 
 }  // namespace
-
-int launch_sa_stats(const SaArgs& a, cudaStream_t stream) {
-    int rc = check(a);
-    if (rc) return rc;
-    SaStatsParams p;
-    for (int i = 0; i < 2; ++i) { p.x[i] = a.x[i]; p.stats[i] = a.stats[i]; }
-    p.npx = (long long)a.B * a.H * a.W; p.C = a.C; p.nv = a.pitch / 8;
-    dim3 grid((unsigned)((p.npx + kStatPx - 1) / kStatPx), a.nprob);
-    return launch_k(sa_stats_kernel, grid, dim3(256), 0, stream, p);
-}
 
 int launch_sa_gate(const SaArgs& a, cudaStream_t stream) {
     int rc = check(a);

@@ -71,10 +71,16 @@ __device__ __forceinline__ int stem_k_to_ct(int k, int* c, int* t) {
 }
 
 __global__ void __launch_bounds__(256)
-stem_mma_kernel(const float* __restrict__ rgb, float* __restrict__ hvi, act_t* __restrict__ i_enc0,
+stem_mma_kernel(const void* __restrict__ rgb_any, float* __restrict__ hvi, act_t* __restrict__ i_enc0,
                 act_t* __restrict__ hv_0, const float* __restrict__ w_hv /*[27][36]*/,
                 const float* __restrict__ w_i /*[9][36]*/, const float* __restrict__ k_dev, float k_host,
-                int H, int W, int pitch, const uint2* __restrict__ bfrag /*[3][5][32], cidnet_pack_stem_bfrag*/) {
+                int H, int W, int pitch, const uint2* __restrict__ bfrag /*[3][5][32], cidnet_pack_stem_bfrag*/,
+                int in_u8, int h_src, int w_src, float gamma) {
+    // in_u8 == 0: rgb_any = fp32 [B,3,H,W] planar.  in_u8 == 1: rgb_any = uint8 [B,h_src,w_src,3] (what a decoder yields):
+    // ToTensor (/255), reflect padding of the bottom / right edge up to (H, W) and `** gamma` happen in the halo fill below
+    // (data/eval_sets.py:22-27, eval.py:64) -- the padded fp32 image never exists in memory.
+    const float* __restrict__ rgb = reinterpret_cast<const float*>(rgb_any);
+    const uint8_t* __restrict__ rgb8 = reinterpret_cast<const uint8_t*>(rgb_any);
     __shared__ float s_hvi[3 * kHalo * kHalo];
     __shared__ __align__(16) uint2 s_bfrag[3][5][32];      // [HVE k-step 0, HVE k-step 1, IE][n8 tile][lane] = {b0, b1}
     __shared__ __align__(16) act_t s_out[8][32 * 40];      // per warp: [pixel][40 channels]
@@ -95,8 +101,17 @@ stem_mma_kernel(const float* __restrict__ rgb, float* __restrict__ hvi, act_t* _
         const int y = min(max(y0 + hy - 1, 0), H - 1);
         const int x = min(max(x0 + hx - 1, 0), W - 1);
         const long long o = (long long)y * W + x;
-        float hh, vv, ii;
-        hvit_px(__ldcg(img + o), __ldcg(img + o + hw), __ldcg(img + o + 2 * hw), k, hh, vv, ii);   // L2 loads: see ptx::pdl_wait
+        float hh, vv, ii, cr, cg, cb;
+        if (in_u8) {
+            const int sy = y < h_src ? y : 2 * (h_src - 1) - y;          // 'reflect': padded row h+i mirrors row h-2-i
+            const int sx = x < w_src ? x : 2 * (w_src - 1) - x;
+            const uint8_t* p = rgb8 + (((long long)b * h_src + sy) * w_src + sx) * 3;
+            cr = __fdiv_rn((float)__ldcg(p), 255.0f); cg = __fdiv_rn((float)__ldcg(p + 1), 255.0f); cb = __fdiv_rn((float)__ldcg(p + 2), 255.0f);
+            if (gamma != 1.0f) { cr = powf(cr, gamma); cg = powf(cg, gamma); cb = powf(cb, gamma); }
+        } else {
+            cr = __ldcg(img + o); cg = __ldcg(img + o + hw); cb = __ldcg(img + o + 2 * hw);   // L2 loads: see ptx::pdl_wait
+        }
+        hvit_px(cr, cg, cb, k, hh, vv, ii);
         s_hvi[i] = hh; s_hvi[kHalo * kHalo + i] = vv; s_hvi[2 * kHalo * kHalo + i] = ii;
     }
     __syncthreads();
@@ -230,7 +245,7 @@ int launch_stem(const StemArgs& a, cudaStream_t stream) {
     CIDNET_CHECK(a.pitch == 40, CIDNET_ERR_INVALID, "stem: pitch must be 40");
     dim3 grid(ceil_div(a.W, kTile), ceil_div(a.H, kTile), a.B);
     return launch_k(stem_mma_kernel, grid, dim3(256), 0, stream, a.rgb, a.hvi, a.i_enc0, a.hv_0, a.w_hv, a.w_i, a.k_dev,
-                    a.k_host, a.H, a.W, a.pitch, a.bfrag);
+                    a.k_host, a.H, a.W, a.pitch, a.bfrag, a.in_u8, a.h_src, a.w_src, a.gamma);
 }
 
 // ------------------------------------------------------------------ head ----
@@ -240,9 +255,13 @@ int launch_stem(const StemArgs& a, cudaStream_t stream) {
 // of the tiles are zeroed when staged, channels 40..47 of the third k-step belong to the next pixel and meet zero weights.
 __global__ void __launch_bounds__(256, 3)
 head_mma_kernel(const act_t* __restrict__ i_dec1, const act_t* __restrict__ hv_1, const float* __restrict__ hvi,
-                float* __restrict__ rgb, float* __restrict__ out_hvi_dbg, const float* __restrict__ w_i /*[9][36]*/,
+                void* __restrict__ rgb_any, float* __restrict__ out_hvi_dbg, const float* __restrict__ w_i /*[9][36]*/,
                 const float* __restrict__ w_hv /*[2][9][36]*/, const float* __restrict__ k_dev, PhvitParams pp,
-                int H, int W, int pitch, const uint2* __restrict__ bfrag /*[2][9][3][32], cidnet_pack_head_bfrag*/) {
+                int H, int W, int pitch, const uint2* __restrict__ bfrag /*[2][9][3][32], cidnet_pack_head_bfrag*/,
+                int out_u8, int h_dst, int w_dst) {
+    // out_u8 == 0: rgb_any = fp32 [B,3,H,W] planar.  out_u8 == 1: rgb_any = uint8 [B,h_dst,w_dst,3]: clamp(0,1), crop to
+    // [:h_dst,:w_dst] and ToPILImage's mul(255).byte() (eval.py:69-73) happen in the store below.
+    float* __restrict__ rgb = reinterpret_cast<float*>(rgb_any);
     extern __shared__ __align__(16) uint8_t head_smem[];
     act_t* s_i = reinterpret_cast<act_t*>(head_smem);                        // [18*18 + 1 pad pixel][40]
     act_t* s_hv = s_i + (kHalo * kHalo + 1) * 40;
@@ -337,6 +356,15 @@ head_mma_kernel(const act_t* __restrict__ i_dec1, const act_t* __restrict__ hv_1
     }
     float r, gg, bl;
     phvit_px(Hh, Vv, Ii, pp, r, gg, bl);
+    if (out_u8) {
+        if (y < h_dst && x < w_dst) {
+            uint8_t* o8 = reinterpret_cast<uint8_t*>(rgb_any) + (((long long)b * h_dst + y) * w_dst + x) * 3;
+            o8[0] = (uint8_t)__float2int_rz(__fmul_rn(fminf(fmaxf(r, 0.0f), 1.0f), 255.0f));      // NaN -> 0 like .byte()
+            o8[1] = (uint8_t)__float2int_rz(__fmul_rn(fminf(fmaxf(gg, 0.0f), 1.0f), 255.0f));
+            o8[2] = (uint8_t)__float2int_rz(__fmul_rn(fminf(fmaxf(bl, 0.0f), 1.0f), 255.0f));
+        }
+        return;
+    }
     float* o = rgb + (long long)b * 3 * hw + pix;
     o[0] = r; o[hw] = gg; o[2 * hw] = bl;
 }
@@ -351,7 +379,7 @@ int launch_head(const HeadArgs& a, cudaStream_t stream) {
     int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(head_mma_kernel), (int)smem);
     if (rc) return rc;
     return launch_k(head_mma_kernel, grid, dim3(256), smem, stream, a.i_dec1, a.hv_1, a.hvi, a.rgb, a.out_hvi_dbg, a.w_i,
-                    a.w_hv, a.k_dev, pp, a.H, a.W, a.pitch, a.bfrag);
+                    a.w_hv, a.k_dev, pp, a.H, a.W, a.pitch, a.bfrag, a.out_u8, a.h_dst, a.w_dst);
 }
 
 }  // namespace cidnet

@@ -239,24 +239,30 @@ class CIDNet(nn.Module, PyTorchModelHubMixin):
         return out if dtypes == torch.float32 else out.to(dtypes)
 
     def enhance_u8(self, img, gamma=1.0, out=None):
-        """8-bit convenience path (extension): img CUDA uint8 [B,h,w,3] (HWC, any h,w) ->
-        enhanced uint8 [B,h,w,3].  Equivalent to the reference's eval loop around the model
-        (ToTensor, reflect-pad to a multiple of 8, **gamma, forward, clamp(0,1), crop, ToPILImage:
-        eval.py:56-73, data/eval_sets.py:22-27) with the conversions done by two elementwise kernels."""
+        """8-bit path (extension): img CUDA uint8 [B,h,w,3] (HWC, any h,w) -> enhanced uint8 [B,h,w,3].
+        Equivalent to the reference's eval loop around the model (ToTensor, reflect-pad to a multiple of 8, **gamma,
+        forward, clamp(0,1), crop, ToPILImage: eval.py:56-73, data/eval_sets.py:22-27); the conversions are fused into
+        the first and the last kernel of the forward (cidnet_forward_u8), so the padded fp32 image never exists."""
         if not isinstance(img, torch.Tensor) or not img.is_cuda or img.dtype != torch.uint8 or img.dim() != 4 or img.shape[3] != 3:
             raise RuntimeError("enhance_u8 expects a CUDA uint8 tensor [B,h,w,3] (no CPU fallback)")
         B, h, w, _ = img.shape
         H, W = -(-h // 8) * 8, -(-w // 8) * 8
         img = img.contiguous()
-        lib = _lib.lib()
-        x = torch.empty(B, 3, H, W, device=img.device, dtype=torch.float32)
         if out is None:
             out = torch.empty_like(img)
+        elif out.shape != img.shape or out.dtype != torch.uint8 or out.device != img.device or not out.is_contiguous():
+            raise RuntimeError("enhance_u8: `out` must be a contiguous uint8 tensor of the input's shape and device")
+        if B == 0:
+            return out
         with torch.cuda.device(img.device):
-            st = _lib.stream_ptr(img.device)
-            _lib.check(lib.cidnet_pre_u8(img.data_ptr(), x.data_ptr(), B, h, w, H, W, float(gamma), st))
-            y = self.forward(x)
-            _lib.check(lib.cidnet_post_u8(y.data_ptr(), out.data_ptr(), B, h, w, H, W, st))
+            ctx = self._ensure_ctx(img.device)
+            ws, ws_ptr, ws_bytes = self._workspace(B, H, W, img.device)
+            t = self.trans
+            t._note_hvit_called()
+            kd = t.density_k.detach() if t.density_k.dtype == torch.float32 else t._this_k_dev
+            _lib.check(_lib.lib().cidnet_forward_u8(ctx, img.data_ptr(), out.data_ptr(), B, h, w, float(gamma), ws_ptr, ws_bytes,
+                                                    kd.data_ptr(), int(bool(t.gated)), float(t.alpha_s), int(bool(t.gated2)),
+                                                    float(t.alpha), _lib.stream_ptr(img.device)))
         return out
 
     def HVIT(self, x):

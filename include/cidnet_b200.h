@@ -179,6 +179,13 @@ CIDNET_API int cidnet_forward_sharded_dry_variant(int variant, int W, const cidn
  *                 and input**gamma (eval.py:64, demo.py:57).
  * cidnet_post_u8: src dev fp32 [B,3,H,W] -> dst dev u8 [B,h,w,3]: clamp(0,1) (eval.py:69), crop to
  *                 [:h,:w] (eval.py:71), transforms.ToPILImage (mul(255).byte(), i.e. truncation). */
+/* cidnet_forward_u8: the whole caller loop around the model in one call -- src dev u8 [B,h,w,3] -> dst dev u8 [B,h,w,3]
+ * with ToTensor + reflect pad + **gamma done inside the stem kernel's tile load and clamp + crop + quantise inside the head
+ * kernel's store (no padded fp32 image in memory; 6 instead of 24 bytes per pixel at the boundary).  The workspace is
+ * cidnet_workspace_bytes(B, H, W) of the PADDED shape (h, w rounded up to multiples of 8 when they are not already). */
+CIDNET_API int cidnet_forward_u8(cidnet_ctx* ctx, const uint8_t* in_hwc, uint8_t* out_hwc, int B, int h, int w, float gamma,
+                                 void* workspace, int64_t workspace_bytes, const float* k_dev, int gated, float alpha_s,
+                                 int gated2, float alpha, void* stream);
 CIDNET_API int cidnet_pre_u8(const uint8_t* src_hwc, float* dst_nchw, int B, int h, int w, int H, int W, float gamma,
                              void* stream);
 CIDNET_API int cidnet_post_u8(const float* src_nchw, uint8_t* dst_hwc, int B, int h, int w, int H, int W, void* stream);

@@ -184,6 +184,16 @@ def test_u8_pre_post_and_enhance(model, h, w, gamma):
     assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 0.1
     with pytest.raises(RuntimeError):
         model.enhance_u8(img)                                     # CPU tensor: no fallback
+    # the fused path (cidnet_forward_u8: conversions inside the stem load / head store) against the three-kernel
+    # composition of the same operations: bit-identical
+    with torch.no_grad():
+        y3 = torch.empty(2, h, w, 3, dtype=torch.uint8, device="cuda")
+        _lib.check(lib.cidnet_post_u8(model(x).data_ptr(), y3.data_ptr(), 2, h, w, H, W, _lib.stream_ptr(y3.device)))
+    assert torch.equal(got, y3.cpu())
+    # streamed 8-bit driver
+    from hvi_cidnet_b200.stream import StreamedCIDNet
+    outs = [o.clone() for o in StreamedCIDNet(model, depth=2).run_u8([img.pin_memory()] * 3, gamma)]
+    assert len(outs) == 3 and all(torch.equal(o, got) for o in outs)
 
 
 @pytest.mark.parametrize("scale_in,scale_dw", [(4.0, 1.0), (16.0, 1.0), (8.0, 8.0)])
