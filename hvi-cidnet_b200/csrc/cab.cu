@@ -156,21 +156,26 @@ __device__ __forceinline__ void hfma8(uint4& acc, const uint4& t, const uint4& w
     acc.z = hfma2u(t.z, w.z, acc.z); acc.w = hfma2u(t.w, w.w, acc.w);
 }
 
-// Per-thread cp.async ring: the three 16-byte loads of every input row (left, centre, right) are issued kDepth rows
-// ahead with cp.async (zero fill outside the image = the conv's padding) into the thread's own shared-memory slots --
-// no registers held by loads in flight, no barriers (a thread only reads what it requested itself); the 9 weight
-// vectors are re-read from shared memory every row (96 registers -> 5 CTAs / SM).  What bounds the kernel is the
-// latency of its own global loads, i.e. how many rows are in flight per SM (profiles/r01_summary.md).
+// Per-thread cp.async ring: the 16-byte loads of every input row are issued kDepth rows ahead with cp.async (zero fill
+// outside the image = the conv's padding) into the thread's own shared-memory slots -- no registers held by loads in
+// flight, no barriers (a thread only reads what it requested itself); the 9 weight vectors are re-read from shared memory
+// every row.
+// Two pixels per thread (x0 = 2 * pair, x0 + 1): ncu on the one-pixel-per-thread kernel of round 1 / early round 2 showed the
+// LSU / shared-memory data pipe as the limiter (l1tex data-pipe wavefronts 74 %: per row and thread 3 cp.async + 3 ring LDS.128 + 9 weight LDS.128 for ONE output
+// vector).  With two adjacent pixels the four columns x0-1 .. x0+2 serve both outputs and every weight vector is loaded
+// once for two uses: 4 + 4 + 9 = 17 LSU operations per TWO outputs instead of 30.  Measured (cfg 2, event-timed): L1 70.8 -> 55.5 us,
+// L2 32.0 -> 25.8 us, L3 23.7 -> 21.2 us per launch; the step 1.620 -> 1.573 ms.  Same tap order and rounding points: bit-identical output.
 template <int kDepth, int kMinBlocks>
 __global__ void __launch_bounds__(kDwThreads, kMinBlocks)
-dw3x3_cpasync_kernel(const Dw3Args a) {
+dw3x3_cpasync2_kernel(const Dw3Args a) {
     extern __shared__ __align__(16) uint8_t dw_smem[];
-    uint4* ring = reinterpret_cast<uint4*>(dw_smem);                       // [kDepth][3][kDwThreads]
-    act_t* s_w = reinterpret_cast<act_t*>(ring + kDepth * 3 * kDwThreads);  // [9][nv * 8]
+    uint4* ring = reinterpret_cast<uint4*>(dw_smem);                       // [kDepth][4][kDwThreads]
+    act_t* s_w = reinterpret_cast<act_t*>(ring + kDepth * 4 * kDwThreads);  // [9][nv * 8]
     const int prob = blockIdx.z % a.nprob, b = blockIdx.z / a.nprob;
     const int nv = a.nv;
     const int idx = blockIdx.x * kDwThreads + threadIdx.x;
-    const int x = idx / nv, v = idx - x * nv;
+    const int xp = idx / nv, v = idx - xp * nv;
+    const int x = 2 * xp;
     const bool active = x < a.W;
     const int seg = active ? v / a.seg_vecs : 0;
     const int c0 = (v - seg * a.seg_vecs) * 8;
@@ -180,7 +185,6 @@ dw3x3_cpasync_kernel(const Dw3Args a) {
     act_t* dst = dw_dst(a, prob, b, seg, c0, hw, &dpitch);
     const int y0 = blockIdx.y * kDwRows;
     const int y1 = min(y0 + kDwRows, a.H);
-
     {
         const float* wp = a.w[prob];
         for (int i = threadIdx.x; i < 9 * nv * 8; i += kDwThreads) s_w[i] = f2act(__ldg(wp + i));
@@ -190,52 +194,55 @@ dw3x3_cpasync_kernel(const Dw3Args a) {
     ptx::pdl_trigger();
     if (!active) return;
     const uint32_t wsm_addr = ptx::smem_u32(s_w) + (uint32_t)(v * 16);
-    // asm volatile: the loads must stay where they are used (hoisted out of the row loop they would occupy the
-    // 36 registers this variant exists to free)
     auto W9 = [&](int t) -> uint4 {
         uint4 r;
         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(wsm_addr + (uint32_t)(t * nv * 16)));
         return r;
     };
-    const bool has_l = x > 0, has_r = x + 1 < a.W;
+    const bool has0 = x > 0, has2 = x + 1 < a.W, has3 = x + 2 < a.W;      // columns x-1, (x always), x+1, x+2 inside the image
     const uint32_t slot0 = ptx::smem_u32(ring) + threadIdx.x * 16;
-    const int n_in = (y1 - y0) + 2;                      // input rows y0-1 .. y1
-    // request input row k (image row y0 - 1 + k) into ring slot k % kDepth; always commits one group
+    const int n_in = (y1 - y0) + 2;
     auto issue = [&](int k) {
         if (k < n_in) {
             const int y = y0 - 1 + k;
             const bool row_ok = y >= 0 && y < a.H;
             const act_t* p = src + ((long long)(row_ok ? y : 0) * a.W + x) * a.src_pitch;
-            const uint32_t d = slot0 + (uint32_t)((k % kDepth) * 3 * kDwThreads * 16);
-            const uint32_t nl = (row_ok && has_l) ? 16u : 0u, nc = row_ok ? 16u : 0u, nr = (row_ok && has_r) ? 16u : 0u;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(has_l ? p - a.src_pitch : p), "r"(nl) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d + kDwThreads * 16), "l"(p), "r"(nc) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d + 2 * kDwThreads * 16), "l"(has_r ? p + a.src_pitch : p), "r"(nr) : "memory");
+            const uint32_t d = slot0 + (uint32_t)((k % kDepth) * 4 * kDwThreads * 16);
+            const uint32_t n0 = (row_ok && has0) ? 16u : 0u, n1 = row_ok ? 16u : 0u, n2 = (row_ok && has2) ? 16u : 0u, n3 = (row_ok && has3) ? 16u : 0u;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(has0 ? p - a.src_pitch : p), "r"(n0) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d + kDwThreads * 16), "l"(p), "r"(n1) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d + 2 * kDwThreads * 16), "l"(has2 ? p + a.src_pitch : p), "r"(n2) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d + 3 * kDwThreads * 16), "l"(has3 ? p + 2 * a.src_pitch : p), "r"(n3) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    // take input row k out of the ring (it has landed once at most kDepth - 1 younger groups are pending) and
-    // re-use its slot for row k + kDepth
     auto fetch = [&](int k, uint4* r) {
         asm volatile("cp.async.wait_group %0;" :: "n"(kDepth - 1) : "memory");
-        const uint32_t d = slot0 + (uint32_t)((k % kDepth) * 3 * kDwThreads * 16);
+        const uint32_t d = slot0 + (uint32_t)((k % kDepth) * 4 * kDwThreads * 16);
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
+        for (int c = 0; c < 4; ++c)
             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r[c].x), "=r"(r[c].y), "=r"(r[c].z), "=r"(r[c].w) : "r"(d + c * kDwThreads * 16));
         issue(k + kDepth);
     };
-    uint4 win0[3], win1[3], win2[3];
+    uint4 win0[4], win1[4], win2[4];
     auto step = [&](const uint4* r0, const uint4* r1, uint4* r2, int y) {
         fetch(y - y0 + 2, r2);                           // row y + 1
-        uint4 pa = hmul8(r0[0], W9(0));
-        uint4 pb = hmul8(r2[0], W9(6));
-        hfma8(pa, r0[1], W9(1)); hfma8(pb, r2[1], W9(7));
-        hfma8(pa, r0[2], W9(2)); hfma8(pb, r2[2], W9(8));
-        hfma8(pa, r1[0], W9(3));
-        hfma8(pa, r1[1], W9(4));
-        hfma8(pa, r1[2], W9(5));
-        const uint4 raw = make_uint4(hadd2u(pa.x, pb.x), hadd2u(pa.y, pb.y), hadd2u(pa.z, pb.z), hadd2u(pa.w, pb.w));
-        *reinterpret_cast<uint4*>(dst + ((long long)y * a.W + x) * dpitch) = raw;
+        // same tap order and rounding points as the one-pixel kernel (chain a: rows 0-1, chain b: row 2)
+        uint4 w = W9(0);
+        uint4 pa0 = hmul8(r0[0], w), pa1 = hmul8(r0[1], w);
+        w = W9(6);
+        uint4 pb0 = hmul8(r2[0], w), pb1 = hmul8(r2[1], w);
+        w = W9(1); hfma8(pa0, r0[1], w); hfma8(pa1, r0[2], w);
+        w = W9(7); hfma8(pb0, r2[1], w); hfma8(pb1, r2[2], w);
+        w = W9(2); hfma8(pa0, r0[2], w); hfma8(pa1, r0[3], w);
+        w = W9(8); hfma8(pb0, r2[2], w); hfma8(pb1, r2[3], w);
+        w = W9(3); hfma8(pa0, r1[0], w); hfma8(pa1, r1[1], w);
+        w = W9(4); hfma8(pa0, r1[1], w); hfma8(pa1, r1[2], w);
+        w = W9(5); hfma8(pa0, r1[2], w); hfma8(pa1, r1[3], w);
+        act_t* o = dst + ((long long)y * a.W + x) * dpitch;
+        *reinterpret_cast<uint4*>(o) = make_uint4(hadd2u(pa0.x, pb0.x), hadd2u(pa0.y, pb0.y), hadd2u(pa0.z, pb0.z), hadd2u(pa0.w, pb0.w));
+        if (has2)
+            *reinterpret_cast<uint4*>(o + dpitch) = make_uint4(hadd2u(pa1.x, pb1.x), hadd2u(pa1.y, pb1.y), hadd2u(pa1.z, pb1.z), hadd2u(pa1.w, pb1.w));
     };
 #pragma unroll
     for (int k = 0; k < kDepth; ++k) issue(k);
@@ -252,13 +259,14 @@ dw3x3_cpasync_kernel(const Dw3Args a) {
 
 int launch_dw3(const Dw3Args& a, cudaStream_t stream) {
     CIDNET_CHECK(a.seg_vecs * 8 <= 144 && a.nv == 3 * a.seg_vecs, CIDNET_ERR_INVALID, "dw3: bad channel layout");
-    dim3 grid(ceil_div(a.W * a.nv, kDwThreads), ceil_div(a.H, kDwRows), a.B * a.nprob);
 #ifndef CIDNET_ACT_BF16
-    const size_t smem = (size_t)4 * 3 * kDwThreads * 16 + (size_t)9 * a.nv * 8 * sizeof(act_t);
-    int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(dw3x3_cpasync_kernel<4, 5>), 64 * 1024);
+    const size_t smem2 = (size_t)4 * 4 * kDwThreads * 16 + (size_t)9 * a.nv * 8 * sizeof(act_t);
+    dim3 grid2(ceil_div(ceil_div(a.W, 2) * a.nv, kDwThreads), ceil_div(a.H, kDwRows), a.B * a.nprob);
+    int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(dw3x3_cpasync2_kernel<4, 4>), 64 * 1024);
     if (rc) return rc;
-    if ((rc = launch_k(dw3x3_cpasync_kernel<4, 5>, grid, dim3(kDwThreads), smem, stream, a))) return rc;
+    if ((rc = launch_k(dw3x3_cpasync2_kernel<4, 4>, grid2, dim3(kDwThreads), smem2, stream, a))) return rc;
 #else
+    dim3 grid(ceil_div(a.W * a.nv, kDwThreads), ceil_div(a.H, kDwRows), a.B * a.nprob);
     int rc = launch_k(dw3x3_f32acc_kernel, grid, dim3(kDwThreads), 0, stream, a);
     if (rc) return rc;
 #endif
