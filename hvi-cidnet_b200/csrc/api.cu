@@ -376,45 +376,73 @@ struct Plan {
     int64_t bytes;
 };
 
+// Workspace layout.  Long-lived tensors (block0 outputs, the HVI image, block / LCA outputs that serve as skip connections)
+// get their own ranges; everything that only lives inside a stage is carved out of two ARENAS (one per branch, so the I and
+// HV launches of a pair never share memory), by liveness:
+//
+//   arena[s], viewed at level l (element offsets per level-l pixel; Cp = channel pitch, hp = padded hidden width):
+//     [0, Cp)            xp   = x + CAB(..)          written by attnv, read until project_out
+//     [Cp, Cp + 2 hp)    tin  = project_in output    written after the Gram / fold, read by the gate
+//       [Cp, 4 Cp)         qkv  (ln_qkv output)        dead once dw3x3 has run   } both inside tin's range: 3 Cp + 2 Cp <= 2 hp
+//       [4 Cp, 6 Cp)       qk   (dw3x3 output)         dead once the Gram has run }
+//     [Cp + 2 hp, Cp + 3 hp)  g = gate output       written by the gate, read by project_out
+//       [3 hp, Cp + 3 hp)      vdw (dw3x3 output)      read by attnv, long before the gate writes g
+//   The level-1 arena (the largest) hosts the level-2 and level-3 views side by side (stages 2-5 run while level 1 is idle) and,
+//   after stage 6, the last up block's outputs id1 / hvd1.  The spatial-attention statistics of the MSSA variant share the
+//   range of the output_hvi tap (the head writes that tap after the last gate has consumed the statistics).
+// ~0.85 KB per input pixel instead of the 1.9 KB of the round-1 bump allocation (cfg 4: 13 GB instead of 29 GB).
 void make_plan(Plan* P, void* ws, int B, int H, int W) {
     Bump bp(ws);
     P->B = B;
     for (int l = 0; l < 4; ++l) { P->H[l] = H >> l; P->W[l] = W >> l; }
     auto px = [&](int l) { return (int64_t)B * P->H[l] * P->W[l]; };
     P->hvi = bp.take<float>(px(0) * 3);
-    P->out_hvi = bp.take<float>(px(0) * 3);
-    for (int s = 0; s < 2; ++s) P->sa_stats[s] = bp.take<float2>(px(0));
+    P->out_hvi = bp.take<float>(px(0) * 4);                        // 12 B/px tap | 16 B/px of (mean, max) statistics
+    P->sa_stats[0] = reinterpret_cast<float2*>(P->out_hvi);
+    P->sa_stats[1] = P->sa_stats[0] ? P->sa_stats[0] + px(0) : nullptr;
     P->i_enc0 = bp.take<act_t>(px(0) * 40); P->hv_0 = bp.take<act_t>(px(0) * 40);
-    P->id1 = bp.take<act_t>(px(0) * 40);    P->hvd1 = bp.take<act_t>(px(0) * 40);
+    int Cp[4], hp[4];
+    for (int l = 1; l <= 3; ++l) { Cp[l] = act_pitch(kCh[l]); hp[l] = round_up((int)(kCh[l] * 2.66), 16); }
+    // the two arenas: sized for the level-1 view, which also covers level 2 + level 3 side by side and id1 / hvd1
+    int64_t arena_elems = px(1) * (Cp[1] + 3 * hp[1]);
+    arena_elems = std::max(arena_elems, px(2) * (Cp[2] + 3 * hp[2]) + px(3) * (Cp[3] + 3 * hp[3]) + 2 * 512);
+    arena_elems = std::max(arena_elems, px(0) * 40);
+    for (int s = 0; s < 2; ++s) {
+        act_t* arena = bp.take<act_t>(arena_elems);
+        auto align512 = [](int64_t e) { return (e + 511) & ~int64_t(511); };      // 1 KB
+        int64_t base[4] = {0, 0, 0, 0};
+        base[3] = align512(px(2) * (Cp[2] + 3 * hp[2]));                       // level 3 behind level 2
+        for (int l = 1; l <= 3; ++l) {
+            act_t* a0 = arena ? arena + base[l] : nullptr;
+            auto at = [&](int64_t per_px) { return a0 ? a0 + px(l) * per_px : nullptr; };
+            P->xp[l][s] = at(0);
+            P->tin[l][s] = at(Cp[l]);
+            P->qkv[l][s] = at(Cp[l]);
+            P->qk[l][s] = at(4 * Cp[l]);
+            P->g[l][s] = at(Cp[l] + 2 * hp[l]);
+            P->vdw[l][s] = at(3 * hp[l]);
+        }
+        (s == 0 ? P->id1 : P->hvd1) = arena;
+    }
     for (int l = 1; l <= 3; ++l) {
-        const int Cp = act_pitch(kCh[l]);
-        P->enc_i[l] = bp.take<act_t>(px(l) * Cp); P->enc_hv[l] = bp.take<act_t>(px(l) * Cp);
+        P->enc_i[l] = bp.take<act_t>(px(l) * Cp[l]); P->enc_hv[l] = bp.take<act_t>(px(l) * Cp[l]);
         const int Cup = act_pitch(kCh[l - 1]);
         P->tup_i[l] = bp.take<act_t>(px(l) * Cup); P->tup_hv[l] = bp.take<act_t>(px(l) * Cup);
-        if (l <= 2) { P->dec_i[l] = bp.take<act_t>(px(l) * Cp); P->dec_hv[l] = bp.take<act_t>(px(l) * Cp); }
-        const int h = (int)(kCh[l] * 2.66), hp = round_up(h, 16);
+        if (l <= 2) { P->dec_i[l] = bp.take<act_t>(px(l) * Cp[l]); P->dec_hv[l] = bp.take<act_t>(px(l) * Cp[l]); }
         PackedWeights f; choose_blocking(kCh[l], &f.block_n, &f.n_blocks);
         const int64_t fold_elems = (int64_t)B * f.block_n * f.n_blocks * ceil_div(kCh[l], 64) * 64;
-        for (int s = 0; s < 2; ++s) {
-            P->qkv[l][s] = bp.take<act_t>(px(l) * 3 * Cp);
-            P->qk[l][s] = bp.take<act_t>(px(l) * 2 * Cp);
-            P->vdw[l][s] = bp.take<act_t>(px(l) * Cp);
-            P->xp[l][s] = bp.take<act_t>(px(l) * Cp);
-            P->tin[l][s] = bp.take<act_t>(px(l) * 2 * hp);
-            P->g[l][s] = bp.take<act_t>(px(l) * hp);
-            P->mfold[l][s] = bp.take<act_t>(fold_elems);
-        }
+        for (int s = 0; s < 2; ++s) P->mfold[l][s] = bp.take<act_t>(fold_elems);
     }
     for (int n = 1; n <= 6; ++n) {
         const int l = n <= 3 ? n : 7 - n;
-        P->lca_i[n] = bp.take<act_t>(px(l) * act_pitch(kCh[l]));
-        P->lca_hv[n] = bp.take<act_t>(px(l) * act_pitch(kCh[l]));
+        P->lca_i[n] = bp.take<act_t>(px(l) * Cp[l]);
+        P->lca_hv[n] = bp.take<act_t>(px(l) * Cp[l]);
     }
     // attention statistics: the split-K slab (re-used by every stage) and the reduced vector of each stage
     P->slab = bp.take<float>((int64_t)gram_max_slab_entries(2 * B) * (8 * 324 + 2 * 144));
     for (int n = 1; n <= 6; ++n) {
         const int l = n <= 3 ? n : 7 - n;
-        P->stat[n - 1] = bp.take<float>((int64_t)2 * B * (kHeads[l] * 324 + 2 * act_pitch(kCh[l])));
+        P->stat[n - 1] = bp.take<float>((int64_t)2 * B * (kHeads[l] * 324 + 2 * Cp[l]));
     }
     P->statsum = bp.take<float>((int64_t)2 * B * (8 * 324 + 2 * 144));
     P->bytes = bp.off + 1024;
@@ -738,7 +766,6 @@ struct Fwd {
             if (P.B == 1) fw.n_img = 1;
             if ((rc = gemm(A, "L" + std::to_string(l) + ".cab_attnv_proj_res", s, both))) return rc;
             setm(P.xp[l][s], m_dw);
-            tap(std::string(s == 0 ? "I_LCA" : "HV_LCA") + std::to_string(n) + ".after_cab", P.xp[l][s], C, l, Cp);
         }
         // the IEL gate chains two depthwise 3x3: two valid halo rows of x' (project_in is recomputed on them).  The exchange
         // is issued on the main stream: both branches must have produced their x' first

@@ -64,6 +64,7 @@ class StripComm:
         self.error = None
         self.log = []                                   # ("halo", [(offset, row_bytes, rows, top, bot)...]) / ("allreduce", offset, count)
         self.bytes_sent = 0
+        self.trace = None                               # tests: set to [] to record a fingerprint of every block sent / received
         self.halo_cb = _clib().HALO_FN(self._halo)
         self.allreduce_cb = _clib().ALLREDUCE_FN(self._allreduce)
 
@@ -91,6 +92,8 @@ class StripComm:
                     recvs.append((t[q.rows - q.halo_bot:], self.rank + 1))
             self.log.append(("halo", entry))
             self.bytes_sent += sum(s.numel() for s, _ in sends)
+            if self.trace is not None:
+                sent_fp = [(p, _fingerprint(s_)) for s_, p in sends]
             if self.direct:
                 ops = [dist.P2POp(dist.isend, s, self._peer(p), self.group) for s, p in sends]
                 ops += [dist.P2POp(dist.irecv, r, self._peer(p), self.group) for r, p in recvs]
@@ -105,6 +108,8 @@ class StripComm:
                     w.wait()
                 for h, (r, _) in zip(hr, recvs):
                     r.copy_(h)
+            if self.trace is not None:
+                self.trace.append(("halo", sent_fp, [(p, _fingerprint(r_)) for r_, p in recvs]))
             return 0
         except BaseException as e:                       # never let an exception cross the C boundary
             self.error = e
@@ -114,12 +119,15 @@ class StripComm:
         try:
             t = self._view(ptr, 4 * count).view(torch.float32)
             self.log.append(("allreduce", ptr - self.buf.data_ptr(), int(count)))
+            before = t.detach().double().cpu().clone() if self.trace is not None else None
             if self.direct:
                 dist.all_reduce(t, group=self.group)
             else:
                 h = t.cpu()
                 dist.all_reduce(h, group=self.group)
                 t.copy_(h)
+            if self.trace is not None:
+                self.trace.append(("allreduce", before, t.detach().double().cpu().clone()))
             return 0
         except BaseException as e:
             self.error = e
@@ -129,6 +137,13 @@ class StripComm:
 def _clib():
     from . import _lib
     return _lib
+
+
+def _fingerprint(t):
+    """(byte sum, position-weighted byte sum) of a uint8 block: equal for the block a rank sent and the block its
+    neighbour received (StripComm.trace, used by the CPU tests of the exchange schedule)"""
+    b = t.detach().reshape(-1).to("cpu", torch.int64)
+    return int(b.sum()), int((b * (torch.arange(b.numel(), dtype=torch.int64) % 8191 + 1)).sum())
 
 
 def strip_plan(H, world_size, rank, halo=16):

@@ -103,39 +103,40 @@ def _dry_worker(rank, world, port, H, W, ret, variant=0):
     ws = raw[off:off + (nbytes // 4) * 4]
     ws.view(torch.float32).copy_(_pattern(rank, ws.numel() // 4))
     comm = StripComm(ws)
+    comm.trace = []
     nh, na = ctypes.c_int(), ctypes.c_int()
     rc = L.cidnet_forward_sharded_dry_variant(variant, W, ctypes.byref(sh), ws.data_ptr(), ws.numel(), comm.halo_cb,
                                               comm.allreduce_cb, None, ctypes.byref(nh), ctypes.byref(na))
     assert rc == 0 and comm.error is None, (rc, comm.error, L.cidnet_last_error())
-    logs = [None] * world
+    logs, traces = [None] * world, [None] * world
     dist.all_gather_object(logs, comm.log)
-    f = ws.view(torch.float32)
+    dist.all_gather_object(traces, comm.trace)
     bad = 0
     kinds = [[e[0] for e in lg] for lg in logs]
     assert all(k == kinds[0] for k in kinds), "ranks disagree on the callback sequence"
+    # The workspace is re-used by liveness (a later tensor may occupy an earlier one's bytes), so every exchange is checked
+    # AT THE TIME IT HAPPENS: the block a rank received from a neighbour must be the block that neighbour sent in the same
+    # call, the geometry of the request must mirror the neighbour's, and an all-reduce must leave the sum of all ranks' inputs.
     for i, e in enumerate(comm.log):
+        tr = comm.trace[i]
         if e[0] == "halo":
             assert all(len(lg[i][1]) == len(e[1]) for lg in logs)
             for j, (o, rb, nr, top, bot) in enumerate(e[1]):
-                t = f[o // 4:(o + nr * rb) // 4].view(nr, rb // 4)
                 if top:
                     po, prb, pnr, ptop, pbot = logs[rank - 1][i][1][j]
                     assert prb == rb and pbot == top
-                    src = _pattern(rank - 1, po // 4 + pnr * prb // 4)[po // 4:].view(pnr, prb // 4)
-                    bad += int(not torch.equal(t[:top], src[pnr - 2 * pbot:pnr - pbot]))
                 if bot:
                     po, prb, pnr, ptop, pbot = logs[rank + 1][i][1][j]
                     assert prb == rb and ptop == bot
-                    src = _pattern(rank + 1, po // 4 + pnr * prb // 4)[po // 4:].view(pnr, prb // 4)
-                    bad += int(not torch.equal(t[nr - bot:], src[ptop:2 * ptop]))
-                # owned rows untouched
-                own = _pattern(rank, o // 4 + nr * rb // 4)[o // 4:].view(nr, rb // 4)
-                bad += int(not torch.equal(t[top:nr - bot], own[top:nr - bot]))
+            # received blocks, in request order, against what the peer sent TO THIS RANK in the same call (same order)
+            for peer in {p for p, _ in tr[2]}:
+                got = [fp for p, fp in tr[2] if p == peer]
+                sent = [fp for p, fp in traces[peer][i][1] if p == rank]
+                bad += int(got != sent)
         else:
-            _, o, cnt = e
-            want = sum(_pattern(r, logs[r][i][1] // 4 + cnt)[logs[r][i][1] // 4:] for r in range(world))
-            assert all(lg[i][2] == cnt for lg in logs)
-            bad += int(not torch.equal(f[o // 4:o // 4 + cnt], want))
+            want = sum(traces[r][i][1] for r in range(world))
+            bad += int(not torch.equal(tr[2], want))
+            assert all(lg[i][2] == e[2] for lg in logs)
     ret[rank] = (bad, nh.value, na.value, len(comm.log), comm.bytes_sent)
     dist.destroy_process_group()
 
