@@ -76,6 +76,7 @@ SIGNATURES = {
     "cidnet_profile_count": (C.c_int, [C.c_void_p]),
     "cidnet_profile_get": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_float),
                                      C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "cidnet_profile_get_span": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     # unit-test hook (csrc/test_hooks.cu): x, w_host, aux, ln_host, out, B, Cin, H, W, Cout, ksize, mode, flat, prelu, stream
     "cidnet_test_conv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -263,7 +263,7 @@ int build_weights(cidnet_ctx* ctx) {
         if ((rc = dev_f32(ctx, &ctx->head_wi, c))) return rc;
         if ((rc = dev_f32(ctx, &ctx->head_whv, d))) return rc;
         // per-lane B fragments of the stem / head tensor-core kernels (uint2 viewed as 2 floats for the upload helper)
-        std::vector<float> fs(3 * 5 * 32 * 2), fh(2 * 9 * 3 * 32 * 2);
+        std::vector<float> fs(3 * 5 * 32 * 2), fh(5 * 3 * 32 * 2);
         pack_stem_bfrag(a.data(), b.data(), reinterpret_cast<uint2*>(fs.data()));
         pack_head_bfrag(c.data(), d.data(), reinterpret_cast<uint2*>(fh.data()));
         float *dfs = nullptr, *dfh = nullptr;
@@ -1334,6 +1334,15 @@ extern "C" int cidnet_profile_get(cidnet_ctx* ctx, int i, char* name, int name_c
     if (alg_bytes) *alg_bytes = r.bytes;
     if (flops) *flops = r.flops;
     if (ms) CIDNET_CUDA_OK(cudaEventElapsedTime(ms, ctx->events[2 * i], ctx->events[2 * i + 1]));
+    return CIDNET_OK;
+}
+
+// start / end of launch i relative to the first launch of the profiled forward (ms): launches of a pair run concurrently on two
+// streams, so the wall time of a pair is max(end) - min(start), not the sum of the two durations
+extern "C" int cidnet_profile_get_span(cidnet_ctx* ctx, int i, float* start_ms, float* end_ms) {
+    CIDNET_CHECK(ctx && i >= 0 && i < (int)ctx->recs.size() && start_ms && end_ms, CIDNET_ERR_INVALID, "profile_get_span: bad index");
+    CIDNET_CUDA_OK(cudaEventElapsedTime(start_ms, ctx->events[0], ctx->events[2 * i]));
+    CIDNET_CUDA_OK(cudaEventElapsedTime(end_ms, ctx->events[0], ctx->events[2 * i + 1]));
     return CIDNET_OK;
 }
 

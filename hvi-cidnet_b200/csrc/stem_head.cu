@@ -33,6 +33,7 @@ __device__ __forceinline__ void fhfma2(float& acc0, float& acc1, uint32_t a, uin
 
 static constexpr int kTile = 16;          // 16x16 output pixels per CTA, 256 threads
 static constexpr int kHalo = kTile + 2;
+static constexpr int kHeadRows = 21 * 16 + 1;   // head: pixel rows of a staged halo tile (18 x 18 = 324, padded to 21 m-tiles of 16 + 1)
 
 // Both block0 stages are tiny GEMMs per pixel (stem: K = 27 / 9, N = 36; head: K = 9 x 36, N = 1 / 2).  The fp32-FMA
 // kernels of round 1 spent 1300-1700 instructions per pixel on them (ncu: issue-bound at 1.2-1.5 TB/s, 4-5x their HBM
@@ -221,17 +222,21 @@ void pack_stem_bfrag(const float* w_hv /*[27][36] (c*9+t major)*/, const float* 
         out[i] = make_uint2(host_pack2(wv[0], wv[1]), host_pack2(wv[2], wv[3]));
     }
 }
-void pack_head_bfrag(const float* w_i /*[9][36]*/, const float* w_hv /*[2][9][36]*/, uint2* out /*[2][9][3][32]*/) {
-    for (int i = 0; i < 2 * 9 * 3 * 32; ++i) {
-        const int l = i & 31, ks = (i >> 5) % 3, t = (i / 96) % 9, br = i / 864;
-        const int n = l >> 2, tg = l & 3;        // output column n: branch 0 -> n == 0 (I), branch 1 -> n == 1, 2 (H, V)
+// head: the taps live in the N dimension (see head_mma_kernel).  n-tiles: 0, 1 = ID_block0 (n = tap 0..8), 2, 3, 4 =
+// HVD_block0 (n = out * 9 + tap, out 0 = H, 1 = V); layout [n-tile 5][k-step 3][lane 32].
+void pack_head_bfrag(const float* w_i /*[9][36]*/, const float* w_hv /*[2][9][36]*/, uint2* out /*[5][3][32]*/) {
+    for (int i = 0; i < 5 * 3 * 32; ++i) {
+        const int l = i & 31, ks = (i >> 5) % 3, nt = i / 96;
+        const int g = l >> 2, tg = l & 3;
+        const bool is_i = nt < 2;
+        const int n = (is_i ? nt : nt - 2) * 8 + g;             // column inside the branch
         float wv[4];
         for (int e = 0; e < 4; ++e) {
             const int c = ks * 16 + 2 * tg + (e & 1) + (e >> 1) * 8;
             float v = 0.f;
             if (c < 36) {
-                if (br == 0 && n == 0) v = w_i[t * 36 + c];
-                if (br == 1 && (n == 1 || n == 2)) v = w_hv[((n - 1) * 9 + t) * 36 + c];
+                if (is_i && n < 9) v = w_i[n * 36 + c];
+                if (!is_i && n < 18) v = w_hv[n * 36 + c];      // [(out * 9 + tap)][36]
             }
             wv[e] = v;
         }
@@ -249,31 +254,37 @@ int launch_stem(const StemArgs& a, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------ head ----
-// head on warp-level tensor cores: per tap and 16-channel k-step one ldmatrix.x4 per 16-pixel row segment (A = the NHWC
-// halo tile itself: row = pixel, 80-byte pitch -> conflict-free) and one m16n8k16 MMA per branch; output columns
-// 0 = I (ID_block0, A = i_dec1 tile), 1, 2 = H, V (HVD_block0, A = hv_1 tile) of ONE accumulator tile.  Channels 36..39
-// of the tiles are zeroed when staged, channels 40..47 of the third k-step belong to the next pixel and meet zero weights.
-__global__ void __launch_bounds__(256, 3)
+// head on warp-level tensor cores, TAPS IN THE N DIMENSION.  Both convs have 1 / 2 output channels, so instead of one
+// 16-pixel x 8 MMA per tap (9 x 3 k-steps x 2 branches = 54 ldmatrix.x4 + 54 MMAs per 16 pixels, of which 5 / 8 of every
+// MMA's columns are padding: ncu on that version showed the LSU / shared-memory pipe at 77 %), the per-pixel partial products
+//     P[halo pixel][tap]        = sum_c  i_dec1[pixel][c] * W_I[tap][c]              (9 columns)
+//     P[halo pixel][9 + 9o + t] = sum_c  hv_1[pixel][c]   * W_HV[o][t][c]            (18 columns, o = H, V)
+// are computed ONCE per halo pixel -- A = the NHWC halo tile itself (row = pixel, 80-byte pitch -> conflict-free ldmatrix),
+// 3 ldmatrix.x4 per 16 halo pixels and branch feed 2 + 3 n-tiles -- and every output pixel then sums its nine shifted
+// entries per output from a 27-float-pitch table (odd pitch: conflict-free LDS.32).  Per 16 x 16 tile: 126 ldmatrix.x4 and
+// 315 MMAs instead of 864 and 864.  Channels 36..39 of the tiles are zeroed when staged, channels 40..47 of the third k-step
+// belong to the next pixel and meet zero weights.
+__global__ void __launch_bounds__(256, 2)
 head_mma_kernel(const act_t* __restrict__ i_dec1, const act_t* __restrict__ hv_1, const float* __restrict__ hvi,
                 void* __restrict__ rgb_any, float* __restrict__ out_hvi_dbg, const float* __restrict__ w_i /*[9][36]*/,
                 const float* __restrict__ w_hv /*[2][9][36]*/, const float* __restrict__ k_dev, PhvitParams pp,
-                int H, int W, int pitch, const uint2* __restrict__ bfrag /*[2][9][3][32], cidnet_pack_head_bfrag*/,
+                int H, int W, int pitch, const uint2* __restrict__ bfrag /*[5][3][32], cidnet_pack_head_bfrag*/,
                 int out_u8, int h_dst, int w_dst) {
     // out_u8 == 0: rgb_any = fp32 [B,3,H,W] planar.  out_u8 == 1: rgb_any = uint8 [B,h_dst,w_dst,3]: clamp(0,1), crop to
     // [:h_dst,:w_dst] and ToPILImage's mul(255).byte() (eval.py:69-73) happen in the store below.
     float* __restrict__ rgb = reinterpret_cast<float*>(rgb_any);
     extern __shared__ __align__(16) uint8_t head_smem[];
-    act_t* s_i = reinterpret_cast<act_t*>(head_smem);                        // [18*18 + 1 pad pixel][40]
-    act_t* s_hv = s_i + (kHalo * kHalo + 1) * 40;
-    uint2* s_bfrag = reinterpret_cast<uint2*>(s_hv + (kHalo * kHalo + 1) * 40);   // [2 branches][9 taps][3 k-steps][32 lanes]
-    float* s_res = reinterpret_cast<float*>(s_bfrag + 2 * 9 * 3 * 32);      // [8 warps][32 pixels][3] = (I, H, V)
+    act_t* s_i = reinterpret_cast<act_t*>(head_smem);                        // [21 m-tiles x 16 = 336 pixel rows + 1 pad pixel][40]
+    act_t* s_hv = s_i + kHeadRows * 40;
+    uint2* s_bfrag = reinterpret_cast<uint2*>(s_hv + kHeadRows * 40);        // [5 n-tiles][3 k-steps][32 lanes]
+    float* s_P = reinterpret_cast<float*>(s_bfrag + 5 * 3 * 32);            // [336 halo pixels][27]: I taps | H taps | V taps
     const int b = blockIdx.z;
     const int y0 = blockIdx.y * kTile, x0 = blockIdx.x * kTile;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, tig = lane & 3;
     const long long hw = (long long)H * W;
 
-    for (int i = tid; i < 2 * 9 * 3 * 32 / 2; i += 256)      // per-lane B fragments, packed once at weight-finalisation time
+    for (int i = tid; i < 5 * 3 * 32 / 2; i += 256)          // per-lane B fragments, packed once at weight-finalisation time
         reinterpret_cast<uint4*>(s_bfrag)[i] = __ldg(reinterpret_cast<const uint4*>(bfrag) + i);
     ptx::pdl_wait();               // constants above; the activations and k belong to the stream's earlier work
     ptx::pdl_trigger();
@@ -296,7 +307,7 @@ head_mma_kernel(const act_t* __restrict__ i_dec1, const act_t* __restrict__ hv_1
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(di + (uint32_t)hy * 1440u), "l"(i_dec1 + gi), "r"(nsrc) : "memory");
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dh + (uint32_t)hy * 1440u), "l"(hv_1 + gi), "r"(nsrc) : "memory");
         }
-    } else if (tid < 185) {                                          // the zero pad pixel behind each tile
+    } else if (tid < 180 + 13 * 5) {                                 // the 13 pad pixel rows behind each tile (m-tile 20 reads them)
         reinterpret_cast<uint4*>(s_i)[kHalo * 90 + tid - 180] = make_uint4(0, 0, 0, 0);
         reinterpret_cast<uint4*>(s_hv)[kHalo * 90 + tid - 180] = make_uint4(0, 0, 0, 0);
     }
@@ -308,45 +319,44 @@ head_mma_kernel(const act_t* __restrict__ i_dec1, const act_t* __restrict__ hv_1
     const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lk = (lane >> 4) * 8;
     const uint32_t si_base = static_cast<uint32_t>(__cvta_generic_to_shared(s_i));
     const uint32_t shv_base = static_cast<uint32_t>(__cvta_generic_to_shared(s_hv));
-    float acc[2][4];
-#pragma unroll
-    for (int m = 0; m < 2; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f; }
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
+    // ---- phase 1: partial products of every halo pixel (21 m-tiles of 16 pixel rows, round-robin over the 8 warps)
+    for (int mt = warp; mt < 21; mt += 8) {
+        uint32_t ai[3][4], ah[3][4];
 #pragma unroll
         for (int ks = 0; ks < 3; ++ks) {
-            const uint2 bi = s_bfrag[(t * 3 + ks) * 32 + lane];
-            const uint2 bh = s_bfrag[((9 + t) * 3 + ks) * 32 + lane];
+            const uint32_t off = (uint32_t)(((mt * 16 + lrow) * 40 + ks * 16 + lk) * 2);
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(ai[ks][0]), "=r"(ai[ks][1]), "=r"(ai[ks][2]), "=r"(ai[ks][3]) : "r"(si_base + off));
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(ah[ks][0]), "=r"(ah[ks][1]), "=r"(ah[ks][2]), "=r"(ah[ks][3]) : "r"(shv_base + off));
+        }
+        float* p0 = s_P + (mt * 16 + g) * 27;                 // C fragment: c0, c1 = (row g, columns 2 tig, +1), c2, c3 = (row g + 8, ..)
+        float* p1 = p0 + 8 * 27;
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                const uint32_t off = (uint32_t)((((2 * warp + m + t / 3) * kHalo + lrow + t % 3) * 40 + ks * 16 + lk) * 2);
-                uint32_t a[4];
-                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(si_base + off));
-                mma16816(acc[m], a, bi.x, bi.y);
-                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(shv_base + off));
-                mma16816(acc[m], a, bh.x, bh.y);
+        for (int nt = 0; nt < 5; ++nt) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ks = 0; ks < 3; ++ks) {
+                const uint2 bf = s_bfrag[(nt * 3 + ks) * 32 + lane];
+                mma16816(acc, nt < 2 ? ai[ks] : ah[ks], bf.x, bf.y);
             }
+            const int n = (nt < 2 ? nt : nt - 2) * 8 + 2 * tig;       // column inside the branch
+            const int lim = nt < 2 ? 9 : 18, col = (nt < 2 ? 0 : 9) + n;
+            if (n < lim) { p0[col] = acc[0]; p1[col] = acc[2]; }
+            if (n + 1 < lim) { p0[col + 1] = acc[1]; p1[col + 1] = acc[3]; }
         }
     }
-    // C fragment: c0, c1 = (row g, columns 2 tig, 2 tig + 1), c2, c3 = (row g + 8, ...): columns 0..2 live in tig 0 / 1
-    float* res = s_res + warp * 96;
-#pragma unroll
-    for (int m = 0; m < 2; ++m) {
-        if (tig == 0) {
-            res[(m * 16 + g) * 3 + 0] = acc[m][0]; res[(m * 16 + g) * 3 + 1] = acc[m][1];
-            res[(m * 16 + g + 8) * 3 + 0] = acc[m][2]; res[(m * 16 + g + 8) * 3 + 1] = acc[m][3];
-        } else if (tig == 1) {
-            res[(m * 16 + g) * 3 + 2] = acc[m][0];
-            res[(m * 16 + g + 8) * 3 + 2] = acc[m][2];
-        }
-    }
-    __syncwarp();
-    const int ty = tid / kTile, tx = tid - ty * kTile;      // == (2 warp + lane / 16, lane % 16): pixel `lane` of the warp
+    __syncthreads();
+    // ---- phase 2: every thread sums the nine shifted entries of its own pixel, per output
+    const int ty = tid / kTile, tx = tid - ty * kTile;
     const int y = y0 + ty, x = x0 + tx;
     if (y >= H || x >= W) return;
-    const float oi = res[lane * 3 + 0], oh = res[lane * 3 + 1], ov = res[lane * 3 + 2];
+    float oi = 0.f, oh = 0.f, ov = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const float* p = s_P + ((ty + t / 3) * kHalo + tx + t % 3) * 27 + t;
+        oi += p[0]; oh += p[9]; ov += p[18];
+    }
     const long long pix = (long long)y * W + x;
     const float* hp = hvi + (long long)b * 3 * hw + pix;
     const float Hh = oh + __ldcg(hp), Vv = ov + __ldcg(hp + hw), Ii = oi + __ldcg(hp + 2 * hw);   // cat([hv_0, i_dec0]) + hvi
@@ -375,7 +385,7 @@ int launch_head(const HeadArgs& a, cudaStream_t stream) {
     CIDNET_CHECK(a.pitch == 40, CIDNET_ERR_INVALID, "head: pitch must be 40");
     dim3 grid(ceil_div(a.W, kTile), ceil_div(a.H, kTile), a.B);
     PhvitParams pp{a.k_host, a.alpha_s, a.alpha, a.gated, a.gated2};
-    const size_t smem = 2 * (kHalo * kHalo + 1) * 40 * sizeof(act_t) + 2 * 9 * 3 * 32 * sizeof(uint2) + 8 * 96 * sizeof(float);
+    const size_t smem = 2 * kHeadRows * 40 * sizeof(act_t) + 5 * 3 * 32 * sizeof(uint2) + 336 * 27 * sizeof(float);
     int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(head_mma_kernel), (int)smem);
     if (rc) return rc;
     return launch_k(head_mma_kernel, grid, dim3(256), smem, stream, a.i_dec1, a.hv_1, a.hvi, a.rgb, a.out_hvi_dbg, a.w_i,

@@ -24,7 +24,7 @@ struct HeadArgs {
     const float* w_hv;   // [2][9][36]
     const float* k_dev; float k_host; float alpha_s; float alpha; int gated; int gated2;
     int B, H, W, pitch;
-    const uint2* bfrag;  // [2][9][3][32] per-lane MMA B fragments (pack_head_bfrag)
+    const uint2* bfrag;  // [5][3][32] per-lane MMA B fragments (pack_head_bfrag)
     int out_u8 = 0, h_dst = 0, w_dst = 0;                       // 8-bit output: clamp + crop + quantise fused into the store
 };
 int launch_head(const HeadArgs& a, cudaStream_t stream);

@@ -308,16 +308,21 @@ class CIDNet(nn.Module, PyTorchModelHubMixin):
             raise RuntimeError("run one forward first")
         _lib.check(_lib.lib().cidnet_profile_enable(self._ctx, int(bool(enable))))
 
-    def read_profile(self):
-        """[(name, ms, algorithmic_bytes, flops)] of the last profiled forward (synchronises)."""
+    def read_profile(self, spans=False):
+        """[(name, ms, algorithmic_bytes, flops)] of the last profiled forward (synchronises); with `spans` each tuple
+        also carries (start_ms, end_ms) relative to the forward's first launch (pairs overlap on two streams)."""
         lib = _lib.lib()
         torch.cuda.synchronize(self._ctx_device)
         out = []
         buf = C.create_string_buffer(96)
-        ms, by, fl = C.c_float(), C.c_double(), C.c_double()
+        ms, by, fl, t0, t1 = C.c_float(), C.c_double(), C.c_double(), C.c_float(), C.c_float()
         for i in range(lib.cidnet_profile_count(self._ctx)):
             _lib.check(lib.cidnet_profile_get(self._ctx, i, buf, 96, C.byref(ms), C.byref(by), C.byref(fl)))
-            out.append((buf.value.decode(), float(ms.value), float(by.value), float(fl.value)))
+            rec = (buf.value.decode(), float(ms.value), float(by.value), float(fl.value))
+            if spans:
+                _lib.check(lib.cidnet_profile_get_span(self._ctx, i, C.byref(t0), C.byref(t1)))
+                rec += (float(t0.value), float(t1.value))
+            out.append(rec)
         return out
 
     def num_launches(self):

@@ -207,6 +207,10 @@ CIDNET_API int cidnet_profile_enable(cidnet_ctx* ctx, int enable);
 CIDNET_API int cidnet_profile_count(cidnet_ctx* ctx);
 CIDNET_API int cidnet_profile_get(cidnet_ctx* ctx, int i, char* name, int name_cap, float* ms,
                                   double* alg_bytes, double* flops);
+/* start / end of launch i in ms since the first launch of the profiled forward.  While profiling the forward runs with the
+ * same two-stream split as the replayed graph: the two launches of an (I, HV) pair overlap, their wall time is
+ * max(end) - min(start). */
+CIDNET_API int cidnet_profile_get_span(cidnet_ctx* ctx, int i, float* start_ms, float* end_ms);
 
 /* ---- unit-test hooks (tests/ only: they allocate scratch memory and synchronise) ------------
  * cidnet_test_conv: one implicit-GEMM convolution with one of the four fused epilogues
