@@ -31,7 +31,6 @@ namespace cidnet {
 
 // ------------------------------------------------------------- depthwise ----
 static constexpr int kDwThreads = 128;
-static constexpr int kDwRows = 32;     // rows per CTA strip
 
 #ifdef CIDNET_ACT_BF16
 #define CIDNET_FHFMA "fma.rn.f32.bf16"
@@ -80,8 +79,8 @@ dw3x3_f32acc_kernel(const Dw3Args a) {
     const act_t* src = a.src[prob][seg] + (long long)b * hw * a.src_pitch + c0;
     int dpitch;
     act_t* dst = dw_dst(a, prob, b, seg, c0, hw, &dpitch);
-    const int y0 = blockIdx.y * kDwRows;
-    const int y1 = min(y0 + kDwRows, a.H);
+    const int y0 = blockIdx.y * a.rows_per_cta;
+    const int y1 = min(y0 + a.rows_per_cta, a.H);
 
     uint4 w[9];
     {
@@ -183,8 +182,8 @@ dw3x3_cpasync2_kernel(const Dw3Args a) {
     const act_t* src = a.src[prob][seg] + (long long)b * hw * a.src_pitch + c0;
     int dpitch;
     act_t* dst = dw_dst(a, prob, b, seg, c0, hw, &dpitch);
-    const int y0 = blockIdx.y * kDwRows;
-    const int y1 = min(y0 + kDwRows, a.H);
+    const int y0 = blockIdx.y * a.rows_per_cta;
+    const int y1 = min(y0 + a.rows_per_cta, a.H);
     {
         const float* wp = a.w[prob];
         for (int i = threadIdx.x; i < 9 * nv * 8; i += kDwThreads) s_w[i] = f2act(__ldg(wp + i));
@@ -257,16 +256,21 @@ dw3x3_cpasync2_kernel(const Dw3Args a) {
 }
 #endif
 
-int launch_dw3(const Dw3Args& a, cudaStream_t stream) {
+int launch_dw3(const Dw3Args& a_in, cudaStream_t stream) {
+    Dw3Args a = a_in;
     CIDNET_CHECK(a.seg_vecs * 8 <= 144 && a.nv == 3 * a.seg_vecs, CIDNET_ERR_INVALID, "dw3: bad channel layout");
 #ifndef CIDNET_ACT_BF16
     const size_t smem2 = (size_t)4 * 4 * kDwThreads * 16 + (size_t)9 * a.nv * 8 * sizeof(act_t);
-    dim3 grid2(ceil_div(ceil_div(a.W, 2) * a.nv, kDwThreads), ceil_div(a.H, kDwRows), a.B * a.nprob);
+    const int gx = ceil_div(ceil_div(a.W, 2) * a.nv, kDwThreads);
+    a.rows_per_cta = pick_strip_rows(a.H, (long long)gx * a.B * a.nprob, 4 * device_sm_count(), 2, 2, 16, 96);
+    dim3 grid2(gx, ceil_div(a.H, a.rows_per_cta), a.B * a.nprob);
     int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(dw3x3_cpasync2_kernel<4, 4>), 64 * 1024);
     if (rc) return rc;
     if ((rc = launch_k(dw3x3_cpasync2_kernel<4, 4>, grid2, dim3(kDwThreads), smem2, stream, a))) return rc;
 #else
-    dim3 grid(ceil_div(a.W * a.nv, kDwThreads), ceil_div(a.H, kDwRows), a.B * a.nprob);
+    const int gx = ceil_div(a.W * a.nv, kDwThreads);
+    a.rows_per_cta = pick_strip_rows(a.H, (long long)gx * a.B * a.nprob, 3 * device_sm_count(), 2, 2, 16, 96);
+    dim3 grid(gx, ceil_div(a.H, a.rows_per_cta), a.B * a.nprob);
     int rc = launch_k(dw3x3_f32acc_kernel, grid, dim3(kDwThreads), 0, stream, a);
     if (rc) return rc;
 #endif

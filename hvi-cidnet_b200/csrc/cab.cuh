@@ -11,6 +11,7 @@ struct Dw3Args {
     act_t* dst_v[2];            // per problem: v after the depthwise conv, pitch Cp
     const float* w[2];          // fp32 [9][nv*8] tap major, segments in the same order
     int B, H, W, nv, seg_vecs, nprob;
+    int rows_per_cta;           // set by launch_dw3 (pick_strip_rows)
 };
 int launch_dw3(const Dw3Args& a, cudaStream_t stream);
 

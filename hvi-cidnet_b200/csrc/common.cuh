@@ -93,6 +93,24 @@ inline int launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem
 }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Rows per CTA of a row-walking kernel (dw3x3, IEL gate): every CTA walks `rows` output rows plus `halo` extra input rows, the
+// grid is ctas_per_strip * ceil(H / rows) CTAs on `slots` concurrently resident CTAs.  A fixed strip height leaves a nearly
+// empty last wave (cfg 2, L1 dw3x3: 660 CTAs on 592 slots = two waves of 34 rows; 40-row strips = ONE wave of 42 rows), so the
+// height is chosen per launch to minimise waves * (rows + halo + fixed), `fixed` ~ the prologue in row-equivalents.
+static inline int pick_strip_rows(int H, long long ctas_per_strip, int slots, int halo, int fixed, int lo, int hi) {
+    int best = lo > H ? H : lo;
+    long long best_cost = -1;
+    for (int r = lo; r <= hi; ++r) {
+        const int rows = r > H ? H : r;
+        const long long ctas = ctas_per_strip * ((H + rows - 1) / rows);
+        const long long waves = (ctas + slots - 1) / slots;
+        const long long cost = waves * (rows + halo + fixed);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = rows; }
+        if (rows == H) break;
+    }
+    return best;
+}
 static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 
 // pitch (in elements) of an NHWC activation with C channels: multiple of 8 so that

@@ -16,7 +16,6 @@
 namespace cidnet {
 
 static constexpr int kCols = 32;       // columns per warp (outputs: lanes 1..30)
-static constexpr int kRows = 32;       // output rows per CTA
 
 #ifdef CIDNET_ACT_BF16
 #define CIDNET_FHFMA "fma.rn.f32.bf16"
@@ -94,8 +93,8 @@ iel_gate_v4_kernel(const __grid_constant__ IelV4Args A) {
     const int cg = blockIdx.x % ngroups, strip = blockIdx.x / ngroups;
     const int c0 = cg * 16;
     const int X0 = strip * (kCols - 2) - 1;               // image column of lane 0
-    const int y0 = blockIdx.y * kRows;
-    const int y1 = min(y0 + kRows, a.H);
+    const int y0 = blockIdx.y * a.rows_per_cta;
+    const int y1 = min(y0 + a.rows_per_cta, a.H);
     const int nrows = (y1 - y0) + 4;                      // t rows y0-2 .. y1+1
     const int nblocks = (nrows + kRB - 1) / kRB;
 
@@ -298,8 +297,8 @@ iel_gate_v6_kernel(const __grid_constant__ IelV4Args A) {
     const int cg = blockIdx.x % ngroups, strip = blockIdx.x / ngroups;
     const int c0 = cg * 16;
     const int X0 = strip * (kCols - 2) - 1;               // image column of lane 0
-    const int y0 = blockIdx.y * kRows;
-    const int y1 = min(y0 + kRows, a.H);
+    const int y0 = blockIdx.y * a.rows_per_cta;
+    const int y1 = min(y0 + a.rows_per_cta, a.H);
     const int nrows = (y1 - y0) + 4;                      // t rows y0-2 .. y1+1
     const int nblocks = (nrows + kRB - 1) / kRB;
 
@@ -416,8 +415,16 @@ iel_gate_v6_kernel(const __grid_constant__ IelV4Args A) {
 int encode_map_generic_swz(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                            const uint32_t* box, int swizzle_bytes);   // conv_gemm.cu
 
-int launch_iel_gate(const IelGateArgs& a, cudaStream_t stream) {
+int launch_iel_gate(const IelGateArgs& a_in, cudaStream_t stream) {
+    IelGateArgs a = a_in;
     CIDNET_CHECK(a.hp % 16 == 0, CIDNET_ERR_INVALID, "iel: hp % 16");
+    const int strips = ceil_div(a.W, kCols - 2);
+#ifndef CIDNET_ACT_BF16
+    const int ctas_per_sm = 3;
+#else
+    const int ctas_per_sm = 2;
+#endif
+    a.rows_per_cta = pick_strip_rows(a.H, (long long)strips * (a.hp / 16) * a.B * a.nprob, ctas_per_sm * device_sm_count(), 4, 2, 12, 96);
     IelV4Args A;
     memset(&A, 0, sizeof A);
     A.g = a;
@@ -430,8 +437,7 @@ int launch_iel_gate(const IelGateArgs& a, cudaStream_t stream) {
         int rc = encode_map_generic_swz(&A.tmT[p], a.t[p], 4, dims, str, box, 32);
         if (rc) return rc;
     }
-    const int strips = ceil_div(a.W, kCols - 2);
-    dim3 grid(strips * (a.hp / 16), ceil_div(a.H, kRows), a.B * a.nprob);
+    dim3 grid(strips * (a.hp / 16), ceil_div(a.H, a.rows_per_cta), a.B * a.nprob);
     int rc;
 #ifndef CIDNET_ACT_BF16
     const size_t smem6 = 1024 + (size_t)kV5Stages * kV4StageBytes + 2 * 4 * kCols * sizeof(uint4) +

@@ -12,6 +12,7 @@ struct IelGateArgs {
     const float* w1[2];      // dwconv1 fp32 [9][hp]
     const float* w2[2];      // dwconv2 fp32 [9][hp]
     int B, H, W, hp, nprob;
+    int rows_per_cta;        // set by launch_iel_gate (pick_strip_rows)
 };
 int launch_iel_gate(const IelGateArgs& a, cudaStream_t stream);
 
