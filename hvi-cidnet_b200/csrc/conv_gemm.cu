@@ -653,13 +653,12 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
 
     // 3x3 halo mode: possible when all 9 taps' weights stay resident next to >= 2 halo stages
     {
-        static const bool no_halo = getenv("CIDNET_NO_HALO") != nullptr;
         // (measured on B200: the SWIZZLE_128B XOR is applied to ABSOLUTE shared-memory address bits, so a
         // descriptor that starts on an arbitrary 128-byte row of a 1024-byte aligned TMA tile reads the
         // right data with base_offset = 0; setting (addr >> 7) & 7 there gives wrong results)
         const size_t fixed1 = 1024 + (size_t)kEpiGroups * kStagingBytes + 512 + 2 * round_up(wt.block_n, 32) * sizeof(float);
         const size_t need = fixed1 + (size_t)9 * wt.kchunks * wt.block_n * 128 + (size_t)2 * ksub * kHaloTileBytes;
-        a.halo = (wt.taps == 9 && !L.in2 && !a.per_image_w && !no_halo && need <= 226 * 1024) ? 1 : 0;
+        a.halo = (wt.taps == 9 && !L.in2 && !a.per_image_w && need <= 226 * 1024) ? 1 : 0;
     }
     const int tw = a.halo ? 14 : 16;                            // halo mode: 16-wide smem rows, 14 valid columns
     const uint64_t pb = (uint64_t)L.in_pitch * sizeof(act_t);   // bytes per pixel row
@@ -750,8 +749,8 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
     const size_t bres = (size_t)nbchunks * b_chunk;
     // A tiles in flight.  Measured on B200 (cfg2 / cfg4): 2, 4 and 6 tiles give the same step time -- the
     // per-tile cost (~3000-3900 cycles whatever N and K) is the epilogue's dependent-latency chain, not the
-    // load pipeline -- so the ring stays at 2 tiles.  CIDNET_GEMM_DEPTH overrides (tiles).
-    static const int depth = getenv("CIDNET_GEMM_DEPTH") ? atoi(getenv("CIDNET_GEMM_DEPTH")) : 2;
+    // load pipeline -- so the ring stays at 2 tiles.
+    const int depth = 2;
     // UP: each epilogue group holds its tile's stages (the low-res box) until it is done -> one more tile of slack
     const int tiles_in_ring = L.mode == EPI_UP ? depth + kEpiGroups : depth;
     const int want = tiles_in_ring * kiters > min_stages ? tiles_in_ring * kiters : min_stages;

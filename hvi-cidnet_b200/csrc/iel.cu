@@ -424,7 +424,7 @@ int launch_iel_gate(const IelGateArgs& a_in, cudaStream_t stream) {
 #else
     const int ctas_per_sm = 2;
 #endif
-    a.rows_per_cta = pick_strip_rows(a.H, (long long)strips * (a.hp / 16) * a.B * a.nprob, ctas_per_sm * device_sm_count(), 4, 2, 12, 96);
+    a.rows_per_cta = pick_strip_rows(a.H, (long long)strips * (a.hp / 16) * a.B * a.nprob, ctas_per_sm * device_sm_count(), 4, 13, 12, 128);   // fixed ~ 5 us of prologue + ring fill per CTA = ~13 rows (measured: L1 / L3 CTA times)
     IelV4Args A;
     memset(&A, 0, sizeof A);
     A.g = a;

@@ -146,6 +146,8 @@ def test_streamed_driver_matches_plain_forward(model):
     assert len(got) == len(want)
     for g, w in zip(got, want):        # same kernels, same shapes, fixed summation orders: bit-equal
         assert torch.equal(g, w)
+    for i in (0, 6):                   # and the streamed results themselves against the oracle
+        _check(got[i], O.forward(xs[i], sd), xs[i], sd)
     with pytest.raises(RuntimeError):
         model(xs[0].cuda(), out=torch.empty(1, 3, 8, 8, device="cuda"))
 
