@@ -500,8 +500,11 @@ def run_ours(args):
         recs = model.read_profile(spans=True)
         groups = []
         for name, ms, by, fl, t0, t1 in recs:
-            g = groups[-1] if groups else None
-            if g is not None and g["name"] == name and t0 < g["t1"] - 0.25 * min(ms, g["t1"] - g["t0"]):
+            g = None
+            for cand in groups[-4:]:              # the sibling launch of a pair is at most a few records back
+                if cand["name"] == name and t0 < cand["t1"] - 0.25 * min(ms, cand["t1"] - cand["t0"]):
+                    g = cand
+            if g is not None:
                 g["t1"] = max(g["t1"], t1); g["t0"] = min(g["t0"], t0); g["by"] += by; g["fl"] += fl; g["n"] += 1
             else:
                 groups.append({"name": name, "t0": t0, "t1": t1, "by": by, "fl": fl, "n": 1})
