@@ -22,6 +22,7 @@ kernels (per-kernel share), cpu_baseline (oracle port on host cores, bounded sam
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -707,6 +708,51 @@ def run_hvi(args):
         hy.copy_(t.PHVIT(t.HVIT(hx.to(dev, non_blocking=True))), non_blocking=True)
     f1.record(); barrier()
     ms_e2e = f0.elapsed_time(f1) / max(2, args.steps // 4)
+    # backward of the transform (train.py:61-62): one launch each, 36 B/pixel (input, upstream gradient, result)
+    from hvi_cidnet_b200 import _lib
+    L = _lib.lib()
+    go = torch.randn(B, 3, H, W, device=dev); gi = torch.empty_like(x)
+    gk = torch.empty(1, device=dev); scratch = torch.empty(int(L.cidnet_hvi_backward_scratch_bytes()) // 4, device=dev)
+    kd = t.density_k.detach().float().contiguous()
+    sp = _lib.stream_ptr(dev)
+    bw = {}
+    for name, call in (("hvit_backward", lambda: L.cidnet_hvit_backward(x.data_ptr(), go.data_ptr(), gi.data_ptr(), gk.data_ptr(),
+                                                                         scratch.data_ptr(), B, H, W, 0.0, kd.data_ptr(), sp)),
+                       ("phvit_backward", lambda: L.cidnet_phvit_backward(hvi.data_ptr(), go.data_ptr(), gi.data_ptr(), B, H, W, 0.0,
+                                                                           kd.data_ptr(), 0, 1.3, 0, 1.0, sp))):
+        for _ in range(3):
+            _lib.check(call())
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(); b0.record()
+        for _ in range(args.steps):
+            _lib.check(call())
+        b1.record(); barrier()
+        ms_b = b0.elapsed_time(b1) / args.steps
+        bw[name] = {"ms": ms_b, "GBps": nbytes * 3 / ms_b / 1e6, "frac_of_hbm_peak": nbytes * 3 / ms_b / 1e6 / peaks["hbm_gbs"],
+                    "algorithmic_bytes_per_px": 36, "launches": 2 if name == "hvit_backward" else 1}
+    # the same backward as torch autograd derives it from the reference's formulation (oracle port, eager on this GPU)
+    with torch.enable_grad():
+        xe = x[:2].clone().requires_grad_(True)
+        ke = torch.full([1], 0.2, device=dev, requires_grad=True)
+        r_, g_, b_ = xe[:, 0], xe[:, 1], xe[:, 2]
+        for it in range(3):
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            val = xe.max(1)[0]; vmin = xe.min(1)[0]; d = val - vmin + 1e-8
+            hue = torch.where(b_ == val, 4.0 + (r_ - g_) / d, torch.zeros_like(val))
+            hue = torch.where(g_ == val, 2.0 + (b_ - r_) / d, hue)
+            hue = torch.where(r_ == val, torch.remainder((g_ - b_) / d, 6), hue)
+            hue = torch.where(vmin == val, torch.zeros_like(hue), hue) / 6.0
+            sat = torch.where(val == 0, torch.zeros_like(val), (val - vmin) / (val + 1e-8))
+            cs = ((val * 0.5 * math.pi).sin() + 1e-8).pow(ke)
+            out = torch.stack([cs * sat * (2.0 * math.pi * hue).cos(), cs * sat * (2.0 * math.pi * hue).sin(), val], dim=1)
+            e1.record()
+            out.backward(go[:2])
+            e2.record(); torch.cuda.synchronize()
+            xe.grad = None; ke.grad = None
+        bw["eager_autograd_hvit"] = {"batch": 2, "forward_ms": e0.elapsed_time(e1), "backward_ms": e1.elapsed_time(e2),
+                                     "backward_MPps": 2 * H * W / e1.elapsed_time(e2) / 1e3,
+                                     "ours_backward_MPps": B * H * W / bw["hvit_backward"]["ms"] / 1e3}
     if world > 1:
         tt = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms_total, ms_e2e = float(tt[0]), float(tt[1])
@@ -731,6 +777,7 @@ def run_hvi(args):
                              "hvit_GBps": gb_h, "phvit_GBps": gb_p, "algorithmic_bytes_per_px": 24},
                 "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                  "sample": f"{n} round trips of 2x3x{H}x{W}, torch CPU fp32 (oracle port)"},
+                "backward": bw,
                 "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -40,6 +40,11 @@ SIGNATURES = {
     "cidnet_hvit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     "cidnet_phvit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
                                C.c_int, C.c_float, C.c_int, C.c_float, C.c_void_p]),
+    "cidnet_hvi_backward_scratch_bytes": (C.c_int64, []),
+    "cidnet_hvit_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                       C.c_float, C.c_void_p, C.c_void_p]),
+    "cidnet_phvit_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
+                                        C.c_int, C.c_float, C.c_int, C.c_float, C.c_void_p]),
     "cidnet_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     "cidnet_destroy": (C.c_int, [C.c_void_p]),
     "cidnet_set_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),

@@ -57,6 +57,21 @@ CIDNET_API int cidnet_hvit(const float* rgb, float* hvi, int B, int H, int W, fl
 CIDNET_API int cidnet_phvit(const float* hvi, float* rgb, int B, int H, int W, float k, const float* k_dev,
                             int gated, float alpha_s, int gated2, float alpha, void* stream);
 
+/* ---- backward of the transform (vector-Jacobian products) -------------------
+ * replaces what autograd derives from RGB_HVI.HVIT / PHVIT (net/HVI_transform.py:16-47, :49-122) in the reference's
+ * training loop: `model.HVIT(output_rgb)` inside the loss (train.py:61-62) and `self.trans.PHVIT(output_hvi)` at the end
+ * of the forward (net/CIDNet.py:121).  One launch each; nothing is saved by the forward: the per-pixel quantities are
+ * recomputed from the forward's INPUT (rgb for HVIT, hvi for PHVIT).  All images dev fp32 [B,3,H,W].
+ *   cidnet_hvit_backward : grad_rgb = J^T grad_hvi; grad_k (optional, dev fp32[1]) = d/d density_k summed over every pixel,
+ *                          deterministic (per-CTA slots in `scratch`, dev memory of cidnet_hvi_backward_scratch_bytes(),
+ *                          added in index order by a finishing launch); scratch may be NULL when grad_k is NULL.
+ *   cidnet_phvit_backward: grad_hvi = J^T grad_rgb; k = this_k (a python float in the reference: no gradient). */
+CIDNET_API int64_t cidnet_hvi_backward_scratch_bytes(void);
+CIDNET_API int cidnet_hvit_backward(const float* rgb, const float* grad_hvi, float* grad_rgb, float* grad_k, void* scratch,
+                                    int B, int H, int W, float k, const float* k_dev, void* stream);
+CIDNET_API int cidnet_phvit_backward(const float* hvi, const float* grad_rgb, float* grad_hvi, int B, int H, int W, float k,
+                                     const float* k_dev, int gated, float alpha_s, int gated2, float alpha, void* stream);
+
 /* ---- model context --------------------------------------------------------
  * replaces CIDNet.__init__ / load_state_dict (net/CIDNet.py:9-69; 191 tensors,
  * SURVEY App. B).  set_weight copies one fp32 state_dict tensor (host memory);

@@ -127,6 +127,46 @@ def forward_mssa_cases():
             f.write(f"{k_} {list(v.shape)}\n")
 
 
+def hvi_backward_cases():
+    """Gradients of HVIT / PHVIT as the reference's training loop sees them (train.py:61-62, CIDNet.py:121): the
+    UNMODIFIED reference under autograd.  Inputs, upstream gradients, input gradients and d/d density_k."""
+    out = {}
+    with torch.enable_grad():
+        for k_val in (0.2, 0.37, 1.0):
+            for kind in ["uniform", "dark", "grid8", "grey8", "onehot", "const:0", "const:0.5", "const:1"]:
+                model = CIDNet().eval()
+                model.trans.density_k.data.fill_(k_val)
+                x = O.make_input(kind, 1, 24, 40, seed=7).requires_grad_(True)
+                go = torch.randn(1, 3, 24, 40, generator=torch.Generator().manual_seed(21))
+                model.trans.HVIT(x).backward(go)
+                tag = f"hvit|{kind}|k={k_val}"
+                out[tag + "|x"] = x.detach().numpy()
+                out[tag + "|go"] = go.numpy()
+                out[tag + "|gx"] = x.grad.numpy()
+                out[tag + "|gk"] = model.trans.density_k.grad.numpy()
+        rng = np.random.default_rng(11)
+        for k_val in (0.2, 0.0, 1.0):
+            for gated in (False, True):
+                for kind in ("wild", "hvit"):
+                    model = CIDNet().eval()
+                    model.trans.this_k = k_val
+                    model.trans.gated, model.trans.gated2 = gated, gated
+                    model.trans.alpha_s, model.trans.alpha = 1.3, 0.8
+                    if kind == "wild":
+                        hv = torch.from_numpy(rng.uniform(-1.3, 1.3, (1, 3, 24, 40)).astype(np.float32))
+                    else:
+                        hv = O.hvit(O.make_input("uniform", 1, 24, 40, seed=3), 0.2)
+                    hv = hv.clone().requires_grad_(True)
+                    go = torch.randn(1, 3, 24, 40, generator=torch.Generator().manual_seed(22))
+                    model.trans.PHVIT(hv).backward(go)
+                    tag = f"phvit|{kind}|k={k_val}|gated={int(gated)}"
+                    out[tag + "|x"] = hv.detach().numpy()
+                    out[tag + "|go"] = go.numpy()
+                    out[tag + "|gx"] = hv.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "hvi_backward.npz"), **out)
+    print("hvi_backward", len(out))
+
+
 def state_dict_keys():
     model = CIDNet()
     with open(os.path.join(OUT, "state_dict_keys.txt"), "w") as f:
@@ -136,7 +176,7 @@ def state_dict_keys():
 
 if __name__ == "__main__":
     torch.manual_seed(0)
-    hvi_cases()
-    forward_cases()
-    forward_mssa_cases()
-    state_dict_keys()
+    only = sys.argv[1:]          # e.g. `python oracle/make_golden.py hvi_backward_cases` regenerates one fixture
+    for fn in (hvi_cases, forward_cases, forward_mssa_cases, hvi_backward_cases, state_dict_keys):
+        if not only or fn.__name__ in only:
+            fn()
