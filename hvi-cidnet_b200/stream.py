@@ -7,7 +7,15 @@ host<->device round trip on the default stream) by a 3-stage pipeline
     copy-out stream : device output slot -> pinned host ring slot     (D2H)
 
 so the PCIe copies of step i+1 / i-1 overlap the kernels of step i.  Results are yielded in input
-order, `depth - 1` steps behind the submissions.  All arithmetic is the unchanged CIDNet.forward."""
+order, `depth - 1` steps behind the submissions.  All arithmetic is the unchanged CIDNet.forward.
+
+`run_to_sink` adds the fourth stage the reference also runs inline (eval.py:71-75: ToPILImage + `save` of
+every result inside the loop): results are handed, in order, to a caller-supplied sink on worker threads
+(PNG encoding, file or socket writes) while the GPU works on the next images; a pinned result buffer is
+recycled only after its sink call has returned."""
+import queue
+import threading
+
 import torch
 
 
@@ -44,6 +52,64 @@ class StreamedCIDNet:
         """host_batches: iterable of fp32 [B,3,H,W] host tensors of ONE shape (pinned memory for real
         overlap).  Yields the enhanced batches as pinned host tensors, in order; a yielded tensor is
         valid until `depth` further results have been produced (copy it if it must live longer)."""
+        for _, y in self._pipeline(host_batches, _u8_gamma, None):
+            yield y
+
+    def run_to_sink(self, host_batches, sink, u8_gamma=None, workers=1):
+        """Asynchronous result sink: `sink(index, host_tensor)` is called once per input batch, on one of `workers`
+        threads, with the pinned result (fp32 [B,3,H,W], or uint8 [B,h,w,3] when `u8_gamma` is given); the tensor is
+        only valid during the call.  Calls START in input order (with one worker they are strictly sequential).  The
+        pipeline keeps feeding the GPU while sinks run and blocks only when all `depth` result buffers are still
+        being consumed.  The first exception raised by a sink is re-raised here after the pipeline has drained.
+        Returns the number of batches processed."""
+        if workers < 1:
+            raise ValueError("workers must be >= 1")
+        jobs, errors = queue.Queue(), []
+        busy = [None] * self.depth                                 # slot -> threading.Event of the sink call using hy[slot]
+
+        def work():
+            while True:
+                item = jobs.get()
+                if item is None:
+                    return
+                idx, t, ev = item
+                try:
+                    if not errors:
+                        sink(idx, t)
+                except BaseException as e:                         # noqa: BLE001 -- re-raised on the caller's thread
+                    errors.append(e)
+                finally:
+                    ev.set()
+
+        threads = [threading.Thread(target=work, daemon=True) for _ in range(int(workers))]
+        for t in threads:
+            t.start()
+
+        def before_reuse(slot):
+            if busy[slot] is not None:
+                busy[slot].wait()
+                busy[slot] = None
+
+        n = 0
+        try:
+            for slot, y in self._pipeline(host_batches, u8_gamma, before_reuse):
+                ev = threading.Event()
+                busy[slot] = ev
+                jobs.put((n, y, ev))
+                n += 1
+                if errors:
+                    break
+        finally:
+            for _ in threads:
+                jobs.put(None)
+            for t in threads:
+                t.join()
+        if errors:
+            raise errors[0]
+        return n
+
+    def _pipeline(self, host_batches, _u8_gamma, before_reuse):
+        """generator of (slot, pinned result); `before_reuse(slot)` is called before hy[slot] is overwritten"""
         m = self.model
         dev = m.trans.density_k.device
         if dev.type != "cuda":
@@ -58,11 +124,16 @@ class StreamedCIDNet:
                     raise RuntimeError(f"StreamedCIDNet expects {want} host tensors")
                 self._setup(hx.shape, dev, want)
                 slot = n % self.depth
+                while pending and pending[0] != slot and self.out_done[pending[0]].query():
+                    done = pending.pop(0)                          # finished early: hand it out now (a sink can start)
+                    yield done, self.hy[done]
                 if n >= self.depth:                                # the slot's previous result must have been handed out
                     while slot in pending:
                         done = pending.pop(0)
                         self.out_done[done].synchronize()
-                        yield self.hy[done]
+                        yield done, self.hy[done]
+                    if before_reuse is not None:
+                        before_reuse(slot)
                 with torch.cuda.stream(self.s_in):
                     if n >= self.depth:
                         self.s_in.wait_event(self.in_free[slot])
@@ -86,4 +157,4 @@ class StreamedCIDNet:
             while pending:
                 done = pending.pop(0)
                 self.out_done[done].synchronize()
-                yield self.hy[done]
+                yield done, self.hy[done]
