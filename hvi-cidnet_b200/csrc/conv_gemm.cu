@@ -390,6 +390,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
             const uint8_t* up_tile = nullptr;
             uint32_t u00 = 0, u01 = 0, u10 = 0, u11 = 0;      // box row index (128-byte rows) of the four neighbours
             float uly = 0.f, ulx = 0.f;
+            uint32_t uw00 = 0, uw01 = 0, uw10 = 0, uw11 = 0;  // the four bilinear weights as packed (w, w) 16-bit pairs
             const uint32_t up_it = it - kiters;               // pipeline iteration of this tile's first stage
             if (kUp) {
                 const uint32_t s0 = up_it % stages;
@@ -409,6 +410,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                 const int r0 = min(max(i0g - by0, 0), kUpBoxH - 1), r1 = min(max(i1g - by0, 0), kUpBoxH - 1);
                 const int c0 = min(max(j0 - bx0, 0), kUpBoxW - 1), c1 = min(max(j1 - bx0, 0), kUpBoxW - 1);
                 u00 = r0 * kUpBoxW + c0; u01 = r0 * kUpBoxW + c1; u10 = r1 * kUpBoxW + c0; u11 = r1 * kUpBoxW + c1;
+#ifndef CIDNET_ACT_BF16
+                const float w11 = uly * ulx, w10 = uly - w11, w01 = ulx - w11, w00 = (1.f - uly) - w01;
+                uw00 = pack2(w00, w00); uw01 = pack2(w01, w01); uw10 = pack2(w10, w10); uw11 = pack2(w11, w11);
+#endif
             }
             // EPI_DOWN geometry: y counts ROW PAIRS == output rows; even lanes own an output pixel
             float dly = 0.f, dlx = 0.f;
@@ -478,6 +483,35 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                             for (int h = 0; h < 4; ++h) {
                                 if (nrem > 8 * h) {                            // warp-uniform
                                     const uint32_t ck = (uint32_t)(hh * 4 + h);   // 16-byte chunk of the 128-byte row
+#ifndef CIDNET_ACT_BF16
+                                    // The four neighbours stay PACKED: acc += w_tap * p_tap as mixed-precision FMAs (FHFMA: exact
+                                    // fp16 x fp16 product, fp32 accumulation straight into the GEMM accumulator) -- 4 instructions
+                                    // per channel instead of 4 conversions + 6 fp32 FMAs.  ncu on the fp32 version: 24.5 M warp
+                                    // instructions per up1 launch (1094 per pixel) on the 8 epilogue warps, issue slots 52 % busy with
+                                    // two warps per scheduler: the layer was bound by this loop, not by HBM (22 %).  The bilinear
+                                    // weights are rounded to fp16 (relative 2^-11, the size of the storage rounding of the result).
+                                    const uint4 q00 = *reinterpret_cast<const uint4*>(ub + u00 * 128 + ((ck ^ (u00 & 7)) << 4));
+                                    const uint4 q01 = *reinterpret_cast<const uint4*>(ub + u01 * 128 + ((ck ^ (u01 & 7)) << 4));
+                                    const uint4 q10 = *reinterpret_cast<const uint4*>(ub + u10 * 128 + ((ck ^ (u10 & 7)) << 4));
+                                    const uint4 q11 = *reinterpret_cast<const uint4*>(ub + u11 * 128 + ((ck ^ (u11 & 7)) << 4));
+                                    float* vv = v + 8 * h;
+                                    fhfma2(vv[0], vv[1], q00.x, uw00); fhfma2(vv[2], vv[3], q00.y, uw00);
+                                    fhfma2(vv[4], vv[5], q00.z, uw00); fhfma2(vv[6], vv[7], q00.w, uw00);
+                                    fhfma2(vv[0], vv[1], q01.x, uw01); fhfma2(vv[2], vv[3], q01.y, uw01);
+                                    fhfma2(vv[4], vv[5], q01.z, uw01); fhfma2(vv[6], vv[7], q01.w, uw01);
+                                    fhfma2(vv[0], vv[1], q10.x, uw10); fhfma2(vv[2], vv[3], q10.y, uw10);
+                                    fhfma2(vv[4], vv[5], q10.z, uw10); fhfma2(vv[6], vv[7], q10.w, uw10);
+                                    fhfma2(vv[0], vv[1], q11.x, uw11); fhfma2(vv[2], vv[3], q11.y, uw11);
+                                    fhfma2(vv[4], vv[5], q11.z, uw11); fhfma2(vv[6], vv[7], q11.w, uw11);
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) {
+                                        vv[e] = prelu_f(vv[e], a.prelu);
+                                        if (kSa && 8 * h + e < nrem) {
+                                            const float r16 = act2f(f2act(vv[e]));             // the value as it is stored
+                                            sa_sum += r16; sa_max = fmaxf(sa_max, r16);
+                                        }
+                                    }
+#else
                                     float p00[8], p01[8], p10[8], p11[8];
                                     load8(reinterpret_cast<const act_t*>(ub + u00 * 128 + ((ck ^ (u00 & 7)) << 4)), p00);
                                     load8(reinterpret_cast<const act_t*>(ub + u01 * 128 + ((ck ^ (u01 & 7)) << 4)), p01);
@@ -493,6 +527,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                                             sa_sum += r16; sa_max = fmaxf(sa_max, r16);
                                         }
                                     }
+#endif
                                 }
                             }
                         }

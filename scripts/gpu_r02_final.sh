@@ -4,7 +4,7 @@ set -u
 O=gpurun_out; T=${1:-r02z}; mkdir -p $O
 timeout 1800 python -m pytest tests -m gpu -q > $O/${T}_pytest.log 2>&1; echo "pytest rc=$?"; grep -E "^FAILED|passed|failed" $O/${T}_pytest.log | tail -5
 grep -E "hvi margin|LCA[0-9] C=" $O/${T}_pytest.log | head -20
-timeout 1800 python -m pytest tests/test_hvi_gpu.py tests/test_lca_gpu.py tests/test_zz_bf16_build_gpu.py -m gpu -q -s 2>&1 | grep -E "hvi margin|LCA[0-9] C=|bf16 build" > $O/${T}_margins.txt; cat $O/${T}_margins.txt | cut -c1-220
+timeout 1800 python -m pytest tests/test_hvi_gpu.py tests/test_hvi_backward_gpu.py tests/test_lca_gpu.py tests/test_zz_bf16_build_gpu.py -m gpu -q -s 2>&1 | grep -E "hvi margin|hvi backward margin|LCA[0-9] C=|bf16 build" > $O/${T}_margins.txt; cat $O/${T}_margins.txt | cut -c1-220
 timeout 300 python __graft_entry__.py smoke 2>&1 | tail -1 | tee $O/${T}_smoke.txt
 timeout 600 python bench.py > $O/${T}_bench_cfg2.json 2> $O/${T}_bench_cfg2.err; echo "bench cfg2 rc=$?"
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $O/${T}_bench_reference.json 2>/dev/null; echo "bench reference rc=$?"
