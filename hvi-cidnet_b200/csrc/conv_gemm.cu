@@ -45,6 +45,11 @@ struct ConvGemmArgs {
     float2* sa_stats;                // EPI_UP, MSSA variant: per-pixel (mean, max) over the output channels (SpatialAttention input)
     int w_early;                     // resident weights are model constants: request them before the programmatic-dependency wait
     int halo;                        // 3x3: tile + halo loaded once per channel chunk, taps = row-shifted views
+    // channels per TMA box (64, or 48 for the C = 36 layers).  Measured on B200: with an inner box narrower than the swizzle
+    // span TMA still lays the rows out at the span's pitch (128 B), i.e. exactly the canonical SWIZZLE_128B K-major tile with
+    // the unused tail of every row left untouched -- and the cost of a box is per BYTE (profiles/r01_tma_rowrate.txt), so a
+    // 48-channel box moves 25 % fewer bytes through the TMA unit than the zero-filled 64-channel one.
+    int boxc, boxc2, boxc_out, boxc_up;
     int w_real;
     const float* bias; const float* wsum; float ln_eps;
     int up_H, up_W, up_chunks; float up_ry, up_rx;   // EPI_UP: low-res source (staged by TMA next to every A tile)
@@ -209,8 +214,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                     const uint32_t ph = (it / stages) & 1u;
                     ptx::mbar_wait(&empty[s], ph ^ 1u);
                     const bool up_here = (kUp) && i == 0;      // the tile's low-res box rides with its first stage
-                    const uint32_t a_bytes = kSub * (a.halo ? kHaloTileBytes : kSubTileBytes);
-                    ptx::mbar_expect_tx(&full[s], a_bytes + (up_here ? a.up_chunks * kUpBoxBytes : 0u) + (a.b_resident ? 0u : b_chunk));
+                    const uint32_t a_bytes = (a.halo || i < k1) ? kSub * (a.halo ? 11u * 16u : 128u) * (uint32_t)a.boxc * 2u
+                                                                : 128u * (uint32_t)a.boxc2 * 2u;
+                    ptx::mbar_expect_tx(&full[s], a_bytes + (up_here ? a.up_chunks * (uint32_t)(kUpBoxW * kUpBoxH) * (uint32_t)a.boxc_up * 2u : 0u) +
+                                                      (a.b_resident ? 0u : b_chunk));
                     uint8_t* dstA = smA + (size_t)s * a_stage;
                     if (up_here) {
                         const int by0 = (int)(a.up_ry * (float)(y0 + a.up_row0)) - a.up_src_row0;
@@ -695,6 +702,11 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
         const size_t need = fixed1 + (size_t)9 * wt.kchunks * wt.block_n * 128 + (size_t)2 * ksub * kHaloTileBytes;
         a.halo = (wt.taps == 9 && !L.in2 && !a.per_image_w && need <= 226 * 1024) ? 1 : 0;
     }
+    auto box_channels = [](int c, int chunks) { return chunks == 1 ? (c <= 48 ? (unsigned)round_up(c, 16) : 64u) : 64u; };
+    a.boxc = (int)box_channels(wt.cin, wt.kchunks);
+    a.boxc2 = L.in2 && L.wt2 ? (int)box_channels(L.wt2->cin, L.wt2->kchunks) : 64;
+    a.boxc_out = wt.n_out <= 48 ? round_up(wt.n_out, 16) : 64;
+    a.boxc_up = a.boxc_out;
     const int tw = a.halo ? 14 : 16;                            // halo mode: 16-wide smem rows, 14 valid columns
     const uint64_t pb = (uint64_t)L.in_pitch * sizeof(act_t);   // bytes per pixel row
     const uint64_t ob = (uint64_t)L.out_pitch * sizeof(act_t);
@@ -708,23 +720,24 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
         a.down_row0 = L.grow / 2;
         const uint64_t dims[5] = {(uint64_t)wt.cin, (uint64_t)L.W, 2, (uint64_t)L.H / 2, (uint64_t)L.B};
         const uint64_t str[4] = {pb, pb * L.W, pb * L.W * 2, pb * hw};
-        const uint32_t box[5] = {64, 16, 1, (uint32_t)(a.halo ? 11 : 8), 1};
+        const uint32_t box[5] = {(uint32_t)a.boxc, 16, 1, (uint32_t)(a.halo ? 11 : 8), 1};
         if ((rc = encode_map(&a.tmA, L.in, 5, dims, str, box))) return rc;
         const uint64_t od[4] = {(uint64_t)wt.n_out, (uint64_t)L.W / 2, (uint64_t)L.H / 2, (uint64_t)L.B};
         const uint64_t os[3] = {ob, ob * (L.W / 2), ob * (hw / 4)};
-        const uint32_t obox[4] = {64, (uint32_t)(tw / 2), 8, 1};
+        const uint32_t obox[4] = {(uint32_t)a.boxc_out, (uint32_t)(tw / 2), 8, 1};
         if ((rc = encode_map(&a.tmOut, L.out, 4, od, os, obox))) return rc;
     } else {
         if (L.flat && L.mode != EPI_UP) { a.Hv = 1; a.Wv = (int)hw; a.TH = 1; a.TW = 128; }   // UP tiles are always 8 x 16 rectangles
         else        { a.Hv = L.H; a.Wv = L.W; a.TH = 8; a.TW = tw; }
         const uint64_t dims[4] = {(uint64_t)wt.cin, (uint64_t)a.Wv, (uint64_t)a.Hv, (uint64_t)L.B};
         const uint64_t str[3] = {pb, pb * a.Wv, pb * hw};
-        const uint32_t box[4] = {64, (uint32_t)a.TW, (uint32_t)a.TH, 1};
-        const uint32_t hbox[4] = {64, 16, 11, 1};
+        const uint32_t box[4] = {(uint32_t)a.boxc, (uint32_t)a.TW, (uint32_t)a.TH, 1};
+        const uint32_t hbox[4] = {(uint32_t)a.boxc, 16, 11, 1};
         if ((rc = encode_map(&a.tmA, L.in, 4, dims, str, a.halo ? hbox : box))) return rc;
         const uint64_t od[4] = {(uint64_t)wt.n_out, (uint64_t)a.Wv, (uint64_t)a.Hv, (uint64_t)L.B};
         const uint64_t os[3] = {ob, ob * a.Wv, ob * hw};
-        if ((rc = encode_map(&a.tmOut, L.out, 4, od, os, box))) return rc;
+        const uint32_t obox[4] = {(uint32_t)a.boxc_out, (uint32_t)a.TW, (uint32_t)a.TH, 1};
+        if ((rc = encode_map(&a.tmOut, L.out, 4, od, os, obox))) return rc;
         if (L.in2) {
             CIDNET_CHECK(L.wt2 && L.wt2->w && L.wt2->taps == 1 && L.wt2->block_n == wt.block_n &&
                              L.wt2->n_blocks == wt.n_blocks && L.wt2->n_img == 1 && L.in2_pitch % 8 == 0,
@@ -733,7 +746,8 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
             const uint64_t pb2 = (uint64_t)L.in2_pitch * sizeof(act_t);
             const uint64_t d2[4] = {(uint64_t)L.wt2->cin, (uint64_t)a.Wv, (uint64_t)a.Hv, (uint64_t)L.B};
             const uint64_t s2[3] = {pb2, pb2 * a.Wv, pb2 * hw};
-            if ((rc = encode_map(&a.tmA2, L.in2, 4, d2, s2, box))) return rc;
+            const uint32_t box2[4] = {(uint32_t)a.boxc2, (uint32_t)a.TW, (uint32_t)a.TH, 1};
+            if ((rc = encode_map(&a.tmA2, L.in2, 4, d2, s2, box2))) return rc;
             const uint64_t kt2 = (uint64_t)L.wt2->ktot();
             const uint64_t bd[3] = {kt2, (uint64_t)L.wt2->n_rows, 1};
             const uint64_t bs[2] = {kt2 * sizeof(act_t), kt2 * sizeof(act_t) * L.wt2->n_rows};
@@ -748,7 +762,7 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
                 const uint64_t ub = (uint64_t)L.up_pitch * sizeof(act_t);
                 const uint64_t ud[4] = {(uint64_t)wt.n_out, (uint64_t)a.up_W, (uint64_t)a.up_H, (uint64_t)L.B};
                 const uint64_t us[3] = {ub, ub * a.up_W, ub * (uint64_t)a.up_W * a.up_H};
-                const uint32_t ubox[4] = {64, (uint32_t)kUpBoxW, (uint32_t)kUpBoxH, 1};
+                const uint32_t ubox[4] = {(uint32_t)a.boxc_up, (uint32_t)kUpBoxW, (uint32_t)kUpBoxH, 1};
                 if ((rc = encode_map(&a.tmUp, L.up, 4, ud, us, ubox))) return rc;
             }
             const int gH = L.gH ? L.gH : L.H;
