@@ -320,6 +320,11 @@ head_mma_kernel(const act_t* __restrict__ i_dec1, const act_t* __restrict__ hv_1
     const uint32_t si_base = static_cast<uint32_t>(__cvta_generic_to_shared(s_i));
     const uint32_t shv_base = static_cast<uint32_t>(__cvta_generic_to_shared(s_hv));
     // ---- phase 1: partial products of every halo pixel (21 m-tiles of 16 pixel rows, round-robin over the 8 warps)
+    uint2 bfr[5][3];                                          // this lane's B fragments: loaded once, used by all its m-tiles
+#pragma unroll
+    for (int nt = 0; nt < 5; ++nt)
+#pragma unroll
+        for (int ks = 0; ks < 3; ++ks) bfr[nt][ks] = s_bfrag[(nt * 3 + ks) * 32 + lane];
     for (int mt = warp; mt < 21; mt += 8) {
         uint32_t ai[3][4], ah[3][4];
 #pragma unroll
@@ -337,8 +342,7 @@ head_mma_kernel(const act_t* __restrict__ i_dec1, const act_t* __restrict__ hv_1
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int ks = 0; ks < 3; ++ks) {
-                const uint2 bf = s_bfrag[(nt * 3 + ks) * 32 + lane];
-                mma16816(acc, nt < 2 ? ai[ks] : ah[ks], bf.x, bf.y);
+                mma16816(acc, nt < 2 ? ai[ks] : ah[ks], bfr[nt][ks].x, bfr[nt][ks].y);
             }
             const int n = (nt < 2 ? nt : nt - 2) * 8 + 2 * tig;       // column inside the branch
             const int lim = nt < 2 ? 9 : 18, col = (nt < 2 ? 0 : 9) + n;
