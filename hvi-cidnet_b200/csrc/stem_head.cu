@@ -97,23 +97,40 @@ stem_mma_kernel(const void* __restrict__ rgb_any, float* __restrict__ hvi, act_t
     ptx::pdl_wait();               // constants above; the image, k and the outputs belong to the stream's earlier work
     ptx::pdl_trigger();
     const float k = k_dev ? __ldcg(k_dev) : k_host;
-    for (int i = tid; i < kHalo * kHalo; i += 256) {
-        const int hy = i / kHalo, hx = i - hy * kHalo;
-        const int y = min(max(y0 + hy - 1, 0), H - 1);
-        const int x = min(max(x0 + hx - 1, 0), W - 1);
-        const long long o = (long long)y * W + x;
-        float hh, vv, ii, cr, cg, cb;
-        if (in_u8) {
-            const int sy = y < h_src ? y : 2 * (h_src - 1) - y;          // 'reflect': padded row h+i mirrors row h-2-i
-            const int sx = x < w_src ? x : 2 * (w_src - 1) - x;
-            const uint8_t* p = rgb8 + (((long long)b * h_src + sy) * w_src + sx) * 3;
-            cr = __fdiv_rn((float)__ldcg(p), 255.0f); cg = __fdiv_rn((float)__ldcg(p + 1), 255.0f); cb = __fdiv_rn((float)__ldcg(p + 2), 255.0f);
-            if (gamma != 1.0f) { cr = powf(cr, gamma); cg = powf(cg, gamma); cb = powf(cb, gamma); }
-        } else {
-            cr = __ldcg(img + o); cg = __ldcg(img + o + hw); cb = __ldcg(img + o + 2 * hw);   // L2 loads: see ptx::pdl_wait
+    // halo fill: 324 pixels on 256 threads -> a thread owns pixel `tid` and (tid < 68) pixel `tid + 256`.  All loads of both
+    // pixels are issued before either is transformed (one exposed memory latency per CTA instead of two).
+    float cr[2], cg[2], cb[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int i = tid + j * 256;
+        cr[j] = cg[j] = cb[j] = 0.f;
+        if (i < kHalo * kHalo) {
+            const int hy = i / kHalo, hx = i - hy * kHalo;
+            const int y = min(max(y0 + hy - 1, 0), H - 1);
+            const int x = min(max(x0 + hx - 1, 0), W - 1);
+            if (in_u8) {
+                const int sy = y < h_src ? y : 2 * (h_src - 1) - y;      // 'reflect': padded row h+i mirrors row h-2-i
+                const int sx = x < w_src ? x : 2 * (w_src - 1) - x;
+                const uint8_t* p = rgb8 + (((long long)b * h_src + sy) * w_src + sx) * 3;
+                cr[j] = (float)__ldcg(p); cg[j] = (float)__ldcg(p + 1); cb[j] = (float)__ldcg(p + 2);
+            } else {
+                const long long o = (long long)y * W + x;
+                cr[j] = __ldcg(img + o); cg[j] = __ldcg(img + o + hw); cb[j] = __ldcg(img + o + 2 * hw);   // L2 loads: see ptx::pdl_wait
+            }
         }
-        hvit_px(cr, cg, cb, k, hh, vv, ii);
-        s_hvi[i] = hh; s_hvi[kHalo * kHalo + i] = vv; s_hvi[2 * kHalo * kHalo + i] = ii;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int i = tid + j * 256;
+        if (i < kHalo * kHalo) {
+            float r = cr[j], g_ = cg[j], b_ = cb[j], hh, vv, ii;
+            if (in_u8) {
+                r = __fdiv_rn(r, 255.0f); g_ = __fdiv_rn(g_, 255.0f); b_ = __fdiv_rn(b_, 255.0f);
+                if (gamma != 1.0f) { r = powf(r, gamma); g_ = powf(g_, gamma); b_ = powf(b_, gamma); }
+            }
+            hvit_px(r, g_, b_, k, hh, vv, ii);
+            s_hvi[i] = hh; s_hvi[kHalo * kHalo + i] = vv; s_hvi[2 * kHalo * kHalo + i] = ii;
+        }
     }
     __syncthreads();
 
@@ -312,6 +329,17 @@ head_mma_kernel(const act_t* __restrict__ i_dec1, const act_t* __restrict__ hv_1
         reinterpret_cast<uint4*>(s_hv)[kHalo * 90 + tid - 180] = make_uint4(0, 0, 0, 0);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+    // this thread's own pixel (phase 2): its three fp32 residual values are requested NOW, so their L2 / DRAM latency runs
+    // under the tile staging and the MMA phase instead of in front of the PHVIT arithmetic
+    const int ty = tid / kTile, tx = tid - ty * kTile;
+    const int y = y0 + ty, x = x0 + tx;
+    const bool inside = y < H && x < W;
+    const long long pix = (long long)y * W + x;
+    float res_h = 0.f, res_v = 0.f, res_i = 0.f;
+    if (inside) {
+        const float* hp = hvi + (long long)b * 3 * hw + pix;
+        res_h = __ldcg(hp); res_v = __ldcg(hp + hw); res_i = __ldcg(hp + 2 * hw);
+    }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
@@ -352,18 +380,14 @@ head_mma_kernel(const act_t* __restrict__ i_dec1, const act_t* __restrict__ hv_1
     }
     __syncthreads();
     // ---- phase 2: every thread sums the nine shifted entries of its own pixel, per output
-    const int ty = tid / kTile, tx = tid - ty * kTile;
-    const int y = y0 + ty, x = x0 + tx;
-    if (y >= H || x >= W) return;
+    if (!inside) return;
     float oi = 0.f, oh = 0.f, ov = 0.f;
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
         const float* p = s_P + ((ty + t / 3) * kHalo + tx + t % 3) * 27 + t;
         oi += p[0]; oh += p[9]; ov += p[18];
     }
-    const long long pix = (long long)y * W + x;
-    const float* hp = hvi + (long long)b * 3 * hw + pix;
-    const float Hh = oh + __ldcg(hp), Vv = ov + __ldcg(hp + hw), Ii = oi + __ldcg(hp + 2 * hw);   // cat([hv_0, i_dec0]) + hvi
+    const float Hh = oh + res_h, Vv = ov + res_v, Ii = oi + res_i;   // cat([hv_0, i_dec0]) + hvi
     if (out_hvi_dbg) {
         float* d = out_hvi_dbg + (long long)b * 3 * hw + pix;
         d[0] = Hh; d[hw] = Vv; d[2 * hw] = Ii;
