@@ -38,18 +38,23 @@ namespace cidnet {
 
 // ------------------------------------------------------------------ params ---
 struct ConvGemmArgs {
-    CUtensorMap tmA, tmA2, tmB, tmB2, tmOut, tmUp;
+    CUtensorMap tmA, tmA2, tmB, tmB2, tmOut, tmUp, tmA_t, tmB_t;
     int taps, kchunks, kchunks2, cin, cin2;
     int Hv, Wv, TH, TW, tiles_x, tiles_y, num_tiles;
     int n_out, block_n, stages, per_image_w, b_resident, stg_bufs;
     float2* sa_stats;                // EPI_UP, MSSA variant: per-pixel (mean, max) over the output channels (SpatialAttention input)
     int w_early;                     // resident weights are model constants: request them before the programmatic-dependency wait
     int halo;                        // 3x3: tile + halo loaded once per channel chunk, taps = row-shifted views
+    int wring;                       // halo mode with STREAMED weights: stages of the weight ring (one [block_n x 64] chunk per
+                                     // (tap, channel chunk)); 0 = weights resident (or riding with the A stages)
     // channels per TMA box (64, or 48 for the C = 36 layers).  Measured on B200: with an inner box narrower than the swizzle
     // span TMA still lays the rows out at the span's pitch (128 B), i.e. exactly the canonical SWIZZLE_128B K-major tile with
     // the unused tail of every row left untouched -- and the cost of a box is per BYTE (profiles/r01_tma_rowrate.txt), so a
     // 48-channel box moves 25 % fewer bytes through the TMA unit than the zero-filled 64-channel one.
     int boxc, boxc2, boxc_out, boxc_up;
+    // halo mode, Cin = 72 / 144: the LAST channel chunk holds 8 / 16 real channels -- its halo tile and its weight chunks
+    // come through 16-channel boxes (tmA_t / tmB_t; same smem tiles, a quarter of the TMA bytes).  0 = no tail box.
+    int tailc;
     int w_real;
     const float* bias; const float* wsum; float ln_eps;
     int up_H, up_W, up_chunks; float up_ry, up_rx;   // EPI_UP: low-res source (staged by TMA next to every A tile)
@@ -66,6 +71,7 @@ struct ConvGemmArgs {
 // (tcgen05.ld -> math -> pack -> st.shared -> fence -> bar -> TMA store).  2 groups are launched; see launch_conv_gemm
 // for the 3-group experiment.
 static constexpr int kMaxEpiGroups = 3;
+static constexpr int kMaxWRing = 12;
 static constexpr uint32_t kSubTileBytes = 128 * 128;   // 128 rows x 64 elements x 2 B
 static constexpr uint32_t kStagingBytes = 128 * 128;   // one 64-channel output block of a tile
 static constexpr uint32_t kHaloTileBytes = 11 * 16 * 128;   // halo mode: 11 rows x 16 columns x 64 channels
@@ -126,7 +132,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
     uint8_t* smBres = smem;                                                // resident weights (optional)
     uint8_t* smA = smBres + (a.b_resident ? (size_t)nbchunks * b_chunk : 0);
     uint8_t* smB = smA + (size_t)stages * a_stage;                         // streamed weights (optional)
-    uint8_t* smOut = smB + (a.b_resident ? 0 : (size_t)stages * b_chunk);  // 2 staging buffers per epilogue group
+    uint8_t* smOut = smB + (a.b_resident ? 0 : (size_t)(a.wring ? a.wring : stages) * b_chunk);  // 2 staging buffers per epilogue group
     uint64_t* full = reinterpret_cast<uint64_t*>(smOut + (size_t)a.stg_bufs * kEpiGroups * kStagingBytes);
     uint64_t* empty = full + stages;
     uint64_t* bfull = empty + stages;
@@ -140,7 +146,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
     // the LayerNorm statistics were read from the previous tile's data (the round-1 "3 epilogue groups lose parity"
     // failure, profiles/r02_summary.md).  The MMA warp arrives once per tile, so a group sees consecutive phases.
     uint64_t* a_ready = tmem_empty + kEpiGroups;           // [kEpiGroups]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + kEpiGroups + (kEpiGroups & 1));   // (+ pad: s_bias stays 16-byte aligned)
+    uint64_t* wfull = a_ready + kEpiGroups + (kEpiGroups & 1);   // [kMaxWRing] weight ring (halo mode with streamed weights)
+    uint64_t* wempty = wfull + kMaxWRing;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wempty + kMaxWRing);   // (s_bias stays 16-byte aligned)
     float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);
     const int bn32 = (a.block_n + 31) & ~31;
     float* s_wsum = s_bias + bn32;
@@ -159,6 +167,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
         ptx::prefetch_tensormap(&a.tmB);
         ptx::prefetch_tensormap(&a.tmOut);
         if (a.kchunks2) { ptx::prefetch_tensormap(&a.tmA2); ptx::prefetch_tensormap(&a.tmB2); }
+        if (a.tailc) { ptx::prefetch_tensormap(&a.tmA_t); ptx::prefetch_tensormap(&a.tmB_t); }
         if (kUp) ptx::prefetch_tensormap(&a.tmUp);
     }
     if (warp == 1) {
@@ -168,6 +177,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
             for (int s = 0; s < stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], empty_count); }
             ptx::mbar_init(bfull, 1);
             for (int i = 0; i < kEpiGroups; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], 4); ptx::mbar_init(&a_ready[i], 1); }
+            for (int i = 0; i < a.wring; ++i) { ptx::mbar_init(&wfull[i], 1); ptx::mbar_init(&wempty[i], 1); }
             ptx::fence_barrier_init();
         }
         __syncwarp();
@@ -188,11 +198,17 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
     // resident weights that are CONSTANTS of the model are requested before the programmatic-dependency wait: they land
     // while the previous kernel of the stream is still finishing.  The attention's folded weights (written by
     // cab_fold_kernel a moment ago; resident when the batch is 1) must wait like every activation.
+    const uint32_t b_tail = (uint32_t)a.block_n * (uint32_t)a.tailc * 2u;        // bytes of a tail weight chunk (tailc != 0)
     auto load_resident_weights = [&]() {
-        ptx::mbar_expect_tx(bfull, (uint32_t)nbchunks * b_chunk);
+        const uint32_t ntail = a.tailc ? (uint32_t)a.taps : 0u;                    // one tail chunk per tap
+        ptx::mbar_expect_tx(bfull, ((uint32_t)nbchunks - ntail) * b_chunk + ntail * b_tail);
         for (int i = 0; i < nbchunks; ++i) {
-            if (i < k1) ptx::tma_load_3d(smBres + (size_t)i * b_chunk, &a.tmB, bfull, i * 64, n0, 0);
-            else        ptx::tma_load_3d(smBres + (size_t)i * b_chunk, &a.tmB2, bfull, (i - k1) * 64, n0, 0);
+            if (i < k1) {
+                const bool tail = a.tailc && (i % a.kchunks) == a.kchunks - 1;
+                ptx::tma_load_3d(smBres + (size_t)i * b_chunk, tail ? &a.tmB_t : &a.tmB, bfull, i * 64, n0, 0);
+            } else {
+                ptx::tma_load_3d(smBres + (size_t)i * b_chunk, &a.tmB2, bfull, (i - k1) * 64, n0, 0);
+            }
         }
     };
     if (warp == 0 && lane == 0 && a.b_resident && a.w_early) load_resident_weights();
@@ -203,7 +219,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
     if (warp == 0) {
         // ------------------------------------------------------- TMA producer
         if (lane == 0) {
-            uint32_t it = 0;
+            uint32_t it = 0, wit = 0;
             for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
                 const int img = t / tiles_per_img;
                 const int trem = t - img * tiles_per_img;
@@ -214,10 +230,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                     const uint32_t ph = (it / stages) & 1u;
                     ptx::mbar_wait(&empty[s], ph ^ 1u);
                     const bool up_here = (kUp) && i == 0;      // the tile's low-res box rides with its first stage
-                    const uint32_t a_bytes = (a.halo || i < k1) ? kSub * (a.halo ? 11u * 16u : 128u) * (uint32_t)a.boxc * 2u
+                    const bool a_tail = a.tailc && a.halo && i == a.kchunks - 1;
+                    const uint32_t a_bytes = (a.halo || i < k1) ? kSub * (a.halo ? 11u * 16u : 128u) * (uint32_t)(a_tail ? a.tailc : a.boxc) * 2u
                                                                 : 128u * (uint32_t)a.boxc2 * 2u;
+                    const CUtensorMap* mapA = a_tail ? &a.tmA_t : &a.tmA;
                     ptx::mbar_expect_tx(&full[s], a_bytes + (up_here ? a.up_chunks * (uint32_t)(kUpBoxW * kUpBoxH) * (uint32_t)a.boxc_up * 2u : 0u) +
-                                                      (a.b_resident ? 0u : b_chunk));
+                                                      ((a.b_resident || a.wring) ? 0u : b_chunk));
                     uint8_t* dstA = smA + (size_t)s * a_stage;
                     if (up_here) {
                         const int by0 = (int)(a.up_ry * (float)(y0 + a.up_row0)) - a.up_src_row0;
@@ -228,10 +246,20 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                     if (a.halo) {
                         // i == channel chunk; one (DOWN: two, even / odd rows) halo box serves all 9 taps
                         if (kMode == EPI_DOWN) {
-                            ptx::tma_load_5d(dstA, &a.tmA, &full[s], i * 64, x0 - 1, 0, y0 - 1, img);
-                            ptx::tma_load_5d(dstA + kHaloTileBytes, &a.tmA, &full[s], i * 64, x0 - 1, 1, y0 - 1, img);
+                            ptx::tma_load_5d(dstA, mapA, &full[s], i * 64, x0 - 1, 0, y0 - 1, img);
+                            ptx::tma_load_5d(dstA + kHaloTileBytes, mapA, &full[s], i * 64, x0 - 1, 1, y0 - 1, img);
                         } else {
-                            ptx::tma_load_4d(dstA, &a.tmA, &full[s], i * 64, x0 - 1, y0 - 1, img);
+                            ptx::tma_load_4d(dstA, mapA, &full[s], i * 64, x0 - 1, y0 - 1, img);
+                        }
+                        if (a.wring) {
+                            // the 9 taps' weight chunks of this channel chunk follow through their own ring: the halo tile is
+                            // loaded ONCE per tile and channel chunk (not once per tap, as the tap-shifted tiles were)
+                            for (int tap = 0; tap < 9; ++tap, ++wit) {
+                                const uint32_t r = wit % (uint32_t)a.wring;
+                                ptx::mbar_wait(&wempty[r], ((wit / (uint32_t)a.wring) & 1u) ^ 1u);
+                                ptx::mbar_expect_tx(&wfull[r], a_tail ? b_tail : b_chunk);
+                                ptx::tma_load_3d(smB + (size_t)r * b_chunk, a_tail ? &a.tmB_t : &a.tmB, &wfull[r], (tap * a.kchunks + i) * 64, n0, 0);
+                            }
                         }
                     } else if (i < k1) {
                         const int tap = i / a.kchunks;
@@ -265,7 +293,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
         const uint32_t idesc = ptx::umma_idesc_f16(CIDNET_UMMA_FMT, (uint32_t)a.block_n);
         if (a.b_resident) { ptx::mbar_wait(bfull, 0); }
         const uint32_t leader = ptx::elect_one() ? 1u : 0u;     // the one lane whose tcgen05.mma / commit take effect
-        uint32_t it = 0, j = 0;
+        uint32_t it = 0, j = 0, wit = 0;
         for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++j) {
             const uint32_t buf = j % kEpiGroups;
             ptx::mbar_wait(&tmem_empty[buf], ((j / kEpiGroups) & 1u) ^ 1u);      // epilogue drained this buffer
@@ -291,6 +319,14 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         const int dy = tap / 3, dx = tap - dy * 3;
+                        uint32_t wr = 0;
+                        if (a.wring) {                      // streamed weights: this tap's chunk comes out of the weight ring
+                            wr = wit % (uint32_t)a.wring;
+                            ptx::mbar_wait(&wfull[wr], (wit / (uint32_t)a.wring) & 1u);
+                            ptx::tc_fence_after();
+                            descB = ptx::umma_smem_desc_sw128(ptx::smem_u32(smB + (size_t)wr * b_chunk));
+                            ++wit;
+                        }
 #pragma unroll
                         for (int sub = 0; sub < kSub; ++sub) {
                             // which halo tile and which first row this (accumulator, tap) reads
@@ -312,7 +348,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                             if (ksteps > 2) ptx::umma_f16_lead<true>(leader, dt, descA + 4, descB + 4, idesc);
                             if (ksteps > 3) ptx::umma_f16_lead<true>(leader, dt, descA + 6, descB + 6, idesc);
                         }
-                        descB += b_tap;
+                        if (a.wring) ptx::umma_commit_lead(leader, &wempty[wr]);     // frees the weight stage when its MMAs retire
+                        else descB += b_tap;
                     }
                     ptx::umma_commit_lead(leader, &empty[s]);
                     if (i == kiters - 1) ptx::umma_commit_lead(leader, &tmem_full[buf]);
@@ -701,6 +738,16 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
         const size_t fixed1 = 1024 + (size_t)kEpiGroups * kStagingBytes + 512 + 2 * round_up(wt.block_n, 32) * sizeof(float);
         const size_t need = fixed1 + (size_t)9 * wt.kchunks * wt.block_n * 128 + (size_t)2 * ksub * kHaloTileBytes;
         a.halo = (wt.taps == 9 && !L.in2 && !a.per_image_w && need <= 226 * 1024) ? 1 : 0;
+        // weights too large to stay resident (72 -> 144, 144 -> 72): keep the halo tile anyway and STREAM the weight chunks
+        // through a ring of their own.  The tap-shifted mode re-loaded the A tile for every tap: 18 x (32 KB + 9 KB) = 742 KB
+        // of TMA traffic per 256-pixel tile of down3 (x 2 N blocks), which at ~25 B / cycle / SM IS the layer's time
+        // (38.7 us per launch at cfg 2, 277 TFLOP/s at cfg 5); with the halo tile resident it is 2 x 45 KB + 18 x 9 KB.
+        const size_t need_ring = fixed1 + (size_t)2 * ksub * kHaloTileBytes + (size_t)4 * wt.block_n * 128;
+        if (!a.halo && wt.taps == 9 && !L.in2 && !a.per_image_w && need_ring <= 226 * 1024) { a.halo = 1; a.wring = 4; }
+    }
+    {   // tail box: halo mode, several channel chunks, the last one at most a quarter full
+        const int rem = wt.cin - (wt.kchunks - 1) * 64;
+        a.tailc = (a.halo && wt.kchunks > 1 && rem <= 16) ? 16 : 0;
     }
     auto box_channels = [](int c, int chunks) { return chunks == 1 ? (c <= 48 ? (unsigned)round_up(c, 16) : 64u) : 64u; };
     a.boxc = (int)box_channels(wt.cin, wt.kchunks);
@@ -722,6 +769,10 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
         const uint64_t str[4] = {pb, pb * L.W, pb * L.W * 2, pb * hw};
         const uint32_t box[5] = {(uint32_t)a.boxc, 16, 1, (uint32_t)(a.halo ? 11 : 8), 1};
         if ((rc = encode_map(&a.tmA, L.in, 5, dims, str, box))) return rc;
+        if (a.tailc) {
+            const uint32_t tbox[5] = {(uint32_t)a.tailc, 16, 1, 11, 1};
+            if ((rc = encode_map(&a.tmA_t, L.in, 5, dims, str, tbox))) return rc;
+        }
         const uint64_t od[4] = {(uint64_t)wt.n_out, (uint64_t)L.W / 2, (uint64_t)L.H / 2, (uint64_t)L.B};
         const uint64_t os[3] = {ob, ob * (L.W / 2), ob * (hw / 4)};
         const uint32_t obox[4] = {(uint32_t)a.boxc_out, (uint32_t)(tw / 2), 8, 1};
@@ -734,6 +785,10 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
         const uint32_t box[4] = {(uint32_t)a.boxc, (uint32_t)a.TW, (uint32_t)a.TH, 1};
         const uint32_t hbox[4] = {(uint32_t)a.boxc, 16, 11, 1};
         if ((rc = encode_map(&a.tmA, L.in, 4, dims, str, a.halo ? hbox : box))) return rc;
+        if (a.tailc) {
+            const uint32_t tbox[4] = {(uint32_t)a.tailc, 16, 11, 1};
+            if ((rc = encode_map(&a.tmA_t, L.in, 4, dims, str, tbox))) return rc;
+        }
         const uint64_t od[4] = {(uint64_t)wt.n_out, (uint64_t)a.Wv, (uint64_t)a.Hv, (uint64_t)L.B};
         const uint64_t os[3] = {ob, ob * a.Wv, ob * hw};
         const uint32_t obox[4] = {(uint32_t)a.boxc_out, (uint32_t)a.TW, (uint32_t)a.TH, 1};
@@ -780,6 +835,10 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
         const uint64_t str[2] = {kt * sizeof(act_t), kt * sizeof(act_t) * wt.n_rows};
         const uint32_t box[3] = {64, (uint32_t)wt.block_n, 1};
         if ((rc = encode_map(&a.tmB, wt.w, 3, dims, str, box))) return rc;
+        if (a.tailc) {
+            const uint32_t tbox[3] = {(uint32_t)a.tailc, (uint32_t)wt.block_n, 1};
+            if ((rc = encode_map(&a.tmB_t, wt.w, 3, dims, str, tbox))) return rc;
+        }
     }
 
     // shared-memory plan: [resident weights] [A ring] [streamed-weight ring] [2 staging] [barriers, bias]
@@ -820,11 +879,23 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
             stages = (int)((budget - fixed) / (a_stage + b_chunk));
         }
     }
+    if (a.wring) {
+        // halo tiles + weight ring: as many halo stages as a second tile needs while >= 6 weight stages remain, else 2
+        a.b_resident = 0; a.stg_bufs = 2;
+        fixed = 1024 + (size_t)2 * kEpiGroups * kStagingBytes + 512 + 2 * round_up(wt.block_n, 32) * sizeof(float);
+        // (measured: 3 halo stages + 6 weight stages and 2 + 11 give the same layer time -- neither ring is the bound)
+        stages = want;
+        while (stages > 2 && fixed + (size_t)stages * a_stage + 6 * b_chunk > budget) --stages;
+        int ring = (int)((budget - fixed - (size_t)stages * a_stage) / b_chunk);
+        a.wring = ring > kMaxWRing ? kMaxWRing : ring;
+        CIDNET_CHECK(a.wring >= 2, CIDNET_ERR_INVALID, "conv_gemm: shared memory budget exceeded (weight ring)");
+    }
     if (stages > 12) stages = 12;
     if (stages > want) stages = want;
     CIDNET_CHECK(stages >= min_stages, CIDNET_ERR_INVALID, "conv_gemm: shared memory budget exceeded");
     a.stages = stages;
-    const size_t smem = fixed + (a.b_resident ? bres : 0) + (size_t)stages * (a_stage + (a.b_resident ? 0 : b_chunk));
+    const size_t smem = a.wring ? fixed + (size_t)stages * a_stage + (size_t)a.wring * b_chunk
+                                : fixed + (a.b_resident ? bres : 0) + (size_t)stages * (a_stage + (a.b_resident ? 0 : b_chunk));
 
     int gx = (L.max_ctas > 0 ? L.max_ctas : device_sm_count()) / wt.n_blocks;
     if (gx < 1) gx = 1;
