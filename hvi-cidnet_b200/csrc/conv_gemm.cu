@@ -113,9 +113,15 @@ __device__ __forceinline__ void fhfma2(float& acc0, float& acc1, uint32_t a, uin
         : "+f"(acc0), "+f"(acc1) : "r"(a), "r"(b));
 }
 
-template <int kMode, int kEpiGroups>
+// kHalo: 0 = 1x1 / tap-shifted tiles, 1 = 3x3 from one halo tile with resident weights, 2 = halo tile + streamed weight ring.
+// A TEMPLATE parameter on purpose: the halo paths unroll 9 taps x 2 accumulators x 4 k-steps of tcgen05.mma issue code; as a
+// run-time flag that code sat in every instantiation (the STORE kernel grew from 1800 to 3120 SASS instructions when the weight
+// ring was added) and every 1x1 layer lost 2-4 us per launch to it (measured: same-box A/B against the previous library).
+template <int kMode, int kEpiGroups, int kHalo>
 __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
+    constexpr bool kHaloOn = kHalo != 0;
+    constexpr bool kWRing = kHalo == 2;
     // 1024-byte alignment is required by the SWIZZLE_128B TMA / UMMA tiles; using the array directly
     // (no integer round trip) keeps the accesses in the shared state space (LDS / STS, not generic LD / ST)
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -123,16 +129,16 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
     constexpr int kSub = (kMode == EPI_DOWN) ? 2 : 1;
     constexpr bool kUp = (kMode == EPI_UP || kMode == EPI_UP_SA);      // EPI_UP_SA: EPI_UP + per-pixel channel (mean, max)
     constexpr bool kSa = (kMode == EPI_UP_SA);
-    const uint32_t a_stage = kSub * (a.halo ? kHaloTileBytes : kSubTileBytes) + (kUp ? a.up_chunks * kUpTileBytes : 0u);
+    const uint32_t a_stage = kSub * (kHaloOn ? kHaloTileBytes : kSubTileBytes) + (kUp ? a.up_chunks * kUpTileBytes : 0u);
     const uint32_t b_chunk = (uint32_t)a.block_n * 128u;
     const int stages = a.stages;
     const int k1 = a.taps * a.kchunks;              // primary K chunks (weight chunks)
     const int nbchunks = k1 + a.kchunks2;           // weight chunks resident / streamed
-    const int kiters = a.halo ? a.kchunks : nbchunks;   // pipeline iterations (A stages) per tile
+    const int kiters = kHaloOn ? a.kchunks : nbchunks;   // pipeline iterations (A stages) per tile
     uint8_t* smBres = smem;                                                // resident weights (optional)
     uint8_t* smA = smBres + (a.b_resident ? (size_t)nbchunks * b_chunk : 0);
     uint8_t* smB = smA + (size_t)stages * a_stage;                         // streamed weights (optional)
-    uint8_t* smOut = smB + (a.b_resident ? 0 : (size_t)(a.wring ? a.wring : stages) * b_chunk);  // 2 staging buffers per epilogue group
+    uint8_t* smOut = smB + (a.b_resident ? 0 : (size_t)(kWRing ? a.wring : stages) * b_chunk);  // 2 staging buffers per epilogue group
     uint64_t* full = reinterpret_cast<uint64_t*>(smOut + (size_t)a.stg_bufs * kEpiGroups * kStagingBytes);
     uint64_t* empty = full + stages;
     uint64_t* bfull = empty + stages;
@@ -177,7 +183,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
             for (int s = 0; s < stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], empty_count); }
             ptx::mbar_init(bfull, 1);
             for (int i = 0; i < kEpiGroups; ++i) { ptx::mbar_init(&tmem_full[i], 1); ptx::mbar_init(&tmem_empty[i], 4); ptx::mbar_init(&a_ready[i], 1); }
-            for (int i = 0; i < a.wring; ++i) { ptx::mbar_init(&wfull[i], 1); ptx::mbar_init(&wempty[i], 1); }
+            if (kWRing) for (int i = 0; i < a.wring; ++i) { ptx::mbar_init(&wfull[i], 1); ptx::mbar_init(&wempty[i], 1); }
             ptx::fence_barrier_init();
         }
         __syncwarp();
@@ -230,12 +236,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                     const uint32_t ph = (it / stages) & 1u;
                     ptx::mbar_wait(&empty[s], ph ^ 1u);
                     const bool up_here = (kUp) && i == 0;      // the tile's low-res box rides with its first stage
-                    const bool a_tail = a.tailc && a.halo && i == a.kchunks - 1;
-                    const uint32_t a_bytes = (a.halo || i < k1) ? kSub * (a.halo ? 11u * 16u : 128u) * (uint32_t)(a_tail ? a.tailc : a.boxc) * 2u
+                    const bool a_tail = a.tailc && kHaloOn && i == a.kchunks - 1;
+                    const uint32_t a_bytes = (kHaloOn || i < k1) ? kSub * (kHaloOn ? 11u * 16u : 128u) * (uint32_t)(a_tail ? a.tailc : a.boxc) * 2u
                                                                 : 128u * (uint32_t)a.boxc2 * 2u;
                     const CUtensorMap* mapA = a_tail ? &a.tmA_t : &a.tmA;
                     ptx::mbar_expect_tx(&full[s], a_bytes + (up_here ? a.up_chunks * (uint32_t)(kUpBoxW * kUpBoxH) * (uint32_t)a.boxc_up * 2u : 0u) +
-                                                      ((a.b_resident || a.wring) ? 0u : b_chunk));
+                                                      ((a.b_resident || kWRing) ? 0u : b_chunk));
                     uint8_t* dstA = smA + (size_t)s * a_stage;
                     if (up_here) {
                         const int by0 = (int)(a.up_ry * (float)(y0 + a.up_row0)) - a.up_src_row0;
@@ -243,7 +249,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                         for (int ch = 0; ch < a.up_chunks; ++ch)
                             ptx::tma_load_4d(dstA + kSubTileBytes + ch * kUpTileBytes, &a.tmUp, &full[s], ch * 64, bx0, by0, img);
                     }
-                    if (a.halo) {
+                    if (kHaloOn) {
                         // i == channel chunk; one (DOWN: two, even / odd rows) halo box serves all 9 taps
                         if (kMode == EPI_DOWN) {
                             ptx::tma_load_5d(dstA, mapA, &full[s], i * 64, x0 - 1, 0, y0 - 1, img);
@@ -251,7 +257,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                         } else {
                             ptx::tma_load_4d(dstA, mapA, &full[s], i * 64, x0 - 1, y0 - 1, img);
                         }
-                        if (a.wring) {
+                        if (kWRing) {
                             // the 9 taps' weight chunks of this channel chunk follow through their own ring: the halo tile is
                             // loaded ONCE per tile and channel chunk (not once per tap, as the tap-shifted tiles were)
                             for (int tap = 0; tap < 9; ++tap, ++wit) {
@@ -305,7 +311,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                 ptx::mbar_wait(&full[s], ph);
                 ptx::tc_fence_after();
                 if ((kMode == EPI_LN || kUp) && i == kiters - 1 && lane == 0) ptx::mbar_arrive(&a_ready[buf]);
-                if (a.halo) {
+                if (kHaloOn) {
                     // One (elected) lane issues every tcgen05.mma, the whole warp runs the loop convergently; ncu showed the tensor pipe busy only ~55 % of the time
                     // behind this loop (~150 cycles of uniform-datapath descriptor arithmetic per MMA), so the
                     // loops are fully unrolled: tap / sub-tile offsets are compile-time constants added to two base
@@ -320,7 +326,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                     for (int tap = 0; tap < 9; ++tap) {
                         const int dy = tap / 3, dx = tap - dy * 3;
                         uint32_t wr = 0;
-                        if (a.wring) {                      // streamed weights: this tap's chunk comes out of the weight ring
+                        if (kWRing) {                      // streamed weights: this tap's chunk comes out of the weight ring
                             wr = wit % (uint32_t)a.wring;
                             ptx::mbar_wait(&wfull[wr], (wit / (uint32_t)a.wring) & 1u);
                             ptx::tc_fence_after();
@@ -348,7 +354,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                             if (ksteps > 2) ptx::umma_f16_lead<true>(leader, dt, descA + 4, descB + 4, idesc);
                             if (ksteps > 3) ptx::umma_f16_lead<true>(leader, dt, descA + 6, descB + 6, idesc);
                         }
-                        if (a.wring) ptx::umma_commit_lead(leader, &wempty[wr]);     // frees the weight stage when its MMAs retire
+                        if (kWRing) ptx::umma_commit_lead(leader, &wempty[wr]);     // frees the weight stage when its MMAs retire
                         else descB += b_tap;
                     }
                     ptx::umma_commit_lead(leader, &empty[s]);
@@ -381,7 +387,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int grp = (warp - 2) >> 2;        // epilogue group == TMEM buffer it drains
         const int row = q * 32 + lane;          // accumulator row == pixel within the tile
-        const int pw = a.halo ? 16 : a.TW;      // halo mode: rows are 16 wide, the last 2 columns are wrap-around garbage
+        const int pw = kHaloOn ? 16 : a.TW;      // halo mode: rows are 16 wide, the last 2 columns are wrap-around garbage
         const int ty = row / pw;
         const int tx = row - ty * pw;
         const bool col_ok = tx < a.TW;
@@ -577,7 +583,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                         }
                     }
                     // 16-bit, swizzled (SWIZZLE_128B) staging row; DOWN: only even lanes own an output pixel
-                    int srow = a.halo ? ty * a.TW + tx : row;      // halo mode: drop the 2 garbage columns
+                    int srow = kHaloOn ? ty * a.TW + tx : row;      // halo mode: drop the 2 garbage columns
                     bool wr = col_ok;
                     if (kMode == EPI_DOWN) { srow = ty * (a.TW >> 1) + (tx >> 1); wr = col_ok && (tx & 1) == 0; }
                     if (wr) {
@@ -678,19 +684,26 @@ static inline float ac_scale(int n_in, int n_out) {
     return n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.f;
 }
 
-template <int kMode, int kEpiGroups>
+template <int kMode, int kEpiGroups, int kHalo>
 static int launch_mode_g(const ConvGemmArgs& args, dim3 grid, size_t smem, cudaStream_t stream) {
-    int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(conv_gemm_kernel<kMode, kEpiGroups>), 227 * 1024);
+    int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(conv_gemm_kernel<kMode, kEpiGroups, kHalo>), 227 * 1024);
     if (rc) return rc;
-    return launch_k(conv_gemm_kernel<kMode, kEpiGroups>, grid, dim3(64 + 128 * kEpiGroups), smem, stream, args);
+    return launch_k(conv_gemm_kernel<kMode, kEpiGroups, kHalo>, grid, dim3(64 + 128 * kEpiGroups), smem, stream, args);
 }
 template <int kMode>
 static int launch_mode(const ConvGemmArgs& args, dim3 grid, size_t smem, cudaStream_t stream, int groups) {
+    const int hm = args.halo ? (args.wring ? 2 : 1) : 0;
 #ifdef CIDNET_GEMM_GROUPS3
-    if (groups == 3) return launch_mode_g<kMode, 3>(args, grid, smem, stream);
+    if (groups == 3 && hm == 0) return launch_mode_g<kMode, 3, 0>(args, grid, smem, stream);
 #endif
     (void)groups;
-    return launch_mode_g<kMode, 2>(args, grid, smem, stream);
+    if constexpr (kMode == EPI_STORE || kMode == EPI_DOWN) {      // the only modes with 3x3 layers
+        if (hm == 1) return launch_mode_g<kMode, 2, 1>(args, grid, smem, stream);
+        if (hm == 2) return launch_mode_g<kMode, 2, 2>(args, grid, smem, stream);
+    } else {
+        CIDNET_CHECK(hm == 0, CIDNET_ERR_INVALID, "conv_gemm: halo tiles are built for the STORE / DOWN epilogues only");
+    }
+    return launch_mode_g<kMode, 2, 0>(args, grid, smem, stream);
 }
 
 int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
@@ -737,13 +750,14 @@ int launch_conv_gemm(const ConvGemmLaunch& L, cudaStream_t stream) {
         // right data with base_offset = 0; setting (addr >> 7) & 7 there gives wrong results)
         const size_t fixed1 = 1024 + (size_t)kEpiGroups * kStagingBytes + 512 + 2 * round_up(wt.block_n, 32) * sizeof(float);
         const size_t need = fixed1 + (size_t)9 * wt.kchunks * wt.block_n * 128 + (size_t)2 * ksub * kHaloTileBytes;
-        a.halo = (wt.taps == 9 && !L.in2 && !a.per_image_w && need <= 226 * 1024) ? 1 : 0;
+        const bool halo_mode_ok = L.mode == EPI_STORE || L.mode == EPI_DOWN;
+        a.halo = (halo_mode_ok && wt.taps == 9 && !L.in2 && !a.per_image_w && need <= 226 * 1024) ? 1 : 0;
         // weights too large to stay resident (72 -> 144, 144 -> 72): keep the halo tile anyway and STREAM the weight chunks
         // through a ring of their own.  The tap-shifted mode re-loaded the A tile for every tap: 18 x (32 KB + 9 KB) = 742 KB
         // of TMA traffic per 256-pixel tile of down3 (x 2 N blocks), which at ~25 B / cycle / SM IS the layer's time
         // (38.7 us per launch at cfg 2, 277 TFLOP/s at cfg 5); with the halo tile resident it is 2 x 45 KB + 18 x 9 KB.
         const size_t need_ring = fixed1 + (size_t)2 * ksub * kHaloTileBytes + (size_t)4 * wt.block_n * 128;
-        if (!a.halo && wt.taps == 9 && !L.in2 && !a.per_image_w && need_ring <= 226 * 1024) { a.halo = 1; a.wring = 4; }
+        if (halo_mode_ok && !a.halo && wt.taps == 9 && !L.in2 && !a.per_image_w && need_ring <= 226 * 1024) { a.halo = 1; a.wring = 4; }
     }
     {   // tail box: halo mode, several channel chunks, the last one at most a quarter full
         const int rem = wt.cin - (wt.kchunks - 1) * 64;

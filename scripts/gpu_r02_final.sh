@@ -29,3 +29,11 @@ timeout 300 python scripts/prof_forward.py 1 640 1120 3 $O/${T}_marks.txt > $O/$
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 178 -c 89 --csv \
     --log-file $O/${T}_launches_traffic.csv python scripts/prof_forward.py 1 640 1120 3 > $O/${T}_ncu.log 2>&1
 echo "ncu rc=$?"
+# per-kernel ncu table of one whole forward of the final tree (reduced section set; summarised ON the box: the report itself is
+# too large to travel back)
+timeout 900 ncu --section SpeedOfLight --section ComputeWorkloadAnalysis --section MemoryWorkloadAnalysis --section WarpStateStats \
+    --section LaunchStats --section Occupancy --section InstructionStats --clock-control none -s 178 -c 89 -o /tmp/${T}_forward -f \
+    python scripts/prof_forward.py 1 640 1120 3 > $O/${T}_ncu_sections.log 2>&1
+echo "ncu sections rc=$?"
+python scripts/ncu_summary.py /tmp/${T}_forward.ncu-rep $O/${T}_marks.txt > $O/${T}_ncu_forward_table.csv 2> $O/${T}_ncu_summary.err; echo "summary rc=$? lines=$(wc -l < $O/${T}_ncu_forward_table.csv)"
+rm -f /tmp/${T}_forward.ncu-rep
