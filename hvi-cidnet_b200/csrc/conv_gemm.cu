@@ -113,6 +113,33 @@ __device__ __forceinline__ void fhfma2(float& acc0, float& acc1, uint32_t a, uin
         : "+f"(acc0), "+f"(acc1) : "r"(a), "r"(b));
 }
 
+// Division-free bookkeeping.  sm_100 has no integer divide: every `t / tiles_per_img`, `trem % tiles_x`, `it % stages` was
+// a ~20-instruction I2F / MUFU.RCP / F2I sequence with a ~100-cycle dependent latency, on the single producer / issuer
+// thread and on every epilogue thread once per tile or per stage (18 of them in the 1x1 kernel: 360 of its 1832 SASS
+// instructions).  TileWalk decodes the first tile with real divisions and then steps by gridDim.x with carries; RingPos
+// counts a ring position and its mbarrier phase.
+struct TileWalk {
+    int t, img, ty, tx;                // linear tile index and its (image, tile row, tile column)
+    int st, s_img, s_ty, s_tx;         // the step (gridDim.x), decomposed the same way
+    int tiles_x, tiles_y;
+    __device__ __forceinline__ TileWalk(int t0, int step, int tiles_x_, int tiles_y_) : tiles_x(tiles_x_), tiles_y(tiles_y_) {
+        const int per_img = tiles_x * tiles_y;
+        t = t0; img = t0 / per_img; { const int r = t0 - img * per_img; ty = r / tiles_x; tx = r - ty * tiles_x; }
+        st = step; s_img = step / per_img; { const int r = step - s_img * per_img; s_ty = r / tiles_x; s_tx = r - s_ty * tiles_x; }
+    }
+    __device__ __forceinline__ void next() {
+        t += st;
+        tx += s_tx; if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+        ty += s_ty; if (ty >= tiles_y) { ty -= tiles_y; ++img; }
+        img += s_img;
+    }
+};
+struct RingPos {
+    uint32_t s = 0, ph = 0;            // stage index, phase bit
+    __device__ __forceinline__ void advance(uint32_t n) { if (++s == n) { s = 0; ph ^= 1u; } }
+    __device__ __forceinline__ void advance_by(uint32_t k, uint32_t n) { s += k; while (s >= n) { s -= n; ph ^= 1u; } }
+};
+
 // kHalo: 0 = 1x1 / tap-shifted tiles, 1 = 3x3 from one halo tile with resident weights, 2 = halo tile + streamed weight ring.
 // A TEMPLATE parameter on purpose: the halo paths unroll 9 taps x 2 accumulators x 4 k-steps of tcgen05.mma issue code; as a
 // run-time flag that code sat in every instantiation (the STORE kernel grew from 1800 to 3120 SASS instructions when the weight
@@ -225,16 +252,15 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
     if (warp == 0) {
         // ------------------------------------------------------- TMA producer
         if (lane == 0) {
-            uint32_t it = 0, wit = 0;
-            for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
-                const int img = t / tiles_per_img;
-                const int trem = t - img * tiles_per_img;
-                const int y0 = (trem / a.tiles_x) * a.TH;
-                const int x0 = (trem % a.tiles_x) * a.TW;
-                for (int i = 0; i < kiters; ++i, ++it) {
-                    const int s = it % stages;
-                    const uint32_t ph = (it / stages) & 1u;
-                    ptx::mbar_wait(&empty[s], ph ^ 1u);
+            RingPos rp, wp;
+            for (TileWalk tw(blockIdx.x, gridDim.x, a.tiles_x, a.tiles_y); tw.t < a.num_tiles; tw.next()) {
+                const int img = tw.img;
+                const int y0 = tw.ty * a.TH;
+                const int x0 = tw.tx * a.TW;
+                int tap_i = 0, kc_i = 0;                       // (tap, channel chunk) of iteration i in the tap-shifted mode
+                for (int i = 0; i < kiters; ++i, rp.advance((uint32_t)stages)) {
+                    const uint32_t s = rp.s;
+                    ptx::mbar_wait(&empty[s], rp.ph ^ 1u);
                     const bool up_here = (kUp) && i == 0;      // the tile's low-res box rides with its first stage
                     const bool a_tail = a.tailc && kHaloOn && i == a.kchunks - 1;
                     const uint32_t a_bytes = (kHaloOn || i < k1) ? kSub * (kHaloOn ? 11u * 16u : 128u) * (uint32_t)(a_tail ? a.tailc : a.boxc) * 2u
@@ -260,18 +286,18 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                         if (kWRing) {
                             // the 9 taps' weight chunks of this channel chunk follow through their own ring: the halo tile is
                             // loaded ONCE per tile and channel chunk (not once per tap, as the tap-shifted tiles were)
-                            for (int tap = 0; tap < 9; ++tap, ++wit) {
-                                const uint32_t r = wit % (uint32_t)a.wring;
-                                ptx::mbar_wait(&wempty[r], ((wit / (uint32_t)a.wring) & 1u) ^ 1u);
+                            for (int tap = 0; tap < 9; ++tap, wp.advance((uint32_t)a.wring)) {
+                                const uint32_t r = wp.s;
+                                ptx::mbar_wait(&wempty[r], wp.ph ^ 1u);
                                 ptx::mbar_expect_tx(&wfull[r], a_tail ? b_tail : b_chunk);
                                 ptx::tma_load_3d(smB + (size_t)r * b_chunk, a_tail ? &a.tmB_t : &a.tmB, &wfull[r], (tap * a.kchunks + i) * 64, n0, 0);
                             }
                         }
                     } else if (i < k1) {
-                        const int tap = i / a.kchunks;
-                        const int kc = i - tap * a.kchunks;
+                        const int tap = tap_i, kc = kc_i;
+                        if (++kc_i == a.kchunks) { kc_i = 0; ++tap_i; }
                         int dy = 1, dx = 1;
-                        if (a.taps == 9) { dy = tap / 3; dx = tap - dy * 3; }
+                        if (a.taps == 9) { dy = (tap * 11) >> 5; dx = tap - dy * 3; }      // tap / 3 for tap < 9
                         if (kMode == EPI_DOWN) {
 #pragma unroll
                             for (int sub = 0; sub < 2; ++sub) {
@@ -299,16 +325,17 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
         const uint32_t idesc = ptx::umma_idesc_f16(CIDNET_UMMA_FMT, (uint32_t)a.block_n);
         if (a.b_resident) { ptx::mbar_wait(bfull, 0); }
         const uint32_t leader = ptx::elect_one() ? 1u : 0u;     // the one lane whose tcgen05.mma / commit take effect
-        uint32_t it = 0, j = 0, wit = 0;
+        uint32_t j = 0;
+        RingPos rp, wp;
         for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++j) {
             const uint32_t buf = j % kEpiGroups;
             ptx::mbar_wait(&tmem_empty[buf], ((j / kEpiGroups) & 1u) ^ 1u);      // epilogue drained this buffer
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * acc_cols;
-            for (int i = 0; i < kiters; ++i, ++it) {
-                const int s = it % stages;
-                const uint32_t ph = (it / stages) & 1u;
-                ptx::mbar_wait(&full[s], ph);
+            int kc_i = 0;                                                        // channel chunk of iteration i (tap-shifted mode)
+            for (int i = 0; i < kiters; ++i, rp.advance((uint32_t)stages)) {
+                const uint32_t s = rp.s;
+                ptx::mbar_wait(&full[s], rp.ph);
                 ptx::tc_fence_after();
                 if ((kMode == EPI_LN || kUp) && i == kiters - 1 && lane == 0) ptx::mbar_arrive(&a_ready[buf]);
                 if (kHaloOn) {
@@ -327,11 +354,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                         const int dy = tap / 3, dx = tap - dy * 3;
                         uint32_t wr = 0;
                         if (kWRing) {                      // streamed weights: this tap's chunk comes out of the weight ring
-                            wr = wit % (uint32_t)a.wring;
-                            ptx::mbar_wait(&wfull[wr], (wit / (uint32_t)a.wring) & 1u);
+                            wr = wp.s;
+                            ptx::mbar_wait(&wfull[wr], wp.ph);
                             ptx::tc_fence_after();
                             descB = ptx::umma_smem_desc_sw128(ptx::smem_u32(smB + (size_t)wr * b_chunk));
-                            ++wit;
+                            wp.advance((uint32_t)a.wring);
                         }
 #pragma unroll
                         for (int sub = 0; sub < kSub; ++sub) {
@@ -360,7 +387,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                     ptx::umma_commit_lead(leader, &empty[s]);
                     if (i == kiters - 1) ptx::umma_commit_lead(leader, &tmem_full[buf]);
                 } else {
-                    int crem = (i < k1) ? a.cin - (i % a.kchunks) * 64 : a.cin2 - (i - k1) * 64;
+                    int crem = (i < k1) ? a.cin - kc_i * 64 : a.cin2 - (i - k1) * 64;
+                    if (++kc_i == a.kchunks) kc_i = 0;
                     int ksteps = (crem + 15) >> 4;
                     if (ksteps > 4) ksteps = 4;
                     const uint8_t* bsrc = a.b_resident ? smBres + (size_t)i * b_chunk : smB + (size_t)s * b_chunk;
@@ -396,13 +424,14 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
         const uint32_t sb_toggle = a.stg_bufs - 1;
         const uint32_t bar_id = 1 + grp;
         const int nblk64 = (min(a.block_n, a.n_out - n0) + 63) >> 6;     // 64-channel output blocks
-        uint32_t it = 0, j = 0, sb = 0;
-        for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++j) {
-            if ((int)(j % kEpiGroups) != grp) { it += kiters; continue; }      // another group's tile
-            const int img = t / tiles_per_img;
-            const int trem = t - img * tiles_per_img;
-            const int y0 = (trem / a.tiles_x) * a.TH;
-            const int x0 = (trem % a.tiles_x) * a.TW;
+        uint32_t j = 0, sb = 0;
+        RingPos rp;                                   // ring position of the current tile's FIRST pipeline stage (LN / UP read it)
+        for (TileWalk tw(blockIdx.x, gridDim.x, a.tiles_x, a.tiles_y); tw.t < a.num_tiles;
+             tw.next(), ++j, rp.advance_by((uint32_t)kiters, (uint32_t)stages)) {
+            if ((int)(j % kEpiGroups) != grp) continue;                        // another group's tile
+            const int img = tw.img;
+            const int y0 = tw.ty * a.TH;
+            const int x0 = tw.tx * a.TW;
             const int y = y0 + ty, x = x0 + tx;
             const bool valid = col_ok && (y < a.Hv) && (x < a.Wv);
 
@@ -414,8 +443,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                 // one pass: sum and sum of squares with FHFMA (x*1 and x*x, exact 16-bit products, fp32
                 // accumulation; channels >= Cin are TMA zero fill and contribute nothing)
                 float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-                for (int kc = 0; kc < a.kchunks; ++kc) {
-                    const uint8_t* rowp = smA + (size_t)((it + kc) % stages) * a_stage + row * 128;
+                uint32_t st = rp.s;
+                for (int kc = 0; kc < a.kchunks; ++kc, st = (st + 1 == (uint32_t)stages) ? 0u : st + 1) {
+                    const uint8_t* rowp = smA + (size_t)st * a_stage + row * 128;
                     const int nvec = min(8, (a.cin - kc * 64 + 7) >> 3);
                     for (int jv = 0; jv < nvec; ++jv) {
                         const uint4 raw = *reinterpret_cast<const uint4*>(rowp + ((jv ^ (row & 7)) << 4));
@@ -430,10 +460,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                 const float var = fmaxf((q0 + q1) * inv_c - mean * mean, 0.f);
                 rstd = 1.0f / sqrtf(var + a.ln_eps);
                 __syncwarp();
-                if (lane == 0)
-                    for (int kc = 0; kc < a.kchunks; ++kc) ptx::mbar_arrive(&empty[(it + kc) % stages]);
+                if (lane == 0) {
+                    uint32_t sr = rp.s;
+                    for (int kc = 0; kc < a.kchunks; ++kc, sr = (sr + 1 == (uint32_t)stages) ? 0u : sr + 1) ptx::mbar_arrive(&empty[sr]);
+                }
             }
-            it += kiters;
 
             // EPI_UP: bilinear x2 taps of the low-res tensor (align_corners=True), read from the box the producer
             // staged with this tile's first pipeline stage (rows of 64 channels, SWIZZLE_128B)
@@ -441,9 +472,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
             uint32_t u00 = 0, u01 = 0, u10 = 0, u11 = 0;      // box row index (128-byte rows) of the four neighbours
             float uly = 0.f, ulx = 0.f;
             uint32_t uw00 = 0, uw01 = 0, uw10 = 0, uw11 = 0;  // the four bilinear weights as packed (w, w) 16-bit pairs
-            const uint32_t up_it = it - kiters;               // pipeline iteration of this tile's first stage
             if (kUp) {
-                const uint32_t s0 = up_it % stages;
+                const uint32_t s0 = rp.s;
                 ptx::mbar_wait(&a_ready[j % kEpiGroups], (j / kEpiGroups) & 1u);
                 up_tile = smA + (size_t)s0 * a_stage + kSubTileBytes;
                 const int yr = y, xr = x;                                    // UP tiles are 8 x 16 rectangles of one image
@@ -610,8 +640,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
             __syncwarp();
             if (lane == 0) {
                 ptx::mbar_arrive(&tmem_empty[buf]);
-                if (kUp)      // the low-res box has been read: co-release the tile's stages
-                    for (int i = 0; i < kiters; ++i) ptx::mbar_arrive(&empty[(up_it + i) % stages]);
+                if (kUp) {    // the low-res box has been read: co-release the tile's stages
+                    uint32_t sr = rp.s;
+                    for (int i = 0; i < kiters; ++i, sr = (sr + 1 == (uint32_t)stages) ? 0u : sr + 1) ptx::mbar_arrive(&empty[sr]);
+                }
             }
         }
         if (issuer) ptx::tma_store_wait_all();
