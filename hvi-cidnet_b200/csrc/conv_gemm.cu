@@ -189,7 +189,6 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * a.block_n;
-    const int tiles_per_img = a.tiles_x * a.tiles_y;
     const uint32_t acc_cols = (uint32_t)(kSub * a.block_n);    // columns of one accumulator buffer
 
     uint32_t ncols = 32;
@@ -245,6 +244,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
         }
     };
     if (warp == 0 && lane == 0 && a.b_resident && a.w_early) load_resident_weights();
+    const TileWalk tw_first(blockIdx.x, gridDim.x, a.tiles_x, a.tiles_y);     // (its four divisions run under the predecessor's tail)
     ptx::pdl_wait();
     ptx::pdl_trigger();
     if (warp == 0 && lane == 0 && a.b_resident && !a.w_early) load_resident_weights();
@@ -253,7 +253,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
         // ------------------------------------------------------- TMA producer
         if (lane == 0) {
             RingPos rp, wp;
-            for (TileWalk tw(blockIdx.x, gridDim.x, a.tiles_x, a.tiles_y); tw.t < a.num_tiles; tw.next()) {
+            for (TileWalk tw = tw_first; tw.t < a.num_tiles; tw.next()) {
                 const int img = tw.img;
                 const int y0 = tw.ty * a.TH;
                 const int x0 = tw.tx * a.TW;
@@ -426,7 +426,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
         const int nblk64 = (min(a.block_n, a.n_out - n0) + 63) >> 6;     // 64-channel output blocks
         uint32_t j = 0, sb = 0;
         RingPos rp;                                   // ring position of the current tile's FIRST pipeline stage (LN / UP read it)
-        for (TileWalk tw(blockIdx.x, gridDim.x, a.tiles_x, a.tiles_y); tw.t < a.num_tiles;
+        for (TileWalk tw = tw_first; tw.t < a.num_tiles;
              tw.next(), ++j, rp.advance_by((uint32_t)kiters, (uint32_t)stages)) {
             if ((int)(j % kEpiGroups) != grp) continue;                        // another group's tile
             const int img = tw.img;
@@ -646,7 +646,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
                 }
             }
         }
-        if (issuer) ptx::tma_store_wait_all();
+        if (issuer) ptx::tma_store_wait_read<0>();      // the staging buffers have been READ; the global writes complete with the grid
     }
 
     ptx::tc_fence_before();
