@@ -558,21 +558,9 @@ def run_ours(args):
     ms_e2e_u8 = f0.elapsed_time(f1)
     del h8
 
-    # ---- the two multi-GPU configs of BASELINE.json, same process group (N > 1, default workload only) -------------
-    extras = None
-    if extras_wanted:
-        del xs, hx, hy, drv
-        model._workspaces = {}
-        torch.cuda.empty_cache()
-        extras = {}
-        try:
-            extras["cfg5"] = measure_cfg5_sharded(model, dev, world, rank, steps=min(args.steps, 10), warmup=3)
-        except Exception as e:               # never lose the headline line to an extra
-            extras["cfg5"] = {"error": repr(e)[:400]}
-        try:
-            extras["cfg4"] = measure_cfg4_batch(model, dev, world, rank, steps=min(args.steps, 5), warmup=3)
-        except Exception as e:
-            extras["cfg4"] = {"error": repr(e)[:400]}
+    del xs, hx, hy, drv
+    model._workspaces = {}
+    torch.cuda.empty_cache()
     if world > 1:
         t = torch.tensor([ms_total, ms_e2e, ms_e2e_sync, ms_e2e_u8], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -629,7 +617,43 @@ def run_ours(args):
                                   "quantise fused into the stem and head kernels (cidnet_forward_u8)"},
                 "gpu_launches": launches, "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
                 "gpu_eager_baseline": eager, "clocks": clocks}
-        if extras is not None:
+    # ---- the two multi-GPU configs of BASELINE.json, same process group (N > 1, default workload only) -------------
+    # They run AFTER the headline line is complete and under a watchdog: whatever happens to an extra (an exception, a
+    # rank that never arrives), rank 0 prints the ONE JSON line -- with what the extras produced so far and the reason --
+    # within CIDNET_EXTRAS_TIMEOUT seconds, and every rank leaves.
+    if extras_wanted:
+        extras = {}
+        deadline = float(os.environ.get("CIDNET_EXTRAS_TIMEOUT", "180"))
+        finished = threading.Event()
+        print_once = threading.Lock()
+
+        def watchdog():
+            if finished.wait(deadline) or not print_once.acquire(blocking=False):
+                return
+            if rank == 0:
+                extras.setdefault("error", f"extra workloads did not finish within {deadline:.0f} s (CIDNET_EXTRAS_TIMEOUT); "
+                                           "the headline above is complete")
+                line["extra_workloads"] = extras
+                print(json.dumps(line), flush=True)
+            os._exit(0)
+        threading.Thread(target=watchdog, daemon=True).start()
+        t_ex = time.perf_counter()
+        try:
+            extras["cfg5"] = measure_cfg5_sharded(model, dev, world, rank, steps=min(args.steps, 10), warmup=3)
+        except Exception as e:               # never lose the headline line to an extra
+            extras["cfg5"] = {"error": repr(e)[:400]}
+        print(f"[bench rank {rank}] extra cfg5 done after {time.perf_counter() - t_ex:.1f} s", file=sys.stderr, flush=True)
+        try:
+            extras["cfg4"] = measure_cfg4_batch(model, dev, world, rank, steps=min(args.steps, 5), warmup=3)
+        except Exception as e:
+            extras["cfg4"] = {"error": repr(e)[:400]}
+        print(f"[bench rank {rank}] extra cfg4 done after {time.perf_counter() - t_ex:.1f} s", file=sys.stderr, flush=True)
+        finished.set()
+        if not print_once.acquire(blocking=False):       # the watchdog is printing / has printed: it also ends the process
+            time.sleep(30)
+            os._exit(0)
+    if rank == 0:
+        if extras_wanted:
             line["extra_workloads"] = extras
         print(json.dumps(line), flush=True)
     if world > 1:
