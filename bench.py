@@ -418,6 +418,39 @@ def measure_cfg4_batch(model, dev, world, rank, steps, warmup):
             "parity_batch_vs_single_maxabs": float(t[1]), "pixels_beyond_5e-4": int(t[2])}
 
 
+def run_extras_under_watchdog(jobs, deadline, rank, line):
+    """Run the extra workloads `jobs` = [(key, callable), ...] and return {key: result | {"error": ...}}.  If they are not
+    done after `deadline` seconds (a rank that never arrives at a collective, a stalled exchange), rank 0 prints the ONE
+    JSON line `line` with the results so far and the reason, and EVERY rank's process ends (os._exit(0)): the headline is
+    never lost to an extra.  `line` is None on the other ranks."""
+    extras = {}
+    finished = threading.Event()
+    print_once = threading.Lock()
+
+    def watchdog():
+        if finished.wait(deadline) or not print_once.acquire(blocking=False):
+            return
+        if rank == 0 and line is not None:
+            extras.setdefault("error", f"extra workloads did not finish within {deadline:.0f} s (CIDNET_EXTRAS_TIMEOUT); "
+                                       "the headline of this line is complete")
+            line["extra_workloads"] = extras
+            print(json.dumps(line), flush=True)
+        os._exit(0)
+    threading.Thread(target=watchdog, daemon=True).start()
+    t0 = time.perf_counter()
+    for key, fn in jobs:
+        try:
+            extras[key] = fn()
+        except Exception as e:               # never lose the headline line to an extra
+            extras[key] = {"error": repr(e)[:400]}
+        print(f"[bench rank {rank}] extra {key} done after {time.perf_counter() - t0:.1f} s", file=sys.stderr, flush=True)
+    finished.set()
+    if not print_once.acquire(blocking=False):       # the watchdog is printing / has printed: it also ends the process
+        time.sleep(30)
+        os._exit(0)
+    return extras
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -622,36 +655,10 @@ def run_ours(args):
     # rank that never arrives), rank 0 prints the ONE JSON line -- with what the extras produced so far and the reason --
     # within CIDNET_EXTRAS_TIMEOUT seconds, and every rank leaves.
     if extras_wanted:
-        extras = {}
-        deadline = float(os.environ.get("CIDNET_EXTRAS_TIMEOUT", "180"))
-        finished = threading.Event()
-        print_once = threading.Lock()
-
-        def watchdog():
-            if finished.wait(deadline) or not print_once.acquire(blocking=False):
-                return
-            if rank == 0:
-                extras.setdefault("error", f"extra workloads did not finish within {deadline:.0f} s (CIDNET_EXTRAS_TIMEOUT); "
-                                           "the headline above is complete")
-                line["extra_workloads"] = extras
-                print(json.dumps(line), flush=True)
-            os._exit(0)
-        threading.Thread(target=watchdog, daemon=True).start()
-        t_ex = time.perf_counter()
-        try:
-            extras["cfg5"] = measure_cfg5_sharded(model, dev, world, rank, steps=min(args.steps, 10), warmup=3)
-        except Exception as e:               # never lose the headline line to an extra
-            extras["cfg5"] = {"error": repr(e)[:400]}
-        print(f"[bench rank {rank}] extra cfg5 done after {time.perf_counter() - t_ex:.1f} s", file=sys.stderr, flush=True)
-        try:
-            extras["cfg4"] = measure_cfg4_batch(model, dev, world, rank, steps=min(args.steps, 5), warmup=3)
-        except Exception as e:
-            extras["cfg4"] = {"error": repr(e)[:400]}
-        print(f"[bench rank {rank}] extra cfg4 done after {time.perf_counter() - t_ex:.1f} s", file=sys.stderr, flush=True)
-        finished.set()
-        if not print_once.acquire(blocking=False):       # the watchdog is printing / has printed: it also ends the process
-            time.sleep(30)
-            os._exit(0)
+        extras = run_extras_under_watchdog(
+            [("cfg5", lambda: measure_cfg5_sharded(model, dev, world, rank, steps=min(args.steps, 10), warmup=3)),
+             ("cfg4", lambda: measure_cfg4_batch(model, dev, world, rank, steps=min(args.steps, 5), warmup=3))],
+            float(os.environ.get("CIDNET_EXTRAS_TIMEOUT", "180")), rank, line if rank == 0 else None)
     if rank == 0:
         if extras_wanted:
             line["extra_workloads"] = extras
